@@ -1,0 +1,72 @@
+"""CPU tests: the oracle (C restatement of ppp.pm:130-245 + Math::Cephes 0.47 bdtrc) against the golden vectors
+that oracle/gen_golden.py produced by running the reference itself (perl + the reference's bundled Cephes binary)."""
+import json
+import os
+
+import numpy as np
+
+from oracle import oracle
+from prophylo_b200 import synth
+
+
+def test_bdtrc_points_match_reference_binary(golden_dir):
+    pts = json.load(open(os.path.join(golden_dir, "bdtrc_points.json")))["points"]
+    assert len(pts) > 3000
+    k = np.array([x[0] for x in pts], dtype=np.int32)
+    n = np.array([x[1] for x in pts], dtype=np.int32)
+    p = np.array([float(x[2]) for x in pts])
+    exp = np.array([float(x[3]) for x in pts])
+    got = oracle.bdtrc_batch(k, n, p)
+    # k == 0 and p < 0.01 binds to the host libm's expm1 in the reference (see oracle/cephes_port.c): allow 1 ulp there
+    libm = (k == 0) & (p < 0.01)
+    assert np.array_equal(got[~libm].view(np.uint64), exp[~libm].view(np.uint64))
+    assert np.all(np.abs(got[libm] - exp[libm]) <= np.spacing(exp[libm]))
+
+
+def test_survey_table_values():
+    # SURVEY.md section 8c `bdtrc` points (binary)
+    assert oracle.bdtrc(0, 1, .02) == 0.020000000000000018
+    assert oracle.bdtrc(8, 12, 9 / 434) == 1.4745387719095076e-13
+    assert oracle.bdtrc(3, 100, .25) == 0.9999999978918347
+    assert oracle.bdtrc(49, 50, .5) == 8.881784197001258e-16
+    assert oracle.bdtrc(99, 4096, .01) == 3.271936483402975e-15
+    assert oracle.bdtrc(500, 4096, .1) == 2.125572110772742e-06
+    assert oracle.bdtrc(-1, 5, .3) == 1.0
+    assert oracle.bdtrc(5, 5, .3) == 0.0
+    assert oracle.bdtrc(150, 4096, 1e-4) == 0.0
+    assert oracle.bdtrc(0, 5, .01) == 0.04900995009999998
+    assert oracle.bdtrc(2, 5, 1.2) == 0.0  # domain error -> 0.0
+
+
+def test_list_cases_match_reference(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "ppp_list_cases.json")))
+    cases = g["known_answers"] + g["fuzz"]
+    assert len(cases) >= 600
+    for c in cases:
+        got = oracle.score_case(c["query"], c["target"], c.get("prob"), bool(c.get("dup")))
+        e = c["expect"]
+        assert got == (float(e[0]), e[1], e[2], e[3], float(e[4])), c["name"]
+
+
+def test_known_answer_1_is_baseline_config_1(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "ppp_list_cases.json")))
+    ka1 = g["known_answers"][0]
+    assert ka1["query_yes_total"] == [9, 434]  # t/00profile.t:10-14
+    assert ka1["expect"] == ["1", 0, 0, 0, "0.020737327188940093"]
+
+
+def test_bit_cases_match_reference(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "ppp_bit_cases.json")))
+    for case in g["cases"]:
+        sp = case["spec"]
+        G = sp["G"]
+        P, Y, p = synth.make_queries(G, sp["nq"], sp["qseed"], sp["kind"])
+        T = synth.make_targets(G, sp["nt"], sp["tseed"], plant_from=Y, plant_frac=0.25)
+        assert [repr(float(x)) for x in p] == case["p"]
+        out, _ = oracle.score_bits_batch(P, Y, p, T, G, nthreads=4)
+        res = case["results"]
+        for q in range(sp["nq"]):
+            for t in range(sp["nt"]):
+                r = res[q * sp["nt"] + t]
+                o = out[q, t]
+                assert (o["score"], o["yes"], o["number"], o["depth"]) == (float(r[0]), r[1], r[2], r[3]), (sp, q, t)
