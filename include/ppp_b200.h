@@ -1,0 +1,141 @@
+/*
+ * include/ppp_b200.h -- C ABI of libppp_b200.so, the B200-native PPP scan.
+ *
+ * The reference (malaybasu/ProPhylo) has no FFI/plugin interface; its seam for this path is the Perl method
+ *     PhyloProf::Algorithm::ppp->new(-prof1,-prof2,[-prob],[-rank],[-taxonomy],[-dup])->get_match_score()
+ * (lib/PhyloProf/Algorithm/ppp.pm:58-110, 130-245) called per (query, target) pair by bin/ppp.pl:559-582,
+ * bin/ppp2d.pl:632, bin/ppp_cross_score.pl:681-699 and bin/ppp_hmmer.pl:222.  These entry points are what an
+ * XS binding of that method binds (perl/PPPB200.xs; INTEGRATION.md shows the stub): plain pointers and sizes,
+ * no C++ or torch types, caller-owned buffers, negative return codes instead of exceptions.
+ *
+ * Semantics fixed by the reference and therefore by this ABI:
+ *   - one *pair* = one get_match_score evaluation -> (score, yes, number, depth)           ppp.pm:244
+ *   - score starts at 1.0; a step improves only on strict `<`; the first minimum wins       ppp.pm:228-237
+ *   - score = Math::Cephes::bdtrc(yes-1, number, p), incl. exact 0.0 underflow, 1-MACHEP saturation,
+ *     "domain error" -> 0.0 for p outside [0,1]                                            ppp.pm:225
+ *   - a pair with no common yes-genome returns (1, 0, 0, 0)
+ *   - p is taken verbatim (the caller evaluates ppp.pm:138-142: -prob, else yes/total)
+ *   - depth is the 1-based position in the target's list (raw position incl. skipped duplicates for ranked
+ *     targets, BlastResult.pm:192-237; popcount prefix for bit-plane targets)
+ * yes, number and depth are bit-exact; score agrees with the reference within 1e-9 relative on -log(score)
+ * (bit-identical wherever the exact tier ran, see prophylo_b200/csrc/cephes_exact.cuh).
+ *
+ * There is no CPU fallback: every call fails with PPP_ERR_CUDA when no sm_100 device is usable.
+ * Threading: a ppp_ctx is owned by one thread at a time.  Create it AFTER any fork() (bin/ppp.pl:910 forks).
+ */
+#ifndef PPP_B200_H
+#define PPP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPP_B200_ABI_VERSION 1
+
+typedef struct ppp_ctx ppp_ctx;
+
+enum {
+    PPP_OK = 0,
+    PPP_ERR_INVALID = -1,  /* bad argument */
+    PPP_ERR_CUDA = -2,     /* CUDA runtime / no usable device */
+    PPP_ERR_NOMEM = -3,    /* host or device allocation failed */
+    PPP_ERR_STATE = -4,    /* call order (e.g. score before set_targets) */
+    PPP_ERR_CAPACITY = -5  /* caller's output buffer too small; *nout holds the needed count */
+};
+
+/* Result filter = what bin/ppp.pl:473-506 / bin/ppp_cutoff.pl:111-162 keep of one query's row. */
+enum {
+    PPP_FILTER_ALL = 0,          /* every pair, dense, out[q * nT + t]                                   */
+    PPP_FILTER_THRESH_LOG10 = 1, /* pairs with log10(score) < thresh  (ppp_cutoff.pl:122,154: thresh=-0.0005
+                                    keeps exactly the rows whose "%.3f" log-score is < 0)                */
+    PPP_FILTER_TOPK = 2          /* the k smallest scores per query; ties by target index                */
+};
+
+typedef struct ppp_filter {
+    uint32_t mode;
+    uint32_t k;     /* PPP_FILTER_TOPK */
+    double thresh;  /* PPP_FILTER_THRESH_LOG10 */
+} ppp_filter;
+
+/* One scored pair: the list get_match_score returns (ppp.pm:244), plus its coordinates. 32 bytes. */
+typedef struct ppp_hit {
+    uint32_t q;      /* query index  */
+    uint32_t t;      /* target index */
+    double score;    /* $score: best binomial upper-tail probability           */
+    uint32_t yes;    /* $best_yes                                              */
+    uint32_t number; /* $best_number                                           */
+    uint32_t depth;  /* $best_depth: cut-off index, 1-based; 0 = no improvement */
+    float margin;    /* ln(second-best) - ln(best) over the sweep (diagnostic; +inf if unique candidate;
+                        0 where the exact tier decided)                          */
+} ppp_hit;
+
+typedef struct ppp_stats {
+    uint64_t pairs;            /* pairs covered by the last run                                   */
+    uint64_t candidates;       /* yes-increment steps examined (popc(T&Y) summed)                 */
+    uint64_t accurate_evals;   /* FP64 series evaluations (tier B)                                */
+    uint64_t exact_pairs;      /* pairs re-swept by the exact Cephes tier (tier C)                */
+    uint64_t kernel_launches;  /* kernels launched by the last run                                */
+    float sweep_kernel_ms;     /* CUDA-event time of the dominant sweep kernel(s), on the ctx stream */
+    float total_device_ms;     /* CUDA-event time of the whole run on the ctx stream              */
+    uint32_t sweep_launches;   /* number of sweep kernel launches in sweep_kernel_ms              */
+    uint32_t reserved;
+} ppp_stats;
+
+/* Lifetime.  devices/ndev: CUDA ordinals this context may use; this implementation is one process per GPU and
+ * uses devices[0] (ndev >= 1).  Returns PPP_OK or a negative code; *out is NULL on failure. */
+int ppp_init(ppp_ctx **out, const int *devices, int ndev);
+void ppp_destroy(ppp_ctx *ctx);
+/* ctx-owned string describing the last failure on ctx (valid until the next call); ctx may be NULL for
+ * failures of ppp_init. */
+const char *ppp_last_error(const ppp_ctx *ctx);
+int ppp_abi_version(void);
+
+/* Targets as bit planes in canonical genome order (replaces the -prof2 ARRAY of a target whose list is its set
+ * genomes in universe order).  T is row-major, nT rows of ppp_words_per_row(G) uint32 words,
+ * genome g = bit (g & 31) of word (g >> 5), padding bits zero.  The data is copied before returning. */
+int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, uint32_t G);
+
+/* Targets as ordered hit lists (replaces -prof2 built by BlastResult::get_profile, BlastResult.pm:192-237, or
+ * the value-sorted HASH of HMMERResult, ppp.pm:147-149).  For target t, entries row_off[t]..row_off[t+1]) give,
+ * in list order and ALREADY de-duplicated by the host (ppp.pm:189-192), the genome index idx[] (0..G-1 in the
+ * query universe; 0xFFFF = taxon foreign to the universe) and the 1-based raw list position rawdepth[].
+ * At most 65535 list positions per target. */
+int ppp_set_targets_ranked(ppp_ctx *ctx, const uint16_t *idx, const uint16_t *rawdepth, const uint64_t *row_off,
+                           size_t nT, uint32_t G);
+
+/* Queries: presence plane P and yes plane Y (Y subset of P; same row layout as T) and p per query
+ * (replaces -prof1 and -prob).  Copied before returning; stays resident until replaced. */
+int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *Y, const double *p, size_t nQ);
+
+/* Score all resident queries against all resident targets; results stay on the device. */
+int ppp_run(ppp_ctx *ctx, const ppp_filter *f);
+/* Number of hits the last run produced, and copy them out (ALL: nQ*nT dense; otherwise grouped by query,
+ * ascending score then target index). */
+int ppp_result_count(ppp_ctx *ctx, size_t *nout);
+int ppp_fetch(ppp_ctx *ctx, ppp_hit *out, size_t cap, size_t *nout);
+
+/* One-call form with host buffers: ppp_set_queries + ppp_run + ppp_fetch. */
+int ppp_score(ppp_ctx *ctx, const uint32_t *P, const uint32_t *Y, const double *p, size_t nQ, const ppp_filter *f,
+              ppp_hit *out, size_t cap, size_t *nout);
+
+int ppp_get_stats(const ppp_ctx *ctx, ppp_stats *out);
+
+/* Options (tests / diagnostics): "force_exact" (0/1: every pair through the exact tier),
+ * "check_bounds" (0/1: verify the fast tier's enclosures against the accurate tier, count violations),
+ * "sweep_warps" (warps per CTA).  Unknown names return PPP_ERR_INVALID. */
+int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value);
+int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *value);
+
+/* Row length in uint32 words of the bit-plane layout for G genomes: ceil(G/128)*4. */
+uint32_t ppp_words_per_row(uint32_t G);
+
+/* Device-side evaluation of the exact tier's bdtrc (diagnostic; parity tests of cephes_exact.cuh). */
+int ppp_debug_bdtrc(ppp_ctx *ctx, const int32_t *k, const int32_t *n, const double *p, double *out, size_t m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPP_B200_H */

