@@ -183,6 +183,11 @@ extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, 
     ctx->G = G;
     ctx->wpl = wpl;
     ctx->nQ = 0; /* queries must be re-uploaded: the device row length may have changed */
+    cudaFree(ctx->d_Q);
+    cudaFree(ctx->d_qc);
+    ctx->d_Q = nullptr;
+    ctx->d_qc = nullptr;
+    ctx->capQ = 0;
     return PPP_OK;
 }
 
