@@ -7,8 +7,8 @@ COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC $ARCH"
 mkdir -p build
 nvcc $COMMON -c ppp_sweep.cu -o build/ppp_sweep.o &
 nvcc $COMMON -fmad=false -c ppp_exact.cu -o build/ppp_exact.o &
-nvcc $COMMON -c ppp_filter.cu -o build/ppp_filter.o &
+nvcc $COMMON -c ppp_topk.cu -o build/ppp_topk.o &
 nvcc $COMMON -c ppp_capi.cu -o build/ppp_capi.o &
 wait
-nvcc $ARCH -shared -o ../libppp_b200.so build/ppp_sweep.o build/ppp_exact.o build/ppp_filter.o build/ppp_capi.o
+nvcc $ARCH -shared -o ../libppp_b200.so build/ppp_sweep.o build/ppp_exact.o build/ppp_topk.o build/ppp_capi.o
 echo "built $(cd .. && pwd)/libppp_b200.so"

@@ -25,14 +25,19 @@ extern "C" cudaError_t ppp_launch_sweep(const SweepParams *prm, int wpl, int nwa
 extern "C" cudaError_t ppp_launch_exact(const SweepParams *prm, int W, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_debug_bdtrc(const int32_t *k, const int32_t *n, const double *p, double *out, size_t m,
                                               cudaStream_t st);
-extern "C" cudaError_t ppp_launch_filter(const void *hits, uint64_t npairs, double thresh_log10, int keep_all, void *out,
-                                         uint64_t cap, unsigned long long *count, int nsm, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_staircase(const QConst *qc, const double *lf, const double *kth, int accept_mode, double thresh_ln,
+                                            const uint32_t *static_off, uint16_t *nmax, uint32_t *active_off, uint32_t nQ, int nsm,
+                                            cudaStream_t st);
+extern "C" cudaError_t ppp_launch_topk_merge(const void *appended, uint32_t *qcnt, uint32_t qcap, void *topk, uint32_t *topk_cnt,
+                                             double *kth, uint32_t k, uint32_t nQ, int nsm, cudaStream_t st);
+extern "C" int ppp_topk_max_k(void);
 
 struct ppp_ctx {
     int device = 0;
     int nsm = 148;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double phase_us[4] = {0, 0, 0, 0}; /* sweep, exact, staircase, merge */
     char err[512] = {0};
 
     /* targets */
@@ -54,8 +59,19 @@ struct ppp_ctx {
     uint32_t *d_exact = nullptr;
     size_t cap_exact = 0;
     unsigned long long *d_counters = nullptr;
-    ppp_hit *d_filtered = nullptr;
-    size_t cap_filtered = 0;
+    /* filtered runs */
+    double *d_kth = nullptr;
+    size_t cap_kth = 0;
+    uint32_t *d_qcnt = nullptr;
+    size_t cap_qcnt = 0;
+    uint32_t *d_off = nullptr;
+    size_t cap_off = 0;
+    uint16_t *d_nmax = nullptr;
+    size_t cap_nmax = 0;
+    ppp_hit *d_topk = nullptr;
+    size_t cap_topk = 0;
+    std::vector<uint32_t> nmax_off_host; /* static staircase offsets: prefix sums of (ny + 1) */
+    size_t nmax_entries = 0;
 
     /* options */
     int force_exact = 0, check_bounds = 0, sweep_warps = 8;
@@ -115,7 +131,7 @@ extern "C" int ppp_init(ppp_ctx **out, const int *devices, int ndev)
         delete ctx;
         return PPP_ERR_CUDA;
     }
-    for (int i = 0; i < 4; ++i) cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
     if ((e = cudaMalloc(&ctx->d_counters, CNT_N * sizeof(unsigned long long))) != cudaSuccess) {
         fail(nullptr, PPP_ERR_CUDA, "ppp_init: %s", cudaGetErrorString(e));
         delete ctx;
@@ -137,8 +153,12 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaFree(ctx->d_hits);
     cudaFree(ctx->d_exact);
     cudaFree(ctx->d_counters);
-    cudaFree(ctx->d_filtered);
-    for (int i = 0; i < 4; ++i)
+    cudaFree(ctx->d_kth);
+    cudaFree(ctx->d_qcnt);
+    cudaFree(ctx->d_off);
+    cudaFree(ctx->d_nmax);
+    cudaFree(ctx->d_topk);
+    for (int i = 0; i < 8; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -199,11 +219,12 @@ extern "C" int ppp_set_targets_ranked(ppp_ctx *ctx, const uint16_t *idx, const u
     return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_ranked: ranked target lists are not built in this round (DESIGN.md, 'next')");
 }
 
-static void make_qconst(double p, uint32_t ny, QConst *qc)
+static void make_qconst(double p, uint32_t ny, uint32_t npres, QConst *qc)
 {
     memset(qc, 0, sizeof(*qc));
     qc->p = p;
     qc->ny = ny;
+    qc->npres = npres;
     if (isnan(p) || p == 0.0 || p == 1.0) {
         qc->flags = PPP_QF_TRIVIAL;
         return;
@@ -249,10 +270,23 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
     if (!nQ) return PPP_OK;
     std::vector<QConst> qc(nQ);
     for (size_t q = 0; q < nQ; ++q) {
-        uint32_t ny = 0;
+        uint32_t ny = 0, npres = 0;
         const uint32_t *pr = P + q * wpr, *yr = Y + q * wpr;
-        for (size_t w = 0; w < wpr; ++w) ny += (uint32_t)__builtin_popcount(pr[w] & yr[w]);
-        make_qconst(p[q], ny, &qc[q]);
+        for (size_t w = 0; w < wpr; ++w) {
+            ny += (uint32_t)__builtin_popcount(pr[w] & yr[w]);
+            npres += (uint32_t)__builtin_popcount(pr[w]);
+        }
+        make_qconst(p[q], ny, npres, &qc[q]);
+    }
+    ctx->nmax_off_host.resize(nQ);
+    {
+        size_t off = 0;
+        for (size_t q = 0; q < nQ; ++q) {
+            ctx->nmax_off_host[q] = (uint32_t)off;
+            off += (size_t)qc[q].ny + 1;
+        }
+        if (off > 0xfffffff0ull) return fail(ctx, PPP_ERR_INVALID, "ppp_set_queries: staircase tables exceed 4G entries");
+        ctx->nmax_entries = off;
     }
     CU(cudaMemsetAsync(ctx->d_Q, 0, ctx->capQ * 2 * W * 4, ctx->stream));
     CU(cudaMemcpy2DAsync(ctx->d_Q, 2 * W * 4, P, wpr * 4, wpr * 4, nQ, cudaMemcpyHostToDevice, ctx->stream));
@@ -263,30 +297,67 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
     return PPP_OK;
 }
 
-static int ensure_buffers(ppp_ctx *ctx, size_t dense_pairs, size_t launch_pairs)
-{
-    if (dense_pairs > ctx->cap_hits) {
-        cudaFree(ctx->d_hits);
-        ctx->d_hits = nullptr;
-        ctx->cap_hits = 0;
-        CU(cudaMalloc(&ctx->d_hits, dense_pairs * sizeof(ppp_hit)));
-        ctx->cap_hits = dense_pairs;
-    }
-    if (launch_pairs > ctx->cap_exact) {
-        cudaFree(ctx->d_exact);
-        ctx->d_exact = nullptr;
-        ctx->cap_exact = 0;
-        CU(cudaMalloc(&ctx->d_exact, launch_pairs * sizeof(uint32_t)));
-        ctx->cap_exact = launch_pairs;
-    }
-    return PPP_OK;
-}
-
 static bool hit_less(const ppp_hit &a, const ppp_hit &b)
 {
     if (a.q != b.q) return a.q < b.q;
     if (a.score != b.score) return a.score < b.score;
     return a.t < b.t;
+}
+
+template <typename T>
+static int grow(ppp_ctx *ctx, T **ptr, size_t *cap, size_t need)
+{
+    if (need <= *cap) return PPP_OK;
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    CU(cudaMalloc(ptr, need * sizeof(T)));
+    *cap = need;
+    return PPP_OK;
+}
+
+static void base_params(const ppp_ctx *ctx, SweepParams *prm)
+{
+    memset(prm, 0, sizeof(*prm));
+    prm->T = ctx->d_T;
+    prm->Q = ctx->d_Q;
+    prm->qc = ctx->d_qc;
+    prm->lf = ctx->d_lf;
+    prm->exact_list = ctx->d_exact;
+    prm->counters = ctx->d_counters;
+    prm->exact_cap = ctx->cap_exact;
+    prm->nQ = (uint32_t)ctx->nQ;
+    prm->nT = (uint32_t)ctx->nT;
+    prm->G = ctx->G;
+    prm->force_exact = (uint32_t)ctx->force_exact;
+    prm->check_bounds = (uint32_t)ctx->check_bounds;
+}
+
+/* one target chunk: sweep + exact tier; accumulates counters and the sweep kernel's event time */
+static int run_chunk(ppp_ctx *ctx, SweepParams *prm, unsigned long long *totals, float *sweep_ms, uint32_t *launches,
+                     unsigned long long *chunk_counters)
+{
+    const int W = 32 * ctx->wpl;
+    CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * sizeof(unsigned long long), ctx->stream));
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    CU(ppp_launch_sweep(prm, ctx->wpl, ctx->sweep_warps, ctx->nsm, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    CU(ppp_launch_exact(prm, W, ctx->nsm, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[4], ctx->stream));
+    *launches += 2;
+    unsigned long long c[CNT_N];
+    CU(cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+    *sweep_ms += ms;
+    ctx->phase_us[0] += 1e3 * ms;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+    ctx->phase_us[1] += 1e3 * ms;
+    for (int i = 0; i < CNT_N; ++i) totals[i] += c[i];
+    if (chunk_counters) memcpy(chunk_counters, c, sizeof(c));
+    if (c[CNT_OVERFLOW]) return fail(ctx, PPP_ERR_CUDA, "ppp_run: internal buffer overflow (%llu records dropped)", c[CNT_OVERFLOW]);
+    return PPP_OK;
 }
 
 extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
@@ -297,19 +368,12 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
     ppp_filter all = {PPP_FILTER_ALL, 0, 0.0};
     if (!f) f = &all;
     if (f->mode > PPP_FILTER_TOPK) return fail(ctx, PPP_ERR_INVALID, "ppp_run: unknown filter mode %u", f->mode);
-    if (f->mode == PPP_FILTER_TOPK && f->k == 0) return fail(ctx, PPP_ERR_INVALID, "ppp_run: top-k with k = 0");
+    if (f->mode == PPP_FILTER_TOPK && (f->k == 0 || (int)f->k > ppp_topk_max_k()))
+        return fail(ctx, PPP_ERR_INVALID, "ppp_run: top-k needs 1 <= k <= %d", ppp_topk_max_k());
+    if (f->mode == PPP_FILTER_THRESH_LOG10 && isnan(f->thresh)) return fail(ctx, PPP_ERR_INVALID, "ppp_run: thresh is NaN");
     CU(cudaSetDevice(ctx->device));
     const size_t nQ = ctx->nQ, nT = ctx->nT;
-    const int W = 32 * ctx->wpl;
-    /* targets per launch: bounded so that launch-local pair ids fit 31 bits; filtered modes also bound the dense
-     * scratch buffer (the dense records of a chunk are filtered on the device before the next chunk overwrites them) */
-    size_t chunk_pairs_max = (size_t)1 << 30;
-    if (f->mode != PPP_FILTER_ALL) chunk_pairs_max = (size_t)1 << 26;
-    size_t tchunk = std::max<size_t>(1, chunk_pairs_max / nQ);
-    if (tchunk > nT) tchunk = nT;
-    const size_t dense_pairs = (f->mode == PPP_FILTER_ALL) ? nQ * nT : nQ * tchunk;
-    int rc = ensure_buffers(ctx, dense_pairs, nQ * tchunk);
-    if (rc) return rc;
+    int rc;
 
     ctx->host_results.clear();
     ctx->results_on_host = (f->mode != PPP_FILTER_ALL);
@@ -317,99 +381,125 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
     memset(totals, 0, sizeof(totals));
     float sweep_ms = 0.f;
     uint32_t sweep_launches = 0, launches = 0;
-    std::vector<std::vector<ppp_hit>> topk; /* per query running best-k (host side of the ABI) */
-    if (f->mode == PPP_FILTER_TOPK) topk.resize(nQ);
 
+    for (int i = 0; i < 4; ++i) ctx->phase_us[i] = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    for (size_t t0 = 0; t0 < nT; t0 += tchunk) {
-        const size_t t1 = std::min(nT, t0 + tchunk);
-        SweepParams prm;
-        memset(&prm, 0, sizeof(prm));
-        prm.T = ctx->d_T;
-        prm.Q = ctx->d_Q;
-        prm.qc = ctx->d_qc;
-        prm.lf = ctx->d_lf;
-        prm.exact_list = ctx->d_exact;
-        prm.counters = ctx->d_counters;
-        prm.exact_cap = ctx->cap_exact;
-        prm.nQ = (uint32_t)nQ;
-        prm.G = ctx->G;
-        prm.force_exact = (uint32_t)ctx->force_exact;
-        prm.check_bounds = (uint32_t)ctx->check_bounds;
-        prm.t0 = (uint32_t)t0;
-        prm.t1 = (uint32_t)t1;
-        if (f->mode == PPP_FILTER_ALL) {
+    if (f->mode == PPP_FILTER_ALL) {
+        /* dense: chunks only bound the launch-local pair ids of the exact-tier list (31 bits) */
+        size_t tchunk = std::max<size_t>(1, ((size_t)1 << 30) / nQ);
+        if (tchunk > nT) tchunk = nT;
+        if ((rc = grow(ctx, &ctx->d_hits, &ctx->cap_hits, nQ * nT))) return rc;
+        if ((rc = grow(ctx, &ctx->d_exact, &ctx->cap_exact, nQ * tchunk))) return rc;
+        for (size_t t0 = 0; t0 < nT; t0 += tchunk) {
+            SweepParams prm;
+            base_params(ctx, &prm);
             prm.hits = ctx->d_hits;
-            prm.nT = (uint32_t)nT;
-        } else {
-            /* chunk-local dense scratch: row stride = chunk width, rows start at column t0 */
-            prm.hits = ctx->d_hits - t0; /* kernels index q * nT + t with nT = chunk width below */
-            prm.nT = (uint32_t)(t1 - t0);
+            prm.t0 = (uint32_t)t0;
+            prm.t1 = (uint32_t)std::min(nT, t0 + tchunk);
+            if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, nullptr))) return rc;
+            sweep_launches++;
         }
-        CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * sizeof(unsigned long long), ctx->stream));
-        CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-        CU(ppp_launch_sweep(&prm, ctx->wpl, ctx->sweep_warps, ctx->nsm, ctx->stream));
-        CU(cudaEventRecord(ctx->ev[3], ctx->stream));
-        CU(ppp_launch_exact(&prm, W, ctx->nsm, ctx->stream));
-        launches += 2;
-        sweep_launches += 1;
-        unsigned long long c[CNT_N];
-        CU(cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
-        if (f->mode != PPP_FILTER_ALL) {
-            /* device-side threshold compaction of the chunk's dense records */
-            const size_t np = nQ * (t1 - t0);
-            if (np > ctx->cap_filtered) {
-                cudaFree(ctx->d_filtered);
-                ctx->d_filtered = nullptr;
-                ctx->cap_filtered = 0;
-                CU(cudaMalloc(&ctx->d_filtered, np * sizeof(ppp_hit)));
-                ctx->cap_filtered = np;
-            }
-            CU(cudaMemsetAsync(ctx->d_counters + CNT_N - 1, 0, sizeof(unsigned long long), ctx->stream));
-            CU(ppp_launch_filter(ctx->d_hits, np, f->thresh, f->mode == PPP_FILTER_TOPK, ctx->d_filtered, ctx->cap_filtered,
-                                 ctx->d_counters + CNT_N - 1, ctx->nsm, ctx->stream));
-            launches += 1;
-            unsigned long long nf = 0;
-            CU(cudaMemcpyAsync(&nf, ctx->d_counters + CNT_N - 1, sizeof(nf), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            std::vector<ppp_hit> part(nf);
-            if (nf) CU(cudaMemcpy(part.data(), ctx->d_filtered, nf * sizeof(ppp_hit), cudaMemcpyDeviceToHost));
-            if (f->mode == PPP_FILTER_THRESH_LOG10) {
-                ctx->host_results.insert(ctx->host_results.end(), part.begin(), part.end());
-            } else {
-                for (const ppp_hit &h : part) topk[h.q].push_back(h);
-                for (size_t q = 0; q < nQ; ++q) {
-                    std::vector<ppp_hit> &v = topk[q];
-                    if (v.size() > f->k) {
-                        std::partial_sort(v.begin(), v.begin() + f->k, v.end(), hit_less);
-                        v.resize(f->k);
-                    }
-                }
-            }
-        } else {
+        ctx->n_results = nQ * nT;
+    } else {
+        /* filtered: per-query staircases prune almost every pair inside the sweep kernel; survivors are appended */
+        const bool topk = (f->mode == PPP_FILTER_TOPK);
+        const uint32_t k = f->k;
+        const size_t maxw = std::min<size_t>(nT, std::max<size_t>(256, ((size_t)1 << 26) / nQ));
+        if ((rc = grow(ctx, &ctx->d_hits, &ctx->cap_hits, nQ * maxw))) return rc;
+        if ((rc = grow(ctx, &ctx->d_exact, &ctx->cap_exact, nQ * maxw))) return rc;
+        if ((rc = grow(ctx, &ctx->d_kth, &ctx->cap_kth, nQ))) return rc;
+        if ((rc = grow(ctx, &ctx->d_qcnt, &ctx->cap_qcnt, 2 * nQ))) return rc; /* [nQ] append counters, [nQ] top-k counts */
+        if ((rc = grow(ctx, &ctx->d_off, &ctx->cap_off, 2 * nQ))) return rc;   /* [nQ] static offsets, [nQ] active offsets */
+        if ((rc = grow(ctx, &ctx->d_nmax, &ctx->cap_nmax, ctx->nmax_entries + 8))) return rc;
+        if (topk && (rc = grow(ctx, &ctx->d_topk, &ctx->cap_topk, nQ * (size_t)k))) return rc;
+        uint32_t *d_qcnt = ctx->d_qcnt, *d_topk_cnt = ctx->d_qcnt + nQ;
+        uint32_t *d_off_static = ctx->d_off, *d_off_active = ctx->d_off + nQ;
+        CU(cudaMemcpyAsync(d_off_static, ctx->nmax_off_host.data(), nQ * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(d_qcnt, 0, 2 * nQ * sizeof(uint32_t), ctx->stream));
+        CU(cudaMemsetAsync(d_off_active, 0xff, nQ * sizeof(uint32_t), ctx->stream)); /* PPP_NO_TABLE */
+        {
+            std::vector<double> two(nQ, 2.0);
+            CU(cudaMemcpyAsync(ctx->d_kth, two.data(), nQ * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
         }
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
-        sweep_ms += ms;
-        for (int i = 0; i < CNT_N; ++i) totals[i] += c[i];
-        if (c[CNT_OVERFLOW])
-            return fail(ctx, PPP_ERR_CUDA, "ppp_run: exact-tier list overflow (%llu pairs dropped)", c[CNT_OVERFLOW]);
+        const double thresh_ln = f->thresh * 2.302585092994045684;
+        if (!topk) {
+            CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 1, thresh_ln, d_off_static, ctx->d_nmax, d_off_active,
+                                    (uint32_t)nQ, ctx->nsm, ctx->stream));
+            launches++;
+        }
+        size_t processed = 0;
+        while (processed < nT) {
+            size_t w = std::min(maxw, nT - processed);
+            if (topk) {
+                const size_t first = std::max<size_t>(256, 3 * (size_t)k);
+                w = std::min(w, processed ? 4 * processed : first);
+            }
+            if (topk && processed) {
+                CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+                CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 0, 0.0, d_off_static, ctx->d_nmax, d_off_active,
+                                        (uint32_t)nQ, ctx->nsm, ctx->stream));
+                CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+                launches++;
+            }
+            SweepParams prm;
+            base_params(ctx, &prm);
+            prm.hits = ctx->d_hits;
+            prm.t0 = (uint32_t)processed;
+            prm.t1 = (uint32_t)(processed + w);
+            prm.append = topk ? 1 : 2;
+            prm.accept_mode = topk ? 0 : 1;
+            prm.thresh_log10 = f->thresh;
+            prm.kth = ctx->d_kth;
+            prm.nmax = ctx->d_nmax;
+            prm.nmax_off = d_off_active;
+            prm.qcnt = d_qcnt;
+            prm.qcap = (uint32_t)maxw;
+            unsigned long long c[CNT_N];
+            if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c))) return rc;
+            sweep_launches++;
+            if (topk && processed) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
+                ctx->phase_us[2] += 1e3 * ms;
+            }
+            if (topk) {
+                CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+                CU(ppp_launch_topk_merge(ctx->d_hits, d_qcnt, (uint32_t)maxw, ctx->d_topk, d_topk_cnt, ctx->d_kth, k, (uint32_t)nQ,
+                                         ctx->nsm, ctx->stream));
+                CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+                CU(cudaEventSynchronize(ctx->ev[6]));
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
+                ctx->phase_us[3] += 1e3 * ms;
+                launches++;
+            } else if (c[CNT_APPEND]) {
+                const size_t old = ctx->host_results.size();
+                ctx->host_results.resize(old + c[CNT_APPEND]);
+                CU(cudaMemcpyAsync(ctx->host_results.data() + old, ctx->d_hits, c[CNT_APPEND] * sizeof(ppp_hit),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+            }
+            processed += w;
+        }
+        if (topk) {
+            std::vector<uint32_t> cnt(nQ);
+            std::vector<ppp_hit> lists(nQ * (size_t)k);
+            CU(cudaMemcpyAsync(cnt.data(), d_topk_cnt, nQ * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(lists.data(), ctx->d_topk, lists.size() * sizeof(ppp_hit), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            for (size_t q = 0; q < nQ; ++q)
+                ctx->host_results.insert(ctx->host_results.end(), lists.begin() + q * k, lists.begin() + q * k + cnt[q]);
+        } else {
+            std::sort(ctx->host_results.begin(), ctx->host_results.end(), hit_less); /* presentation order only */
+        }
+        ctx->n_results = ctx->host_results.size();
     }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     float total_ms = 0.f;
     cudaEventElapsedTime(&total_ms, ctx->ev[0], ctx->ev[1]);
 
-    if (f->mode == PPP_FILTER_TOPK) {
-        for (size_t q = 0; q < nQ; ++q) {
-            std::sort(topk[q].begin(), topk[q].end(), hit_less);
-            ctx->host_results.insert(ctx->host_results.end(), topk[q].begin(), topk[q].end());
-        }
-    } else if (f->mode == PPP_FILTER_THRESH_LOG10) {
-        std::sort(ctx->host_results.begin(), ctx->host_results.end(), hit_less);
-    }
-    ctx->n_results = (f->mode == PPP_FILTER_ALL) ? nQ * nT : ctx->host_results.size();
     memcpy(ctx->last_counters, totals, sizeof(totals));
     ctx->stats.pairs = (uint64_t)nQ * nT;
     ctx->stats.candidates = totals[CNT_CAND];
@@ -485,7 +575,12 @@ extern "C" int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *va
     else if (!strcmp(name, "accurate_evals")) i = CNT_ACCURATE;
     else if (!strcmp(name, "bound_violations")) i = CNT_VIOL;
     else if (!strcmp(name, "bound_checks")) i = CNT_CHECKS;
+    else if (!strcmp(name, "full_pairs")) i = CNT_FULL;
     else if (!strcmp(name, "num_sms")) { *value = ctx->nsm; return PPP_OK; }
+    else if (!strcmp(name, "us_sweep")) { *value = (int64_t)ctx->phase_us[0]; return PPP_OK; }
+    else if (!strcmp(name, "us_exact")) { *value = (int64_t)ctx->phase_us[1]; return PPP_OK; }
+    else if (!strcmp(name, "us_staircase")) { *value = (int64_t)ctx->phase_us[2]; return PPP_OK; }
+    else if (!strcmp(name, "us_merge")) { *value = (int64_t)ctx->phase_us[3]; return PPP_OK; }
     if (i < 0) return PPP_ERR_INVALID;
     *value = (int64_t)ctx->last_counters[i];
     return PPP_OK;

@@ -33,7 +33,8 @@ struct __attribute__((aligned(64))) QConst {
     float varf_unit; /* p (1-p) */
     uint32_t flags;
     uint32_t ny;     /* |Y| (Profile::get_yes, ppp.pm:136) */
-    uint32_t pad_[2];
+    uint32_t npres;  /* |P| (Profile::get_total, Profile.pm:342-354) */
+    uint32_t pad_;
 };
 
 /* pair flags carried in the top bits of the packed result while a pair waits for the exact tier */
@@ -51,6 +52,55 @@ struct SweepParams {
     uint32_t G;            /* real genome count */
     uint32_t force_exact;
     uint32_t check_bounds;
+    /* filtered runs (PPP_FILTER_TOPK / PPP_FILTER_THRESH_LOG10) */
+    uint32_t append;           /* 0: dense hits[q*nT+t]; 1: per-query append hits[q*qcap + qcnt[q]++]; 2: global append */
+    uint32_t accept_mode;      /* 0: score < kth[q] (top-k, kth = 2.0 while the list is not full); 1: log10(score) < thresh */
+    double thresh_log10;
+    const double *kth;         /* [nQ] */
+    const uint16_t *nmax;      /* prefilter staircase: candidate (yes, number) can pass only if number <= nmax[off + yes] */
+    const uint32_t *nmax_off;  /* [nQ] offset of query q's staircase, PPP_NO_TABLE = accept every pair */
+    uint32_t *qcnt;            /* [nQ] append counters */
+    uint32_t qcap;             /* per-query append capacity (>= targets per launch) */
+    uint32_t pad2_;
 };
 
-enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_ACCURATE = 2, CNT_VIOL = 3, CNT_CHECKS = 4, CNT_OVERFLOW = 5, CNT_N = 8 };
+#define PPP_NO_TABLE 0xffffffffu
+
+enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_ACCURATE = 2, CNT_VIOL = 3, CNT_CHECKS = 4, CNT_OVERFLOW = 5, CNT_APPEND = 6,
+       CNT_FULL = 7, CNT_N = 8 };
+
+#ifdef __CUDACC__
+#include "../../include/ppp_b200.h"
+/* does a finished pair belong to the filtered output? */
+__device__ __forceinline__ bool ppp_accept(const SweepParams &prm, uint32_t q, double score)
+{
+    if (prm.accept_mode == 0) return score < prm.kth[q];
+    return log10(score) < prm.thresh_log10;
+}
+/* write one result record: dense slot, per-query append or global append */
+__device__ __forceinline__ void ppp_emit(const SweepParams &prm, uint32_t q, uint32_t t, double score, uint32_t yes,
+                                         uint32_t number, uint32_t depth, float margin)
+{
+    ppp_hit *base = reinterpret_cast<ppp_hit *>(prm.hits);
+    size_t idx;
+    if (prm.append == 0) {
+        idx = (size_t)q * prm.nT + t;
+    } else {
+        if (!ppp_accept(prm, q, score)) return;
+        if (prm.append == 1) {
+            const uint32_t slot = atomicAdd(&prm.qcnt[q], 1u);
+            if (slot >= prm.qcap) {
+                atomicAdd(&prm.counters[CNT_OVERFLOW], 1ull);
+                return;
+            }
+            idx = (size_t)q * prm.qcap + slot;
+        } else {
+            idx = (size_t)atomicAdd(&prm.counters[CNT_APPEND], 1ull);
+        }
+    }
+    const unsigned long long sb = (unsigned long long)__double_as_longlong(score);
+    uint4 *dst = reinterpret_cast<uint4 *>(base + idx);
+    dst[0] = make_uint4(q, t, (uint32_t)sb, (uint32_t)(sb >> 32));
+    dst[1] = make_uint4(yes, number, depth, __float_as_uint(margin));
+}
+#endif

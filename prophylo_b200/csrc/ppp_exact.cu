@@ -61,10 +61,7 @@ __global__ void ppp_exact_kernel(const SweepParams prm, int W)
                 if (answer <= 0) { stop = true; break; } /* ppp.pm:239-241 */
             }
         }
-        ppp_hit h;
-        h.q = q; h.t = t; h.score = score; h.yes = best_yes; h.number = best_number; h.depth = best_depth;
-        h.margin = 0.f;
-        reinterpret_cast<ppp_hit *>(prm.hits)[(size_t)q * prm.nT + t] = h;
+        ppp_emit(prm, q, t, score, (uint32_t)best_yes, (uint32_t)best_number, (uint32_t)best_depth, 0.f);
     }
 }
 

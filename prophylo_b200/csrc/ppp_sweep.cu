@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
     constexpr int LF_BYTES = (((GD + 2) * 8) + 127) & ~127;
     uint32_t *s_q = reinterpret_cast<uint32_t *>(smem_raw + 128 + LF_BYTES);    /* PPP_QTILE * 2 * W words */
     QConst *s_qc = reinterpret_cast<QConst *>(reinterpret_cast<unsigned char *>(s_q) + PPP_QTILE * 2 * W * 4);
-    uint32_t *s_queue = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(s_qc) + PPP_QTILE * sizeof(QConst));
+    uint32_t *s_off = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(s_qc) + PPP_QTILE * sizeof(QConst)); /* [32] */
+    uint32_t *s_queue = s_off + PPP_QTILE;
     uint32_t *my_queue = s_queue + warp * (2 * PPP_QCAP);                   /* [QCAP] (n | g<<16), then [QCAP] float lo */
     float *my_lo = reinterpret_cast<float *>(my_queue + PPP_QCAP);
 
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
     const uint32_t nTblocks = (nTl + nwarps - 1) / nwarps;
     const uint64_t nItems = (uint64_t)nQtiles * nTblocks;
 
-    unsigned long long cnt_cand = 0, cnt_acc = 0, cnt_viol = 0, cnt_chk = 0;
+    unsigned long long cnt_cand = 0, cnt_acc = 0, cnt_viol = 0, cnt_chk = 0, cnt_full = 0;
     uint32_t tile_parity = 0;
     uint32_t cur_qt = 0xffffffffu;
     mbar_wait(&bars[0], 0);
@@ -242,9 +243,12 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
                 tma_load_1d(s_q, prm.Q + (size_t)q0 * 2 * W, b1, &bars[1]);
                 tma_load_1d(s_qc, prm.qc + q0, b2, &bars[1]);
             }
+            if (prm.append && threadIdx.x < PPP_QTILE)
+                s_off[threadIdx.x] = (threadIdx.x < nq && prm.nmax_off) ? prm.nmax_off[q0 + threadIdx.x] : PPP_NO_TABLE;
             mbar_wait(&bars[1], tile_parity);
             tile_parity ^= 1;
             cur_qt = qt;
+            if (prm.append) __syncthreads();
         }
         const uint32_t tl = tb * nwarps + warp;
         if (tl >= nTl) continue; /* warp-uniform */
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
 
         PairOut mine;
         mine.score = 1.0; mine.yes = 0; mine.number = 0; mine.depth = 0; mine.margin = INFINITY;
-        bool mine_exact = false;
+        bool mine_exact = false, mine_rejected = false;
 
         for (uint32_t qi = 0; qi < nq; ++qi) {
             const QConst &qc = s_qc[qi];
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
             }
             PairOut res;
             res.score = 1.0; res.yes = 0; res.number = 0; res.depth = 0; res.margin = INFINITY;
-            bool need_exact = false;
+            bool need_exact = false, rejected = false;
 
             if (qc.flags & PPP_QF_DOMAIN) {
                 /* p outside [0,1]: bdtrc -> 0.0 at the first element of the list (ppp.pm:225-241) */
@@ -338,7 +342,39 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
                 const uint32_t E = __shfl_sync(FULL, incl, 31) & 0xffffu;
                 cnt_cand += (lane == 0) ? E : 0;
 
-                if (E > 0 && (prm.force_exact || (qc.flags & PPP_QF_EXACT))) {
+                /* filtered runs: the staircase nmax[yes] bounds the number a candidate may have and still pass the
+                 * query's threshold (tail increases with number, decreases with yes); one lookup per lane decides
+                 * whether ANY candidate of the lane's words can pass.  Most pairs end here. */
+                if (prm.append) {
+                    const uint32_t off = s_off[qi];
+                    if (off != PPP_NO_TABLE) {
+                        const uint16_t *stair = prm.nmax + off;
+                        const bool lane_pass = cy > 0 && ((excl >> 16) + 1u) <= (uint32_t)__ldg(stair + (excl & 0xffffu) + cy);
+                        rejected = !__any_sync(FULL, lane_pass);
+                        if (!rejected) {
+                            /* second look, exact per candidate: number <= nmax[yes] for at least one set bit of T&Y */
+                            bool cand_pass = false;
+                            if (lane_pass) {
+                                uint32_t yrun = excl & 0xffffu, nbase = excl >> 16;
+#pragma unroll
+                                for (int w = 0; w < WPL; ++w) {
+                                    uint32_t mbits = ty[w];
+                                    while (mbits) {
+                                        const uint32_t b = __ffs(mbits) - 1;
+                                        mbits &= mbits - 1;
+                                        ++yrun;
+                                        const uint32_t nn = nbase + __popc(tp[w] & ((2u << b) - 1u));
+                                        cand_pass |= nn <= (uint32_t)__ldg(stair + yrun);
+                                    }
+                                    nbase += __popc(tp[w]);
+                                }
+                            }
+                            rejected = !__any_sync(FULL, cand_pass);
+                        }
+                    }
+                }
+                if (rejected) {
+                } else if (E > 0 && (prm.force_exact || (qc.flags & PPP_QF_EXACT))) {
                     need_exact = true;
                 } else if (E > 0) {
                     double best_lnf = INFINITY, best_f = 1.0, second_lnf = INFINITY;
@@ -444,24 +480,22 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
             if (lane == (int)qi) {
                 mine = res;
                 mine_exact = need_exact;
+                mine_rejected = rejected;
             }
         }
         /* lane i holds the result of query q0 + i */
-        if ((uint32_t)lane < nq) {
+        if ((uint32_t)lane < nq && !mine_rejected) {
             const uint32_t q = q0 + lane;
-            const uint64_t pid = (uint64_t)q * prm.nT + t;
-            float mg = mine.margin;
             if (mine_exact) {
                 const unsigned long long slot = atomicAdd(&prm.counters[CNT_EXACT], 1ull);
                 if (slot < prm.exact_cap) prm.exact_list[slot] = (uint32_t)((uint64_t)q * nTl + tl);
                 else atomicAdd(&prm.counters[CNT_OVERFLOW], 1ull);
-                mg = -1.f;
+                if (!prm.append) ppp_emit(prm, q, t, mine.score, mine.yes, mine.number, mine.depth, -1.f);
+            } else {
+                ppp_emit(prm, q, t, mine.score, mine.yes, mine.number, mine.depth, mine.margin);
             }
-            const unsigned long long sb = (unsigned long long)__double_as_longlong(mine.score);
-            uint4 *dst = reinterpret_cast<uint4 *>(reinterpret_cast<ppp_hit *>(prm.hits) + pid);
-            dst[0] = make_uint4(q, t, (uint32_t)sb, (uint32_t)(sb >> 32));
-            dst[1] = make_uint4(mine.yes, mine.number, mine.depth, __float_as_uint(mg));
         }
+        if (prm.append) cnt_full += __popc(__ballot_sync(FULL, (uint32_t)lane < nq && !mine_rejected));
     }
     /* flush per-warp statistics */
     cnt_cand = (unsigned long long)warp_sum_d((double)cnt_cand);
@@ -470,6 +504,7 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
         if (cnt_acc) atomicAdd(&prm.counters[CNT_ACCURATE], cnt_acc);
         if (cnt_viol) atomicAdd(&prm.counters[CNT_VIOL], cnt_viol);
         if (cnt_chk) atomicAdd(&prm.counters[CNT_CHECKS], cnt_chk);
+        if (cnt_full) atomicAdd(&prm.counters[CNT_FULL], cnt_full);
     }
 }
 
@@ -477,7 +512,7 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
 static size_t sweep_smem_bytes(int wpl, int nwarps)
 {
     const size_t W = 32 * (size_t)wpl, GD = 32 * W;
-    return 128 + ((((GD + 2) * 8) + 127) & ~(size_t)127) + PPP_QTILE * 2 * W * 4 + PPP_QTILE * sizeof(QConst) + (size_t)nwarps * 2 * PPP_QCAP * 4 + 64;
+    return 128 + ((((GD + 2) * 8) + 127) & ~(size_t)127) + PPP_QTILE * 2 * W * 4 + PPP_QTILE * sizeof(QConst) + PPP_QTILE * 4 + (size_t)nwarps * 2 * PPP_QCAP * 4 + 64;
 }
 
 template <int WPL>

@@ -1,0 +1,170 @@
+/*
+ * prophylo_b200/csrc/ppp_topk.cu -- device side of the result filters:
+ *
+ *  ppp_build_staircase_kernel   per query, the exact integer pre-filter of a score threshold tau (ln domain):
+ *        nmax[yes] = largest `number` for which P(X >= yes | number, p) can still be <= exp(tau).
+ *     The binomial tail increases with number and decreases with yes, so a sweep candidate (yes, number) can
+ *     reach the threshold iff number <= nmax[yes]; the sweep kernel rejects a whole lane of words with one
+ *     lookup.  tau is the query's current k-th best score (top-k, bin/ppp.pl:473-506 keeps the best rows) or the
+ *     fixed ppp_cutoff.pl:122 threshold.  Built with the FP64 ratio series and a safety margin, so it never
+ *     rejects a pair the reference would keep.
+ *
+ *  ppp_topk_merge_kernel        per query, merge the hits appended by the last target chunk into the running
+ *     top-k list (ascending score, ties by target index) with a shared-memory bitonic sort, publish the new
+ *     k-th score and reset the append counter.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/ppp_b200.h"
+#include "ppp_common.cuh"
+
+/* ln P(X >= y | n, p) <= tau ?  Serial FP64 ratio series (upper side); on the lower side (y + 1 <= (n+1) p) the
+ * tail is >= 1/2 because the binomial median is >= floor(n p), and tau < ln(1/2) is guaranteed by the caller. */
+__device__ static bool tail_le(int y, int n, const QConst &qc, const double *__restrict__ lf, double tau)
+{
+    const int m = n - y;
+    if (!((double)m * qc.theta < (double)(y + 1))) return false;
+    const double lead = ((lf[n] - lf[y]) - lf[m]) + ((double)y * qc.lnp + (double)m * qc.lnq);
+    if (lead > tau) return false; /* R >= 1 */
+    double t = 1.0, s = 1.0;
+    for (int i = 1; i <= m; ++i) {
+        t *= (double)(m - i + 1) * qc.theta / (double)(y + i);
+        s += t;
+        if (t < 1e-17 * s) break;
+    }
+    return lead + log(s) <= tau;
+}
+
+__global__ void ppp_build_staircase_kernel(const QConst *__restrict__ qc, const double *__restrict__ lf, const double *__restrict__ kth,
+                                           int accept_mode, double thresh_ln, const uint32_t *__restrict__ static_off,
+                                           uint16_t *__restrict__ nmax, uint32_t *__restrict__ active_off, uint32_t nQ)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nQ; q += warps) {
+        const QConst c = qc[q];
+        double tau;
+        if (accept_mode == 0) {
+            const double kq = kth[q];
+            tau = (kq < 1.0) ? ((kq > 0.0) ? log(kq) : -INFINITY) : INFINITY;
+        } else {
+            tau = thresh_ln;
+        }
+        /* no pruning near or above the median, for odd p, or for empty queries */
+        if (!(tau < -0.70) || (c.flags & (PPP_QF_TRIVIAL | PPP_QF_DOMAIN | PPP_QF_EXACT)) || c.ny == 0) {
+            if (lane == 0) active_off[q] = PPP_NO_TABLE;
+            continue;
+        }
+        const double tau_m = tau + 1e-5 + 1e-9 * fabs(tau); /* safety margin >> series + table error */
+        uint16_t *tab = nmax + static_off[q];
+        const int ny = (int)c.ny, np_ = (int)c.npres;
+        if (lane == 0) tab[0] = 0;
+        for (int y = 1 + lane; y <= ny; y += 32) {
+            int res = 0;
+            if (isfinite(tau_m) && tail_le(y, y, c, lf, tau_m)) {
+                int lo = y, hi = np_; /* invariant: tail_le(lo) true */
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (tail_le(y, mid, c, lf, tau_m)) lo = mid;
+                    else hi = mid - 1;
+                }
+                res = lo;
+            }
+            tab[y] = (uint16_t)res;
+        }
+        __syncwarp();
+        if (lane == 0) { /* enforce the staircase's monotonicity in yes (independent searches may differ by rounding) */
+            uint16_t run = 0;
+            for (int y = 1; y <= ny; ++y) {
+                run = max(run, tab[y]);
+                tab[y] = run;
+            }
+            active_off[q] = static_off[q];
+        }
+        __syncwarp();
+    }
+}
+
+extern "C" cudaError_t ppp_launch_staircase(const QConst *qc, const double *lf, const double *kth, int accept_mode, double thresh_ln,
+                                            const uint32_t *static_off, uint16_t *nmax, uint32_t *active_off, uint32_t nQ, int nsm,
+                                            cudaStream_t st)
+{
+    ppp_build_staircase_kernel<<<nsm * 4, 128, 0, st>>>(qc, lf, kth, accept_mode, thresh_ln, static_off, nmax, active_off, nQ);
+    return cudaGetLastError();
+}
+
+/* ------------------------------------------------------------------------------------------------ top-k merge */
+#define TOPK_M 4096 /* records sorted at once (128 KB of shared memory); k <= TOPK_M / 2 */
+
+__device__ __forceinline__ bool rec_less(const ppp_hit &a, const ppp_hit &b)
+{
+    if (a.score != b.score) return a.score < b.score;
+    return a.t < b.t;
+}
+
+__global__ void __launch_bounds__(256) ppp_topk_merge_kernel(const ppp_hit *__restrict__ appended, uint32_t *__restrict__ qcnt,
+                                                             uint32_t qcap, ppp_hit *__restrict__ topk, uint32_t *__restrict__ topk_cnt,
+                                                             double *__restrict__ kth, uint32_t k, uint32_t nQ)
+{
+    extern __shared__ __align__(16) unsigned char smem_topk[];
+    ppp_hit *rec = reinterpret_cast<ppp_hit *>(smem_topk);
+    for (uint32_t q = blockIdx.x; q < nQ; q += gridDim.x) {
+        const uint32_t nnew = min(qcnt[q], qcap);
+        uint32_t cur = topk_cnt[q];
+        if (nnew == 0) continue; /* block-uniform */
+        for (uint32_t i = threadIdx.x; i < cur; i += blockDim.x) rec[i] = topk[(size_t)q * k + i];
+        uint32_t done = 0;
+        while (done < nnew) {
+            const uint32_t batch = min(nnew - done, (uint32_t)TOPK_M - cur);
+            for (uint32_t i = threadIdx.x; i < batch; i += blockDim.x) rec[cur + i] = appended[(size_t)q * qcap + done + i];
+            const uint32_t tot = cur + batch;
+            uint32_t n2 = 1;
+            while (n2 < tot) n2 <<= 1;
+            for (uint32_t i = tot + threadIdx.x; i < n2; i += blockDim.x) {
+                rec[i].score = INFINITY;
+                rec[i].t = 0xffffffffu;
+            }
+            __syncthreads();
+            for (uint32_t size = 2; size <= n2; size <<= 1) {
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    for (uint32_t i = threadIdx.x; i < (n2 >> 1); i += blockDim.x) {
+                        const uint32_t lo = 2 * i - (i & (stride - 1));
+                        const uint32_t hi = lo + stride;
+                        const bool asc = ((lo & size) == 0);
+                        const ppp_hit a = rec[lo], b = rec[hi];
+                        if (rec_less(b, a) == asc) {
+                            rec[lo] = b;
+                            rec[hi] = a;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            cur = min(tot, k);
+            done += batch;
+        }
+        for (uint32_t i = threadIdx.x; i < cur; i += blockDim.x) topk[(size_t)q * k + i] = rec[i];
+        if (threadIdx.x == 0) {
+            topk_cnt[q] = cur;
+            kth[q] = (cur >= k) ? rec[k - 1].score : 2.0;
+            qcnt[q] = 0;
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" cudaError_t ppp_launch_topk_merge(const void *appended, uint32_t *qcnt, uint32_t qcap, void *topk, uint32_t *topk_cnt,
+                                             double *kth, uint32_t k, uint32_t nQ, int nsm, cudaStream_t st)
+{
+    const int smem = TOPK_M * (int)sizeof(ppp_hit);
+    cudaError_t e = cudaFuncSetAttribute(ppp_topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)min((uint32_t)(nsm * 2), nQ);
+    ppp_topk_merge_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const ppp_hit *>(appended), qcnt, qcap,
+                                                   reinterpret_cast<ppp_hit *>(topk), topk_cnt, kth, k, nQ);
+    return cudaGetLastError();
+}
+
+extern "C" int ppp_topk_max_k(void) { return TOPK_M / 2; }
