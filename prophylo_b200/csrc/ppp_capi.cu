@@ -22,12 +22,16 @@
 #include "ppp_common.cuh"
 
 extern "C" cudaError_t ppp_launch_sweep(const SweepParams *prm, int wpl, int nwarps, int nsm, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, uint32_t *surv,
+                                           unsigned long long *surv_count, unsigned long long surv_cap, int nwarps, int nsm,
+                                           cudaStream_t st);
+extern "C" cudaError_t ppp_launch_transpose(const void *T, void *Tt, uint32_t nT, int wpl, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_exact(const SweepParams *prm, int W, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_debug_bdtrc(const int32_t *k, const int32_t *n, const double *p, double *out, size_t m,
                                               cudaStream_t st);
 extern "C" cudaError_t ppp_launch_staircase(const QConst *qc, const double *lf, const double *kth, int accept_mode, double thresh_ln,
-                                            const uint32_t *static_off, uint16_t *nmax, uint32_t *active_off, uint32_t nQ, int nsm,
-                                            cudaStream_t st);
+                                            const uint32_t *static_off, uint16_t *nmax, uint32_t *active_off, double *last_tau,
+                                            uint32_t nQ, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_topk_merge(const void *appended, uint32_t *qcnt, uint32_t qcap, void *topk, uint32_t *topk_cnt,
                                              double *kth, uint32_t k, uint32_t nQ, int nsm, cudaStream_t st);
 extern "C" int ppp_topk_max_k(void);
@@ -38,10 +42,18 @@ struct ppp_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double phase_us[4] = {0, 0, 0, 0}; /* sweep, exact, staircase, merge */
+    unsigned long long survivors = 0;
     char err[512] = {0};
 
     /* targets */
     uint32_t *d_T = nullptr;
+    size_t cap_T = 0;
+    uint32_t *d_Tt = nullptr; /* chunk-major transposed planes for the thread-per-pair pre-filter */
+    size_t cap_Tt = 0;
+    bool Tt_valid = false;
+    uint32_t *d_surv = nullptr;
+    size_t cap_surv = 0;
+    int lf_wpl = 0;
     size_t nT = 0;
     uint32_t G = 0;
     int wpl = 0; /* device words per lane: device row = 32*wpl words */
@@ -98,6 +110,18 @@ static int fail(ppp_ctx *ctx, int code, const char *fmt, ...)
                         cudaGetErrorString(e_));                                                       \
     } while (0)
 
+template <typename T>
+static int grow(ppp_ctx *ctx, T **ptr, size_t *cap, size_t need)
+{
+    if (need <= *cap) return PPP_OK;
+    cudaFree(*ptr);
+    *ptr = nullptr;
+    *cap = 0;
+    CU(cudaMalloc(ptr, need * sizeof(T)));
+    *cap = need;
+    return PPP_OK;
+}
+
 extern "C" uint32_t ppp_words_per_row(uint32_t G) { return ((G + 127u) / 128u) * 4u; }
 extern "C" int ppp_abi_version(void) { return PPP_B200_ABI_VERSION; }
 
@@ -132,7 +156,7 @@ extern "C" int ppp_init(ppp_ctx **out, const int *devices, int ndev)
         return PPP_ERR_CUDA;
     }
     for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
-    if ((e = cudaMalloc(&ctx->d_counters, CNT_N * sizeof(unsigned long long))) != cudaSuccess) {
+    if ((e = cudaMalloc(&ctx->d_counters, (CNT_N + 1) * sizeof(unsigned long long))) != cudaSuccess) {
         fail(nullptr, PPP_ERR_CUDA, "ppp_init: %s", cudaGetErrorString(e));
         delete ctx;
         return PPP_ERR_CUDA;
@@ -147,6 +171,8 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_T);
+    cudaFree(ctx->d_Tt);
+    cudaFree(ctx->d_surv);
     cudaFree(ctx->d_lf);
     cudaFree(ctx->d_Q);
     cudaFree(ctx->d_qc);
@@ -182,32 +208,39 @@ extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, 
     CU(cudaSetDevice(ctx->device));
     const int wpl = pick_wpl(G);
     const size_t W = 32 * (size_t)wpl, wpr = ppp_words_per_row(G);
-    cudaFree(ctx->d_T);
-    ctx->d_T = nullptr;
-    cudaFree(ctx->d_lf);
-    ctx->d_lf = nullptr;
     ctx->nT = 0;
+    ctx->Tt_valid = false;
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_T, &ctx->cap_T, std::max<size_t>(1, nT * W)))) return rc; /* buffers are reused across calls */
     if (nT) {
-        CU(cudaMalloc(&ctx->d_T, nT * W * 4));
-        CU(cudaMemsetAsync(ctx->d_T, 0, nT * W * 4, ctx->stream));
+        if (wpr != W) CU(cudaMemsetAsync(ctx->d_T, 0, nT * W * 4, ctx->stream));
         CU(cudaMemcpy2DAsync(ctx->d_T, W * 4, T, wpr * 4, wpr * 4, nT, cudaMemcpyHostToDevice, ctx->stream));
     }
-    /* log-factorial table lf[k] = lgamma(k+1), k = 0..Gd+1, computed in long double */
-    const size_t Gd = 32 * W;
-    std::vector<double> lf(Gd + 2);
-    for (size_t k = 0; k < Gd + 2; ++k) lf[k] = (double)lgammal((long double)k + 1.0L);
-    CU(cudaMalloc(&ctx->d_lf, (Gd + 2) * sizeof(double)));
-    CU(cudaMemcpyAsync(ctx->d_lf, lf.data(), (Gd + 2) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->lf_wpl != wpl) {
+        /* log-factorial table lf[k] = lgamma(k+1), k = 0..Gd+1, computed in long double */
+        const size_t Gd = 32 * W;
+        std::vector<double> lf(Gd + 2);
+        for (size_t k = 0; k < Gd + 2; ++k) lf[k] = (double)lgammal((long double)k + 1.0L);
+        cudaFree(ctx->d_lf);
+        ctx->d_lf = nullptr;
+        ctx->lf_wpl = 0;
+        CU(cudaMalloc(&ctx->d_lf, (Gd + 2) * sizeof(double)));
+        CU(cudaMemcpyAsync(ctx->d_lf, lf.data(), (Gd + 2) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->lf_wpl = wpl;
+    }
     CU(cudaStreamSynchronize(ctx->stream));
+    if (ctx->wpl != wpl || ctx->G != G) {
+        ctx->nQ = 0; /* queries must be re-uploaded: the row layout changed */
+        cudaFree(ctx->d_Q);
+        cudaFree(ctx->d_qc);
+        ctx->d_Q = nullptr;
+        ctx->d_qc = nullptr;
+        ctx->capQ = 0;
+    }
     ctx->nT = nT;
     ctx->G = G;
     ctx->wpl = wpl;
-    ctx->nQ = 0; /* queries must be re-uploaded: the device row length may have changed */
-    cudaFree(ctx->d_Q);
-    cudaFree(ctx->d_qc);
-    ctx->d_Q = nullptr;
-    ctx->d_qc = nullptr;
-    ctx->capQ = 0;
     return PPP_OK;
 }
 
@@ -304,18 +337,6 @@ static bool hit_less(const ppp_hit &a, const ppp_hit &b)
     return a.t < b.t;
 }
 
-template <typename T>
-static int grow(ppp_ctx *ctx, T **ptr, size_t *cap, size_t need)
-{
-    if (need <= *cap) return PPP_OK;
-    cudaFree(*ptr);
-    *ptr = nullptr;
-    *cap = 0;
-    CU(cudaMalloc(ptr, need * sizeof(T)));
-    *cap = need;
-    return PPP_OK;
-}
-
 static void base_params(const ppp_ctx *ctx, SweepParams *prm)
 {
     memset(prm, 0, sizeof(*prm));
@@ -335,19 +356,26 @@ static void base_params(const ppp_ctx *ctx, SweepParams *prm)
 
 /* one target chunk: sweep + exact tier; accumulates counters and the sweep kernel's event time */
 static int run_chunk(ppp_ctx *ctx, SweepParams *prm, unsigned long long *totals, float *sweep_ms, uint32_t *launches,
-                     unsigned long long *chunk_counters)
+                     unsigned long long *chunk_counters, bool prefiltered)
 {
     const int W = 32 * ctx->wpl;
-    CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_N * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, (CNT_N + 1) * sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-    CU(ppp_launch_sweep(prm, ctx->wpl, ctx->sweep_warps, ctx->nsm, ctx->stream));
+    if (prefiltered) {
+        CU(ppp_launch_filtered(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_surv, ctx->d_counters + CNT_N, ctx->cap_surv,
+                               ctx->sweep_warps, ctx->nsm, ctx->stream));
+        *launches += 1;
+    } else {
+        CU(ppp_launch_sweep(prm, ctx->wpl, ctx->sweep_warps, ctx->nsm, ctx->stream));
+    }
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     CU(ppp_launch_exact(prm, W, ctx->nsm, ctx->stream));
     CU(cudaEventRecord(ctx->ev[4], ctx->stream));
     *launches += 2;
-    unsigned long long c[CNT_N];
+    unsigned long long c[CNT_N + 1];
     CU(cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    ctx->survivors += c[CNT_N];
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
     *sweep_ms += ms;
@@ -355,7 +383,7 @@ static int run_chunk(ppp_ctx *ctx, SweepParams *prm, unsigned long long *totals,
     cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
     ctx->phase_us[1] += 1e3 * ms;
     for (int i = 0; i < CNT_N; ++i) totals[i] += c[i];
-    if (chunk_counters) memcpy(chunk_counters, c, sizeof(c));
+    if (chunk_counters) memcpy(chunk_counters, c, CNT_N * sizeof(unsigned long long));
     if (c[CNT_OVERFLOW]) return fail(ctx, PPP_ERR_CUDA, "ppp_run: internal buffer overflow (%llu records dropped)", c[CNT_OVERFLOW]);
     return PPP_OK;
 }
@@ -383,6 +411,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
     uint32_t sweep_launches = 0, launches = 0;
 
     for (int i = 0; i < 4; ++i) ctx->phase_us[i] = 0;
+    ctx->survivors = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (f->mode == PPP_FILTER_ALL) {
         /* dense: chunks only bound the launch-local pair ids of the exact-tier list (31 bits) */
@@ -396,7 +425,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             prm.hits = ctx->d_hits;
             prm.t0 = (uint32_t)t0;
             prm.t1 = (uint32_t)std::min(nT, t0 + tchunk);
-            if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, nullptr))) return rc;
+            if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, nullptr, false))) return rc;
             sweep_launches++;
         }
         ctx->n_results = nQ * nT;
@@ -404,28 +433,36 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         /* filtered: per-query staircases prune almost every pair inside the sweep kernel; survivors are appended */
         const bool topk = (f->mode == PPP_FILTER_TOPK);
         const uint32_t k = f->k;
-        const size_t maxw = std::min<size_t>(nT, std::max<size_t>(256, ((size_t)1 << 26) / nQ));
+        const size_t maxw = std::min<size_t>(nT, std::max<size_t>(256, ((size_t)1 << 28) / nQ));
         if ((rc = grow(ctx, &ctx->d_hits, &ctx->cap_hits, nQ * maxw))) return rc;
         if ((rc = grow(ctx, &ctx->d_exact, &ctx->cap_exact, nQ * maxw))) return rc;
-        if ((rc = grow(ctx, &ctx->d_kth, &ctx->cap_kth, nQ))) return rc;
+        if ((rc = grow(ctx, &ctx->d_kth, &ctx->cap_kth, 2 * nQ))) return rc; /* [nQ] k-th scores, [nQ] tau of the resident staircase */
         if ((rc = grow(ctx, &ctx->d_qcnt, &ctx->cap_qcnt, 2 * nQ))) return rc; /* [nQ] append counters, [nQ] top-k counts */
         if ((rc = grow(ctx, &ctx->d_off, &ctx->cap_off, 2 * nQ))) return rc;   /* [nQ] static offsets, [nQ] active offsets */
         if ((rc = grow(ctx, &ctx->d_nmax, &ctx->cap_nmax, ctx->nmax_entries + 8))) return rc;
         if (topk && (rc = grow(ctx, &ctx->d_topk, &ctx->cap_topk, nQ * (size_t)k))) return rc;
+        if ((rc = grow(ctx, &ctx->d_surv, &ctx->cap_surv, nQ * maxw))) return rc;
+        if (!ctx->Tt_valid) {
+            const size_t W = 32 * (size_t)ctx->wpl;
+            if ((rc = grow(ctx, &ctx->d_Tt, &ctx->cap_Tt, nT * W))) return rc;
+            CU(ppp_launch_transpose(ctx->d_T, ctx->d_Tt, (uint32_t)nT, ctx->wpl, ctx->stream));
+            ctx->Tt_valid = true;
+            launches++;
+        }
         uint32_t *d_qcnt = ctx->d_qcnt, *d_topk_cnt = ctx->d_qcnt + nQ;
         uint32_t *d_off_static = ctx->d_off, *d_off_active = ctx->d_off + nQ;
         CU(cudaMemcpyAsync(d_off_static, ctx->nmax_off_host.data(), nQ * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemsetAsync(d_qcnt, 0, 2 * nQ * sizeof(uint32_t), ctx->stream));
         CU(cudaMemsetAsync(d_off_active, 0xff, nQ * sizeof(uint32_t), ctx->stream)); /* PPP_NO_TABLE */
         {
-            std::vector<double> two(nQ, 2.0);
-            CU(cudaMemcpyAsync(ctx->d_kth, two.data(), nQ * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            std::vector<double> two(2 * nQ, 2.0);
+            CU(cudaMemcpyAsync(ctx->d_kth, two.data(), 2 * nQ * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
         }
         const double thresh_ln = f->thresh * 2.302585092994045684;
         if (!topk) {
             CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 1, thresh_ln, d_off_static, ctx->d_nmax, d_off_active,
-                                    (uint32_t)nQ, ctx->nsm, ctx->stream));
+                                    ctx->d_kth + nQ, (uint32_t)nQ, ctx->nsm, ctx->stream));
             launches++;
         }
         size_t processed = 0;
@@ -438,7 +475,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             if (topk && processed) {
                 CU(cudaEventRecord(ctx->ev[5], ctx->stream));
                 CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 0, 0.0, d_off_static, ctx->d_nmax, d_off_active,
-                                        (uint32_t)nQ, ctx->nsm, ctx->stream));
+                                        ctx->d_kth + nQ, (uint32_t)nQ, ctx->nsm, ctx->stream));
                 CU(cudaEventRecord(ctx->ev[6], ctx->stream));
                 launches++;
             }
@@ -456,7 +493,8 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             prm.qcnt = d_qcnt;
             prm.qcap = (uint32_t)maxw;
             unsigned long long c[CNT_N];
-            if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c))) return rc;
+            /* the first top-k chunk has no thresholds yet: tile kernel over every pair; afterwards thread-per-pair screen */
+            if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c, !(topk && !processed)))) return rc;
             sweep_launches++;
             if (topk && processed) {
                 float ms = 0.f;
@@ -577,6 +615,7 @@ extern "C" int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *va
     else if (!strcmp(name, "bound_checks")) i = CNT_CHECKS;
     else if (!strcmp(name, "full_pairs")) i = CNT_FULL;
     else if (!strcmp(name, "num_sms")) { *value = ctx->nsm; return PPP_OK; }
+    else if (!strcmp(name, "survivors")) { *value = (int64_t)ctx->survivors; return PPP_OK; }
     else if (!strcmp(name, "us_sweep")) { *value = (int64_t)ctx->phase_us[0]; return PPP_OK; }
     else if (!strcmp(name, "us_exact")) { *value = (int64_t)ctx->phase_us[1]; return PPP_OK; }
     else if (!strcmp(name, "us_staircase")) { *value = (int64_t)ctx->phase_us[2]; return PPP_OK; }

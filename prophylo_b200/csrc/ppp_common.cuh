@@ -13,7 +13,7 @@
 #include <stdint.h>
 
 #define PPP_QTILE 32      /* queries per shared-memory tile = lanes of a warp (lane i keeps query i's result) */
-#define PPP_QCAP 1024     /* candidates per warp queue pass */
+#define PPP_QCAP 512      /* candidates per warp queue pass */
 #define PPP_K_TERMS 8     /* series terms of the float enclosure tier */
 
 /* per-query flags */
@@ -103,4 +103,68 @@ __device__ __forceinline__ void ppp_emit(const SweepParams &prm, uint32_t q, uin
     dst[0] = make_uint4(q, t, (uint32_t)sb, (uint32_t)(sb >> 32));
     dst[1] = make_uint4(yes, number, depth, __float_as_uint(margin));
 }
+
+/* ---------------------------------------------------------------- tier A: float enclosure of ln P(X >= y | n, p)
+ * Unified form: upper tail of Bin(n, p*) at k with m = n - k, ratio_i = (m - i + 1) r / (k + i), r = p* / (1 - p*):
+ *   "up"    (y + 1 > (n+1) p):   p* = p, k = y,         lead = ln pmf_p(y; n),      ln f = lead + ln R
+ *   "lower" (otherwise):         p* = q, k = n - y + 1, lead = ln pmf_p(y - 1; n),  ln f = ln(1 - exp(lead) R)
+ * R = sum_{i>=0} prod_{j<=i} ratio_j.  After K terms the remainder t_K * ratio_{K+1} * R' is enclosed by
+ *   R' <= 1 / (1 - ratio_{K+1})                       (ratios decrease)
+ *   R' >= max(1, G'' z^2 / (1 + z^2))                 (Bahadur 1960; G'' = 1/(1 - ratio_{K+2}), z the standardised
+ *                                                      distance of k + K + 1 from the mean n p*)
+ * Division-free Horner keeps numerator and denominator products separately (k + K <= 8200 so k^8 < 2^127).
+ */
+__device__ __forceinline__ void tier_a(int y, int n, const QConst &qc, const double *__restrict__ lf, float &lo, float &hi)
+{
+    const int N_ = n - y;
+    const bool up = (float)N_ * qc.thetaf < (float)(y + 1);
+    const int k = up ? y : N_ + 1;
+    const int m = n - k;
+    const int kk = up ? y : y - 1;
+    const float r = up ? qc.thetaf : qc.inv_thetaf;
+    const double lead_d = ((lf[n] - lf[kk]) - lf[n - kk]) + ((double)kk * qc.lnp + (double)(n - kk) * qc.lnq);
+    const float lead = (float)lead_d;
+
+    float mf = (float)m, bf = (float)(k + 1);
+    float tn = 1.f, D = 1.f, X = 1.f;
+#pragma unroll
+    for (int i = 0; i < PPP_K_TERMS; ++i) {
+        const float a = fmaxf(mf, 0.f) * r;
+        tn *= a;
+        D *= bf;
+        X = fmaf(X, bf, tn);
+        mf -= 1.f;
+        bf += 1.f;
+    }
+    const float invD = __fdividef(1.f, D);
+    const float S = X * invD, tK = tn * invD;
+    const float rho = __fdividef(fmaxf(mf, 0.f) * r, bf);              /* ratio_{K+1} */
+    const float rho2 = __fdividef(fmaxf(mf - 1.f, 0.f) * r, bf + 1.f); /* ratio_{K+2} */
+    float rem_lo = tK * rho;
+    float rem_hi = (rho < 0.999f) ? __fdividef(rem_lo, 1.f - rho) : INFINITY;
+    {
+        const float pstar = up ? qc.pf : 1.f - qc.pf;
+        const float d = bf - (float)n * pstar;
+        if (d > 0.f && rho2 < 0.999f) {
+            const float z2 = __fdividef(d * d, (float)n * qc.varf_unit);
+            const float gb = __fdividef(z2, (1.f + z2) * (1.f - rho2));
+            rem_lo *= fmaxf(1.f, gb * 0.9999f);
+        }
+    }
+    const float Rlo = (S + rem_lo) * 0.9999f, Rhi = (S + rem_hi) * 1.0001f;
+    if (up) {
+        lo = lead + __logf(Rlo);
+        hi = fminf(lead + __logf(Rhi), 0.f);
+        lo -= 1e-4f + 2e-5f * fabsf(lo);
+        hi = fminf(hi + 1e-4f + 2e-5f * fabsf(hi), 0.f);
+    } else {
+        const float e = __expf(lead);
+        const float glo = e * Rlo * 0.999f, ghi = e * Rhi * 1.001f;
+        hi = (glo < 0.5f) ? fminf(-glo, 0.f) : __logf(fmaxf(1.f - glo, 0.f)) + 1e-4f; /* ln(1-g) <= -g */
+        hi = fminf(hi, 0.f);
+        lo = (ghi < 0.9f) ? __logf(1.f - ghi) - 1e-4f : -INFINITY;
+        if (ghi < 1e-3f) lo = -ghi * (1.f + ghi) - 1e-30f;
+    }
+}
+
 #endif

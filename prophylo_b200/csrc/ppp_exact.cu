@@ -17,57 +17,135 @@
 #include "cephes_exact.cuh"
 #include "ppp_common.cuh"
 
-__global__ void ppp_exact_kernel(const SweepParams prm, int W)
+#define EXQ 1024 /* steps per queue pass */
+#define FULLM 0xffffffffu
+
+/* One WARP per flagged pair.  The steps of the reference loop that can change (yes, number) are the set bits of T & P
+ * (an element outside P repeats the previous answer, which can neither improve on the running minimum nor move the
+ * point where the loop stops); they are enumerated in list order into a shared-memory queue exactly as in the sweep
+ * kernel, evaluated 32 at a time (one bdtrc per lane) and then folded in order with the reference's rule.
+ *
+ * Underflow mode (bit 31 of the list id; set when the sweep saw ln p < -700): the answer is decided among steps whose
+ * tail is below e^-600 -- the global minimum is there and exact zeros only occur there -- so steps whose leading
+ * binomial term alone exceeds e^-600 (tail >= leading term) are not evaluated. */
+template <int WPL>
+__global__ void __launch_bounds__(128) ppp_exact_kernel(const SweepParams prm)
 {
+    constexpr int W = 32 * WPL;
+    __shared__ unsigned long long s_queue[4][EXQ];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long *queue = s_queue[warp];
     const unsigned long long n_list = min(prm.counters[CNT_EXACT], (unsigned long long)prm.exact_cap);
     const uint32_t nTl = prm.t1 - prm.t0;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_list;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint32_t id = prm.exact_list[i];
+    const unsigned long long nwarps = (unsigned long long)gridDim.x * 4;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * 4 + warp; i < n_list; i += nwarps) {
+        const uint32_t raw = prm.exact_list[i];
+        const bool underflow_mode = (raw >> 31) != 0;
+        const uint32_t id = raw & 0x7fffffffu;
         const uint32_t q = id / nTl, t = prm.t0 + id % nTl;
-        const uint32_t *Tw = prm.T + (size_t)t * W;
-        const uint32_t *Pw = prm.Q + (size_t)q * 2 * W;
+        const uint32_t *Tw = prm.T + (size_t)t * W + lane * WPL;
+        const uint32_t *Pw = prm.Q + (size_t)q * 2 * W + lane * WPL;
         const uint32_t *Yw = Pw + W;
-        const double p = prm.qc[q].p;
-        const int max_yes = (int)prm.qc[q].ny;
-        const bool p_in_range = (p >= 0.0) && (p <= 1.0); /* false for NaN as well: then nothing can be skipped */
+        const QConst qc = prm.qc[q];
+        const double p = qc.p;
+        const int max_yes = (int)qc.ny;
+
+        uint32_t tw[WPL], tp[WPL], ty[WPL];
+        uint32_t cy = 0, cn = 0, cd = 0;
+#pragma unroll
+        for (int w = 0; w < WPL; ++w) {
+            tw[w] = Tw[w];
+            tp[w] = tw[w] & Pw[w];
+            ty[w] = tp[w] & Yw[w];
+            cy += __popc(ty[w]);
+            cn += __popc(tp[w]);
+            cd += __popc(tw[w]);
+        }
+        uint32_t iy = cy, in_ = cn, id_ = cd;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(FULLM, iy, o), b = __shfl_up_sync(FULLM, in_, o), c = __shfl_up_sync(FULLM, id_, o);
+            if (lane >= o) { iy += a; in_ += b; id_ += c; }
+        }
+        const uint32_t ypre = iy - cy, npre = in_ - cn, dpre = id_ - cd;
+        const uint32_t S = __shfl_sync(FULLM, in_, 31); /* number of steps = popc(T & P) */
 
         double score = 1.0; /* ppp.pm:132 */
-        int yes = 0, number = 0, depth = 0;
-        int best_yes = 0, best_number = 0, best_depth = 0;
+        uint32_t best_yes = 0, best_number = 0, best_depth = 0;
         bool stop = false;
-        for (int w = 0; w < W && !stop; ++w) {
-            uint32_t m = Tw[w];
-            const uint32_t pw = Pw[w], yw = Yw[w] & pw;
-            while (m) {
-                const uint32_t b = __ffs(m) - 1;
-                m &= m - 1;
-                ++depth; /* $i + 1 (ppp.pm:169,231) */
-                const int in_p = (pw >> b) & 1u, in_y = (yw >> b) & 1u;
-                /* an element outside P repeats the previous (yes, number): for p in [0,1] its answer equals the
-                 * previous one (or 1.0 while yes == 0), so it can neither improve nor change where the loop ends */
-                if (!in_p && p_in_range) continue;
-                number += in_p; /* ppp.pm:207-210 */
-                yes += in_y;    /* ppp.pm:212-220 */
-                if (yes > max_yes) { stop = true; break; } /* ppp.pm:222-224 */
-                const double answer = dc_bdtrc(yes - 1, number, p); /* ppp.pm:225 */
-                if (answer < score) {                                /* ppp.pm:228-237 */
-                    best_depth = depth;
-                    score = answer;
-                    best_yes = yes;
-                    best_number = number;
-                    continue;
+        for (uint32_t qbase = 0; qbase < S && !stop; qbase += EXQ) {
+            { /* enqueue steps [qbase, qbase + EXQ): slot = number - 1 */
+                uint32_t yrun = ypre, nrun = npre, drun = dpre;
+#pragma unroll
+                for (int w = 0; w < WPL; ++w) {
+                    uint32_t mbits = tp[w];
+                    while (mbits) {
+                        const uint32_t b = __ffs(mbits) - 1;
+                        mbits &= mbits - 1;
+                        const uint32_t below = (2u << b) - 1u;
+                        ++nrun;
+                        const uint32_t yy = yrun + __popc(ty[w] & below);
+                        const uint32_t dd = drun + __popc(tw[w] & below);
+                        const uint32_t slot = nrun - 1 - qbase;
+                        if (slot < EXQ) queue[slot] = (unsigned long long)yy | ((unsigned long long)dd << 16) | ((unsigned long long)nrun << 32);
+                    }
+                    yrun += __popc(ty[w]);
+                    drun += __popc(tw[w]);
                 }
-                if (answer <= 0) { stop = true; break; } /* ppp.pm:239-241 */
             }
+            __syncwarp();
+            const uint32_t cnt = min((uint32_t)EXQ, S - qbase);
+            for (uint32_t j0 = 0; j0 < cnt && !stop; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                double answer = 2.0; /* 2.0 = "not evaluated" (can neither improve nor stop) */
+                uint32_t yy = 0, nn = 0, dd = 0;
+                if (j < cnt) {
+                    const unsigned long long e = queue[j];
+                    yy = (uint32_t)(e & 0xffffu);
+                    dd = (uint32_t)((e >> 16) & 0xffffu);
+                    nn = (uint32_t)(e >> 32);
+                    bool eval = true;
+                    if (underflow_mode) {
+                        if (yy == 0) eval = false; /* bdtrc(-1, n, p) = 1.0 */
+                        else {
+                            const double lead = ((prm.lf[nn] - prm.lf[yy]) - prm.lf[nn - yy]) + ((double)yy * qc.lnp + (double)(nn - yy) * qc.lnq);
+                            eval = !(lead > -600.0);
+                        }
+                    }
+                    if (eval) answer = ((int)yy > max_yes) ? -1.0 : dc_bdtrc((int)yy - 1, (int)nn, p); /* ppp.pm:222-225 */
+                }
+                /* fold the 32 answers in list order (ppp.pm:228-241) */
+                const uint32_t lim = min(32u, cnt - j0);
+                for (uint32_t s = 0; s < lim; ++s) {
+                    const double a = __shfl_sync(FULLM, answer, s);
+                    if (a == 2.0) continue;
+                    if (a == -1.0) { stop = true; break; } /* yes > max_yes: `last` before bdtrc */
+                    if (a < score) {
+                        score = a;
+                        best_yes = __shfl_sync(FULLM, yy, s);
+                        best_number = __shfl_sync(FULLM, nn, s);
+                        best_depth = __shfl_sync(FULLM, dd, s);
+                        continue;
+                    }
+                    if (a <= 0) { stop = true; break; }
+                }
+            }
+            __syncwarp();
         }
-        ppp_emit(prm, q, t, score, (uint32_t)best_yes, (uint32_t)best_number, (uint32_t)best_depth, 0.f);
+        if (lane == 0) ppp_emit(prm, q, t, score, best_yes, best_number, best_depth, 0.f);
     }
 }
 
 extern "C" cudaError_t ppp_launch_exact(const SweepParams *prm, int W, int nsm, cudaStream_t st)
 {
-    ppp_exact_kernel<<<nsm * 4, 64, 0, st>>>(*prm, W);
+    const int grid = nsm * 8;
+    switch (W / 32) {
+    case 1: ppp_exact_kernel<1><<<grid, 128, 0, st>>>(*prm); break;
+    case 2: ppp_exact_kernel<2><<<grid, 128, 0, st>>>(*prm); break;
+    case 4: ppp_exact_kernel<4><<<grid, 128, 0, st>>>(*prm); break;
+    case 8: ppp_exact_kernel<8><<<grid, 128, 0, st>>>(*prm); break;
+    default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

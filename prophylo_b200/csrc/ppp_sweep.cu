@@ -25,6 +25,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "../../include/ppp_b200.h"
 #include "ppp_common.cuh"
 
@@ -81,68 +83,7 @@ __device__ __forceinline__ double warp_sum_d(double v)
     return v;
 }
 
-/* ---------------------------------------------------------------- tier A: float enclosure of ln P(X >= y | n, p)
- * Unified form: upper tail of Bin(n, p*) at k with m = n - k, ratio_i = (m - i + 1) r / (k + i), r = p* / (1 - p*):
- *   "up"    (y + 1 > (n+1) p):   p* = p, k = y,         lead = ln pmf_p(y; n),      ln f = lead + ln R
- *   "lower" (otherwise):         p* = q, k = n - y + 1, lead = ln pmf_p(y - 1; n),  ln f = ln(1 - exp(lead) R)
- * R = sum_{i>=0} prod_{j<=i} ratio_j.  After K terms the remainder t_K * ratio_{K+1} * R' is enclosed by
- *   R' <= 1 / (1 - ratio_{K+1})                       (ratios decrease)
- *   R' >= max(1, G'' z^2 / (1 + z^2))                 (Bahadur 1960; G'' = 1/(1 - ratio_{K+2}), z the standardised
- *                                                      distance of k + K + 1 from the mean n p*)
- * Division-free Horner keeps numerator and denominator products separately (k + K <= 8200 so k^8 < 2^127).
- */
-__device__ __forceinline__ void tier_a(int y, int n, const QConst &qc, const double *__restrict__ lf, float &lo, float &hi)
-{
-    const int N_ = n - y;
-    const bool up = (float)N_ * qc.thetaf < (float)(y + 1);
-    const int k = up ? y : N_ + 1;
-    const int m = n - k;
-    const int kk = up ? y : y - 1;
-    const float r = up ? qc.thetaf : qc.inv_thetaf;
-    const double lead_d = ((lf[n] - lf[kk]) - lf[n - kk]) + ((double)kk * qc.lnp + (double)(n - kk) * qc.lnq);
-    const float lead = (float)lead_d;
-
-    float mf = (float)m, bf = (float)(k + 1);
-    float tn = 1.f, D = 1.f, X = 1.f;
-#pragma unroll
-    for (int i = 0; i < PPP_K_TERMS; ++i) {
-        const float a = fmaxf(mf, 0.f) * r;
-        tn *= a;
-        D *= bf;
-        X = fmaf(X, bf, tn);
-        mf -= 1.f;
-        bf += 1.f;
-    }
-    const float invD = __fdividef(1.f, D);
-    const float S = X * invD, tK = tn * invD;
-    const float rho = __fdividef(fmaxf(mf, 0.f) * r, bf);              /* ratio_{K+1} */
-    const float rho2 = __fdividef(fmaxf(mf - 1.f, 0.f) * r, bf + 1.f); /* ratio_{K+2} */
-    float rem_lo = tK * rho;
-    float rem_hi = (rho < 0.999f) ? __fdividef(rem_lo, 1.f - rho) : INFINITY;
-    {
-        const float pstar = up ? qc.pf : 1.f - qc.pf;
-        const float d = bf - (float)n * pstar;
-        if (d > 0.f && rho2 < 0.999f) {
-            const float z2 = __fdividef(d * d, (float)n * qc.varf_unit);
-            const float gb = __fdividef(z2, (1.f + z2) * (1.f - rho2));
-            rem_lo *= fmaxf(1.f, gb * 0.9999f);
-        }
-    }
-    const float Rlo = (S + rem_lo) * 0.9999f, Rhi = (S + rem_hi) * 1.0001f;
-    if (up) {
-        lo = lead + __logf(Rlo);
-        hi = fminf(lead + __logf(Rhi), 0.f);
-        lo -= 1e-4f + 2e-5f * fabsf(lo);
-        hi = fminf(hi + 1e-4f + 2e-5f * fabsf(hi), 0.f);
-    } else {
-        const float e = __expf(lead);
-        const float glo = e * Rlo * 0.999f, ghi = e * Rhi * 1.001f;
-        hi = (glo < 0.5f) ? fminf(-glo, 0.f) : __logf(fmaxf(1.f - glo, 0.f)) + 1e-4f; /* ln(1-g) <= -g */
-        hi = fminf(hi, 0.f);
-        lo = (ghi < 0.9f) ? __logf(1.f - ghi) - 1e-4f : -INFINITY;
-        if (ghi < 1e-3f) lo = -ghi * (1.f + ghi) - 1e-30f;
-    }
-}
+/* tier A (the float enclosure) lives in ppp_common.cuh: the staircase builder shares it. */
 
 /* ---------------------------------------------------------------- tier B: warp-cooperative FP64 evaluation
  * Sums the same ratio series to convergence, 32 terms per round: t_i = exp(lf[m]-lf[m-i] - (lf[k+i]-lf[k]) + i ln r).
@@ -179,13 +120,283 @@ __device__ __forceinline__ double tier_b(int y, int n, const QConst &qc, const d
     return lnf;
 }
 
-/* ---------------------------------------------------------------- the sweep kernel */
+/* ---------------------------------------------------------------- one pair, one warp */
 struct PairOut {
     double score;
     uint32_t yes, number, depth;
     float margin;
 };
+enum { PF_REJECTED = 1, PF_EXACT = 2, PF_UNDERFLOW = 4 };
 
+struct WarpCounters {
+    unsigned long long cand = 0, acc = 0, viol = 0, chk = 0, full = 0;
+};
+
+/* Evaluate one (query, target) pair with the whole warp.  Lane l owns words [l*WPL, (l+1)*WPL): tw = target words,
+ * tp = tw & P, ty = tp & Y.  dpre / dtotal are the lane's exclusive depth prefix and the target's total popcount.
+ * stair != nullptr: the query's pre-filter staircase (filtered runs); the pair is dropped (PF_REJECTED) unless some
+ * candidate satisfies number <= stair[yes].  Returns flags; *out is valid unless rejected or flagged exact. */
+template <int WPL>
+__device__ __forceinline__ uint32_t evaluate_pair(const uint32_t (&tw)[WPL], const uint32_t (&tp)[WPL], const uint32_t (&ty)[WPL],
+                                                  uint32_t dpre, uint32_t dtotal, const QConst &qc, const double *__restrict__ s_lf,
+                                                  uint32_t *__restrict__ my_queue, uint32_t *__restrict__ my_y, float *__restrict__ my_lo,
+                                                  const uint16_t *__restrict__ stair, const SweepParams &prm, int lane,
+                                                  WarpCounters &wc, PairOut *out)
+{
+    PairOut res;
+    res.score = 1.0; res.yes = 0; res.number = 0; res.depth = 0; res.margin = INFINITY;
+    uint32_t flags = 0;
+
+    if (qc.flags & PPP_QF_DOMAIN) {
+        /* p outside [0,1]: bdtrc -> 0.0 at the first element of the list (ppp.pm:225-241) */
+        if (dtotal) {
+            uint32_t first = 0, fp = 0, fy = 0;
+            bool have = false;
+#pragma unroll
+            for (int w = WPL - 1; w >= 0; --w)
+                if (tw[w]) { first = tw[w]; fp = tp[w]; fy = ty[w]; have = true; }
+            const uint32_t has = __ballot_sync(FULL, have);
+            const int src = __ffs(has) - 1;
+            uint32_t y1 = 0, n1 = 0;
+            if (lane == src) {
+                const uint32_t b = __ffs(first) - 1;
+                n1 = (fp >> b) & 1u;
+                y1 = (fy >> b) & 1u;
+            }
+            res.score = 0.0;
+            res.yes = __shfl_sync(FULL, y1, src);
+            res.number = __shfl_sync(FULL, n1, src);
+            res.depth = 1;
+            res.margin = 0.f;
+        }
+        *out = res;
+        return 0;
+    }
+    if (qc.flags & PPP_QF_TRIVIAL) {
+        *out = res;
+        return 0;
+    }
+    /* 1. counts + packed prefix scan (yes in the low 16 bits, number in the high 16 bits) */
+    uint32_t cy = 0, cn = 0;
+#pragma unroll
+    for (int w = 0; w < WPL; ++w) {
+        cy += __popc(ty[w]);
+        cn += __popc(tp[w]);
+    }
+    const uint32_t packed = cy | (cn << 16);
+    uint32_t incl = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint32_t excl = incl - packed;
+    const uint32_t E = __shfl_sync(FULL, incl, 31) & 0xffffu;
+    wc.cand += (lane == 0) ? E : 0;
+
+    if (E == 0) {
+        if (stair) return PF_REJECTED; /* score 1.0 cannot beat a threshold below 1/2 */
+        *out = res;
+        return 0;
+    }
+    if (prm.force_exact || (qc.flags & PPP_QF_EXACT)) return PF_EXACT;
+
+    /* 2. candidates.  Unfiltered: every set bit of T&Y.  Filtered: only those with number <= stair[yes] -- the
+     * pair is only kept if its minimum is below the threshold, and then the minimum (and anything within the
+     * staircase's margin of it, i.e. every possible near-tie) is among them. */
+    uint32_t mycnt = 0;
+    {
+        uint32_t yrun = excl & 0xffffu, nbase = excl >> 16;
+#pragma unroll
+        for (int w = 0; w < WPL; ++w) {
+            const uint32_t cyw = __popc(ty[w]);
+            if (!stair) {
+                mycnt += cyw;
+            } else if (cyw && (nbase + 1u) <= (uint32_t)__ldg(stair + yrun + cyw)) { /* word-level screen, one lookup */
+                uint32_t mbits = ty[w], yy = yrun;
+                while (mbits) {
+                    const uint32_t b = __ffs(mbits) - 1;
+                    mbits &= mbits - 1;
+                    ++yy;
+                    const uint32_t nn = nbase + __popc(tp[w] & ((2u << b) - 1u));
+                    mycnt += nn <= (uint32_t)__ldg(stair + yy);
+                }
+            }
+            yrun += cyw;
+            nbase += __popc(tp[w]);
+        }
+    }
+    uint32_t cincl = mycnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, cincl, o);
+        if (lane >= o) cincl += v;
+    }
+    const uint32_t cexcl = cincl - mycnt;
+    const uint32_t EC = __shfl_sync(FULL, cincl, 31);
+    if (stair && EC == 0) return PF_REJECTED; /* no candidate can reach the query's threshold */
+    wc.full += (lane == 0);
+
+    double best_lnf = INFINITY, best_f = 1.0, second_lnf = INFINITY;
+    uint32_t best_y = 0, best_n = 0, best_g = 0;
+    float Ustar = INFINITY;
+    /* candidates are processed in passes of PPP_QCAP queue slots (one pass unless more than 512 candidates) */
+    for (uint32_t qbase = 0; qbase < EC; qbase += PPP_QCAP) {
+        {
+            uint32_t yrun = excl & 0xffffu, nbase = excl >> 16, slot = cexcl - qbase;
+#pragma unroll
+            for (int w = 0; w < WPL; ++w) {
+                uint32_t mbits = ty[w];
+                const uint32_t cyw = __popc(mbits);
+                if (stair && !(cyw && (nbase + 1u) <= (uint32_t)__ldg(stair + yrun + cyw))) mbits = 0; /* word-level screen */
+                const uint32_t yword = yrun;
+                yrun += cyw;
+                uint32_t yy = yword;
+                while (mbits) {
+                    const uint32_t b = __ffs(mbits) - 1;
+                    mbits &= mbits - 1;
+                    ++yy;
+                    const uint32_t nn = nbase + __popc(tp[w] & ((2u << b) - 1u));
+                    if (!stair || nn <= (uint32_t)__ldg(stair + yy)) {
+                        if (slot < PPP_QCAP) {
+                            my_queue[slot] = nn | ((uint32_t)((lane * WPL + w) * 32 + b) << 16);
+                            my_y[slot] = yy;
+                        }
+                        ++slot;
+                    }
+                }
+                nbase += __popc(tp[w]);
+            }
+        }
+        __syncwarp();
+        const uint32_t cnt = min((uint32_t)PPP_QCAP, EC - qbase);
+        /* 3. tier A enclosures */
+        float umin = INFINITY;
+        for (uint32_t j = lane; j < cnt; j += 32) {
+            const uint32_t ent = my_queue[j];
+            float lo, hi;
+            tier_a((int)my_y[j], (int)(ent & 0xffffu), qc, s_lf, lo, hi);
+            my_lo[j] = lo;
+            umin = fminf(umin, hi);
+        }
+        Ustar = fminf(Ustar, warp_min_f(umin));
+        __syncwarp();
+        /* 4. survivors -> tier B (in rank order, so that the earliest minimum wins) */
+        const float cut = Ustar + 1e-5f + 1e-6f * fabsf(Ustar);
+        for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const bool sv = (j < cnt) && !(my_lo[j] > cut); /* NaN-safe: unknown = survivor */
+            uint32_t ball = __ballot_sync(FULL, sv);
+            while (ball) {
+                const int src = __ffs(ball) - 1;
+                ball &= ball - 1;
+                const uint32_t ent = my_queue[j0 + src];
+                const int yy = (int)my_y[j0 + src], nn = (int)(ent & 0xffffu);
+                double f;
+                const double lnf = tier_b(yy, nn, qc, s_lf, lane, &f);
+                wc.acc += (lane == 0);
+                if (lnf < best_lnf) {
+                    second_lnf = best_lnf;
+                    best_lnf = lnf; best_f = f;
+                    best_y = yy; best_n = nn; best_g = ent >> 16;
+                } else if (lnf < second_lnf) {
+                    second_lnf = lnf;
+                }
+            }
+        }
+        if (prm.check_bounds) { /* diagnostic: every enclosure must contain the accurate value */
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const uint32_t ent = my_queue[j];
+                double f;
+                const double lnf = tier_b((int)my_y[j], (int)(ent & 0xffffu), qc, s_lf, lane, &f);
+                float lo, hi;
+                tier_a((int)my_y[j], (int)(ent & 0xffffu), qc, s_lf, lo, hi);
+                wc.chk += (lane == 0);
+                if (!((double)lo <= lnf && lnf <= (double)hi)) wc.viol += (lane == 0);
+            }
+        }
+        __syncwarp();
+    }
+    /* 5. decide */
+    const double margin = second_lnf - best_lnf;
+    const double tie_eps = 1e-7; /* >> Cephes' and tier B's relative error on f */
+    if (!(best_lnf < 0.0)) return PF_EXACT; /* nothing provably below 1: saturation at 1 - MACHEP is Cephes' call */
+    if (margin < tie_eps || best_lnf < -700.0 || best_lnf > -1e-6)
+        return PF_EXACT | (best_lnf < -700.0 ? PF_UNDERFLOW : 0);
+    res.score = best_f;
+    res.yes = best_y;
+    res.number = best_n;
+    res.margin = (float)margin;
+    { /* depth = popc(T[0..g]): the lane that owns the word of g finishes it */
+        const int owner = (int)(best_g >> 5) / WPL;
+        uint32_t dd = 0;
+        if (lane == owner) {
+            dd = dpre;
+            const int wsel = (int)(best_g >> 5) % WPL;
+#pragma unroll
+            for (int w = 0; w < WPL; ++w) {
+                if (w < wsel) dd += __popc(tw[w]);
+                if (w == wsel) dd += __popc(tw[w] & ((2u << (best_g & 31)) - 1u));
+            }
+        }
+        res.depth = __shfl_sync(FULL, dd, owner);
+    }
+    *out = res;
+    return 0;
+}
+
+template <int WPL>
+__device__ __forceinline__ void load_row(const uint32_t *__restrict__ row, uint32_t (&v)[WPL])
+{
+    if constexpr (WPL == 4) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(row));
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    } else if constexpr (WPL == 8) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(row));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(row) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else if constexpr (WPL == 2) {
+        const uint2 a = __ldg(reinterpret_cast<const uint2 *>(row));
+        v[0] = a.x; v[1] = a.y;
+    } else {
+        v[0] = __ldg(row);
+    }
+}
+
+__device__ __forceinline__ void depth_prefix(uint32_t dlane, int lane, uint32_t &dpre, uint32_t &dtotal)
+{
+    uint32_t dincl = dlane;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, dincl, o);
+        if (lane >= o) dincl += v;
+    }
+    dpre = dincl - dlane;
+    dtotal = __shfl_sync(FULL, dincl, 31);
+}
+
+__device__ __forceinline__ void flush_counters(const SweepParams &prm, WarpCounters &wc, int lane)
+{
+    wc.cand = (unsigned long long)warp_sum_d((double)wc.cand);
+    if (lane == 0) {
+        if (wc.cand) atomicAdd(&prm.counters[CNT_CAND], wc.cand);
+        if (wc.acc) atomicAdd(&prm.counters[CNT_ACCURATE], wc.acc);
+        if (wc.viol) atomicAdd(&prm.counters[CNT_VIOL], wc.viol);
+        if (wc.chk) atomicAdd(&prm.counters[CNT_CHECKS], wc.chk);
+        if (wc.full) atomicAdd(&prm.counters[CNT_FULL], wc.full);
+    }
+}
+
+__device__ __forceinline__ void push_exact(const SweepParams &prm, uint32_t local_id, bool underflow)
+{
+    const unsigned long long slot = atomicAdd(&prm.counters[CNT_EXACT], 1ull);
+    if (slot < prm.exact_cap) prm.exact_list[slot] = local_id | (underflow ? 0x80000000u : 0u);
+    else atomicAdd(&prm.counters[CNT_OVERFLOW], 1ull);
+}
+
+/* ---------------------------------------------------------------- tile kernel: every pair of (query tile x targets)
+ * One warp owns one target row (registers) and walks a 32-query tile staged in shared memory by TMA. */
 template <int WPL>
 __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
 {
@@ -196,7 +407,6 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
     const int warp = threadIdx.x >> 5;
     const int nwarps = blockDim.x >> 5;
 
-    /* shared memory carve-up */
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);                /* [0]: lf table, [1]: query tile */
     double *s_lf = reinterpret_cast<double *>(smem_raw + 128);              /* GD + 2 doubles */
     constexpr int LF_BYTES = (((GD + 2) * 8) + 127) & ~127;
@@ -204,8 +414,9 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
     QConst *s_qc = reinterpret_cast<QConst *>(reinterpret_cast<unsigned char *>(s_q) + PPP_QTILE * 2 * W * 4);
     uint32_t *s_off = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(s_qc) + PPP_QTILE * sizeof(QConst)); /* [32] */
     uint32_t *s_queue = s_off + PPP_QTILE;
-    uint32_t *my_queue = s_queue + warp * (2 * PPP_QCAP);                   /* [QCAP] (n | g<<16), then [QCAP] float lo */
-    float *my_lo = reinterpret_cast<float *>(my_queue + PPP_QCAP);
+    uint32_t *my_queue = s_queue + warp * (3 * PPP_QCAP);                   /* [QCAP] n | g<<16, [QCAP] yes, [QCAP] float lo */
+    uint32_t *my_y = my_queue + PPP_QCAP;
+    float *my_lo = reinterpret_cast<float *>(my_queue + 2 * PPP_QCAP);
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1);
@@ -224,7 +435,7 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
     const uint32_t nTblocks = (nTl + nwarps - 1) / nwarps;
     const uint64_t nItems = (uint64_t)nQtiles * nTblocks;
 
-    unsigned long long cnt_cand = 0, cnt_acc = 0, cnt_viol = 0, cnt_chk = 0, cnt_full = 0;
+    WarpCounters wc;
     uint32_t tile_parity = 0;
     uint32_t cur_qt = 0xffffffffu;
     mbar_wait(&bars[0], 0);
@@ -254,43 +465,18 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
         if (tl >= nTl) continue; /* warp-uniform */
         const uint32_t t = prm.t0 + tl;
 
-        /* target row -> registers; depth offsets once per target */
         uint32_t tw[WPL];
-        {
-            const uint32_t *row = prm.T + (size_t)t * W + lane * WPL;
-            if constexpr (WPL == 4) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row));
-                tw[0] = v.x; tw[1] = v.y; tw[2] = v.z; tw[3] = v.w;
-            } else if constexpr (WPL == 8) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(row));
-                const uint4 u = __ldg(reinterpret_cast<const uint4 *>(row) + 1);
-                tw[0] = v.x; tw[1] = v.y; tw[2] = v.z; tw[3] = v.w;
-                tw[4] = u.x; tw[5] = u.y; tw[6] = u.z; tw[7] = u.w;
-            } else if constexpr (WPL == 2) {
-                const uint2 v = __ldg(reinterpret_cast<const uint2 *>(row));
-                tw[0] = v.x; tw[1] = v.y;
-            } else {
-                tw[0] = __ldg(row);
-            }
-        }
+        load_row<WPL>(prm.T + (size_t)t * W + lane * WPL, tw);
         uint32_t dlane = 0;
 #pragma unroll
         for (int w = 0; w < WPL; ++w) dlane += __popc(tw[w]);
-        uint32_t dincl = dlane;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(FULL, dincl, o);
-            if (lane >= o) dincl += v;
-        }
-        const uint32_t dpre = dincl - dlane;
-        const uint32_t dtotal = __shfl_sync(FULL, dincl, 31);
+        uint32_t dpre, dtotal;
+        depth_prefix(dlane, lane, dpre, dtotal);
 
         PairOut mine;
         mine.score = 1.0; mine.yes = 0; mine.number = 0; mine.depth = 0; mine.margin = INFINITY;
-        bool mine_exact = false, mine_rejected = false;
-
+        uint32_t mine_flags = 0;
         for (uint32_t qi = 0; qi < nq; ++qi) {
-            const QConst &qc = s_qc[qi];
             const uint32_t *pw_ = s_q + (size_t)qi * 2 * W + lane * WPL;
             const uint32_t *yw_ = pw_ + W;
             uint32_t tp[WPL], ty[WPL];
@@ -299,221 +485,258 @@ __global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
                 tp[w] = tw[w] & pw_[w];
                 ty[w] = tp[w] & yw_[w];
             }
-            PairOut res;
-            res.score = 1.0; res.yes = 0; res.number = 0; res.depth = 0; res.margin = INFINITY;
-            bool need_exact = false, rejected = false;
-
-            if (qc.flags & PPP_QF_DOMAIN) {
-                /* p outside [0,1]: bdtrc -> 0.0 at the first element of the list (ppp.pm:225-241) */
-                if (dtotal) {
-                    uint32_t firstword = 0xffffffffu;
-#pragma unroll
-                    for (int w = WPL - 1; w >= 0; --w) if (tw[w]) firstword = w;
-                    const uint32_t has = __ballot_sync(FULL, firstword != 0xffffffffu);
-                    const int src = __ffs(has) - 1;
-                    uint32_t y1 = 0, n1 = 0;
-                    if (lane == src) {
-                        const uint32_t b = __ffs(tw[firstword]) - 1;
-                        n1 = (tp[firstword] >> b) & 1u;
-                        y1 = (ty[firstword] >> b) & 1u;
-                    }
-                    res.score = 0.0;
-                    res.yes = __shfl_sync(FULL, y1, src);
-                    res.number = __shfl_sync(FULL, n1, src);
-                    res.depth = 1;
-                    res.margin = 0.f;
-                }
-            } else if (!(qc.flags & PPP_QF_TRIVIAL)) {
-                /* 1. counts + packed prefix scan (yes in low 16 bits, number in high 16 bits) */
-                uint32_t cy = 0, cn = 0;
-#pragma unroll
-                for (int w = 0; w < WPL; ++w) {
-                    cy += __popc(ty[w]);
-                    cn += __popc(tp[w]);
-                }
-                const uint32_t packed = cy | (cn << 16);
-                uint32_t incl = packed;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t v = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                const uint32_t excl = incl - packed;
-                const uint32_t E = __shfl_sync(FULL, incl, 31) & 0xffffu;
-                cnt_cand += (lane == 0) ? E : 0;
-
-                /* filtered runs: the staircase nmax[yes] bounds the number a candidate may have and still pass the
-                 * query's threshold (tail increases with number, decreases with yes); one lookup per lane decides
-                 * whether ANY candidate of the lane's words can pass.  Most pairs end here. */
-                if (prm.append) {
-                    const uint32_t off = s_off[qi];
-                    if (off != PPP_NO_TABLE) {
-                        const uint16_t *stair = prm.nmax + off;
-                        const bool lane_pass = cy > 0 && ((excl >> 16) + 1u) <= (uint32_t)__ldg(stair + (excl & 0xffffu) + cy);
-                        rejected = !__any_sync(FULL, lane_pass);
-                        if (!rejected) {
-                            /* second look, exact per candidate: number <= nmax[yes] for at least one set bit of T&Y */
-                            bool cand_pass = false;
-                            if (lane_pass) {
-                                uint32_t yrun = excl & 0xffffu, nbase = excl >> 16;
-#pragma unroll
-                                for (int w = 0; w < WPL; ++w) {
-                                    uint32_t mbits = ty[w];
-                                    while (mbits) {
-                                        const uint32_t b = __ffs(mbits) - 1;
-                                        mbits &= mbits - 1;
-                                        ++yrun;
-                                        const uint32_t nn = nbase + __popc(tp[w] & ((2u << b) - 1u));
-                                        cand_pass |= nn <= (uint32_t)__ldg(stair + yrun);
-                                    }
-                                    nbase += __popc(tp[w]);
-                                }
-                            }
-                            rejected = !__any_sync(FULL, cand_pass);
-                        }
-                    }
-                }
-                if (rejected) {
-                } else if (E > 0 && (prm.force_exact || (qc.flags & PPP_QF_EXACT))) {
-                    need_exact = true;
-                } else if (E > 0) {
-                    double best_lnf = INFINITY, best_f = 1.0, second_lnf = INFINITY;
-                    uint32_t best_y = 0, best_n = 0, best_g = 0;
-                    float Ustar = INFINITY;
-                    /* candidates are processed in passes of PPP_QCAP ranks (one pass unless |T&Y| > 1024) */
-                    for (uint32_t qbase = 0; qbase < E; qbase += PPP_QCAP) {
-                        /* 2. enqueue: rank (= yes) is the queue slot */
-                        {
-                            uint32_t yrun = excl & 0xffffu, nbase = excl >> 16;
-#pragma unroll
-                            for (int w = 0; w < WPL; ++w) {
-                                uint32_t mbits = ty[w];
-                                while (mbits) {
-                                    const uint32_t b = __ffs(mbits) - 1;
-                                    mbits &= mbits - 1;
-                                    const uint32_t nn = nbase + __popc(tp[w] & ((2u << b) - 1u));
-                                    const uint32_t slot = yrun - qbase;
-                                    if (slot < PPP_QCAP) my_queue[slot] = nn | ((uint32_t)((lane * WPL + w) * 32 + b) << 16);
-                                    ++yrun;
-                                }
-                                nbase += __popc(tp[w]);
-                            }
-                        }
-                        __syncwarp();
-                        const uint32_t cnt = min((uint32_t)PPP_QCAP, E - qbase);
-                        /* 3. tier A enclosures */
-                        float umin = INFINITY;
-                        for (uint32_t j = lane; j < cnt; j += 32) {
-                            const uint32_t ent = my_queue[j];
-                            float lo, hi;
-                            tier_a((int)(qbase + j + 1), (int)(ent & 0xffffu), qc, s_lf, lo, hi);
-                            my_lo[j] = lo;
-                            umin = fminf(umin, hi);
-                        }
-                        Ustar = fminf(Ustar, warp_min_f(umin));
-                        __syncwarp();
-                        /* 4. survivors -> tier B (in rank order, so that the earliest minimum wins) */
-                        const float cut = Ustar + 1e-5f + 1e-6f * fabsf(Ustar);
-                        for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
-                            const uint32_t j = j0 + lane;
-                            const bool sv = (j < cnt) && !(my_lo[j] > cut); /* NaN-safe: unknown = survivor */
-                            uint32_t ball = __ballot_sync(FULL, sv);
-                            while (ball) {
-                                const int src = __ffs(ball) - 1;
-                                ball &= ball - 1;
-                                const uint32_t ent = my_queue[j0 + src];
-                                const int yy = (int)(qbase + j0 + src + 1), nn = (int)(ent & 0xffffu);
-                                double f;
-                                const double lnf = tier_b(yy, nn, qc, s_lf, lane, &f);
-                                cnt_acc += (lane == 0);
-                                if (lnf < best_lnf) {
-                                    second_lnf = best_lnf;
-                                    best_lnf = lnf; best_f = f;
-                                    best_y = yy; best_n = nn; best_g = ent >> 16;
-                                } else if (lnf < second_lnf) {
-                                    second_lnf = lnf;
-                                }
-                            }
-                        }
-                        if (prm.check_bounds) { /* diagnostic: every enclosure must contain the accurate value */
-                            for (uint32_t j = 0; j < cnt; ++j) {
-                                const uint32_t ent = my_queue[j];
-                                double f;
-                                const double lnf = tier_b((int)(qbase + j + 1), (int)(ent & 0xffffu), qc, s_lf, lane, &f);
-                                float lo, hi;
-                                tier_a((int)(qbase + j + 1), (int)(ent & 0xffffu), qc, s_lf, lo, hi);
-                                cnt_chk += (lane == 0);
-                                if (!((double)lo <= lnf && lnf <= (double)hi)) cnt_viol += (lane == 0);
-                            }
-                        }
-                        __syncwarp();
-                    }
-                    /* 5. decide */
-                    const double margin = second_lnf - best_lnf;
-                    const double tie_eps = 1e-7; /* >> Cephes' and tier B's relative error on f */
-                    if (!(best_lnf < 0.0)) {
-                        /* nothing provably below 1: leave it to the exact tier (saturation at 1 - MACHEP) */
-                        need_exact = true;
-                    } else if (margin < tie_eps || best_lnf < -700.0 || best_lnf > -1e-6) {
-                        need_exact = true;
-                    } else {
-                        res.score = best_f;
-                        res.yes = best_y;
-                        res.number = best_n;
-                        res.margin = (float)margin;
-                        /* depth = popc(T[0..g]) : the lane that owns the word of g finishes it */
-                        const int owner = (int)(best_g >> 5) / WPL;
-                        uint32_t dd = 0;
-                        if (lane == owner) {
-                            dd = dpre;
-                            const int wsel = (int)(best_g >> 5) % WPL;
-#pragma unroll
-                            for (int w = 0; w < WPL; ++w) {
-                                if (w < wsel) dd += __popc(tw[w]);
-                                if (w == wsel) dd += __popc(tw[w] & ((2u << (best_g & 31)) - 1u));
-                            }
-                        }
-                        res.depth = __shfl_sync(FULL, dd, owner);
-                    }
-                }
+            const uint16_t *stair = nullptr;
+            if (prm.append) {
+                const uint32_t off = s_off[qi];
+                if (off != PPP_NO_TABLE) stair = prm.nmax + off;
             }
+            PairOut res;
+            const uint32_t fl = evaluate_pair<WPL>(tw, tp, ty, dpre, dtotal, s_qc[qi], s_lf, my_queue, my_y, my_lo, stair, prm, lane, wc, &res);
             if (lane == (int)qi) {
                 mine = res;
-                mine_exact = need_exact;
-                mine_rejected = rejected;
+                mine_flags = fl;
             }
         }
         /* lane i holds the result of query q0 + i */
-        if ((uint32_t)lane < nq && !mine_rejected) {
+        if ((uint32_t)lane < nq && !(mine_flags & PF_REJECTED)) {
             const uint32_t q = q0 + lane;
-            if (mine_exact) {
-                const unsigned long long slot = atomicAdd(&prm.counters[CNT_EXACT], 1ull);
-                if (slot < prm.exact_cap) prm.exact_list[slot] = (uint32_t)((uint64_t)q * nTl + tl);
-                else atomicAdd(&prm.counters[CNT_OVERFLOW], 1ull);
-                if (!prm.append) ppp_emit(prm, q, t, mine.score, mine.yes, mine.number, mine.depth, -1.f);
+            if (mine_flags & PF_EXACT) {
+                push_exact(prm, (uint32_t)((uint64_t)q * nTl + tl), (mine_flags & PF_UNDERFLOW) != 0);
+                if (!prm.append) ppp_emit(prm, q, t, 1.0, 0, 0, 0, -1.f);
             } else {
                 ppp_emit(prm, q, t, mine.score, mine.yes, mine.number, mine.depth, mine.margin);
             }
         }
-        if (prm.append) cnt_full += __popc(__ballot_sync(FULL, (uint32_t)lane < nq && !mine_rejected));
     }
-    /* flush per-warp statistics */
-    cnt_cand = (unsigned long long)warp_sum_d((double)cnt_cand);
-    if (lane == 0) {
-        if (cnt_cand) atomicAdd(&prm.counters[CNT_CAND], cnt_cand);
-        if (cnt_acc) atomicAdd(&prm.counters[CNT_ACCURATE], cnt_acc);
-        if (cnt_viol) atomicAdd(&prm.counters[CNT_VIOL], cnt_viol);
-        if (cnt_chk) atomicAdd(&prm.counters[CNT_CHECKS], cnt_chk);
-        if (cnt_full) atomicAdd(&prm.counters[CNT_FULL], cnt_full);
+    flush_counters(prm, wc, lane);
+}
+
+/* ---------------------------------------------------------------- pre-filter kernel (filtered runs): thread per pair
+ * Integer-only screen of EVERY pair of the chunk against the query's staircase, one thread per target, a 32-query
+ * tile per pass: the thread streams its target row once (transposed planes Tt[w/4][t][4] -> one coalesced 16-byte
+ * load per 4 words) and keeps (yes, number) running counts of 32 queries in registers.  For every word it asks
+ * "number_before + 1 <= stair[yes_after]": no candidate inside the word can reach the query's threshold otherwise
+ * (stair is non-decreasing in yes and a candidate's number exceeds number_before).  Pairs with at least one passing
+ * word are appended to the survivor list for the warp-per-pair refine kernel; everything else -- the overwhelming
+ * majority -- is finished here with 2 AND + 2 POPC + 1 lookup per word.  */
+/* exact per-candidate test of one word that passed the word-level screen (rare; kept out of line on purpose) */
+__device__ __noinline__ bool word_has_passing_candidate(uint32_t a, uint32_t b, uint32_t nb, uint32_t yy, const uint16_t *__restrict__ stair)
+{
+    bool ok = false;
+    while (b) {
+        const uint32_t bit = __ffs(b) - 1;
+        b &= b - 1;
+        ++yy;
+        ok |= nb + __popc(a & ((2u << bit) - 1u)) <= (uint32_t)__ldg(stair + yy);
+    }
+    return ok;
+}
+
+template <int WPL>
+__global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams prm, const uint4 *__restrict__ Tt, uint32_t ntt,
+                                                            uint32_t *__restrict__ surv, unsigned long long *__restrict__ surv_count,
+                                                            unsigned long long surv_cap)
+{
+    constexpr int W = 32 * WPL;
+    constexpr int C = W / 4; /* 16-byte chunks per row */
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *s_q = reinterpret_cast<uint32_t *>(smem_raw + 128); /* PPP_QTILE * 2 * W words */
+    uint32_t *s_off = s_q + PPP_QTILE * 2 * W;
+    const uint32_t nTl = prm.t1 - prm.t0;
+    const uint32_t nQtiles = (prm.nQ + PPP_QTILE - 1) / PPP_QTILE;
+    const uint32_t nTblocks = (nTl + blockDim.x - 1) / blockDim.x;
+    const uint64_t nItems = (uint64_t)nQtiles * nTblocks;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0, cur_qt = 0xffffffffu;
+    for (uint64_t item = blockIdx.x; item < nItems; item += gridDim.x) {
+        const uint32_t qt = (uint32_t)(item / nTblocks), tb = (uint32_t)(item % nTblocks);
+        const uint32_t q0 = qt * PPP_QTILE;
+        const uint32_t nq = min((uint32_t)PPP_QTILE, prm.nQ - q0);
+        if (qt != cur_qt) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                fence_proxy_async();
+                const uint32_t b1 = nq * 2 * W * 4;
+                mbar_expect_tx(bar, b1);
+                tma_load_1d(s_q, prm.Q + (size_t)q0 * 2 * W, b1, bar);
+            }
+            if (threadIdx.x < PPP_QTILE) s_off[threadIdx.x] = (threadIdx.x < nq) ? prm.nmax_off[q0 + threadIdx.x] : PPP_NO_TABLE;
+            mbar_wait(bar, parity);
+            parity ^= 1;
+            cur_qt = qt;
+            __syncthreads();
+        }
+        const uint32_t tl = tb * blockDim.x + threadIdx.x;
+        const bool live = tl < nTl;
+        const uint32_t t = prm.t0 + (live ? tl : 0);
+        uint32_t state[PPP_QTILE]; /* yes | number << 16 per query */
+#pragma unroll
+        for (int i = 0; i < PPP_QTILE; ++i) state[i] = 0;
+        uint32_t pass = 0;
+        for (int c = 0; c < C; ++c) {
+            const uint4 tv = live ? __ldg(Tt + (size_t)c * ntt + t) : make_uint4(0, 0, 0, 0);
+            const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+#pragma unroll
+            for (int qi = 0; qi < PPP_QTILE; ++qi) {
+                if ((uint32_t)qi >= nq) break; /* block-uniform */
+                const uint4 pv = *reinterpret_cast<const uint4 *>(s_q + (size_t)qi * 2 * W + c * 4);      /* broadcast */
+                const uint4 yv = *reinterpret_cast<const uint4 *>(s_q + (size_t)qi * 2 * W + W + c * 4);
+                const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+                const uint32_t off = s_off[qi];
+                const uint32_t st0 = state[qi];
+                uint32_t a[4], b[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    a[w] = tw[w] & pw[w];
+                    b[w] = a[w] & yw[w];
+                }
+                const uint32_t cy = __popc(b[0]) + __popc(b[1]) + __popc(b[2]) + __popc(b[3]);
+                const uint32_t cn = __popc(a[0]) + __popc(a[1]) + __popc(a[2]) + __popc(a[3]);
+                const uint32_t st = st0 + cy + (cn << 16);
+                /* 128-genome screen, one lookup: no candidate of the chunk can pass unless number_before + 1 <=
+                 * stair[yes_after]; the rare chunks that survive it are re-screened word by word */
+                const uint32_t lim = (off != PPP_NO_TABLE) ? (uint32_t)__ldg(prm.nmax + off + (st & 0xffffu)) : 0xffffu;
+                if (cy && (st0 >> 16) + 1u <= lim) {
+                    uint32_t sw = st0;
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const uint32_t cyw = __popc(b[w]);
+                        const uint32_t nb = sw >> 16;
+                        sw += cyw + (__popc(a[w]) << 16);
+                        if (cyw) {
+                            const uint32_t l2 = (off != PPP_NO_TABLE) ? (uint32_t)__ldg(prm.nmax + off + (sw & 0xffffu)) : 0xffffu;
+                            if (nb + 1u <= l2 && word_has_passing_candidate(a[w], b[w], nb, (sw & 0xffffu) - cyw, prm.nmax + off))
+                                pass |= 1u << qi;
+                        }
+                    }
+                }
+                state[qi] = st;
+            }
+        }
+        if (!live) pass = 0;
+        /* queries without a staircase accept every pair (also the ones with no candidate at all) */
+#pragma unroll
+        for (int qi = 0; qi < PPP_QTILE; ++qi)
+            if (live && (uint32_t)qi < nq && s_off[qi] == PPP_NO_TABLE) pass |= 1u << qi;
+        if ((uint32_t)nq < 32u) pass &= (1u << nq) - 1u;
+        /* append survivors: warp-aggregated reservation */
+        const uint32_t mycnt = __popc(pass);
+        uint32_t incl = mycnt;
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        if (total) {
+            unsigned long long base = 0;
+            if (lane == 31) base = atomicAdd(surv_count, (unsigned long long)total);
+            base = __shfl_sync(FULL, base, 31);
+            unsigned long long slot = base + (incl - mycnt);
+            while (pass) {
+                const uint32_t qi = __ffs(pass) - 1;
+                pass &= pass - 1;
+                if (slot < surv_cap) surv[slot] = (uint32_t)((uint64_t)(q0 + qi) * nTl + tl);
+                ++slot;
+            }
+        }
     }
 }
 
-/* ---------------------------------------------------------------- launcher */
+/* ---------------------------------------------------------------- refine kernel: warp per surviving pair */
+template <int WPL>
+__global__ void __launch_bounds__(512) ppp_refine_kernel(const SweepParams prm, const uint32_t *__restrict__ surv,
+                                                         const unsigned long long *__restrict__ surv_count, unsigned long long surv_cap)
+{
+    constexpr int W = 32 * WPL;
+    constexpr int GD = 32 * W;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    double *s_lf = reinterpret_cast<double *>(smem_raw + 128);
+    constexpr int LF_BYTES = (((GD + 2) * 8) + 127) & ~127;
+    uint32_t *s_queue = reinterpret_cast<uint32_t *>(smem_raw + 128 + LF_BYTES);
+    uint32_t *my_queue = s_queue + warp * (3 * PPP_QCAP);
+    uint32_t *my_y = my_queue + PPP_QCAP;
+    float *my_lo = reinterpret_cast<float *>(my_queue + 2 * PPP_QCAP);
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)((GD + 2) * 8);
+        mbar_expect_tx(&bars[0], bytes);
+        tma_load_1d(s_lf, prm.lf, bytes, &bars[0]);
+    }
+    mbar_wait(&bars[0], 0);
+    const unsigned long long n = min(*surv_count, surv_cap);
+    const uint32_t nTl = prm.t1 - prm.t0;
+    WarpCounters wc;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * nwarps + warp; i < n; i += (unsigned long long)gridDim.x * nwarps) {
+        const uint32_t id = surv[i];
+        const uint32_t q = id / nTl, tl = id % nTl, t = prm.t0 + tl;
+        uint32_t tw[WPL], pw[WPL], yw[WPL], tp[WPL], ty[WPL];
+        load_row<WPL>(prm.T + (size_t)t * W + lane * WPL, tw);
+        load_row<WPL>(prm.Q + (size_t)q * 2 * W + lane * WPL, pw);
+        load_row<WPL>(prm.Q + (size_t)q * 2 * W + W + lane * WPL, yw);
+        uint32_t dlane = 0;
+#pragma unroll
+        for (int w = 0; w < WPL; ++w) {
+            tp[w] = tw[w] & pw[w];
+            ty[w] = tp[w] & yw[w];
+            dlane += __popc(tw[w]);
+        }
+        uint32_t dpre, dtotal;
+        depth_prefix(dlane, lane, dpre, dtotal);
+        const QConst qc = prm.qc[q];
+        const uint32_t off = prm.nmax_off[q];
+        const uint16_t *stair = (off != PPP_NO_TABLE) ? prm.nmax + off : nullptr;
+        PairOut res;
+        const uint32_t fl = evaluate_pair<WPL>(tw, tp, ty, dpre, dtotal, qc, s_lf, my_queue, my_y, my_lo, stair, prm, lane, wc, &res);
+        if (lane == 0 && !(fl & PF_REJECTED)) {
+            if (fl & PF_EXACT) push_exact(prm, id, (fl & PF_UNDERFLOW) != 0);
+            else ppp_emit(prm, q, t, res.score, res.yes, res.number, res.depth, res.margin);
+        }
+    }
+    flush_counters(prm, wc, lane);
+}
+
+/* transpose row-major planes T[nT][W] into chunk-major Tt[W/4][nT] of uint4 (coalesced per-thread row streaming) */
+__global__ void ppp_transpose_kernel(const uint4 *__restrict__ T, uint4 *__restrict__ Tt, uint32_t nT, uint32_t C)
+{
+    __shared__ uint4 tile[32][33];
+    const uint32_t t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const uint32_t t = t0 + r, c = c0 + threadIdx.x;
+        if (t < nT && c < C) tile[r][threadIdx.x] = T[(size_t)t * C + c];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const uint32_t c = c0 + r, t = t0 + threadIdx.x;
+        if (t < nT && c < C) Tt[(size_t)c * nT + t] = tile[threadIdx.x][r];
+    }
+}
+
+/* ---------------------------------------------------------------- launchers */
 static size_t sweep_smem_bytes(int wpl, int nwarps)
 {
     const size_t W = 32 * (size_t)wpl, GD = 32 * W;
-    return 128 + ((((GD + 2) * 8) + 127) & ~(size_t)127) + PPP_QTILE * 2 * W * 4 + PPP_QTILE * sizeof(QConst) + PPP_QTILE * 4 + (size_t)nwarps * 2 * PPP_QCAP * 4 + 64;
+    return 128 + ((((GD + 2) * 8) + 127) & ~(size_t)127) + PPP_QTILE * 2 * W * 4 + PPP_QTILE * sizeof(QConst) + PPP_QTILE * 4 +
+           (size_t)nwarps * 3 * PPP_QCAP * 4 + 64;
 }
+static size_t refine_smem_bytes(int wpl, int nwarps)
+{
+    const size_t W = 32 * (size_t)wpl, GD = 32 * W;
+    return 128 + ((((GD + 2) * 8) + 127) & ~(size_t)127) + (size_t)nwarps * 3 * PPP_QCAP * 4 + 64;
+}
+static size_t prefilter_smem_bytes(int wpl) { return 128 + PPP_QTILE * 2 * 32 * (size_t)wpl * 4 + PPP_QTILE * 4 + 64; }
 
 template <int WPL>
 static cudaError_t launch_t(const SweepParams &prm, int nwarps, int nsm, cudaStream_t st)
@@ -534,6 +757,39 @@ static cudaError_t launch_t(const SweepParams &prm, int nwarps, int nsm, cudaStr
     return cudaGetLastError();
 }
 
+template <int WPL>
+static cudaError_t launch_filtered_t(const SweepParams &prm, const void *Tt, uint32_t ntt, uint32_t *surv, unsigned long long *surv_count,
+                                     unsigned long long surv_cap, int nwarps, int nsm, cudaStream_t st)
+{
+    cudaError_t e;
+    {
+        const size_t smem = prefilter_smem_bytes(WPL);
+        e = cudaFuncSetAttribute(ppp_prefilter_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_prefilter_kernel<WPL>, 256, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        const uint32_t nTl = prm.t1 - prm.t0;
+        const uint64_t items = (uint64_t)((prm.nQ + PPP_QTILE - 1) / PPP_QTILE) * ((nTl + 255) / 256);
+        uint64_t grid = std::min<uint64_t>((uint64_t)nsm * per_sm, items);
+        if (grid < 1) grid = 1;
+        ppp_prefilter_kernel<WPL><<<(unsigned)grid, 256, smem, st>>>(prm, reinterpret_cast<const uint4 *>(Tt), ntt, surv, surv_count, surv_cap);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    {
+        const size_t smem = refine_smem_bytes(WPL, nwarps);
+        e = cudaFuncSetAttribute(ppp_refine_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_refine_kernel<WPL>, nwarps * 32, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) per_sm = 1;
+        ppp_refine_kernel<WPL><<<(unsigned)(nsm * per_sm), nwarps * 32, smem, st>>>(prm, surv, surv_count, surv_cap);
+        return cudaGetLastError();
+    }
+}
+
 extern "C" cudaError_t ppp_launch_sweep(const SweepParams *prm, int wpl, int nwarps, int nsm, cudaStream_t st)
 {
     switch (wpl) {
@@ -543,4 +799,26 @@ extern "C" cudaError_t ppp_launch_sweep(const SweepParams *prm, int wpl, int nwa
     case 8: return launch_t<8>(*prm, nwarps, nsm, st);
     default: return cudaErrorInvalidValue;
     }
+}
+
+/* pre-filter (thread per pair) + refine (warp per surviving pair); *surv_count must be zero on entry */
+extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, uint32_t *surv,
+                                           unsigned long long *surv_count, unsigned long long surv_cap, int nwarps, int nsm,
+                                           cudaStream_t st)
+{
+    switch (wpl) {
+    case 1: return launch_filtered_t<1>(*prm, Tt, ntt, surv, surv_count, surv_cap, nwarps, nsm, st);
+    case 2: return launch_filtered_t<2>(*prm, Tt, ntt, surv, surv_count, surv_cap, nwarps, nsm, st);
+    case 4: return launch_filtered_t<4>(*prm, Tt, ntt, surv, surv_count, surv_cap, nwarps, nsm, st);
+    case 8: return launch_filtered_t<8>(*prm, Tt, ntt, surv, surv_count, surv_cap, nwarps, nsm, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+extern "C" cudaError_t ppp_launch_transpose(const void *T, void *Tt, uint32_t nT, int wpl, cudaStream_t st)
+{
+    const uint32_t C = 8u * (uint32_t)wpl;
+    dim3 grid((nT + 31) / 32, (C + 31) / 32), block(32, 8);
+    ppp_transpose_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const uint4 *>(T), reinterpret_cast<uint4 *>(Tt), nT, C);
+    return cudaGetLastError();
 }

@@ -20,26 +20,26 @@
 #include "../../include/ppp_b200.h"
 #include "ppp_common.cuh"
 
-/* ln P(X >= y | n, p) <= tau ?  Serial FP64 ratio series (upper side); on the lower side (y + 1 <= (n+1) p) the
- * tail is >= 1/2 because the binomial median is >= floor(n p), and tau < ln(1/2) is guaranteed by the caller. */
-__device__ static bool tail_le(int y, int n, const QConst &qc, const double *__restrict__ lf, double tau)
+/* Can ln P(X >= y | n, p) be <= tau (tau < ln 1/2)?
+ *   - lower side (y + 1 <= (n+1) p): no -- the binomial median is >= floor(n p), so the tail is >= 1/2;
+ *   - otherwise the sweep kernel's own float enclosure (tier_a) decides: its lower bound `lo` never exceeds the
+ *     true value, so "lo <= tau" holds wherever the true tail is <= tau.
+ * The answer may err on the side of "yes" only (by the width of the enclosure, a few percent of a nat), which makes
+ * the staircase slightly looser, never wrong.  The predicate need not be monotone beyond the true boundary: a
+ * bisection that only moves its upper end past a FALSE probe still ends at or above the true boundary. */
+__device__ static bool tail_may_be_le(int y, int n, const QConst &qc, const double *__restrict__ lf, double tau)
 {
     const int m = n - y;
     if (!((double)m * qc.theta < (double)(y + 1))) return false;
-    const double lead = ((lf[n] - lf[y]) - lf[m]) + ((double)y * qc.lnp + (double)m * qc.lnq);
-    if (lead > tau) return false; /* R >= 1 */
-    double t = 1.0, s = 1.0;
-    for (int i = 1; i <= m; ++i) {
-        t *= (double)(m - i + 1) * qc.theta / (double)(y + i);
-        s += t;
-        if (t < 1e-17 * s) break;
-    }
-    return lead + log(s) <= tau;
+    float lo, hi;
+    tier_a(y, n, qc, lf, lo, hi);
+    return !(lo > (float)tau + 1e-3f + 1e-6f * fabsf((float)tau)); /* NaN-safe; margin covers the float cast of tau */
 }
 
 __global__ void ppp_build_staircase_kernel(const QConst *__restrict__ qc, const double *__restrict__ lf, const double *__restrict__ kth,
                                            int accept_mode, double thresh_ln, const uint32_t *__restrict__ static_off,
-                                           uint16_t *__restrict__ nmax, uint32_t *__restrict__ active_off, uint32_t nQ)
+                                           uint16_t *__restrict__ nmax, uint32_t *__restrict__ active_off,
+                                           double *__restrict__ last_tau, uint32_t nQ)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -57,17 +57,20 @@ __global__ void ppp_build_staircase_kernel(const QConst *__restrict__ qc, const 
             if (lane == 0) active_off[q] = PPP_NO_TABLE;
             continue;
         }
+        /* the k-th score only ever decreases: a staircase built for a slightly larger tau stays valid (just looser) */
+        if (active_off[q] != PPP_NO_TABLE && tau > last_tau[q] - 0.05) continue;
+        if (lane == 0) last_tau[q] = tau;
         const double tau_m = tau + 1e-5 + 1e-9 * fabs(tau); /* safety margin >> series + table error */
         uint16_t *tab = nmax + static_off[q];
         const int ny = (int)c.ny, np_ = (int)c.npres;
         if (lane == 0) tab[0] = 0;
         for (int y = 1 + lane; y <= ny; y += 32) {
             int res = 0;
-            if (isfinite(tau_m) && tail_le(y, y, c, lf, tau_m)) {
+            if (isfinite(tau_m) && tail_may_be_le(y, y, c, lf, tau_m)) {
                 int lo = y, hi = np_; /* invariant: tail_le(lo) true */
                 while (lo < hi) {
                     const int mid = (lo + hi + 1) >> 1;
-                    if (tail_le(y, mid, c, lf, tau_m)) lo = mid;
+                    if (tail_may_be_le(y, mid, c, lf, tau_m)) lo = mid;
                     else hi = mid - 1;
                 }
                 res = lo;
@@ -88,10 +91,10 @@ __global__ void ppp_build_staircase_kernel(const QConst *__restrict__ qc, const 
 }
 
 extern "C" cudaError_t ppp_launch_staircase(const QConst *qc, const double *lf, const double *kth, int accept_mode, double thresh_ln,
-                                            const uint32_t *static_off, uint16_t *nmax, uint32_t *active_off, uint32_t nQ, int nsm,
-                                            cudaStream_t st)
+                                            const uint32_t *static_off, uint16_t *nmax, uint32_t *active_off, double *last_tau,
+                                            uint32_t nQ, int nsm, cudaStream_t st)
 {
-    ppp_build_staircase_kernel<<<nsm * 4, 128, 0, st>>>(qc, lf, kth, accept_mode, thresh_ln, static_off, nmax, active_off, nQ);
+    ppp_build_staircase_kernel<<<nsm * 4, 128, 0, st>>>(qc, lf, kth, accept_mode, thresh_ln, static_off, nmax, active_off, last_tau, nQ);
     return cudaGetLastError();
 }
 

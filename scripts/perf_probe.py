@@ -21,7 +21,7 @@ def run(G, kind, nq, nt, warps=8, reps=3, flt=None):
     print(f"G={G} {kind} nq={nq} nt={nt} warps={warps}: sweep {best['sweep_kernel_ms']:.2f} ms total {best['total_device_ms']:.2f} ms "
           f"-> {pairs / best['sweep_kernel_ms'] / 1e6:.2f} Mpairs/s/ms... = {pairs / (best['sweep_kernel_ms'] * 1e-3):.3e} pairs/s; "
           f"cand/pair {best['candidates'] / pairs:.1f} acc/pair {best['accurate_evals'] / pairs:.2f} exact {best['exact_pairs']} "
-          f"full {c.counter('full_pairs')} launches {best['kernel_launches']} us: sweep {c.counter('us_sweep')} exact {c.counter('us_exact')} stair {c.counter('us_staircase')} merge {c.counter('us_merge')}", flush=True)
+          f"surv {c.counter('survivors')} full {c.counter('full_pairs')} launches {best['kernel_launches']} us: sweep {c.counter('us_sweep')} exact {c.counter('us_exact')} stair {c.counter('us_staircase')} merge {c.counter('us_merge')}", flush=True)
     c.close()
 
 if __name__ == "__main__":
