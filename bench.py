@@ -138,7 +138,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from prophylo_b200 import capi
+    from prophylo_b200 import capi, parallel
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -172,28 +172,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def merge_global(hits):
-        """optional global top-k merge over ranks (the path's only exchange step): NCCL all-gather + per-query sort."""
+        """optional global top-k merge over ranks (the path's only exchange step): NCCL all-gather + k-way merge"""
         if world == 1:
             return hits
-        loc = torch.from_numpy(hits.view(np.uint8).reshape(-1)).cuda()
-        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([loc.numel()], dtype=torch.int64, device="cuda"))
-        mx = int(max(s.item() for s in sizes))
-        buf = torch.zeros(mx, dtype=torch.uint8, device="cuda")
-        buf[: loc.numel()] = loc
-        allb = [torch.empty(mx, dtype=torch.uint8, device="cuda") for _ in range(world)]
-        dist.all_gather(allb, buf)
-        parts = []
-        for r, (b, s) in enumerate(zip(allb, sizes)):
-            h = b[: int(s.item())].cpu().numpy().view(capi.HIT_DTYPE).copy()
-            h["t"] += r * nt  # global target index
-            parts.append(h)
-        allh = np.concatenate(parts)
-        order = np.lexsort((allh["t"], allh["score"], allh["q"]))
-        allh = allh[order]
-        first = np.searchsorted(allh["q"], np.arange(nq), side="left")
-        rankin = np.arange(allh.size) - first[allh["q"]]
-        return allh[rankin < k]
+        return parallel.global_topk(hits, rank * nt, k, nq, device=torch.device("cuda", local_rank))
 
     # ---- resident-input steps (value)
     for _ in range(args.warmup):

@@ -610,7 +610,8 @@ __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams pr
                         sw += cyw + (__popc(a[w]) << 16);
                         if (cyw) {
                             const uint32_t l2 = (off != PPP_NO_TABLE) ? (uint32_t)__ldg(prm.nmax + off + (sw & 0xffffu)) : 0xffffu;
-                            if (nb + 1u <= l2 && word_has_passing_candidate(a[w], b[w], nb, (sw & 0xffffu) - cyw, prm.nmax + off))
+                            if (nb + 1u <= l2 &&
+                                (off == PPP_NO_TABLE || word_has_passing_candidate(a[w], b[w], nb, (sw & 0xffffu) - cyw, prm.nmax + off)))
                                 pass |= 1u << qi;
                         }
                     }

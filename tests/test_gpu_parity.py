@@ -209,3 +209,61 @@ def test_filters_match_dense(ctx):
         got = tk[q * k:(q + 1) * k]
         for f in ("t", "score", "yes", "number", "depth"):
             assert np.array_equal(got[f], exp[f]), (q, f)
+
+
+@pytest.mark.parametrize("G,kind,nq,nt,k", [(4096, "mixed", 70, 9000, 100), (1024, "single", 1, 60000, 25), (2048, "prefix", 40, 5000, 1),
+                                            (8192, "family", 33, 3000, 10)])
+def test_topk_multichunk_matches_dense(ctx, G, kind, nq, nt, k):
+    """Several target chunks -> staircase rebuilds, thread-per-pair pre-filter, refine, device merge: the lists must be
+    exactly the first k rows of the dense result sorted by (score, target)."""
+    P, Y, p = synth.make_queries(G, nq, 300 + G, kind)
+    T = synth.make_targets(G, nt, 400 + G, plant_from=Y, plant_frac=0.02)
+    ctx.set_targets_bits(T, G)
+    dense = ctx.score(P, Y, p).reshape(nq, nt)
+    tk = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
+    assert ctx.counter("survivors") > 0 and ctx.counter("full_pairs") < nq * nt
+    assert tk.size == nq * k
+    for q in range(nq):
+        exp = np.sort(dense[q], order=["score", "t"])[:k]
+        got = tk[q * k:(q + 1) * k]
+        for f in ("q", "t", "score", "yes", "number", "depth"):
+            assert np.array_equal(got[f], exp[f]), (q, f)
+
+
+def test_threshold_filter_uses_staircase_and_matches_dense(ctx):
+    G, nq, nt = 4096, 48, 4000
+    P, Y, p = synth.make_queries(G, nq, 51, "mixed")
+    T = synth.make_targets(G, nt, 52, plant_from=Y, plant_frac=0.02)
+    ctx.set_targets_bits(T, G)
+    dense = ctx.score(P, Y, p).reshape(nq, nt)
+    for thresh in (-3.0, -0.0005):
+        th = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_THRESH_LOG10, thresh=thresh))
+        with np.errstate(divide="ignore"):
+            keep = np.log10(dense["score"]) < thresh
+        exp = np.sort(dense[keep], order=["q", "score", "t"])
+        assert th.size == exp.size
+        for f in ("q", "t", "score", "yes", "number", "depth"):
+            assert np.array_equal(th[f], exp[f]), (thresh, f)
+
+
+def test_full_size_properties(ctx):
+    """Size-independent properties at BASELINE genome counts: every top-k list is sorted, within range, idempotent
+    under a second run, a sub-list of the k+5 list, and each reported hit re-scores to the same record alone."""
+    G, nq, nt, k = 4096, 256, 20000, 20
+    P, Y, p = synth.make_queries(G, nq, 61, "mixed")
+    T = synth.make_targets(G, nt, 62, plant_from=Y, plant_frac=0.01)
+    ctx.set_targets_bits(T, G)
+    a = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k)).copy()
+    b = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k)).copy()
+    assert np.array_equal(a, b)
+    c = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k + 5)).copy()
+    for q in range(0, nq, 7):
+        la, lc = a[a["q"] == q], c[c["q"] == q]
+        assert la.size == k and np.all(np.diff(la["score"]) >= 0) and la["t"].max() < nt
+        assert np.array_equal(la[["t", "score", "depth"]], lc[:k][["t", "score", "depth"]])
+    # re-score a sample of reported hits as single dense pairs
+    pick = a[:: max(1, a.size // 40)]
+    for h in pick:
+        ctx.set_targets_bits(T[h["t"]:h["t"] + 1], G)
+        one = ctx.score(P[h["q"]:h["q"] + 1], Y[h["q"]:h["q"] + 1], p[h["q"]:h["q"] + 1])[0]
+        assert (one["score"], one["yes"], one["number"], one["depth"]) == (h["score"], h["yes"], h["number"], h["depth"])
