@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libppp_b200.so")
+LIB_PATH = os.environ.get("PPP_B200_LIB") or os.path.join(_HERE, "libppp_b200.so")  # env override: A/B builds
 
 PPP_OK = 0
 FILTER_ALL, FILTER_THRESH_LOG10, FILTER_TOPK = 0, 1, 2

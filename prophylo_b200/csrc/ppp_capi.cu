@@ -22,7 +22,7 @@
 #include "ppp_common.cuh"
 
 extern "C" cudaError_t ppp_launch_sweep(const SweepParams *prm, int wpl, int nwarps, int nsm, cudaStream_t st);
-extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, uint32_t *surv,
+extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, const uint32_t *qflags, uint32_t *surv,
                                            unsigned long long *surv_count, unsigned long long surv_cap, int nwarps, int nsm,
                                            cudaStream_t st);
 extern "C" cudaError_t ppp_launch_transpose(const void *T, void *Tt, uint32_t nT, int wpl, cudaStream_t st);
@@ -61,6 +61,7 @@ struct ppp_ctx {
     /* queries */
     uint32_t *d_Q = nullptr;
     QConst *d_qc = nullptr;
+    uint32_t *d_qflags = nullptr; /* bit 0: presence plane is all ones over the G genomes */
     size_t nQ = 0, capQ = 0;
     /* results */
     ppp_hit *d_hits = nullptr;
@@ -176,6 +177,7 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaFree(ctx->d_lf);
     cudaFree(ctx->d_Q);
     cudaFree(ctx->d_qc);
+    cudaFree(ctx->d_qflags);
     cudaFree(ctx->d_hits);
     cudaFree(ctx->d_exact);
     cudaFree(ctx->d_counters);
@@ -234,8 +236,10 @@ extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, 
         ctx->nQ = 0; /* queries must be re-uploaded: the row layout changed */
         cudaFree(ctx->d_Q);
         cudaFree(ctx->d_qc);
+        cudaFree(ctx->d_qflags);
         ctx->d_Q = nullptr;
         ctx->d_qc = nullptr;
+        ctx->d_qflags = nullptr;
         ctx->capQ = 0;
     }
     ctx->nT = nT;
@@ -290,13 +294,16 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
     if (nQ > ctx->capQ) {
         cudaFree(ctx->d_Q);
         cudaFree(ctx->d_qc);
+        cudaFree(ctx->d_qflags);
         ctx->d_Q = nullptr;
         ctx->d_qc = nullptr;
+        ctx->d_qflags = nullptr;
         ctx->capQ = 0;
         /* round up to a whole tile so that a tile's TMA bulk copy never reads past the allocation */
         const size_t cap = ((nQ + PPP_QTILE - 1) / PPP_QTILE) * PPP_QTILE;
         CU(cudaMalloc(&ctx->d_Q, cap * 2 * W * 4));
         CU(cudaMalloc(&ctx->d_qc, cap * sizeof(QConst)));
+        CU(cudaMalloc(&ctx->d_qflags, cap * sizeof(uint32_t)));
         ctx->capQ = cap;
     }
     ctx->nQ = 0;
@@ -325,6 +332,9 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
     CU(cudaMemcpy2DAsync(ctx->d_Q, 2 * W * 4, P, wpr * 4, wpr * 4, nQ, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpy2DAsync(ctx->d_Q + W, 2 * W * 4, Y, wpr * 4, wpr * 4, nQ, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->d_qc, qc.data(), nQ * sizeof(QConst), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<uint32_t> qfl(nQ);
+    for (size_t q = 0; q < nQ; ++q) qfl[q] = (qc[q].npres == ctx->G) ? 1u : 0u;
+    CU(cudaMemcpyAsync(ctx->d_qflags, qfl.data(), nQ * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream)); /* inputs are copied before returning (Perl SV buffers may move) */
     ctx->nQ = nQ;
     return PPP_OK;
@@ -362,7 +372,7 @@ static int run_chunk(ppp_ctx *ctx, SweepParams *prm, unsigned long long *totals,
     CU(cudaMemsetAsync(ctx->d_counters, 0, (CNT_N + 1) * sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (prefiltered) {
-        CU(ppp_launch_filtered(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_surv, ctx->d_counters + CNT_N, ctx->cap_surv,
+        CU(ppp_launch_filtered(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qflags, ctx->d_surv, ctx->d_counters + CNT_N, ctx->cap_surv,
                                ctx->sweep_warps, ctx->nsm, ctx->stream));
         *launches += 1;
     } else {

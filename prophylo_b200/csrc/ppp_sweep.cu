@@ -532,9 +532,13 @@ __device__ __noinline__ bool word_has_passing_candidate(uint32_t a, uint32_t b, 
     return ok;
 }
 
+#ifndef PF_QG
+#define PF_QG 8 /* queries per unrolled group of the pre-filter */
+#endif
+
 template <int WPL>
 __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams prm, const uint4 *__restrict__ Tt, uint32_t ntt,
-                                                            uint32_t *__restrict__ surv, unsigned long long *__restrict__ surv_count,
+                                                            const uint32_t *__restrict__ qflags, uint32_t *__restrict__ surv, unsigned long long *__restrict__ surv_count,
                                                             unsigned long long surv_cap)
 {
     constexpr int W = 32 * WPL;
@@ -543,6 +547,7 @@ __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams pr
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
     uint32_t *s_q = reinterpret_cast<uint32_t *>(smem_raw + 128); /* PPP_QTILE * 2 * W words */
     uint32_t *s_off = s_q + PPP_QTILE * 2 * W;
+    uint32_t *s_pall = s_off + PPP_QTILE; /* 1 = presence plane all ones: T & P == T */
     const uint32_t nTl = prm.t1 - prm.t0;
     const uint32_t nQtiles = (prm.nQ + PPP_QTILE - 1) / PPP_QTILE;
     const uint32_t nTblocks = (nTl + blockDim.x - 1) / blockDim.x;
@@ -565,7 +570,10 @@ __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams pr
                 mbar_expect_tx(bar, b1);
                 tma_load_1d(s_q, prm.Q + (size_t)q0 * 2 * W, b1, bar);
             }
-            if (threadIdx.x < PPP_QTILE) s_off[threadIdx.x] = (threadIdx.x < nq) ? prm.nmax_off[q0 + threadIdx.x] : PPP_NO_TABLE;
+            if (threadIdx.x < PPP_QTILE) {
+                s_off[threadIdx.x] = (threadIdx.x < nq) ? prm.nmax_off[q0 + threadIdx.x] : PPP_NO_TABLE;
+                s_pall[threadIdx.x] = (threadIdx.x < nq) ? (qflags[q0 + threadIdx.x] & 1u) : 0u;
+            }
             mbar_wait(bar, parity);
             parity ^= 1;
             cur_qt = qt;
@@ -574,49 +582,59 @@ __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams pr
         const uint32_t tl = tb * blockDim.x + threadIdx.x;
         const bool live = tl < nTl;
         const uint32_t t = prm.t0 + (live ? tl : 0);
-        uint32_t state[PPP_QTILE]; /* yes | number << 16 per query */
-#pragma unroll
-        for (int i = 0; i < PPP_QTILE; ++i) state[i] = 0;
         uint32_t pass = 0;
-        for (int c = 0; c < C; ++c) {
-            const uint4 tv = live ? __ldg(Tt + (size_t)c * ntt + t) : make_uint4(0, 0, 0, 0);
-            const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+        /* PF_QG queries at a time: the unrolled body stays small enough for the instruction cache; the target row is
+         * re-streamed per group from L1/L2 (coalesced 16-byte loads) */
+        for (uint32_t g0 = 0; g0 < nq; g0 += PF_QG) {
+            uint32_t state[PF_QG]; /* yes | number << 16 per query */
 #pragma unroll
-            for (int qi = 0; qi < PPP_QTILE; ++qi) {
-                if ((uint32_t)qi >= nq) break; /* block-uniform */
-                const uint4 pv = *reinterpret_cast<const uint4 *>(s_q + (size_t)qi * 2 * W + c * 4);      /* broadcast */
-                const uint4 yv = *reinterpret_cast<const uint4 *>(s_q + (size_t)qi * 2 * W + W + c * 4);
-                const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
-                const uint32_t off = s_off[qi];
-                const uint32_t st0 = state[qi];
-                uint32_t a[4], b[4];
+            for (int i = 0; i < PF_QG; ++i) state[i] = 0;
+            for (int c = 0; c < C; ++c) {
+                const uint4 tv = live ? __ldg(Tt + (size_t)c * ntt + t) : make_uint4(0, 0, 0, 0);
+                const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+                const uint32_t ct = __popc(tw[0]) + __popc(tw[1]) + __popc(tw[2]) + __popc(tw[3]); /* number when P is all ones */
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    a[w] = tw[w] & pw[w];
-                    b[w] = a[w] & yw[w];
-                }
-                const uint32_t cy = __popc(b[0]) + __popc(b[1]) + __popc(b[2]) + __popc(b[3]);
-                const uint32_t cn = __popc(a[0]) + __popc(a[1]) + __popc(a[2]) + __popc(a[3]);
-                const uint32_t st = st0 + cy + (cn << 16);
-                /* 128-genome screen, one lookup: no candidate of the chunk can pass unless number_before + 1 <=
-                 * stair[yes_after]; the rare chunks that survive it are re-screened word by word */
-                const uint32_t lim = (off != PPP_NO_TABLE) ? (uint32_t)__ldg(prm.nmax + off + (st & 0xffffu)) : 0xffffu;
-                if (cy && (st0 >> 16) + 1u <= lim) {
-                    uint32_t sw = st0;
+                for (int qj = 0; qj < PF_QG; ++qj) {
+                    const uint32_t qi = g0 + qj;
+                    if (qi >= nq) break; /* block-uniform */
+                    const uint4 yv = *reinterpret_cast<const uint4 *>(s_q + (size_t)qi * 2 * W + W + c * 4); /* broadcast */
+                    const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+                    const uint32_t off = s_off[qi];
+                    const uint32_t st0 = state[qj];
+                    uint32_t a[4], b[4], cn;
+                    if (s_pall[qi]) { /* block-uniform: T & P == T, popcount shared by all such queries */
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) {
-                        const uint32_t cyw = __popc(b[w]);
-                        const uint32_t nb = sw >> 16;
-                        sw += cyw + (__popc(a[w]) << 16);
-                        if (cyw) {
-                            const uint32_t l2 = (off != PPP_NO_TABLE) ? (uint32_t)__ldg(prm.nmax + off + (sw & 0xffffu)) : 0xffffu;
-                            if (nb + 1u <= l2 &&
-                                (off == PPP_NO_TABLE || word_has_passing_candidate(a[w], b[w], nb, (sw & 0xffffu) - cyw, prm.nmax + off)))
-                                pass |= 1u << qi;
+                        for (int w = 0; w < 4; ++w) a[w] = tw[w];
+                        cn = ct;
+                    } else {
+                        const uint4 pv = *reinterpret_cast<const uint4 *>(s_q + (size_t)qi * 2 * W + c * 4);
+                        a[0] = tw[0] & pv.x; a[1] = tw[1] & pv.y; a[2] = tw[2] & pv.z; a[3] = tw[3] & pv.w;
+                        cn = __popc(a[0]) + __popc(a[1]) + __popc(a[2]) + __popc(a[3]);
+                    }
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) b[w] = a[w] & yw[w];
+                    const uint32_t cy = __popc(b[0]) + __popc(b[1]) + __popc(b[2]) + __popc(b[3]);
+                    const uint32_t st = st0 + cy + (cn << 16);
+                    /* 128-genome screen, one lookup: no candidate of the chunk can pass unless number_before + 1 <=
+                     * stair[yes_after]; the rare chunks that survive it are re-screened word by word, then per candidate */
+                    const uint32_t lim = (off != PPP_NO_TABLE) ? (uint32_t)__ldg(prm.nmax + off + (st & 0xffffu)) : 0xffffu;
+                    if (cy && (st0 >> 16) + 1u <= lim) {
+                        uint32_t sw = st0;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            const uint32_t cyw = __popc(b[w]);
+                            const uint32_t nb = sw >> 16;
+                            sw += cyw + (__popc(a[w]) << 16);
+                            if (cyw) {
+                                const uint32_t l2 = (off != PPP_NO_TABLE) ? (uint32_t)__ldg(prm.nmax + off + (sw & 0xffffu)) : 0xffffu;
+                                if (nb + 1u <= l2 &&
+                                    (off == PPP_NO_TABLE || word_has_passing_candidate(a[w], b[w], nb, (sw & 0xffffu) - cyw, prm.nmax + off)))
+                                    pass |= 1u << qi;
+                            }
                         }
                     }
+                    state[qj] = st;
                 }
-                state[qi] = st;
             }
         }
         if (!live) pass = 0;
@@ -737,7 +755,7 @@ static size_t refine_smem_bytes(int wpl, int nwarps)
     const size_t W = 32 * (size_t)wpl, GD = 32 * W;
     return 128 + ((((GD + 2) * 8) + 127) & ~(size_t)127) + (size_t)nwarps * 3 * PPP_QCAP * 4 + 64;
 }
-static size_t prefilter_smem_bytes(int wpl) { return 128 + PPP_QTILE * 2 * 32 * (size_t)wpl * 4 + PPP_QTILE * 4 + 64; }
+static size_t prefilter_smem_bytes(int wpl) { return 128 + PPP_QTILE * 2 * 32 * (size_t)wpl * 4 + 2 * PPP_QTILE * 4 + 64; }
 
 template <int WPL>
 static cudaError_t launch_t(const SweepParams &prm, int nwarps, int nsm, cudaStream_t st)
@@ -759,7 +777,7 @@ static cudaError_t launch_t(const SweepParams &prm, int nwarps, int nsm, cudaStr
 }
 
 template <int WPL>
-static cudaError_t launch_filtered_t(const SweepParams &prm, const void *Tt, uint32_t ntt, uint32_t *surv, unsigned long long *surv_count,
+static cudaError_t launch_filtered_t(const SweepParams &prm, const void *Tt, uint32_t ntt, const uint32_t *qflags, uint32_t *surv, unsigned long long *surv_count,
                                      unsigned long long surv_cap, int nwarps, int nsm, cudaStream_t st)
 {
     cudaError_t e;
@@ -775,7 +793,7 @@ static cudaError_t launch_filtered_t(const SweepParams &prm, const void *Tt, uin
         const uint64_t items = (uint64_t)((prm.nQ + PPP_QTILE - 1) / PPP_QTILE) * ((nTl + 255) / 256);
         uint64_t grid = std::min<uint64_t>((uint64_t)nsm * per_sm, items);
         if (grid < 1) grid = 1;
-        ppp_prefilter_kernel<WPL><<<(unsigned)grid, 256, smem, st>>>(prm, reinterpret_cast<const uint4 *>(Tt), ntt, surv, surv_count, surv_cap);
+        ppp_prefilter_kernel<WPL><<<(unsigned)grid, 256, smem, st>>>(prm, reinterpret_cast<const uint4 *>(Tt), ntt, qflags, surv, surv_count, surv_cap);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     {
@@ -803,15 +821,15 @@ extern "C" cudaError_t ppp_launch_sweep(const SweepParams *prm, int wpl, int nwa
 }
 
 /* pre-filter (thread per pair) + refine (warp per surviving pair); *surv_count must be zero on entry */
-extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, uint32_t *surv,
+extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, const uint32_t *qflags, uint32_t *surv,
                                            unsigned long long *surv_count, unsigned long long surv_cap, int nwarps, int nsm,
                                            cudaStream_t st)
 {
     switch (wpl) {
-    case 1: return launch_filtered_t<1>(*prm, Tt, ntt, surv, surv_count, surv_cap, nwarps, nsm, st);
-    case 2: return launch_filtered_t<2>(*prm, Tt, ntt, surv, surv_count, surv_cap, nwarps, nsm, st);
-    case 4: return launch_filtered_t<4>(*prm, Tt, ntt, surv, surv_count, surv_cap, nwarps, nsm, st);
-    case 8: return launch_filtered_t<8>(*prm, Tt, ntt, surv, surv_count, surv_cap, nwarps, nsm, st);
+    case 1: return launch_filtered_t<1>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st);
+    case 2: return launch_filtered_t<2>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st);
+    case 4: return launch_filtered_t<4>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st);
+    case 8: return launch_filtered_t<8>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st);
     default: return cudaErrorInvalidValue;
     }
 }
