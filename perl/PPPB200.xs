@@ -1,0 +1,99 @@
+/* perl/PPPB200.xs -- XS binding of the C ABI in include/ppp_b200.h for the Perl host (PhyloProf::B200).
+ * Replaces the per-pair Perl sweep of lib/PhyloProf/Algorithm/ppp.pm:130-245 by one call into libppp_b200.so.
+ * FFI::Platypus / Inline::C are not installed in this image; xsubpp + the perl headers are, hence XS.
+ * Buffers are Perl strings of packed little-endian uint32 words (pack "V*" / vec), copied by the library before
+ * the call returns, so Perl is free to move its SVs. Errors croak with ppp_last_error(). */
+#include "EXTERN.h"
+#include "perl.h"
+#include "XSUB.h"
+#include "ppp_b200.h"
+
+typedef ppp_ctx *PhyloProf__B200__Ctx;
+
+MODULE = PhyloProf::B200  PACKAGE = PhyloProf::B200
+
+IV
+_init(device)
+    int device
+  CODE:
+    ppp_ctx *ctx = NULL;
+    int dev[1];
+    dev[0] = device;
+    int rc = ppp_init(&ctx, dev, 1);
+    if (rc != PPP_OK) croak("PhyloProf::B200: %s", ppp_last_error(NULL));
+    RETVAL = PTR2IV(ctx);
+  OUTPUT:
+    RETVAL
+
+void
+_destroy(h)
+    IV h
+  CODE:
+    ppp_destroy(INT2PTR(ppp_ctx *, h));
+
+int
+words_per_row(G)
+    unsigned int G
+  CODE:
+    RETVAL = (int)ppp_words_per_row(G);
+  OUTPUT:
+    RETVAL
+
+void
+_set_targets_bits(h, planes, nT, G)
+    IV h
+    SV *planes
+    UV nT
+    unsigned int G
+  CODE:
+    ppp_ctx *ctx = INT2PTR(ppp_ctx *, h);
+    STRLEN len;
+    const char *buf = SvPVbyte(planes, len);
+    if (len < (STRLEN)nT * ppp_words_per_row(G) * 4) croak("PhyloProf::B200: target buffer too short");
+    if (ppp_set_targets_bits(ctx, (const uint32_t *)buf, (size_t)nT, G) != PPP_OK)
+        croak("PhyloProf::B200: %s", ppp_last_error(ctx));
+
+void
+_score(h, pplanes, yplanes, probs, nQ, mode, k, thresh)
+    IV h
+    SV *pplanes
+    SV *yplanes
+    SV *probs
+    UV nQ
+    unsigned int mode
+    unsigned int k
+    double thresh
+  PPCODE:
+    ppp_ctx *ctx = INT2PTR(ppp_ctx *, h);
+    STRLEN lp, ly, lq;
+    const char *pb = SvPVbyte(pplanes, lp);
+    const char *yb = SvPVbyte(yplanes, ly);
+    const char *qb = SvPVbyte(probs, lq); /* packed native doubles: pack "d*" */
+    if (lq < (STRLEN)nQ * sizeof(double) || lp != ly) croak("PhyloProf::B200: query buffers inconsistent");
+    ppp_filter f;
+    f.mode = mode; f.k = k; f.thresh = thresh;
+    if (ppp_set_queries(ctx, (const uint32_t *)pb, (const uint32_t *)yb, (const double *)qb, (size_t)nQ) != PPP_OK)
+        croak("PhyloProf::B200: %s", ppp_last_error(ctx));
+    if (ppp_run(ctx, &f) != PPP_OK) croak("PhyloProf::B200: %s", ppp_last_error(ctx));
+    size_t n = 0;
+    ppp_result_count(ctx, &n);
+    ppp_hit *hits = NULL;
+    Newx(hits, n ? n : 1, ppp_hit);
+    if (ppp_fetch(ctx, hits, n, &n) != PPP_OK) {
+        Safefree(hits);
+        croak("PhyloProf::B200: %s", ppp_last_error(ctx));
+    }
+    /* one array ref [q, t, score, yes, number, depth] per hit */
+    EXTEND(SP, (SSize_t)n);
+    for (size_t i = 0; i < n; ++i) {
+        AV *av = newAV();
+        av_push(av, newSVuv(hits[i].q));
+        av_push(av, newSVuv(hits[i].t));
+        av_push(av, newSVnv(hits[i].score));
+        av_push(av, newSVuv(hits[i].yes));
+        av_push(av, newSVuv(hits[i].number));
+        av_push(av, newSVuv(hits[i].depth));
+        PUSHs(sv_2mortal(newRV_noinc((SV *)av)));
+    }
+    Safefree(hits);
+

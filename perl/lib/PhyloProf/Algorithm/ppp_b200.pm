@@ -1,0 +1,69 @@
+package PhyloProf::Algorithm::ppp_b200;
+
+# Drop-in for PhyloProf::Algorithm::ppp (lib/PhyloProf/Algorithm/ppp.pm:58-245): same constructor arguments
+# (named -prof1,-prof2,[-prob],[-rank],[-taxonomy],[-dup] or positional, Root.pm:5-17), same 5-element return
+# list of get_match_score(), scored on the B200 through PhyloProf::B200.
+#
+# A single pair is embedded exactly by taking the TARGET's own de-duplicated list as the genome order: the target
+# plane is then a run of ones, the query planes are permuted to match, and the raw list position (duplicates and
+# foreign taxa included, ppp.pm:169,231) is restored from the de-duplicated depth on return.
+use strict;
+use warnings;
+use Carp;
+use PhyloProf::B200;
+
+my $GPU;    # one context per process, created lazily (after any fork)
+
+sub new {
+    my $class = shift;
+    my %a;
+    if ( @_ && defined $_[0] && !ref( $_[0] ) && $_[0] =~ /^-/ ) {
+        my %in = @_;
+        $a{ lc( substr( $_, 1 ) ) } = $in{$_} for keys %in;
+    } else {
+        @a{qw(prof1 prof2 prob rank taxonomy dup)} = @_;
+    }
+    croak "Parameter is undefined\n" unless $a{prof1} || $a{prof2};
+    croak "Parameter mismatch\n"
+        unless ( ref $a{prof1} && $a{prof1}->isa("PhyloProf::Profile") ) || ( ref $a{prof2} && $a{prof2}->isa("PhyloProf::Profile") );
+    my $self = bless { _prof1 => $a{prof1}, _prof2 => $a{prof2} }, ref($class) || $class;
+    $self->{_prob} = $a{prob}     if $a{prob};
+    $self->{_rank} = $a{rank}     if $a{rank};
+    $self->{_dbh}  = $a{taxonomy} if $a{taxonomy};
+    $self->{_dup}  = 1            if $a{dup};
+    return $self;
+}
+
+sub _taxon {    # ppp.pm:328-370: identity unless -rank; collapse, fall back to genus, then to the raw id
+    my ( $self, $t ) = @_;
+    return $t unless $self->{_rank} && $self->{_dbh};
+    return $self->{_dbh}->collapse_taxon( $t, $self->{_rank} ) || $self->{_dbh}->collapse_taxon( $t, "genus" ) || $t;
+}
+
+sub get_match_score {
+    my $self = shift;
+    croak "PhyloProf::Algorithm::ppp_b200: -dup is not accelerated (reference quirk ppp.pm:189-200); use PhyloProf::Algorithm::ppp"
+        if $self->{_dup};
+    my $q = $self->{_prof1}->get_hash();
+    my $p = exists $self->{_prob} ? $self->{_prob} : $self->{_prof1}->get_yes() / $self->{_prof1}->get_total();
+    my $t = $self->{_prof2}->get_hash();
+    my @list = ref($t) eq 'HASH' ? ( sort { $t->{$a} <=> $t->{$b} } keys %$t ) : @{ $t || [] };
+    my ( %seen, @order, @rawpos );
+    for my $i ( 0 .. $#list ) {
+        my $taxon = $self->_taxon( $list[$i] );
+        die "Taxon not found" unless $taxon;    # ppp.pm:179
+        next if $seen{$taxon}++;                # ppp.pm:189-192
+        push @order,  $taxon;
+        push @rawpos, $i + 1;
+    }
+    return ( 1, 0, 0, 0, $p ) unless @order;
+    croak "target list of " . scalar(@order) . " distinct taxa exceeds 8192" if @order > 8192;
+    $GPU ||= PhyloProf::B200->new( -device => $ENV{PPP_B200_DEVICE} || 0 );
+    my %qh = map { $_ => $q->{$_} } grep { $seen{$_} } keys %$q;    # taxa outside the target never take part
+    my $hits = $GPU->score_bits( \@order, [ \%qh ], [ \@order ], -probs => [$p] );
+    my ( undef, undef, $score, $yes, $number, $depth ) = @{ $hits->[0] };
+    $depth = $rawpos[ $depth - 1 ] if $depth > 0;
+    return ( $score, $yes, $number, $depth, $p );
+}
+
+1;

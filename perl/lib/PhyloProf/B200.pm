@@ -1,0 +1,86 @@
+package PhyloProf::B200;
+
+# Perl host of the B200-native PPP scan: loads the XS binding of libppp_b200.so (include/ppp_b200.h), packs
+# PhyloProf::Profile objects into bit planes and scores them on the GPU.  There is no CPU fallback: without the
+# shared objects or without an sm_100 device every entry point croaks.
+#
+#   my $gpu  = PhyloProf::B200->new(-device => 0);                 # after any fork (bin/ppp.pl:910 forks workers)
+#   my $hits = $gpu->score_bits(\@universe, \@queries, \@targets, [-filter => 'topk', -k => 100]);
+#
+# Data model (SURVEY.md section 8d): @universe is the ordered taxon list (ascending taxon id as data/taxdis.txt and
+# bin/hmm3profile.pl:175-181 print it); a query is a PhyloProf::Profile (taxon => 0/1 hash, Profile.pm:433-514), a
+# target is a set of taxa whose list order is the universe order.
+use strict;
+use warnings;
+use Carp;
+require DynaLoader;
+our @ISA     = qw(DynaLoader);
+our $VERSION = '0.1';
+
+sub dl_load_flags { 0x01 }    # RTLD_GLOBAL not needed; keep lazy binding
+
+my $loaded = 0;
+
+sub _load {
+    return if $loaded;
+    ( my $dir = __FILE__ ) =~ s{lib/PhyloProf/B200\.pm$}{};
+    my $so = $ENV{PPP_B200_XS} || "${dir}blib/PPPB200.so";
+    croak "PhyloProf::B200: $so not built (make -C perl); there is no pure-Perl or CPU path" unless -e $so;
+    my $lib = DynaLoader::dl_load_file( $so, 0 ) or croak "PhyloProf::B200: " . DynaLoader::dl_error();
+    my $sym = DynaLoader::dl_find_symbol( $lib, "boot_PhyloProf__B200" ) or croak DynaLoader::dl_error();
+    my $xs  = DynaLoader::dl_install_xsub( "PhyloProf::B200::_bootstrap", $sym, $so );
+    &$xs("PhyloProf::B200");
+    $loaded = 1;
+}
+
+sub new {
+    my ( $class, %a ) = @_;
+    _load();
+    my $self = bless { h => _init( $a{-device} || 0 ) }, $class;
+    return $self;
+}
+
+sub DESTROY { my $s = shift; _destroy( $s->{h} ) if $s->{h}; $s->{h} = 0 }
+
+# taxon list -> index map
+sub _index { my $u = shift; my %i; @i{@$u} = ( 0 .. $#$u ); return \%i }
+
+sub _plane {
+    my ( $wpr, $idx, $taxa ) = @_;
+    my $v = "\0" x ( $wpr * 4 );
+    foreach my $t (@$taxa) {
+        my $g = $idx->{$t};
+        next unless defined $g;
+        vec( $v, $g, 1 ) = 1;    # vec bit g of the string = bit (g & 7) of byte g >> 3 = bit (g & 31) of LE word g >> 5
+    }
+    return $v;
+}
+
+# score every query (PhyloProf::Profile or {taxon=>0/1}) against every target ([taxa] in universe order semantics)
+sub score_bits {
+    my ( $self, $universe, $queries, $targets, %o ) = @_;
+    my $G = scalar @$universe;
+    croak "universe of $G genomes outside [1, 8192]" if $G < 1 || $G > 8192;
+    my $idx = _index($universe);
+    my $wpr = words_per_row($G);
+    my $tb  = join '', map { _plane( $wpr, $idx, $_ ) } @$targets;
+    _set_targets_bits( $self->{h}, $tb, scalar(@$targets), $G );
+    my ( $pb, $yb, @p ) = ( '', '' );
+    foreach my $q (@$queries) {
+        my $h = ref($q) eq 'HASH' ? $q : $q->get_hash();
+        my @present = grep { exists $idx->{$_} } keys %$h;
+        my @yes     = grep { $h->{$_} != 0 } @present;
+        $pb .= _plane( $wpr, $idx, \@present );
+        $yb .= _plane( $wpr, $idx, \@yes );
+        my $prob = ref($q) eq 'HASH' ? undef : undef;
+        push @p, defined $o{-prob} ? $o{-prob} : ( @present ? @yes / @present : 0 );    # ppp.pm:138-142
+    }
+    @p = @{ $o{-probs} } if $o{-probs};
+    my %mode = ( all => 0, thresh => 1, topk => 2 );
+    my $m = $mode{ $o{-filter} || 'all' };
+    croak "unknown -filter" unless defined $m;
+    my @hits = _score( $self->{h}, $pb, $yb, pack( "d*", @p ), scalar(@$queries), $m, $o{-k} || 0, $o{-thresh} || 0 );
+    return \@hits;    # [q, t, score, yes, number, depth]
+}
+
+1;

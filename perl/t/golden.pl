@@ -1,0 +1,39 @@
+#!/usr/bin/perl
+# perl/t/golden.pl -- GPU test of the Perl drop-in: PhyloProf::Algorithm::ppp_b200->new(...)->get_match_score() on the
+# committed golden cases (tests/golden/ppp_list_cases.json, produced by the reference itself): ARRAY targets with
+# duplicates and foreign taxa, HASH targets, -prob.  yes/number/depth exact, score within 1e-9 on -log p.
+use strict;
+use warnings;
+use FindBin;
+use lib "$FindBin::Bin/../lib", "$FindBin::Bin/lib";
+use JSON::PP;
+use PhyloProf::Profile;
+use PhyloProf::Algorithm::ppp_b200;
+
+my $file = shift || "$FindBin::Bin/../../tests/golden/ppp_list_cases.json";
+open( my $fh, "<", $file ) or die "$file: $!";
+my $g = decode_json( do { local $/; <$fh> } );
+my ( $n, $bad, $skipped ) = ( 0, 0, 0 );
+foreach my $c ( @{ $g->{known_answers} }, @{ $g->{fuzz} } ) {
+    if ( $c->{dup} ) { $skipped++; next; }
+    my $t = $c->{target};
+    my $cnt = ref($t) eq 'ARRAY' ? scalar(@$t) : scalar( keys %$t );
+    my $p1 = PhyloProf::Profile->new( -profile => $c->{query} );
+    my $p2 = PhyloProf::Profile->new( -raw => $t, -yes => $cnt, -no => 0 );
+    my @args = ( -prof1 => $p1, -prof2 => $p2 );
+    push @args, ( -prob => $c->{prob} ) if defined $c->{prob};
+    my @r = PhyloProf::Algorithm::ppp_b200->new(@args)->get_match_score();
+    my @e = @{ $c->{expect} };
+    $n++;
+    my $ok = $r[1] == $e[1] && $r[2] == $e[2] && $r[3] == $e[3] && $r[4] == $e[4];
+    if ($ok) {
+        my ( $a, $b ) = ( $r[0], $e[0] + 0 );
+        if ( $a != $b ) {
+            $ok = 0 if $a <= 0 || $b <= 0;
+            $ok = 0 if $ok && abs( log($a) - log($b) ) > 1e-9 * abs( log($b) );
+        }
+    }
+    unless ($ok) { $bad++; print "MISMATCH $c->{name}: got @r expected @e\n" if $bad < 10; }
+}
+print "perl drop-in: $n cases, $bad mismatches, $skipped -dup cases skipped\n";
+exit( $bad ? 1 : 0 );

@@ -24,7 +24,7 @@
 extern "C" cudaError_t ppp_launch_sweep(const SweepParams *prm, int wpl, int nwarps, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, const uint32_t *qflags, uint32_t *surv,
                                            unsigned long long *surv_count, unsigned long long surv_cap, int nwarps, int nsm,
-                                           cudaStream_t st);
+                                           cudaStream_t st, cudaEvent_t between);
 extern "C" cudaError_t ppp_launch_transpose(const void *T, void *Tt, uint32_t nT, int wpl, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_exact(const SweepParams *prm, int W, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_debug_bdtrc(const int32_t *k, const int32_t *n, const double *p, double *out, size_t m,
@@ -42,7 +42,8 @@ struct ppp_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double phase_us[4] = {0, 0, 0, 0}; /* sweep, exact, staircase, merge */
-    unsigned long long survivors = 0;
+    unsigned long long survivors = 0, prefilter_pairs = 0;
+    double prefilter_us = 0;
     char err[512] = {0};
 
     /* targets */
@@ -373,7 +374,7 @@ static int run_chunk(ppp_ctx *ctx, SweepParams *prm, unsigned long long *totals,
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (prefiltered) {
         CU(ppp_launch_filtered(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qflags, ctx->d_surv, ctx->d_counters + CNT_N, ctx->cap_surv,
-                               ctx->sweep_warps, ctx->nsm, ctx->stream));
+                               ctx->sweep_warps, ctx->nsm, ctx->stream, ctx->ev[7]));
         *launches += 1;
     } else {
         CU(ppp_launch_sweep(prm, ctx->wpl, ctx->sweep_warps, ctx->nsm, ctx->stream));
@@ -390,6 +391,11 @@ static int run_chunk(ppp_ctx *ctx, SweepParams *prm, unsigned long long *totals,
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
     *sweep_ms += ms;
     ctx->phase_us[0] += 1e3 * ms;
+    if (prefiltered) {
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[7]);
+        ctx->prefilter_us += 1e3 * ms;
+        ctx->prefilter_pairs += (unsigned long long)prm->nQ * (prm->t1 - prm->t0);
+    }
     cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
     ctx->phase_us[1] += 1e3 * ms;
     for (int i = 0; i < CNT_N; ++i) totals[i] += c[i];
@@ -422,6 +428,8 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
 
     for (int i = 0; i < 4; ++i) ctx->phase_us[i] = 0;
     ctx->survivors = 0;
+    ctx->prefilter_pairs = 0;
+    ctx->prefilter_us = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     if (f->mode == PPP_FILTER_ALL) {
         /* dense: chunks only bound the launch-local pair ids of the exact-tier list (31 bits) */
@@ -625,6 +633,8 @@ extern "C" int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *va
     else if (!strcmp(name, "bound_checks")) i = CNT_CHECKS;
     else if (!strcmp(name, "full_pairs")) i = CNT_FULL;
     else if (!strcmp(name, "num_sms")) { *value = ctx->nsm; return PPP_OK; }
+    else if (!strcmp(name, "us_prefilter")) { *value = (int64_t)ctx->prefilter_us; return PPP_OK; }
+    else if (!strcmp(name, "prefilter_pairs")) { *value = (int64_t)ctx->prefilter_pairs; return PPP_OK; }
     else if (!strcmp(name, "survivors")) { *value = (int64_t)ctx->survivors; return PPP_OK; }
     else if (!strcmp(name, "us_sweep")) { *value = (int64_t)ctx->phase_us[0]; return PPP_OK; }
     else if (!strcmp(name, "us_exact")) { *value = (int64_t)ctx->phase_us[1]; return PPP_OK; }

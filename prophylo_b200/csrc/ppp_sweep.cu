@@ -778,7 +778,7 @@ static cudaError_t launch_t(const SweepParams &prm, int nwarps, int nsm, cudaStr
 
 template <int WPL>
 static cudaError_t launch_filtered_t(const SweepParams &prm, const void *Tt, uint32_t ntt, const uint32_t *qflags, uint32_t *surv, unsigned long long *surv_count,
-                                     unsigned long long surv_cap, int nwarps, int nsm, cudaStream_t st)
+                                     unsigned long long surv_cap, int nwarps, int nsm, cudaStream_t st, cudaEvent_t between)
 {
     cudaError_t e;
     {
@@ -795,6 +795,7 @@ static cudaError_t launch_filtered_t(const SweepParams &prm, const void *Tt, uin
         if (grid < 1) grid = 1;
         ppp_prefilter_kernel<WPL><<<(unsigned)grid, 256, smem, st>>>(prm, reinterpret_cast<const uint4 *>(Tt), ntt, qflags, surv, surv_count, surv_cap);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (between && (e = cudaEventRecord(between, st)) != cudaSuccess) return e;
     }
     {
         const size_t smem = refine_smem_bytes(WPL, nwarps);
@@ -823,13 +824,13 @@ extern "C" cudaError_t ppp_launch_sweep(const SweepParams *prm, int wpl, int nwa
 /* pre-filter (thread per pair) + refine (warp per surviving pair); *surv_count must be zero on entry */
 extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, const uint32_t *qflags, uint32_t *surv,
                                            unsigned long long *surv_count, unsigned long long surv_cap, int nwarps, int nsm,
-                                           cudaStream_t st)
+                                           cudaStream_t st, cudaEvent_t between)
 {
     switch (wpl) {
-    case 1: return launch_filtered_t<1>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st);
-    case 2: return launch_filtered_t<2>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st);
-    case 4: return launch_filtered_t<4>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st);
-    case 8: return launch_filtered_t<8>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st);
+    case 1: return launch_filtered_t<1>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st, between);
+    case 2: return launch_filtered_t<2>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st, between);
+    case 4: return launch_filtered_t<4>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st, between);
+    case 8: return launch_filtered_t<8>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st, between);
     default: return cudaErrorInvalidValue;
     }
 }

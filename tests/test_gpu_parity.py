@@ -267,3 +267,15 @@ def test_full_size_properties(ctx):
         ctx.set_targets_bits(T[h["t"]:h["t"] + 1], G)
         one = ctx.score(P[h["q"]:h["q"] + 1], Y[h["q"]:h["q"] + 1], p[h["q"]:h["q"] + 1])[0]
         assert (one["score"], one["yes"], one["number"], one["depth"]) == (h["score"], h["yes"], h["number"], h["depth"])
+
+
+def test_perl_dropin_on_golden_cases():
+    """The reference-facing binding: perl XS -> libppp_b200.so, PhyloProf::Algorithm::ppp_b200 (same constructor and
+    return list as ppp.pm) on the golden list cases generated by the reference."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "perl")], stdout=subprocess.DEVNULL)
+    r = subprocess.run(["perl", os.path.join(root, "perl", "t", "golden.pl")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 mismatches" in r.stdout
