@@ -175,7 +175,8 @@ def run_ours(args):
         """optional global top-k merge over ranks (the path's only exchange step): NCCL all-gather + k-way merge"""
         if world == 1:
             return hits
-        return parallel.global_topk(hits, rank * nt, k, nq, device=torch.device("cuda", local_rank))
+        out, cnt = parallel.global_topk_device(ctx, lambda r: r * nt, k, nq, torch.device("cuda", local_rank))
+        return out
 
     # ---- resident-input steps (value)
     for _ in range(args.warmup):

@@ -121,6 +121,15 @@ int ppp_fetch(ppp_ctx *ctx, ppp_hit *out, size_t cap, size_t *nout);
 int ppp_score(ppp_ctx *ctx, const uint32_t *P, const uint32_t *Y, const double *p, size_t nQ, const ppp_filter *f,
               ppp_hit *out, size_t cap, size_t *nout);
 
+/* Multi-GPU global top-k (the path's only exchange step).  ppp_topk_device exposes the DEVICE
+ * pointers of the last top-k run ([nQ][k] hits, [nQ] counts; valid until the next run) so that the host can
+ * all-gather them over NCCL without a round trip through host memory; ppp_merge_topk_device merges `nlists`
+ * gathered lists (device memory, list l at lists + l*nQ*k, counts at counts + l*nQ), adds t_offsets[l] to the target
+ * indices of list l and writes the global [nQ][k] lists and [nQ] counts to HOST buffers. */
+int ppp_topk_device(ppp_ctx *ctx, const ppp_hit **lists, const uint32_t **counts, uint32_t *k, size_t *nQ);
+int ppp_merge_topk_device(ppp_ctx *ctx, const ppp_hit *lists, const uint32_t *counts, uint32_t nlists,
+                          const uint32_t *t_offsets, size_t nQ, uint32_t k, ppp_hit *out, uint32_t *out_counts);
+
 int ppp_get_stats(const ppp_ctx *ctx, ppp_stats *out);
 
 /* Options (tests / diagnostics): "force_exact" (0/1: every pair through the exact tier),

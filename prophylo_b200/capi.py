@@ -25,7 +25,7 @@ assert HIT_DTYPE.itemsize == 32
 EXPORTS = [
     "ppp_init", "ppp_destroy", "ppp_last_error", "ppp_abi_version", "ppp_set_targets_bits", "ppp_set_targets_ranked",
     "ppp_set_queries", "ppp_run", "ppp_result_count", "ppp_fetch", "ppp_score", "ppp_get_stats", "ppp_set_option",
-    "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc",
+    "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc", "ppp_topk_device", "ppp_merge_topk_device",
 ]
 
 
@@ -88,6 +88,10 @@ def load():
     L.ppp_get_counter.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int64)]
     L.ppp_words_per_row.restype = u32
     L.ppp_words_per_row.argtypes = [u32]
+    L.ppp_topk_device.restype = ctypes.c_int
+    L.ppp_topk_device.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(u32), ctypes.POINTER(sz)]
+    L.ppp_merge_topk_device.restype = ctypes.c_int
+    L.ppp_merge_topk_device.argtypes = [vp, vp, vp, u32, vp, sz, u32, vp, vp]
     L.ppp_debug_bdtrc.restype = ctypes.c_int
     L.ppp_debug_bdtrc.argtypes = [vp, vp, vp, vp, vp, sz]
     _lib = L
@@ -187,6 +191,21 @@ class Context:
             self._check(rc)
         self.nQ = P.shape[0]
         return out[: got.value]
+
+    def topk_device(self):
+        """(lists_ptr, counts_ptr, k, nQ): device addresses of the last top-k run's [nQ][k] hits and [nQ] counts."""
+        lp, cp, k, nq = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_uint32(), ctypes.c_size_t()
+        self._check(self.lib.ppp_topk_device(self._h, ctypes.byref(lp), ctypes.byref(cp), ctypes.byref(k), ctypes.byref(nq)))
+        return lp.value, cp.value, k.value, nq.value
+
+    def merge_topk_device(self, lists_ptr: int, counts_ptr: int, nlists: int, t_offsets, n_queries: int, k: int):
+        """Merge `nlists` gathered device lists into the global per-query top-k; returns (hits [nQ*k], counts [nQ]) on the host."""
+        offs = np.ascontiguousarray(t_offsets, dtype=np.uint32)
+        out = np.empty(n_queries * k, dtype=HIT_DTYPE)
+        cnt = np.empty(n_queries, dtype=np.uint32)
+        self._check(self.lib.ppp_merge_topk_device(self._h, ctypes.c_void_p(lists_ptr), ctypes.c_void_p(counts_ptr), nlists, _ptr(offs),
+                                                   n_queries, k, _ptr(out), _ptr(cnt)))
+        return out, cnt
 
     def stats(self) -> dict:
         s = Stats()

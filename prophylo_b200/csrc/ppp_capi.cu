@@ -33,7 +33,7 @@ extern "C" cudaError_t ppp_launch_staircase(const QConst *qc, const double *lf, 
                                             const uint32_t *static_off, uint16_t *nmax, uint32_t *active_off, double *last_tau,
                                             uint32_t nQ, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_topk_merge(const void *appended, uint32_t *qcnt, uint32_t qcap, void *topk, uint32_t *topk_cnt,
-                                             double *kth, uint32_t k, uint32_t nQ, int nsm, cudaStream_t st);
+                                             double *kth, uint32_t k, uint32_t nQ, uint32_t t_offset, int nsm, cudaStream_t st);
 extern "C" int ppp_topk_max_k(void);
 
 struct ppp_ctx {
@@ -84,6 +84,14 @@ struct ppp_ctx {
     size_t cap_nmax = 0;
     ppp_hit *d_topk = nullptr;
     size_t cap_topk = 0;
+    uint32_t last_topk_k = 0; /* k of the resident device top-k lists (0 = none) */
+    size_t last_topk_nq = 0;
+    ppp_hit *d_mtopk = nullptr; /* scratch of ppp_merge_topk_device */
+    size_t cap_mtopk = 0;
+    double *d_mkth = nullptr;
+    size_t cap_mkth = 0;
+    uint32_t *d_mcnt = nullptr;
+    size_t cap_mcnt = 0;
     std::vector<uint32_t> nmax_off_host; /* static staircase offsets: prefix sums of (ny + 1) */
     size_t nmax_entries = 0;
 
@@ -187,6 +195,9 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaFree(ctx->d_off);
     cudaFree(ctx->d_nmax);
     cudaFree(ctx->d_topk);
+    cudaFree(ctx->d_mtopk);
+    cudaFree(ctx->d_mkth);
+    cudaFree(ctx->d_mcnt);
     for (int i = 0; i < 8; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -421,6 +432,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
 
     ctx->host_results.clear();
     ctx->results_on_host = (f->mode != PPP_FILTER_ALL);
+    ctx->last_topk_k = 0;
     unsigned long long totals[CNT_N];
     memset(totals, 0, sizeof(totals));
     float sweep_ms = 0.f;
@@ -522,7 +534,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             if (topk) {
                 CU(cudaEventRecord(ctx->ev[5], ctx->stream));
                 CU(ppp_launch_topk_merge(ctx->d_hits, d_qcnt, (uint32_t)maxw, ctx->d_topk, d_topk_cnt, ctx->d_kth, k, (uint32_t)nQ,
-                                         ctx->nsm, ctx->stream));
+                                         0u, ctx->nsm, ctx->stream));
                 CU(cudaEventRecord(ctx->ev[6], ctx->stream));
                 CU(cudaEventSynchronize(ctx->ev[6]));
                 float ms = 0.f;
@@ -546,6 +558,8 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             CU(cudaStreamSynchronize(ctx->stream));
             for (size_t q = 0; q < nQ; ++q)
                 ctx->host_results.insert(ctx->host_results.end(), lists.begin() + q * k, lists.begin() + q * k + cnt[q]);
+            ctx->last_topk_k = k;
+            ctx->last_topk_nq = nQ;
         } else {
             std::sort(ctx->host_results.begin(), ctx->host_results.end(), hit_less); /* presentation order only */
         }
@@ -600,6 +614,39 @@ extern "C" int ppp_score(ppp_ctx *ctx, const uint32_t *P, const uint32_t *Y, con
     rc = ppp_run(ctx, f);
     if (rc) return rc;
     return ppp_fetch(ctx, out, cap, nout);
+}
+
+extern "C" int ppp_topk_device(ppp_ctx *ctx, const ppp_hit **lists, const uint32_t **counts, uint32_t *k, size_t *nQ)
+{
+    if (!ctx || !lists || !counts || !k || !nQ) return PPP_ERR_INVALID;
+    if (!ctx->last_topk_k) return fail(ctx, PPP_ERR_STATE, "ppp_topk_device: the last run was not a top-k run");
+    *lists = ctx->d_topk;
+    *counts = ctx->d_qcnt + ctx->last_topk_nq;
+    *k = ctx->last_topk_k;
+    *nQ = ctx->last_topk_nq;
+    return PPP_OK;
+}
+
+extern "C" int ppp_merge_topk_device(ppp_ctx *ctx, const ppp_hit *lists, const uint32_t *counts, uint32_t nlists,
+                                     const uint32_t *t_offsets, size_t nQ, uint32_t k, ppp_hit *out, uint32_t *out_counts)
+{
+    if (!ctx || !lists || !counts || !t_offsets || !out || !out_counts || !nlists || !nQ) return PPP_ERR_INVALID;
+    if (k == 0 || (int)k > ppp_topk_max_k()) return fail(ctx, PPP_ERR_INVALID, "ppp_merge_topk_device: k out of range");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_mtopk, &ctx->cap_mtopk, nQ * (size_t)k))) return rc;
+    if ((rc = grow(ctx, &ctx->d_mkth, &ctx->cap_mkth, nQ))) return rc;
+    if ((rc = grow(ctx, &ctx->d_mcnt, &ctx->cap_mcnt, nQ * ((size_t)nlists + 1)))) return rc;
+    /* the merge kernel consumes (zeroes) its input counters: work on a copy */
+    CU(cudaMemcpyAsync(ctx->d_mcnt + nQ, counts, nQ * nlists * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_mcnt, 0, nQ * sizeof(uint32_t), ctx->stream));
+    for (uint32_t l = 0; l < nlists; ++l)
+        CU(ppp_launch_topk_merge(lists + (size_t)l * nQ * k, ctx->d_mcnt + nQ * ((size_t)l + 1), k, ctx->d_mtopk, ctx->d_mcnt, ctx->d_mkth,
+                                 k, (uint32_t)nQ, t_offsets[l], ctx->nsm, ctx->stream));
+    CU(cudaMemcpyAsync(out, ctx->d_mtopk, nQ * (size_t)k * sizeof(ppp_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(out_counts, ctx->d_mcnt, nQ * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PPP_OK;
 }
 
 extern "C" int ppp_get_stats(const ppp_ctx *ctx, ppp_stats *out)

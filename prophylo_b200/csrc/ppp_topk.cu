@@ -109,7 +109,7 @@ __device__ __forceinline__ bool rec_less(const ppp_hit &a, const ppp_hit &b)
 
 __global__ void __launch_bounds__(256) ppp_topk_merge_kernel(const ppp_hit *__restrict__ appended, uint32_t *__restrict__ qcnt,
                                                              uint32_t qcap, ppp_hit *__restrict__ topk, uint32_t *__restrict__ topk_cnt,
-                                                             double *__restrict__ kth, uint32_t k, uint32_t nQ)
+                                                             double *__restrict__ kth, uint32_t k, uint32_t nQ, uint32_t t_offset)
 {
     extern __shared__ __align__(16) unsigned char smem_topk[];
     ppp_hit *rec = reinterpret_cast<ppp_hit *>(smem_topk);
@@ -121,7 +121,11 @@ __global__ void __launch_bounds__(256) ppp_topk_merge_kernel(const ppp_hit *__re
         uint32_t done = 0;
         while (done < nnew) {
             const uint32_t batch = min(nnew - done, (uint32_t)TOPK_M - cur);
-            for (uint32_t i = threadIdx.x; i < batch; i += blockDim.x) rec[cur + i] = appended[(size_t)q * qcap + done + i];
+            for (uint32_t i = threadIdx.x; i < batch; i += blockDim.x) {
+                ppp_hit h = appended[(size_t)q * qcap + done + i];
+                h.t += t_offset; /* shard-local -> global target index (multi-GPU merge); 0 otherwise */
+                rec[cur + i] = h;
+            }
             const uint32_t tot = cur + batch;
             uint32_t n2 = 1;
             while (n2 < tot) n2 <<= 1;
@@ -159,14 +163,14 @@ __global__ void __launch_bounds__(256) ppp_topk_merge_kernel(const ppp_hit *__re
 }
 
 extern "C" cudaError_t ppp_launch_topk_merge(const void *appended, uint32_t *qcnt, uint32_t qcap, void *topk, uint32_t *topk_cnt,
-                                             double *kth, uint32_t k, uint32_t nQ, int nsm, cudaStream_t st)
+                                             double *kth, uint32_t k, uint32_t nQ, uint32_t t_offset, int nsm, cudaStream_t st)
 {
     const int smem = TOPK_M * (int)sizeof(ppp_hit);
     cudaError_t e = cudaFuncSetAttribute(ppp_topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     const unsigned grid = (unsigned)min((uint32_t)(nsm * 2), nQ);
     ppp_topk_merge_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const ppp_hit *>(appended), qcnt, qcap,
-                                                   reinterpret_cast<ppp_hit *>(topk), topk_cnt, kth, k, nQ);
+                                                   reinterpret_cast<ppp_hit *>(topk), topk_cnt, kth, k, nQ, t_offset);
     return cudaGetLastError();
 }
 

@@ -64,3 +64,31 @@ def global_topk(hits: np.ndarray, t_offset: int, k: int, n_queries: int, device=
         h["t"] += np.uint32(t_offset)
         return merge_topk([h], k, n_queries)
     return merge_topk(all_gather_hits(hits, t_offset, device), k, n_queries)
+
+
+class _DevBuf:
+    """Expose a raw device allocation of the library to torch through __cuda_array_interface__ (zero copy)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def global_topk_device(ctx, t_offset_of_rank, k: int, n_queries: int, device):
+    """Global top-k over the ranks' target shards without a host round trip: NCCL all-gather of the DEVICE-resident
+    per-rank lists (ppp_topk_device), then the library's merge kernel (ppp_merge_topk_device).  Returns (hits, counts)
+    on the host, identical on every rank.  t_offset_of_rank(r) = first global target index of rank r's shard."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size()
+    lp, cp, kk, nq = ctx.topk_device()
+    assert kk == k and nq == n_queries
+    lists = torch.as_tensor(_DevBuf(lp, nq * k * HIT_DTYPE.itemsize), device=device)
+    counts = torch.as_tensor(_DevBuf(cp, nq * 4), device=device)
+    g_lists = torch.empty(world * lists.numel(), dtype=torch.uint8, device=device)
+    g_counts = torch.empty(world * counts.numel(), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(g_lists, lists)
+    dist.all_gather_into_tensor(g_counts, counts)
+    torch.cuda.synchronize(device)
+    offs = [t_offset_of_rank(r) for r in range(world)]
+    return ctx.merge_topk_device(g_lists.data_ptr(), g_counts.data_ptr(), world, offs, n_queries, k)

@@ -279,3 +279,37 @@ def test_perl_dropin_on_golden_cases():
     r = subprocess.run(["perl", os.path.join(root, "perl", "t", "golden.pl")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 mismatches" in r.stdout
+
+
+def test_device_global_topk_merge_of_two_shards(ctx):
+    """The multi-GPU exchange step on one device: per-shard top-k lists, merged by ppp_merge_topk_device with shard
+    offsets, must equal the top-k of the unsharded run."""
+    import torch
+
+    from prophylo_b200 import parallel
+
+    G, nq, nt, k = 1024, 50, 3000, 16
+    P, Y, p = synth.make_queries(G, nq, 71, "mixed")
+    T = synth.make_targets(G, nt, 72, plant_from=Y, plant_frac=0.02)
+    flt = capi.make_filter(capi.FILTER_TOPK, k=k)
+    ctx.set_targets_bits(T, G)
+    full = ctx.score(P, Y, p, flt).copy()
+    parts, cnts, offs = [], [], []
+    for r in range(2):
+        t0, t1 = parallel.shard_range(nt, r, 2)
+        ctx.set_targets_bits(T[t0:t1], G)
+        h = ctx.score(P, Y, p, flt)
+        lp, cp, kk, nqq = ctx.topk_device()
+        assert (kk, nqq) == (k, nq)
+        dev = torch.as_tensor(parallel._DevBuf(lp, nq * k * 32), device="cuda").clone()
+        cnt = torch.as_tensor(parallel._DevBuf(cp, nq * 4), device="cuda").clone()
+        assert np.array_equal(dev.cpu().numpy().view(capi.HIT_DTYPE), h)
+        parts.append(dev)
+        cnts.append(cnt)
+        offs.append(t0)
+    g_lists, g_counts = torch.cat(parts), torch.cat(cnts)
+    torch.cuda.synchronize()
+    out, cnt = ctx.merge_topk_device(g_lists.data_ptr(), g_counts.data_ptr(), 2, offs, nq, k)
+    assert np.all(cnt == k)
+    for f in ("q", "t", "score", "yes", "number", "depth"):
+        assert np.array_equal(out[f], full[f]), f
