@@ -144,6 +144,15 @@ class Context:
         self._check(self.lib.ppp_set_targets_bits(self._h, _ptr(T), T.shape[0], G))
         self.G, self.nT = G, T.shape[0]
 
+    def set_targets_ranked(self, idx, rawdepth, row_off, G: int):
+        """Ordered, de-duplicated hit lists (packer.pack_ranked_targets)."""
+        idx = np.ascontiguousarray(idx, dtype=np.uint16)
+        rawdepth = np.ascontiguousarray(rawdepth, dtype=np.uint16)
+        row_off = np.ascontiguousarray(row_off, dtype=np.uint64)
+        assert idx.shape == rawdepth.shape and row_off.ndim == 1 and row_off.size >= 1
+        self._check(self.lib.ppp_set_targets_ranked(self._h, _ptr(idx), _ptr(rawdepth), _ptr(row_off), row_off.size - 1, G))
+        self.G, self.nT = G, row_off.size - 1
+
     def set_queries(self, P, Y, p):
         P = np.ascontiguousarray(P, dtype=np.uint32)
         Y = np.ascontiguousarray(Y, dtype=np.uint32)

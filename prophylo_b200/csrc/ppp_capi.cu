@@ -27,6 +27,8 @@ extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, cons
                                            cudaStream_t st, cudaEvent_t between);
 extern "C" cudaError_t ppp_launch_transpose(const void *T, void *Tt, uint32_t nT, int wpl, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_exact(const SweepParams *prm, int W, int nsm, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_sweep_ranked(const SweepParams *prm, int rwpl, int nwarps, int nsm, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_exact_ranked(const SweepParams *prm, int rwpl, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_debug_bdtrc(const int32_t *k, const int32_t *n, const double *p, double *out, size_t m,
                                               cudaStream_t st);
 extern "C" cudaError_t ppp_launch_staircase(const QConst *qc, const double *lf, const double *kth, int accept_mode, double thresh_ln,
@@ -54,6 +56,13 @@ struct ppp_ctx {
     bool Tt_valid = false;
     uint32_t *d_surv = nullptr;
     size_t cap_surv = 0;
+    /* ranked targets */
+    bool ranked = false;
+    int rwpl = 0; /* list words per lane: 1 (<= 1024 entries) or 2 (<= 2048) */
+    uint16_t *d_ridx = nullptr, *d_rraw = nullptr;
+    size_t cap_ridx = 0, cap_rraw = 0;
+    unsigned long long *d_roff = nullptr;
+    size_t cap_roff = 0;
     int lf_wpl = 0;
     size_t nT = 0;
     uint32_t G = 0;
@@ -183,6 +192,9 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaFree(ctx->d_T);
     cudaFree(ctx->d_Tt);
     cudaFree(ctx->d_surv);
+    cudaFree(ctx->d_ridx);
+    cudaFree(ctx->d_rraw);
+    cudaFree(ctx->d_roff);
     cudaFree(ctx->d_lf);
     cudaFree(ctx->d_Q);
     cudaFree(ctx->d_qc);
@@ -204,6 +216,19 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     delete ctx;
 }
 
+/* log-factorial table lf[k] = lgamma(k+1), k = 0..8193, computed in long double once per context */
+static int ensure_lf(ppp_ctx *ctx)
+{
+    if (ctx->d_lf) return PPP_OK;
+    const size_t n = 8192 + 2;
+    std::vector<double> lf(n);
+    for (size_t k = 0; k < n; ++k) lf[k] = (double)lgammal((long double)k + 1.0L);
+    CU(cudaMalloc(&ctx->d_lf, n * sizeof(double)));
+    CU(cudaMemcpyAsync(ctx->d_lf, lf.data(), n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PPP_OK;
+}
+
 static int pick_wpl(uint32_t G)
 {
     if (G <= 1024) return 1;
@@ -212,6 +237,8 @@ static int pick_wpl(uint32_t G)
     if (G <= 8192) return 8;
     return 0;
 }
+
+static void reset_queries_if_layout_changed(ppp_ctx *ctx, int wpl, uint32_t G);
 
 extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, uint32_t G)
 {
@@ -230,20 +257,18 @@ extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, 
         if (wpr != W) CU(cudaMemsetAsync(ctx->d_T, 0, nT * W * 4, ctx->stream));
         CU(cudaMemcpy2DAsync(ctx->d_T, W * 4, T, wpr * 4, wpr * 4, nT, cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (ctx->lf_wpl != wpl) {
-        /* log-factorial table lf[k] = lgamma(k+1), k = 0..Gd+1, computed in long double */
-        const size_t Gd = 32 * W;
-        std::vector<double> lf(Gd + 2);
-        for (size_t k = 0; k < Gd + 2; ++k) lf[k] = (double)lgammal((long double)k + 1.0L);
-        cudaFree(ctx->d_lf);
-        ctx->d_lf = nullptr;
-        ctx->lf_wpl = 0;
-        CU(cudaMalloc(&ctx->d_lf, (Gd + 2) * sizeof(double)));
-        CU(cudaMemcpyAsync(ctx->d_lf, lf.data(), (Gd + 2) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        ctx->lf_wpl = wpl;
-    }
+    if ((rc = ensure_lf(ctx))) return rc;
+    ctx->ranked = false;
     CU(cudaStreamSynchronize(ctx->stream));
+    reset_queries_if_layout_changed(ctx, wpl, G);
+    ctx->nT = nT;
+    ctx->G = G;
+    ctx->wpl = wpl;
+    return PPP_OK;
+}
+
+static void reset_queries_if_layout_changed(ppp_ctx *ctx, int wpl, uint32_t G)
+{
     if (ctx->wpl != wpl || ctx->G != G) {
         ctx->nQ = 0; /* queries must be re-uploaded: the row layout changed */
         cudaFree(ctx->d_Q);
@@ -254,18 +279,47 @@ extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, 
         ctx->d_qflags = nullptr;
         ctx->capQ = 0;
     }
-    ctx->nT = nT;
-    ctx->G = G;
-    ctx->wpl = wpl;
-    return PPP_OK;
 }
 
 extern "C" int ppp_set_targets_ranked(ppp_ctx *ctx, const uint16_t *idx, const uint16_t *rawdepth, const uint64_t *row_off,
                                       size_t nT, uint32_t G)
 {
-    (void)idx; (void)rawdepth; (void)row_off; (void)nT; (void)G;
     if (!ctx) return PPP_ERR_INVALID;
-    return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_ranked: ranked target lists are not built in this round (DESIGN.md, 'next')");
+    if (!row_off || (nT && row_off[nT] && (!idx || !rawdepth))) return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_ranked: NULL input");
+    if (G == 0 || G > 8192) return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_ranked: G = %u outside [1, 8192]", G);
+    if (nT > 0xffffffffull) return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_ranked: nT too large");
+    size_t lmax = 0;
+    for (size_t t = 0; t < nT; ++t) {
+        if (row_off[t + 1] < row_off[t]) return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_ranked: row_off not monotone at %zu", t);
+        lmax = std::max<size_t>(lmax, row_off[t + 1] - row_off[t]);
+    }
+    if (lmax > 2048)
+        return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_ranked: a list has %zu distinct taxa; at most 2048 are supported", lmax);
+    const size_t total = nT ? row_off[nT] : 0;
+    for (size_t i = 0; i < total; ++i)
+        if (idx[i] != 0xFFFF && idx[i] >= G) return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_ranked: idx[%zu] = %u >= G", i, idx[i]);
+    CU(cudaSetDevice(ctx->device));
+    ctx->nT = 0;
+    ctx->Tt_valid = false;
+    int rc;
+    if ((rc = ensure_lf(ctx))) return rc;
+    if ((rc = grow(ctx, &ctx->d_ridx, &ctx->cap_ridx, total + 64))) return rc;
+    if ((rc = grow(ctx, &ctx->d_rraw, &ctx->cap_rraw, total + 64))) return rc;
+    if ((rc = grow(ctx, &ctx->d_roff, &ctx->cap_roff, nT + 1))) return rc;
+    if (total) {
+        CU(cudaMemcpyAsync(ctx->d_ridx, idx, total * 2, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_rraw, rawdepth, total * 2, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CU(cudaMemcpyAsync(ctx->d_roff, row_off, (nT + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const int wpl = pick_wpl(G);
+    reset_queries_if_layout_changed(ctx, wpl, G);
+    ctx->nT = nT;
+    ctx->G = G;
+    ctx->wpl = wpl;
+    ctx->ranked = true;
+    ctx->rwpl = lmax <= 1024 ? 1 : 2;
+    return PPP_OK;
 }
 
 static void make_qconst(double p, uint32_t ny, uint32_t npres, QConst *qc)
@@ -374,6 +428,10 @@ static void base_params(const ppp_ctx *ctx, SweepParams *prm)
     prm->G = ctx->G;
     prm->force_exact = (uint32_t)ctx->force_exact;
     prm->check_bounds = (uint32_t)ctx->check_bounds;
+    prm->qwords = 32u * (uint32_t)ctx->wpl;
+    prm->ridx = ctx->d_ridx;
+    prm->rraw = ctx->d_rraw;
+    prm->roff = ctx->d_roff;
 }
 
 /* one target chunk: sweep + exact tier; accumulates counters and the sweep kernel's event time */
@@ -387,11 +445,14 @@ static int run_chunk(ppp_ctx *ctx, SweepParams *prm, unsigned long long *totals,
         CU(ppp_launch_filtered(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qflags, ctx->d_surv, ctx->d_counters + CNT_N, ctx->cap_surv,
                                ctx->sweep_warps, ctx->nsm, ctx->stream, ctx->ev[7]));
         *launches += 1;
+    } else if (ctx->ranked) {
+        CU(ppp_launch_sweep_ranked(prm, ctx->rwpl, ctx->sweep_warps, ctx->nsm, ctx->stream));
     } else {
         CU(ppp_launch_sweep(prm, ctx->wpl, ctx->sweep_warps, ctx->nsm, ctx->stream));
     }
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
-    CU(ppp_launch_exact(prm, W, ctx->nsm, ctx->stream));
+    if (ctx->ranked) CU(ppp_launch_exact_ranked(prm, ctx->rwpl, ctx->nsm, ctx->stream));
+    else CU(ppp_launch_exact(prm, W, ctx->nsm, ctx->stream));
     CU(cudaEventRecord(ctx->ev[4], ctx->stream));
     *launches += 2;
     unsigned long long c[CNT_N + 1];
@@ -419,6 +480,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
 {
     if (!ctx) return PPP_ERR_INVALID;
     if (!ctx->wpl || !ctx->nT) return fail(ctx, PPP_ERR_STATE, "ppp_run: no targets resident");
+    if (!ctx->ranked && !ctx->d_T) return fail(ctx, PPP_ERR_STATE, "ppp_run: no targets resident");
     if (!ctx->nQ) return fail(ctx, PPP_ERR_STATE, "ppp_run: no queries resident");
     ppp_filter all = {PPP_FILTER_ALL, 0, 0.0};
     if (!f) f = &all;
@@ -472,7 +534,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         if ((rc = grow(ctx, &ctx->d_nmax, &ctx->cap_nmax, ctx->nmax_entries + 8))) return rc;
         if (topk && (rc = grow(ctx, &ctx->d_topk, &ctx->cap_topk, nQ * (size_t)k))) return rc;
         if ((rc = grow(ctx, &ctx->d_surv, &ctx->cap_surv, nQ * maxw))) return rc;
-        if (!ctx->Tt_valid) {
+        if (!ctx->ranked && !ctx->Tt_valid) {
             const size_t W = 32 * (size_t)ctx->wpl;
             if ((rc = grow(ctx, &ctx->d_Tt, &ctx->cap_Tt, nT * W))) return rc;
             CU(ppp_launch_transpose(ctx->d_T, ctx->d_Tt, (uint32_t)nT, ctx->wpl, ctx->stream));
@@ -524,7 +586,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             prm.qcap = (uint32_t)maxw;
             unsigned long long c[CNT_N];
             /* the first top-k chunk has no thresholds yet: tile kernel over every pair; afterwards thread-per-pair screen */
-            if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c, !(topk && !processed)))) return rc;
+            if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c, !ctx->ranked && !(topk && !processed)))) return rc;
             sweep_launches++;
             if (topk && processed) {
                 float ms = 0.f;

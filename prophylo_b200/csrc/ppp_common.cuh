@@ -61,7 +61,11 @@ struct SweepParams {
     const uint32_t *nmax_off;  /* [nQ] offset of query q's staircase, PPP_NO_TABLE = accept every pair */
     uint32_t *qcnt;            /* [nQ] append counters */
     uint32_t qcap;             /* per-query append capacity (>= targets per launch) */
-    uint32_t pad2_;
+    uint32_t qwords;           /* words per query plane row (universe width; = W for bit-plane targets) */
+    /* ranked targets (ppp_set_targets_ranked): per target an ordered, de-duplicated list of genome indices */
+    const uint16_t *ridx;      /* genome index in the query universe, 0xFFFF = foreign taxon */
+    const uint16_t *rraw;      /* 1-based raw list position of each entry (duplicates counted) */
+    const unsigned long long *roff; /* [nT+1] entry offsets */
 };
 
 #define PPP_NO_TABLE 0xffffffffu

@@ -313,3 +313,81 @@ def test_device_global_topk_merge_of_two_shards(ctx):
     assert np.all(cnt == k)
     for f in ("q", "t", "score", "yes", "number", "depth"):
         assert np.array_equal(out[f], full[f]), f
+
+
+def test_python_operator_mirror_on_golden_list_cases(golden_dir):
+    """prophylo_b200.algorithm mirrors PhyloProf::Profile / PhyloProf::Algorithm::ppp; every golden list case from the
+    reference (ARRAY targets with duplicates and foreign taxa, HASH targets, -prob) through the ranked-target path."""
+    from prophylo_b200.algorithm import Profile, ppp
+
+    g = json.load(open(os.path.join(golden_dir, "ppp_list_cases.json")))
+    n = 0
+    for c in g["known_answers"] + g["fuzz"]:
+        if c.get("dup"):
+            continue
+        t = c["target"]
+        prof1 = Profile(profile=c["query"])
+        prof2 = Profile(raw=t, yes=len(t), no=0)
+        got = ppp(prof1, prof2, prob=c.get("prob")).get_match_score()
+        e = c["expect"]
+        assert got[1:4] == (e[1], e[2], e[3]), (c["name"], got, e)
+        assert got[4] == float(e[4])
+        es = float(e[0])
+        assert got[0] == es or abs(np.log(got[0]) - np.log(es)) <= REL_TOL_NEGLOG * abs(np.log(es)), (c["name"], got, e)
+        n += 1
+    assert n > 500
+
+
+def test_ranked_targets_batch_vs_oracle(ctx):
+    """Many ranked targets (own order, duplicates, foreign taxa) x many queries in one call, dense / top-k / threshold."""
+    from prophylo_b200 import packer
+
+    rng = np.random.default_rng(5)
+    G, nq, nt = 600, 37, 300
+    universe = [f"g{i}" for i in range(G)]
+    index = packer.universe_index(universe)
+    queries = []
+    for _ in range(nq):
+        pres = rng.random(G) < rng.choice([1.0, 0.6])
+        dens = float(np.exp(rng.uniform(np.log(0.01), np.log(0.3))))
+        queries.append({universe[g]: int(rng.random() < dens) for g in np.nonzero(pres)[0]})
+    lists = []
+    for t in range(nt):
+        L = int(rng.integers(0, 1500))
+        pool = rng.permutation(G)[: max(1, int(G * rng.uniform(0.05, 0.9)))]
+        lst = [universe[int(pool[int(rng.integers(len(pool)))])] if rng.random() > 0.03 else f"foreign{int(rng.integers(40))}"
+               for _ in range(L)]
+        if t % 17 == 0 and queries[t % nq]:  # planted: enriched in some query's yes taxa
+            ys = [k for k, v in queries[t % nq].items() if v]
+            lst = [ys[int(rng.integers(len(ys)))] for _ in range(min(L, 3 * len(ys) + 1))] + lst
+        lists.append(lst)
+    P, Y, p = packer.pack_queries(queries, index)
+    idx, raw, off = packer.pack_ranked_targets(lists, index)
+    ctx.set_targets_ranked(idx, raw, off, G)
+    dense = ctx.score(P, Y, p).reshape(nq, nt)
+    # oracle: list form with integer ids; foreign taxa get ids >= G
+    fid = {}
+    for qi, q in enumerate(queries):
+        present = np.zeros(G, dtype=np.uint8)
+        isyes = np.zeros(G, dtype=np.uint8)
+        for k, v in q.items():
+            present[index[k]] = 1
+            isyes[index[k]] = int(v != 0)
+        for ti, lst in enumerate(lists):
+            ids = [index[x] if x in index else G + fid.setdefault(x, len(fid)) for x in lst]
+            exp = oracle.score_list(present, isyes, int(isyes.sum()), ids, float(p[qi]))
+            h = dense[qi, ti]
+            assert (h["yes"], h["number"], h["depth"]) == exp[1:4], (qi, ti, h, exp)
+            assert h["score"] == exp[0] or abs(np.log(h["score"]) - np.log(exp[0])) <= REL_TOL_NEGLOG * abs(np.log(exp[0]))
+    k = 7
+    tk = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
+    for q in range(nq):
+        e = np.sort(dense[q], order=["score", "t"])[:k]
+        got = tk[q * k:(q + 1) * k]
+        for f in ("t", "score", "yes", "number", "depth"):
+            assert np.array_equal(got[f], e[f]), (q, f)
+    th = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_THRESH_LOG10, thresh=-2.5))
+    with np.errstate(divide="ignore"):
+        keep = np.log10(dense["score"]) < -2.5
+    e = np.sort(dense[keep], order=["q", "score", "t"])
+    assert th.size == e.size and np.array_equal(th["t"], e["t"]) and np.array_equal(th["depth"], e["depth"])
