@@ -54,6 +54,24 @@ _set_targets_bits(h, planes, nT, G)
         croak("PhyloProf::B200: %s", ppp_last_error(ctx));
 
 void
+_set_targets_ranked(h, idx, raw, off, nT, G)
+    IV h
+    SV *idx
+    SV *raw
+    SV *off
+    UV nT
+    unsigned int G
+  CODE:
+    ppp_ctx *ctx = INT2PTR(ppp_ctx *, h);
+    STRLEN li, lr, lo;
+    const char *ib = SvPVbyte(idx, li);   /* pack "S*": uint16 genome indices, 0xFFFF = foreign taxon */
+    const char *rb = SvPVbyte(raw, lr);   /* pack "S*": 1-based raw list positions                      */
+    const char *ob = SvPVbyte(off, lo);   /* pack "Q*": nT + 1 entry offsets                            */
+    if (lo < (STRLEN)(nT + 1) * 8 || li != lr) croak("PhyloProf::B200: ranked target buffers inconsistent");
+    if (ppp_set_targets_ranked(ctx, (const uint16_t *)ib, (const uint16_t *)rb, (const uint64_t *)ob, (size_t)nT, G) != PPP_OK)
+        croak("PhyloProf::B200: %s", ppp_last_error(ctx));
+
+void
 _score(h, pplanes, yplanes, probs, nQ, mode, k, thresh)
     IV h
     SV *pplanes

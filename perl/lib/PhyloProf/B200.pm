@@ -56,6 +56,26 @@ sub _plane {
     return $v;
 }
 
+# score every query against every target; targets are ORDERED hit lists in their own order, duplicates and foreign taxa
+# allowed (BlastResult.pm:192-237 / value-sorted HMMERResult hash): de-duplicated here, raw positions kept (ppp.pm:169-231)
+sub score_ranked {
+    my ( $self, $universe, $queries, $lists, %o ) = @_;
+    my $idx = _index($universe);
+    my ( @gi, @raw, @off ) = ();
+    push @off, 0;
+    foreach my $l (@$lists) {
+        my %seen;
+        for my $i ( 0 .. $#$l ) {
+            next if $seen{ $l->[$i] }++;
+            push @gi, ( exists $idx->{ $l->[$i] } ? $idx->{ $l->[$i] } : 0xFFFF );
+            push @raw, $i + 1;
+        }
+        push @off, scalar @gi;
+    }
+    _set_targets_ranked( $self->{h}, pack( "S*", @gi ), pack( "S*", @raw ), pack( "Q*", @off ), scalar(@$lists), scalar(@$universe) );
+    return $self->_score_queries( $universe, $idx, $queries, %o );
+}
+
 # score every query (PhyloProf::Profile or {taxon=>0/1}) against every target ([taxa] in universe order semantics)
 sub score_bits {
     my ( $self, $universe, $queries, $targets, %o ) = @_;
@@ -65,6 +85,13 @@ sub score_bits {
     my $wpr = words_per_row($G);
     my $tb  = join '', map { _plane( $wpr, $idx, $_ ) } @$targets;
     _set_targets_bits( $self->{h}, $tb, scalar(@$targets), $G );
+    return $self->_score_queries( $universe, $idx, $queries, %o );
+}
+
+sub _score_queries {
+    my ( $self, $universe, $idx, $queries, %o ) = @_;
+    my $G   = scalar @$universe;
+    my $wpr = words_per_row($G);
     my ( $pb, $yb, @p ) = ( '', '' );
     foreach my $q (@$queries) {
         my $h = ref($q) eq 'HASH' ? $q : $q->get_hash();

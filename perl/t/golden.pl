@@ -35,5 +35,18 @@ foreach my $c ( @{ $g->{known_answers} }, @{ $g->{fuzz} } ) {
     }
     unless ($ok) { $bad++; print "MISMATCH $c->{name}: got @r expected @e\n" if $bad < 10; }
 }
+# batch entry with ranked lists: the KA-2 query against three target lists in one call
+{
+    my $ka = $g->{known_answers}[1];
+    my @universe = sort keys %{ $ka->{query} };
+    my $gpu = PhyloProf::B200->new( -device => $ENV{PPP_B200_DEVICE} || 0 );
+    my $hits = $gpu->score_ranked( \@universe, [ $ka->{query} ], [ $ka->{target}, [ reverse @{ $ka->{target} } ], [] ] );
+    my @e = @{ $ka->{expect} };
+    my $h = $hits->[0];
+    unless ( @$hits == 3 && $h->[3] == $e[1] && $h->[4] == $e[2] && $h->[5] == $e[3] && $hits->[2][2] == 1 ) {
+        $bad++;
+        print "MISMATCH ranked batch: @$h vs @e\n";
+    }
+}
 print "perl drop-in: $n cases, $bad mismatches, $skipped -dup cases skipped\n";
 exit( $bad ? 1 : 0 );

@@ -558,13 +558,47 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             launches++;
         }
         size_t processed = 0;
+        bool seeded_pass = false;
+        bool seeded = !topk; /* top-k: thresholds are seeded from cheap upper bounds of the first targets' scores */
         while (processed < nT) {
+            if (!seeded) {
+                /* Seeding pass: the k-th smallest UPPER bound (float enclosure only, no series, no exact tier) over the
+                 * first targets is a valid threshold for the query's k-th best score; the provisional records are then
+                 * dropped and every target -- these included -- goes through the screened path. */
+                const size_t w0 = std::min<size_t>(std::min(maxw, nT), std::max<size_t>(256, 3 * (size_t)k));
+                if (w0 < (size_t)k) {
+                    seeded = true; /* fewer targets than k: nothing to prune */
+                } else {
+                    SweepParams prm;
+                    base_params(ctx, &prm);
+                    prm.hits = ctx->d_hits;
+                    prm.t0 = 0;
+                    prm.t1 = (uint32_t)w0;
+                    prm.append = 1;
+                    prm.accept_mode = 0;
+                    prm.kth = ctx->d_kth;
+                    prm.nmax = ctx->d_nmax;
+                    prm.nmax_off = d_off_active;
+                    prm.qcnt = d_qcnt;
+                    prm.qcap = (uint32_t)maxw;
+                    prm.bounds_only = 1;
+                    unsigned long long c[CNT_N];
+                    if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c, false))) return rc;
+                    sweep_launches++;
+                    CU(ppp_launch_topk_merge(ctx->d_hits, d_qcnt, (uint32_t)maxw, ctx->d_topk, d_topk_cnt, ctx->d_kth, k, (uint32_t)nQ,
+                                             0u, ctx->nsm, ctx->stream));
+                    CU(cudaMemsetAsync(d_topk_cnt, 0, nQ * sizeof(uint32_t), ctx->stream)); /* drop the provisional records, keep kth */
+                    launches++;
+                    seeded = true;
+                    seeded_pass = true;
+                }
+            }
             size_t w = std::min(maxw, nT - processed);
             if (topk) {
                 const size_t first = std::max<size_t>(256, 3 * (size_t)k);
-                w = std::min(w, processed ? 4 * processed : first);
+                w = std::min(w, processed ? 4 * processed : (seeded_pass ? 4 * first : first));
             }
-            if (topk && processed) {
+            if (topk && (processed || seeded_pass)) {
                 CU(cudaEventRecord(ctx->ev[5], ctx->stream));
                 CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 0, 0.0, d_off_static, ctx->d_nmax, d_off_active,
                                         ctx->d_kth + nQ, (uint32_t)nQ, ctx->nsm, ctx->stream));
@@ -586,9 +620,9 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             prm.qcap = (uint32_t)maxw;
             unsigned long long c[CNT_N];
             /* the first top-k chunk has no thresholds yet: tile kernel over every pair; afterwards thread-per-pair screen */
-            if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c, !ctx->ranked && !(topk && !processed)))) return rc;
+            if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c, !ctx->ranked && !(topk && !processed && !seeded_pass)))) return rc;
             sweep_launches++;
-            if (topk && processed) {
+            if (topk && (processed || seeded_pass)) {
                 float ms = 0.f;
                 cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
                 ctx->phase_us[2] += 1e3 * ms;

@@ -62,6 +62,8 @@ struct SweepParams {
     uint32_t *qcnt;            /* [nQ] append counters */
     uint32_t qcap;             /* per-query append capacity (>= targets per launch) */
     uint32_t qwords;           /* words per query plane row (universe width; = W for bit-plane targets) */
+    uint32_t bounds_only;      /* 1: report exp(min upper enclosure) as a provisional score (threshold seeding); no tier B/C */
+    uint32_t pad3_;
     /* ranked targets (ppp_set_targets_ranked): per target an ordered, de-duplicated list of genome indices */
     const uint16_t *ridx;      /* genome index in the query universe, 0xFFFF = foreign taxon */
     const uint16_t *rraw;      /* 1-based raw list position of each entry (duplicates counted) */
@@ -87,6 +89,9 @@ __device__ __forceinline__ void ppp_emit(const SweepParams &prm, uint32_t q, uin
 {
     ppp_hit *base = reinterpret_cast<ppp_hit *>(prm.hits);
     size_t idx;
+    /* threshold seeding: a provisional score must stay STRICTLY above the real (Cephes-rounded) score of its pair,
+     * also when that is exactly 0.0 (underflow), 1.0 (no hit) or a denormal -- acceptance is `score < kth` */
+    if (prm.bounds_only) score = score * (1.0 + 1e-6) + 1e-300;
     if (prm.append == 0) {
         idx = (size_t)q * prm.nT + t;
     } else {

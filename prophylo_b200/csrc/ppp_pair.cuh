@@ -181,7 +181,13 @@ __device__ __forceinline__ uint32_t evaluate_pair(const uint32_t (&tw)[WPL], con
         *out = res;
         return 0;
     }
-    if (prm.force_exact || (qc.flags & PPP_QF_EXACT)) return PF_EXACT;
+    if (prm.force_exact || (qc.flags & PPP_QF_EXACT)) {
+        if (prm.bounds_only) { /* 1.0 is a valid upper bound of any score */
+            *out = res;
+            return 0;
+        }
+        return PF_EXACT;
+    }
 
     /* 2. candidates.  Unfiltered: every set bit of T&Y.  Filtered: only those with number <= stair[yes] -- the
      * pair is only kept if its minimum is below the threshold, and then the minimum (and anything within the
@@ -263,6 +269,7 @@ __device__ __forceinline__ uint32_t evaluate_pair(const uint32_t (&tw)[WPL], con
         }
         Ustar = fminf(Ustar, warp_min_f(umin));
         __syncwarp();
+        if (prm.bounds_only) continue; /* threshold seeding: only the enclosure's upper end is needed */
         /* 4. survivors -> tier B (in rank order, so that the earliest minimum wins) */
         const float cut = Ustar + 1e-5f + 1e-6f * fabsf(Ustar);
         for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
@@ -298,6 +305,12 @@ __device__ __forceinline__ uint32_t evaluate_pair(const uint32_t (&tw)[WPL], con
             }
         }
         __syncwarp();
+    }
+    if (prm.bounds_only) {
+        /* provisional record: score <= exp(U) is guaranteed, which is all the k-th-best seeding needs */
+        res.score = exp((double)Ustar);
+        *out = res;
+        return 0;
     }
     /* 5. decide */
     const double margin = second_lnf - best_lnf;

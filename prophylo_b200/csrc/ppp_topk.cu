@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) ppp_topk_merge_kernel(const ppp_hit *__re
         for (uint32_t i = threadIdx.x; i < cur; i += blockDim.x) topk[(size_t)q * k + i] = rec[i];
         if (threadIdx.x == 0) {
             topk_cnt[q] = cur;
-            kth[q] = (cur >= k) ? rec[k - 1].score : 2.0;
+            if (cur >= k) kth[q] = rec[k - 1].score; /* otherwise keep the previous (seeded) bound; 2.0 initially */
             qcnt[q] = 0;
         }
         __syncthreads();

@@ -391,3 +391,37 @@ def test_ranked_targets_batch_vs_oracle(ctx):
         keep = np.log10(dense["score"]) < -2.5
     e = np.sort(dense[keep], order=["q", "score", "t"])
     assert th.size == e.size and np.array_equal(th["t"], e["t"]) and np.array_equal(th["depth"], e["depth"])
+
+
+def test_topk_ties_at_zero_and_one(ctx):
+    """Top-k lists whose k-th score is exactly 0.0 (Cephes underflow / domain error) or exactly 1.0 (no common
+    yes-genome): ties are broken by target index and nothing may be lost to the strict `score < kth` acceptance."""
+    G, nt, k = 2048, 2500, 40
+    rng = np.random.default_rng(8)
+    Pb = np.ones((6, G), dtype=np.uint8)
+    Yb = np.zeros((6, G), dtype=np.uint8)
+    Yb[0, :900] = 1                      # dense yes set: hundreds of targets underflow to exactly 0.0
+    Yb[1, rng.choice(G, 5, replace=False)] = 1   # 5 yes genomes: most targets score exactly 1.0 or near it
+    Yb[2] = rng.random(G) < 0.1          # domain error p = 1.2 -> every non-empty target scores 0.0 at depth 1
+    Yb[3] = 1                            # p = 1 -> every target scores 1.0
+    Yb[4] = rng.random(G) < 0.05
+    Yb[5] = 0                            # p = 0
+    p = Yb.sum(1) / G
+    p[2] = 1.2
+    p[0] = 0.01                          # -prob: 800 common yes genomes at p = 0.01 underflow Cephes to exactly 0.0
+    Tb = (rng.random((nt, G)) < rng.uniform(0.0, 0.5, size=(nt, 1))).astype(np.uint8)
+    Tb[::3, :900] |= (rng.random((len(Tb[::3]), 900)) < 0.9).astype(np.uint8)   # many targets rich in query 0's yes set
+    Tb[5] = 0
+    Tb[:, np.nonzero(Yb[1])[0]] &= (rng.random((nt, 5)) < 0.02).astype(np.uint8)  # query 1's yes genomes are rare
+    P, Y, T = synth.pack_bits(Pb), synth.pack_bits(Yb), synth.pack_bits(Tb)
+    ctx.set_targets_bits(T, G)
+    dense = ctx.score(P, Y, p).reshape(6, nt)
+    nz, no = int((dense[0]["score"] == 0).sum()), int((dense[1]["score"] == 1).sum())
+    assert nz > k and no > nt // 2, (nz, no)
+    tk = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
+    assert tk.size == 6 * k
+    for q in range(6):
+        exp = np.sort(dense[q], order=["score", "t"])[:k]
+        got = tk[q * k:(q + 1) * k]
+        for f in ("t", "score", "yes", "number", "depth"):
+            assert np.array_equal(got[f], exp[f]), (q, f)
