@@ -1,0 +1,135 @@
+"""Host-side drivers around the GPU scan: the parts of bin/ppp.pl and bin/ppp_cutoff.pl that sit either side of the hot
+path -- `.bla` hit-list reader, batch scoring of one query profile against a genome's genes,
+the stdout table of ppp.pl and the slope filter of ppp_cutoff.pl -- with the reference's formats kept byte for byte.
+
+    rows = ppp_scan(ctx, Profile(file="q.profile"), {"500010": "db/blast/1140/500010.bla", ...})
+    print(format_ppp_table(rows, slope=30), end="")          # == stdout of  ppp.pl -t 1140 -p q.profile -m 30
+    print(ppp_cutoff(table_text, slope=20)[0], end="")       # == stdout of  ppp_cutoff.pl -s 20
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+
+from . import capi, packer
+from .algorithm import Profile
+
+
+def read_bla(path):
+    """One gene's cached BLAST hits -> the ordered taxon list the reference scores (bin/ppp.pl:606-673 +
+    lib/PhyloProf/BlastResult.pm:192-237): 4 tab columns query, subject, e-value, subject taxon; subjects keep their
+    first-occurrence order, a subject's LAST taxon wins, subjects with a false taxon ('' or '0') are dropped,
+    different subjects of the same taxon stay as duplicates (they count in the depth)."""
+    order, taxon = [], {}
+    with open(path) as fh:
+        for line in fh:
+            f = line.rstrip("\n").split("\t")
+            if len(f) < 4:
+                f += [""] * (4 - len(f))
+            if f[1] not in taxon:
+                order.append(f[1])
+            taxon[f[1]] = f[3]
+    return [taxon[s] for s in order if taxon[s] not in ("", "0")]
+
+
+def ppp_scan(ctx: capi.Context, query: Profile, targets: dict, prob=None):
+    """Score one query profile against every target hit list in ONE GPU call (replaces the chunk files, forked
+    `ppp.pl --client` workers and per-gene Perl sweeps of bin/ppp.pl:354-462, 519-593).
+    targets: {locus: path of a .bla file | ordered taxon list}.  Returns [(locus, score, yes, number, depth, p)]."""
+    q = query.get_hash()
+    loci = list(targets)
+    lists = [read_bla(t) if isinstance(t, (str, os.PathLike)) else list(t) for t in targets.values()]
+    p = float(prob) if prob else query.get_yes() / query.get_total()  # bin/ppp.pl:559-572, ppp.pm:138-142
+    if not loci:
+        return []
+    index = packer.universe_index(list(q.keys()))
+    P, Y, _ = packer.pack_queries([q], index)
+    idx, raw, off = packer.pack_ranked_targets(lists, index)
+    ctx.set_targets_ranked(idx, raw, off, len(index))
+    hits = ctx.score(P, Y, np.array([p], dtype=np.float64))
+    return [(loci[int(h["t"])], float(h["score"]), int(h["yes"]), int(h["number"]), int(h["depth"]), p) for h in hits]
+
+
+def _perl_num(x: float) -> float:
+    """The client writes $score / $p with Perl's default %.15g stringification before the server reads them back
+    (bin/ppp.pl:582, 443-462)."""
+    return float("%.15g" % x)
+
+
+def _log10_3f(score: float) -> str:
+    if score == 0:
+        raise ValueError("Can't take log of 0")  # bin/ppp.pl:476 dies the same way
+    return "%.3f" % (math.log(score) / math.log(10))
+
+
+def _handle_negative_zero(s: str) -> str:
+    # bin/ppp.pl:595-604: "-0.000" -> "0.000"
+    if s.startswith("-") and set(s[1:]) <= set("0."):
+        return s[1:]
+    return s
+
+
+def format_ppp_table(rows, slope=None, desc=None) -> str:
+    """stdout of the ppp.pl server (bin/ppp.pl:468-506): header, rows sorted ascending by raw score, `%.3f` Prob and
+    log10 Score, optional slope marker line.  Ties in the raw score are ordered by locus here (hash order in Perl)."""
+    out = ["Locus\t#Yes\t#Total\tDepth\tProb\tScore\tDesc\n"]
+    rows = sorted(((loc, _perl_num(s), y, n, d, _perl_num(p)) for loc, s, y, n, d, p in rows), key=lambda r: (r[1], str(r[0])))
+    last_score = None
+    cutoff_found = False
+    for loc, s, y, n, d, p in rows:
+        log_score = _log10_3f(s)
+        if last_score is None:
+            last_score = log_score  # set once to the best row, never updated (bin/ppp.pl:477)
+        if slope and not cutoff_found:
+            pl, ps = abs(float(last_score)), abs(float(log_score))
+            if pl == 0:
+                raise ZeroDivisionError("Illegal division by zero")
+            if (pl - ps) / pl * 100 > float(slope):
+                out.append("-------------------------------------------\n")
+                cutoff_found = True
+        out.append(f"{loc}\t{y}\t{n}\t{d}\t{'%.3f' % p}\t{_handle_negative_zero(log_score)}\t{(desc or {}).get(loc, '')}\n")
+    return "".join(out)
+
+
+def ppp_cutoff(table_text: str, slope: float):
+    """bin/ppp_cutoff.pl:111-162 on the text of a ppp.pl table.  Returns (stdout text, cutoff or None)."""
+    lines = table_text.split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    header = lines[0] + "\n" if lines else ""
+    kept, scores = [], []
+    for line in lines[1:]:
+        if line and set(line) == {"-"}:
+            continue
+        kept.append(line)
+        if not line.startswith("#"):
+            f = line.split("\t")
+            if float(f[5]) > -0.001:
+                continue
+            scores.append(float(f[5]))
+    cutoff = None
+    last = None
+    for s in sorted(scores, reverse=True):
+        if s > -1:
+            continue
+        if not last:
+            last = s
+            continue
+        if abs((last - s) / last * 100) > slope:
+            cutoff = last
+            break
+        last = s
+    out = [header, "Significant hits:\n"]
+    marker = False
+    for line in kept:
+        f = line.split("\t")
+        v = float(f[5])
+        if v >= 0:
+            continue
+        if v > (cutoff if cutoff is not None else 0.0) and not marker:
+            out.append("Insignificant hits:\n")
+            marker = True
+        out.append(line + "\n")
+    return "".join(out), cutoff

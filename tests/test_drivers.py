@@ -1,0 +1,89 @@
+"""Either side of the hot path: the `.bla` reader, the ppp.pl stdout table and the ppp_cutoff.pl
+slope filter, against golden outputs of the UNMODIFIED reference drivers (oracle/gen_golden_e2e.py ran bin/ppp.pl with
+forked clients and bin/ppp_cutoff.pl in the build container)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from prophylo_b200 import drivers
+from prophylo_b200.algorithm import Profile
+
+
+@pytest.fixture(scope="module")
+def e2e(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "ppp_pl_e2e.json")))["cases"]
+
+
+def materialise(case, tmp_path):
+    d = tmp_path / f"case{case['seed']}"
+    (d / "bla").mkdir(parents=True)
+    (d / "q.profile").write_text(case["profile"])
+    paths = {}
+    for gi, txt in case["bla"].items():
+        p = d / "bla" / f"{gi}.bla"
+        p.write_text(txt)
+        paths[gi] = str(p)
+    return str(d / "q.profile"), paths
+
+
+def normalise(table):
+    """The reference orders rows with equal raw score by Perl hash order (bin/ppp.pl:473-474): compare tie groups as
+    sets -- rows are grouped by their printed Score column and sorted inside a group; marker lines stay in place."""
+    lines = table.rstrip("\n").split("\n")
+    out, group, key = [lines[0]], [], None
+    for ln in lines[1:]:
+        k = ln.split("\t")[5] if "\t" in ln else ln
+        if k != key and group:
+            out += sorted(group)
+            group = []
+        key = k
+        group.append(ln)
+    return out + sorted(group)
+
+
+def test_ppp_cutoff_matches_reference_script(e2e):
+    n = 0
+    for case in e2e:
+        for slope, ref in case["cutoff"].items():
+            text, cutoff = drivers.ppp_cutoff(case["ppp_pl_stdout"], float(slope))
+            assert text == ref["stdout"], (case["seed"], slope)
+            exp = [ln for ln in ref["stderr"].split("\n") if ln.startswith("CUTOFF=")][-1]
+            if exp == "CUTOFF=":
+                assert cutoff is None
+            else:
+                assert float(exp[7:]) == cutoff
+            n += 1
+    assert n == 12
+
+
+def test_table_format_matches_reference_with_oracle_scores(e2e, tmp_path):
+    """CPU-only check of the reader + formatter: rows scored by the oracle, table must equal ppp.pl's stdout."""
+    for case in e2e:
+        prof, paths = materialise(case, tmp_path)
+        q = Profile(file=prof)
+        qd = {k: int(v) for k, v in q.get_hash().items()}
+        rows = []
+        for gi, path in paths.items():
+            lst = drivers.read_bla(path)
+            s, y, n, d, p = oracle.score_case(qd, lst, case["prob"])
+            rows.append((gi, s, y, n, d, p))
+        got = drivers.format_ppp_table(rows, slope=case["slope"])
+        assert normalise(got) == normalise(case["ppp_pl_stdout"]), case["seed"]
+
+
+@pytest.mark.gpu
+def test_ppp_scan_on_gpu_reproduces_ppp_pl_stdout(e2e, tmp_path):
+    """One query profile vs a genome's genes in ONE GPU call (ranked targets), formatted: byte-identical to the stdout of
+    the reference's bin/ppp.pl server run (modulo Perl's hash order inside score ties)."""
+    from prophylo_b200 import capi
+
+    ctx = capi.Context(0)
+    for case in e2e:
+        prof, paths = materialise(case, tmp_path)
+        rows = drivers.ppp_scan(ctx, Profile(file=prof), paths, prob=case["prob"])
+        got = drivers.format_ppp_table(rows, slope=case["slope"])
+        assert normalise(got) == normalise(case["ppp_pl_stdout"]), case["seed"]
+    ctx.close()
