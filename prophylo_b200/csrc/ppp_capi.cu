@@ -37,6 +37,7 @@ extern "C" cudaError_t ppp_launch_staircase(const QConst *qc, const double *lf, 
 extern "C" cudaError_t ppp_launch_topk_merge(const void *appended, uint32_t *qcnt, uint32_t qcap, void *topk, uint32_t *topk_cnt,
                                              double *kth, uint32_t k, uint32_t nQ, uint32_t t_offset, int nsm, cudaStream_t st);
 extern "C" int ppp_topk_max_k(void);
+extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const unsigned long long *counters, int n, cudaStream_t st);
 
 struct ppp_ctx {
     int device = 0;
@@ -44,6 +45,11 @@ struct ppp_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double phase_us[4] = {0, 0, 0, 0}; /* sweep, exact, staircase, merge */
+    std::vector<cudaEvent_t> evpool; /* deferred per-chunk timing: events are read after the final synchronize */
+    size_t ev_used = 0;
+    struct Span { size_t a, b; int phase; }; /* phase: 0 sweep, 1 exact, 2 staircase, 3 merge, 4 prefilter */
+    std::vector<Span> spans;
+    unsigned long long *d_totals = nullptr; /* [CNT_N + 1] accumulated on the device across chunks */
     unsigned long long survivors = 0, prefilter_pairs = 0;
     double prefilter_us = 0;
     char err[512] = {0};
@@ -79,6 +85,8 @@ struct ppp_ctx {
     size_t n_results = 0;
     std::vector<ppp_hit> host_results; /* filtered modes: finalised on the host side of the ABI */
     bool results_on_host = false;
+    bool results_topk = false;           /* results are the device top-k lists (d_topk, counts in topk_counts) */
+    std::vector<uint32_t> topk_counts;
     uint32_t *d_exact = nullptr;
     size_t cap_exact = 0;
     unsigned long long *d_counters = nullptr;
@@ -180,6 +188,11 @@ extern "C" int ppp_init(ppp_ctx **out, const int *devices, int ndev)
         delete ctx;
         return PPP_ERR_CUDA;
     }
+    if ((e = cudaMalloc(&ctx->d_totals, (CNT_N + 1) * sizeof(unsigned long long))) != cudaSuccess) {
+        fail(nullptr, PPP_ERR_CUDA, "ppp_init: %s", cudaGetErrorString(e));
+        delete ctx;
+        return PPP_ERR_CUDA;
+    }
     *out = ctx;
     return PPP_OK;
 }
@@ -202,6 +215,8 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaFree(ctx->d_hits);
     cudaFree(ctx->d_exact);
     cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_totals);
+    for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
     cudaFree(ctx->d_kth);
     cudaFree(ctx->d_qcnt);
     cudaFree(ctx->d_off);
@@ -434,6 +449,55 @@ static void base_params(const ppp_ctx *ctx, SweepParams *prm)
     prm->roff = ctx->d_roff;
 }
 
+static int mark(ppp_ctx *ctx, size_t *idx)
+{
+    if (ctx->ev_used == ctx->evpool.size()) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        ctx->evpool.push_back(e);
+    }
+    *idx = ctx->ev_used++;
+    CU(cudaEventRecord(ctx->evpool[*idx], ctx->stream));
+    return PPP_OK;
+}
+
+/* one target chunk without any host synchronisation (top-k runs): counters are accumulated on the device, event
+ * spans are resolved after the run's final synchronize */
+static int launch_chunk_deferred(ppp_ctx *ctx, SweepParams *prm, uint32_t *launches, bool prefiltered)
+{
+    const int W = 32 * ctx->wpl;
+    int rc;
+    size_t e0, e1, e2, em = 0;
+    CU(cudaMemsetAsync(ctx->d_counters, 0, (CNT_N + 1) * sizeof(unsigned long long), ctx->stream));
+    if ((rc = mark(ctx, &e0))) return rc;
+    if (prefiltered) {
+        if (ctx->ev_used == ctx->evpool.size()) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            ctx->evpool.push_back(e);
+        }
+        em = ctx->ev_used++;
+        CU(ppp_launch_filtered(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qflags, ctx->d_surv, ctx->d_counters + CNT_N, ctx->cap_surv,
+                               ctx->sweep_warps, ctx->nsm, ctx->stream, ctx->evpool[em]));
+        *launches += 1;
+        ctx->spans.push_back({e0, em, 4});
+        ctx->prefilter_pairs += (unsigned long long)prm->nQ * (prm->t1 - prm->t0);
+    } else if (ctx->ranked) {
+        CU(ppp_launch_sweep_ranked(prm, ctx->rwpl, ctx->sweep_warps, ctx->nsm, ctx->stream));
+    } else {
+        CU(ppp_launch_sweep(prm, ctx->wpl, ctx->sweep_warps, ctx->nsm, ctx->stream));
+    }
+    if ((rc = mark(ctx, &e1))) return rc;
+    if (ctx->ranked) CU(ppp_launch_exact_ranked(prm, ctx->rwpl, ctx->nsm, ctx->stream));
+    else CU(ppp_launch_exact(prm, W, ctx->nsm, ctx->stream));
+    if ((rc = mark(ctx, &e2))) return rc;
+    CU(ppp_launch_accumulate(ctx->d_totals, ctx->d_counters, CNT_N + 1, ctx->stream));
+    *launches += 3;
+    ctx->spans.push_back({e0, e1, 0});
+    ctx->spans.push_back({e1, e2, 1});
+    return PPP_OK;
+}
+
 /* one target chunk: sweep + exact tier; accumulates counters and the sweep kernel's event time */
 static int run_chunk(ppp_ctx *ctx, SweepParams *prm, unsigned long long *totals, float *sweep_ms, uint32_t *launches,
                      unsigned long long *chunk_counters, bool prefiltered)
@@ -494,6 +558,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
 
     ctx->host_results.clear();
     ctx->results_on_host = (f->mode != PPP_FILTER_ALL);
+    ctx->results_topk = false;
     ctx->last_topk_k = 0;
     unsigned long long totals[CNT_N];
     memset(totals, 0, sizeof(totals));
@@ -525,7 +590,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         /* filtered: per-query staircases prune almost every pair inside the sweep kernel; survivors are appended */
         const bool topk = (f->mode == PPP_FILTER_TOPK);
         const uint32_t k = f->k;
-        const size_t maxw = std::min<size_t>(nT, std::max<size_t>(256, ((size_t)1 << 28) / nQ));
+        const size_t maxw = std::min<size_t>(nT, std::max<size_t>(256, ((size_t)1 << 29) / nQ));
         if ((rc = grow(ctx, &ctx->d_hits, &ctx->cap_hits, nQ * maxw))) return rc;
         if ((rc = grow(ctx, &ctx->d_exact, &ctx->cap_exact, nQ * maxw))) return rc;
         if ((rc = grow(ctx, &ctx->d_kth, &ctx->cap_kth, 2 * nQ))) return rc; /* [nQ] k-th scores, [nQ] tau of the resident staircase */
@@ -552,64 +617,16 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             CU(cudaStreamSynchronize(ctx->stream));
         }
         const double thresh_ln = f->thresh * 2.302585092994045684;
-        if (!topk) {
-            CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 1, thresh_ln, d_off_static, ctx->d_nmax, d_off_active,
-                                    ctx->d_kth + nQ, (uint32_t)nQ, ctx->nsm, ctx->stream));
-            launches++;
-        }
         size_t processed = 0;
         bool seeded_pass = false;
-        bool seeded = !topk; /* top-k: thresholds are seeded from cheap upper bounds of the first targets' scores */
-        while (processed < nT) {
-            if (!seeded) {
-                /* Seeding pass: the k-th smallest UPPER bound (float enclosure only, no series, no exact tier) over the
-                 * first targets is a valid threshold for the query's k-th best score; the provisional records are then
-                 * dropped and every target -- these included -- goes through the screened path. */
-                const size_t w0 = std::min<size_t>(std::min(maxw, nT), std::max<size_t>(256, 3 * (size_t)k));
-                if (w0 < (size_t)k) {
-                    seeded = true; /* fewer targets than k: nothing to prune */
-                } else {
-                    SweepParams prm;
-                    base_params(ctx, &prm);
-                    prm.hits = ctx->d_hits;
-                    prm.t0 = 0;
-                    prm.t1 = (uint32_t)w0;
-                    prm.append = 1;
-                    prm.accept_mode = 0;
-                    prm.kth = ctx->d_kth;
-                    prm.nmax = ctx->d_nmax;
-                    prm.nmax_off = d_off_active;
-                    prm.qcnt = d_qcnt;
-                    prm.qcap = (uint32_t)maxw;
-                    prm.bounds_only = 1;
-                    unsigned long long c[CNT_N];
-                    if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c, false))) return rc;
-                    sweep_launches++;
-                    CU(ppp_launch_topk_merge(ctx->d_hits, d_qcnt, (uint32_t)maxw, ctx->d_topk, d_topk_cnt, ctx->d_kth, k, (uint32_t)nQ,
-                                             0u, ctx->nsm, ctx->stream));
-                    CU(cudaMemsetAsync(d_topk_cnt, 0, nQ * sizeof(uint32_t), ctx->stream)); /* drop the provisional records, keep kth */
-                    launches++;
-                    seeded = true;
-                    seeded_pass = true;
-                }
-            }
-            size_t w = std::min(maxw, nT - processed);
-            if (topk) {
-                const size_t first = std::max<size_t>(256, 3 * (size_t)k);
-                w = std::min(w, processed ? 4 * processed : (seeded_pass ? 4 * first : first));
-            }
-            if (topk && (processed || seeded_pass)) {
-                CU(cudaEventRecord(ctx->ev[5], ctx->stream));
-                CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 0, 0.0, d_off_static, ctx->d_nmax, d_off_active,
-                                        ctx->d_kth + nQ, (uint32_t)nQ, ctx->nsm, ctx->stream));
-                CU(cudaEventRecord(ctx->ev[6], ctx->stream));
-                launches++;
-            }
-            SweepParams prm;
+        ctx->ev_used = 0;
+        ctx->spans.clear();
+        CU(cudaMemsetAsync(ctx->d_totals, 0, (CNT_N + 1) * sizeof(unsigned long long), ctx->stream));
+        auto fill_filtered = [&](SweepParams &prm, size_t t0, size_t t1) {
             base_params(ctx, &prm);
             prm.hits = ctx->d_hits;
-            prm.t0 = (uint32_t)processed;
-            prm.t1 = (uint32_t)(processed + w);
+            prm.t0 = (uint32_t)t0;
+            prm.t1 = (uint32_t)t1;
             prm.append = topk ? 1 : 2;
             prm.accept_mode = topk ? 0 : 1;
             prm.thresh_log10 = f->thresh;
@@ -618,48 +635,99 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             prm.nmax_off = d_off_active;
             prm.qcnt = d_qcnt;
             prm.qcap = (uint32_t)maxw;
-            unsigned long long c[CNT_N];
-            /* the first top-k chunk has no thresholds yet: tile kernel over every pair; afterwards thread-per-pair screen */
-            if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c, !ctx->ranked && !(topk && !processed && !seeded_pass)))) return rc;
-            sweep_launches++;
-            if (topk && (processed || seeded_pass)) {
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
-                ctx->phase_us[2] += 1e3 * ms;
-            }
-            if (topk) {
-                CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+        };
+        if (topk) {
+            /* ---- top-k: no host synchronisation until the lists are final ---- */
+            const size_t first = std::max<size_t>(256, 3 * (size_t)k);
+            const size_t w0 = std::min<size_t>(std::min(maxw, nT), first);
+            if (w0 >= (size_t)k) {
+                /* Seeding pass: the k-th smallest UPPER bound (float enclosure only, no series, no exact tier) over the
+                 * first targets is a valid threshold for the query's k-th best score; the provisional records are then
+                 * dropped and every target -- these included -- goes through the screened path. */
+                SweepParams prm;
+                fill_filtered(prm, 0, w0);
+                prm.bounds_only = 1;
+                if ((rc = launch_chunk_deferred(ctx, &prm, &launches, false))) return rc;
+                sweep_launches++;
                 CU(ppp_launch_topk_merge(ctx->d_hits, d_qcnt, (uint32_t)maxw, ctx->d_topk, d_topk_cnt, ctx->d_kth, k, (uint32_t)nQ,
                                          0u, ctx->nsm, ctx->stream));
-                CU(cudaEventRecord(ctx->ev[6], ctx->stream));
-                CU(cudaEventSynchronize(ctx->ev[6]));
-                float ms = 0.f;
-                cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
-                ctx->phase_us[3] += 1e3 * ms;
+                CU(cudaMemsetAsync(d_topk_cnt, 0, nQ * sizeof(uint32_t), ctx->stream)); /* drop the provisional records, keep kth */
                 launches++;
-            } else if (c[CNT_APPEND]) {
-                const size_t old = ctx->host_results.size();
-                ctx->host_results.resize(old + c[CNT_APPEND]);
-                CU(cudaMemcpyAsync(ctx->host_results.data() + old, ctx->d_hits, c[CNT_APPEND] * sizeof(ppp_hit),
-                                   cudaMemcpyDeviceToHost, ctx->stream));
-                CU(cudaStreamSynchronize(ctx->stream));
+                seeded_pass = true;
             }
-            processed += w;
-        }
-        if (topk) {
-            std::vector<uint32_t> cnt(nQ);
-            std::vector<ppp_hit> lists(nQ * (size_t)k);
-            CU(cudaMemcpyAsync(cnt.data(), d_topk_cnt, nQ * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaMemcpyAsync(lists.data(), ctx->d_topk, lists.size() * sizeof(ppp_hit), cudaMemcpyDeviceToHost, ctx->stream));
+            while (processed < nT) {
+                size_t w = std::min(maxw, nT - processed);
+                w = std::min(w, processed ? 4 * processed : (seeded_pass ? 4 * first : first));
+                size_t ea, eb;
+                if (processed || seeded_pass) {
+                    if ((rc = mark(ctx, &ea))) return rc;
+                    CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 0, 0.0, d_off_static, ctx->d_nmax, d_off_active,
+                                            ctx->d_kth + nQ, (uint32_t)nQ, ctx->nsm, ctx->stream));
+                    if ((rc = mark(ctx, &eb))) return rc;
+                    ctx->spans.push_back({ea, eb, 2});
+                    launches++;
+                }
+                SweepParams prm;
+                fill_filtered(prm, processed, processed + w);
+                /* without thresholds (fewer targets than k so far): tile kernel over every pair; otherwise thread-per-pair screen */
+                if ((rc = launch_chunk_deferred(ctx, &prm, &launches, !ctx->ranked && (processed || seeded_pass)))) return rc;
+                sweep_launches++;
+                if ((rc = mark(ctx, &ea))) return rc;
+                CU(ppp_launch_topk_merge(ctx->d_hits, d_qcnt, (uint32_t)maxw, ctx->d_topk, d_topk_cnt, ctx->d_kth, k, (uint32_t)nQ,
+                                         0u, ctx->nsm, ctx->stream));
+                if ((rc = mark(ctx, &eb))) return rc;
+                ctx->spans.push_back({ea, eb, 3});
+                launches++;
+                processed += w;
+            }
+            unsigned long long c[CNT_N + 1];
+            CU(cudaMemcpyAsync(c, ctx->d_totals, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
-            for (size_t q = 0; q < nQ; ++q)
-                ctx->host_results.insert(ctx->host_results.end(), lists.begin() + q * k, lists.begin() + q * k + cnt[q]);
+            for (int i = 0; i < CNT_N; ++i) totals[i] += c[i];
+            ctx->survivors = c[CNT_N];
+            if (c[CNT_OVERFLOW]) return fail(ctx, PPP_ERR_CUDA, "ppp_run: internal buffer overflow (%llu records dropped)", c[CNT_OVERFLOW]);
+            for (const ppp_ctx::Span &sp : ctx->spans) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ctx->evpool[sp.a], ctx->evpool[sp.b]);
+                if (sp.phase == 4) ctx->prefilter_us += 1e3 * ms;
+                else ctx->phase_us[sp.phase] += 1e3 * ms;
+                if (sp.phase == 0) sweep_ms += ms;
+            }
+            /* the lists stay on the device (ppp_fetch copies them straight into the caller's buffer) */
             ctx->last_topk_k = k;
             ctx->last_topk_nq = nQ;
+            ctx->topk_counts.resize(nQ);
+            CU(cudaMemcpyAsync(ctx->topk_counts.data(), d_topk_cnt, nQ * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            size_t n = 0;
+            for (size_t q = 0; q < nQ; ++q) n += ctx->topk_counts[q];
+            ctx->n_results = n;
+            ctx->results_on_host = false;
+            ctx->results_topk = true;
         } else {
+            /* ---- threshold: one staircase build, survivors of every chunk are copied out as they come ---- */
+            CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 1, thresh_ln, d_off_static, ctx->d_nmax, d_off_active,
+                                    ctx->d_kth + nQ, (uint32_t)nQ, ctx->nsm, ctx->stream));
+            launches++;
+            while (processed < nT) {
+                const size_t w = std::min(maxw, nT - processed);
+                SweepParams prm;
+                fill_filtered(prm, processed, processed + w);
+                unsigned long long c[CNT_N];
+                if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c, !ctx->ranked))) return rc;
+                sweep_launches++;
+                if (c[CNT_APPEND]) {
+                    const size_t old = ctx->host_results.size();
+                    ctx->host_results.resize(old + c[CNT_APPEND]);
+                    CU(cudaMemcpyAsync(ctx->host_results.data() + old, ctx->d_hits, c[CNT_APPEND] * sizeof(ppp_hit),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+                    CU(cudaStreamSynchronize(ctx->stream));
+                }
+                processed += w;
+            }
             std::sort(ctx->host_results.begin(), ctx->host_results.end(), hit_less); /* presentation order only */
+            ctx->n_results = ctx->host_results.size();
         }
-        ctx->n_results = ctx->host_results.size();
     }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -693,7 +761,22 @@ extern "C" int ppp_fetch(ppp_ctx *ctx, ppp_hit *out, size_t cap, size_t *nout)
     if (!ctx->n_results) return PPP_OK;
     if (!out) return fail(ctx, PPP_ERR_INVALID, "ppp_fetch: out is NULL");
     CU(cudaSetDevice(ctx->device));
-    if (ctx->results_on_host) {
+    if (ctx->results_topk) {
+        const size_t nQ = ctx->last_topk_nq, k = ctx->last_topk_k;
+        if (ctx->n_results == nQ * k) { /* every list is full: one copy straight into the caller's buffer */
+            CU(cudaMemcpyAsync(out, ctx->d_topk, nQ * k * sizeof(ppp_hit), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        } else {
+            std::vector<ppp_hit> lists(nQ * k);
+            CU(cudaMemcpyAsync(lists.data(), ctx->d_topk, lists.size() * sizeof(ppp_hit), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            size_t o = 0;
+            for (size_t q = 0; q < nQ; ++q) {
+                memcpy(out + o, lists.data() + q * k, ctx->topk_counts[q] * sizeof(ppp_hit));
+                o += ctx->topk_counts[q];
+            }
+        }
+    } else if (ctx->results_on_host) {
         memcpy(out, ctx->host_results.data(), ctx->n_results * sizeof(ppp_hit));
     } else {
         CU(cudaMemcpyAsync(out, ctx->d_hits, ctx->n_results * sizeof(ppp_hit), cudaMemcpyDeviceToHost, ctx->stream));

@@ -175,3 +175,14 @@ extern "C" cudaError_t ppp_launch_topk_merge(const void *appended, uint32_t *qcn
 }
 
 extern "C" int ppp_topk_max_k(void) { return TOPK_M / 2; }
+
+__global__ void ppp_accumulate_kernel(unsigned long long *totals, const unsigned long long *counters, int n)
+{
+    if ((int)threadIdx.x < n) totals[threadIdx.x] += counters[threadIdx.x];
+}
+
+extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const unsigned long long *counters, int n, cudaStream_t st)
+{
+    ppp_accumulate_kernel<<<1, 32, 0, st>>>(totals, counters, n);
+    return cudaGetLastError();
+}
