@@ -133,3 +133,69 @@ def ppp_cutoff(table_text: str, slope: float):
             marker = True
         out.append(line + "\n")
     return "".join(out), cutoff
+
+
+def ppp2d_prefix_queries(gi: str, bla_path, taxdis, start=5, end=None, skip=1, total_taxa=1459):
+    """The depth-prefix query profiles of bin/ppp2d.pl:253-315 for one gene: walk its `.bla` lines; the self hit only
+    marks its taxon; a subject whose taxon was already seen is skipped; at every remaining line (subject to --skip,
+    --start-depth, --end-depth) the profile is {seen taxa: 1, every other taxon of data/taxdis.txt: 0} and
+    p = taxon_count / 1459 (the reference's hard-coded $total_taxa_count, passed through `--prob` as a %.15g string).
+    Returns [(line_count, taxon_count, profile dict, p)]."""
+    out, seen, line_count = [], {}, 0
+    with open(bla_path) as fh:
+        for line in fh:
+            line_count += 1
+            f = line.rstrip("\n").split("\t")
+            if f[0] == f[1]:
+                seen[f[3]] = 1
+                continue
+            if f[3] in seen:
+                continue
+            seen[f[3]] = 1
+            if line_count % skip:
+                continue
+            tc = len(seen)
+            if end and tc > end:
+                break
+            if tc >= start:
+                prof = {t: 1 for t in seen}
+                for t in taxdis:
+                    if t not in seen:
+                        prof[t] = 0
+                out.append((line_count, tc, prof, float("%.15g" % (tc / total_taxa))))
+    return out
+
+
+def ppp2d_scan(ctx: capi.Context, gi: str, bla_path, genome_targets: dict, taxdis, start=5, end=None, skip=1, total_taxa=1459):
+    """bin/ppp2d.pl in process: every depth prefix of gene `gi`'s hit list is one query, all of them are scored against
+    every gene of the genome in ONE GPU call (the reference forks `perl ppp.pl` once per depth, bin/ppp2d.pl:317-320),
+    the best non-self locus per depth is kept unless its printed score is 0.000, rows are sorted by printed score.
+    Returns the stdout text of ppp2d.pl (bin/ppp2d.pl:354-364)."""
+    qs = ppp2d_prefix_queries(gi, bla_path, taxdis, start, end, skip, total_taxa)
+    header = "#Subject_best_depth\tLocus\t#Yes\t#Total\tDepth\tProb\tScore\tDesc\n"
+    if not qs:
+        return header
+    loci = list(genome_targets)
+    lists = [read_bla(t) if isinstance(t, (str, os.PathLike)) else list(t) for t in genome_targets.values()]
+    universe = list(qs[-1][2].keys())  # the last prefix profile holds every taxon any prefix uses
+    index = packer.universe_index(universe)
+    P, Y, _ = packer.pack_queries([q[2] for q in qs], index)
+    p = np.array([q[3] for q in qs], dtype=np.float64)
+    idx, raw, off = packer.pack_ranked_targets(lists, index)
+    ctx.set_targets_ranked(idx, raw, off, len(index))
+    k = min(2, len(loci))
+    hits = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
+    rows = []
+    for qi, (line_count, tc, _, pq) in enumerate(qs):
+        mine = [h for h in hits[hits["q"] == qi] if loci[int(h["t"])] != gi]
+        if not mine:
+            continue
+        h = mine[0]
+        s = _perl_num(float(h["score"]))
+        score_str = _handle_negative_zero(_log10_3f(s))
+        if float(score_str) == 0.0:  # bin/ppp2d.pl:340 compares the PRINTED score
+            continue
+        fields = [loci[int(h["t"])], str(int(h["yes"])), str(int(h["number"])), str(int(h["depth"])), "%.3f" % _perl_num(pq), score_str, ""]
+        rows.append((float(score_str), line_count, fields))
+    rows.sort(key=lambda r: (r[0], r[1]))
+    return header + "".join(f"{lc}\t" + "\t".join(f) + "\n" for _, lc, f in rows)

@@ -87,3 +87,43 @@ def test_ppp_scan_on_gpu_reproduces_ppp_pl_stdout(e2e, tmp_path):
         got = drivers.format_ppp_table(rows, slope=case["slope"])
         assert normalise(got) == normalise(case["ppp_pl_stdout"]), case["seed"]
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_ppp2d_in_process_matches_oracle_restatement(e2e, tmp_path):
+    """bin/ppp2d.pl:253-364 in one GPU call vs the same driver logic scored pair by pair with the oracle."""
+    import math
+
+    from prophylo_b200 import capi
+
+    case = e2e[3]
+    prof, paths = materialise(case, tmp_path)
+    gi = sorted(paths)[4]
+    taxdis = [str(1000 + i) for i in range(0, 400, 2)]
+    ctx = capi.Context(0)
+    got = drivers.ppp2d_scan(ctx, gi, paths[gi], paths, taxdis, start=3, skip=1, total_taxa=1459)
+    ctx.close()
+    # oracle restatement
+    lists = {g: drivers.read_bla(p) for g, p in paths.items()}
+    rows = []
+    for line_count, tc, profq, pq in drivers.ppp2d_prefix_queries(gi, paths[gi], taxdis, start=3):
+        best = None
+        for g, lst in lists.items():
+            if g == gi:
+                continue
+            s, y, n, d, _ = oracle.score_case(profq, lst, pq)
+            key = (float("%.15g" % s), list(paths).index(g))
+            if best is None or key < best[0]:
+                best = (key, g, y, n, d)
+        (s, _), g, y, n, d = best
+        sc = "%.3f" % (math.log(s) / math.log(10))
+        if sc.startswith("-") and set(sc[1:]) <= set("0."):
+            sc = sc[1:]
+        if float(sc) == 0:
+            continue
+        rows.append((float(sc), line_count, [g, str(y), str(n), str(d), "%.3f" % float("%.15g" % pq), sc, ""]))
+    rows.sort(key=lambda r: (r[0], r[1]))
+    exp = "#Subject_best_depth\tLocus\t#Yes\t#Total\tDepth\tProb\tScore\tDesc\n" + "".join(
+        f"{lc}\t" + "\t".join(f) + "\n" for _, lc, f in rows)
+    assert len(rows) > 5
+    assert got == exp
