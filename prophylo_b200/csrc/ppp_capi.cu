@@ -183,7 +183,7 @@ extern "C" int ppp_init(ppp_ctx **out, const int *devices, int ndev)
         return PPP_ERR_CUDA;
     }
     for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
-    if ((e = cudaMalloc(&ctx->d_counters, (CNT_N + 1) * sizeof(unsigned long long))) != cudaSuccess) {
+    if ((e = cudaMalloc(&ctx->d_counters, CNT_SLOTS * sizeof(unsigned long long))) != cudaSuccess) {
         fail(nullptr, PPP_ERR_CUDA, "ppp_init: %s", cudaGetErrorString(e));
         delete ctx;
         return PPP_ERR_CUDA;
@@ -468,7 +468,7 @@ static int launch_chunk_deferred(ppp_ctx *ctx, SweepParams *prm, uint32_t *launc
     const int W = 32 * ctx->wpl;
     int rc;
     size_t e0, e1, e2, em = 0;
-    CU(cudaMemsetAsync(ctx->d_counters, 0, (CNT_N + 1) * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_SLOTS * sizeof(unsigned long long), ctx->stream));
     if ((rc = mark(ctx, &e0))) return rc;
     if (prefiltered) {
         if (ctx->ev_used == ctx->evpool.size()) {
@@ -503,7 +503,7 @@ static int run_chunk(ppp_ctx *ctx, SweepParams *prm, unsigned long long *totals,
                      unsigned long long *chunk_counters, bool prefiltered)
 {
     const int W = 32 * ctx->wpl;
-    CU(cudaMemsetAsync(ctx->d_counters, 0, (CNT_N + 1) * sizeof(unsigned long long), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_SLOTS * sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (prefiltered) {
         CU(ppp_launch_filtered(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qflags, ctx->d_surv, ctx->d_counters + CNT_N, ctx->cap_surv,

@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #define PPP_QTILE 32      /* queries per shared-memory tile = lanes of a warp (lane i keeps query i's result) */
+#define PPP_SB 128       /* targets per work item of the tile kernels (warps draw them dynamically) */
 #define PPP_QCAP 512      /* candidates per warp queue pass */
 #define PPP_K_TERMS 8     /* series terms of the float enclosure tier */
 
@@ -73,7 +74,10 @@ struct SweepParams {
 #define PPP_NO_TABLE 0xffffffffu
 
 enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_ACCURATE = 2, CNT_VIOL = 3, CNT_CHECKS = 4, CNT_OVERFLOW = 5, CNT_APPEND = 6,
-       CNT_FULL = 7, CNT_N = 8 };
+       CNT_FULL = 7, CNT_N = 8,
+       CNT_SURV = 8, /* survivor count of the pre-filter (slot CNT_N) */
+       CNT_ITEM = 9, /* work-item counter of the tile kernels */
+       CNT_SLOTS = 10 };
 
 #ifdef __CUDACC__
 #include "../../include/ppp_b200.h"
