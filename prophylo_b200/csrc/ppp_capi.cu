@@ -37,6 +37,8 @@ extern "C" cudaError_t ppp_launch_staircase(const QConst *qc, const double *lf, 
 extern "C" cudaError_t ppp_launch_topk_merge(const void *appended, uint32_t *qcnt, uint32_t qcap, void *topk, uint32_t *topk_cnt,
                                              double *kth, uint32_t k, uint32_t nQ, uint32_t t_offset, int nsm, cudaStream_t st);
 extern "C" int ppp_topk_max_k(void);
+extern "C" cudaError_t ppp_launch_topk_merge_lists(const void *lists, const uint32_t *counts, uint32_t nlists, const uint32_t *t_offsets,
+                                                   uint32_t nQ, uint32_t k, void *out, uint32_t *out_cnt, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const unsigned long long *counters, int n, cudaStream_t st);
 
 struct ppp_ctx {
@@ -816,12 +818,19 @@ extern "C" int ppp_merge_topk_device(ppp_ctx *ctx, const ppp_hit *lists, const u
     if ((rc = grow(ctx, &ctx->d_mtopk, &ctx->cap_mtopk, nQ * (size_t)k))) return rc;
     if ((rc = grow(ctx, &ctx->d_mkth, &ctx->cap_mkth, nQ))) return rc;
     if ((rc = grow(ctx, &ctx->d_mcnt, &ctx->cap_mcnt, nQ * ((size_t)nlists + 1)))) return rc;
-    /* the merge kernel consumes (zeroes) its input counters: work on a copy */
-    CU(cudaMemcpyAsync(ctx->d_mcnt + nQ, counts, nQ * nlists * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_mcnt, 0, nQ * sizeof(uint32_t), ctx->stream));
-    for (uint32_t l = 0; l < nlists; ++l)
-        CU(ppp_launch_topk_merge(lists + (size_t)l * nQ * k, ctx->d_mcnt + nQ * ((size_t)l + 1), k, ctx->d_mtopk, ctx->d_mcnt, ctx->d_mkth,
-                                 k, (uint32_t)nQ, t_offsets[l], ctx->nsm, ctx->stream));
+    cudaError_t me = ppp_launch_topk_merge_lists(lists, counts, nlists, t_offsets, (uint32_t)nQ, k, ctx->d_mtopk, ctx->d_mcnt, ctx->nsm,
+                                                 ctx->stream);
+    if (me == cudaErrorNotSupported) {
+        /* too many records for one sort: merge list by list; the merge kernel consumes (zeroes) its input counters,
+         * so work on a copy */
+        CU(cudaMemcpyAsync(ctx->d_mcnt + nQ, counts, nQ * nlists * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_mcnt, 0, nQ * sizeof(uint32_t), ctx->stream));
+        for (uint32_t l = 0; l < nlists; ++l)
+            CU(ppp_launch_topk_merge(lists + (size_t)l * nQ * k, ctx->d_mcnt + nQ * ((size_t)l + 1), k, ctx->d_mtopk, ctx->d_mcnt, ctx->d_mkth,
+                                     k, (uint32_t)nQ, t_offsets[l], ctx->nsm, ctx->stream));
+    } else {
+        CU(me);
+    }
     CU(cudaMemcpyAsync(out, ctx->d_mtopk, nQ * (size_t)k * sizeof(ppp_hit), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(out_counts, ctx->d_mcnt, nQ * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));

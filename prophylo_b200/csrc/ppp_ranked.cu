@@ -48,18 +48,26 @@ __global__ void __launch_bounds__(256) ppp_sweep_ranked_kernel(const SweepParams
     }
     const uint32_t nTl = prm.t1 - prm.t0;
     const uint32_t nQtiles = (prm.nQ + PPP_QTILE - 1) / PPP_QTILE;
-    const uint32_t nTblocks = (nTl + nwarps - 1) / nwarps;
-    const uint64_t nItems = (uint64_t)nQtiles * nTblocks;
+    const uint32_t nSB = (nTl + PPP_SB - 1) / PPP_SB;
+    const uint64_t nItems = (uint64_t)nQtiles * nSB;
+    uint32_t *s_next = reinterpret_cast<uint32_t *>(smem_raw + 64);
+    unsigned long long *s_item = reinterpret_cast<unsigned long long *>(smem_raw + 72);
+    (void)nwarps;
     WarpCounters wc;
     uint32_t tile_parity = 0, cur_qt = 0xffffffffu;
     mbar_wait(&bars[0], 0);
 
-    for (uint64_t item = blockIdx.x; item < nItems; item += gridDim.x) {
-        const uint32_t qt = (uint32_t)(item / nTblocks), tb = (uint32_t)(item % nTblocks);
+    for (;;) { /* items from a global counter, targets of an item from a shared one (see ppp_sweep.cu) */
+        __syncthreads();
+        if (threadIdx.x == 0) *s_item = atomicAdd(&prm.counters[CNT_ITEM], 1ull);
+        __syncthreads();
+        const uint64_t item = *s_item;
+        if (item >= nItems) break;
+        const uint32_t qt = (uint32_t)(item / nSB), sb = (uint32_t)(item % nSB);
         const uint32_t q0 = qt * PPP_QTILE;
         const uint32_t nq = min((uint32_t)PPP_QTILE, prm.nQ - q0);
+        if (threadIdx.x == 0) *s_next = 0;
         if (qt != cur_qt) {
-            __syncthreads();
             if (threadIdx.x == 0) {
                 fence_proxy_async();
                 const uint32_t b1 = nq * 2 * Wg * 4, b2 = nq * (uint32_t)sizeof(QConst);
@@ -72,10 +80,15 @@ __global__ void __launch_bounds__(256) ppp_sweep_ranked_kernel(const SweepParams
             mbar_wait(&bars[1], tile_parity);
             tile_parity ^= 1;
             cur_qt = qt;
-            if (prm.append) __syncthreads();
         }
-        const uint32_t tl = tb * nwarps + warp;
-        if (tl >= nTl) continue;
+        __syncthreads();
+        const uint32_t sb_count = min((uint32_t)PPP_SB, nTl - sb * PPP_SB);
+      for (;;) {
+        uint32_t pick = 0;
+        if (lane == 0) pick = atomicAdd(s_next, 1u);
+        pick = __shfl_sync(FULL, pick, 0);
+        if (pick >= sb_count) break;
+        const uint32_t tl = sb * PPP_SB + pick;
         const uint32_t t = prm.t0 + tl;
         const unsigned long long off0 = prm.roff[t];
         const uint32_t L = (uint32_t)(prm.roff[t + 1] - off0);
@@ -142,6 +155,7 @@ __global__ void __launch_bounds__(256) ppp_sweep_ranked_kernel(const SweepParams
                 ppp_emit(prm, q, t, mine.score, mine.yes, mine.number, depth, mine.margin);
             }
         }
+      } /* targets of the item */
     }
     flush_counters(prm, wc, lane);
 }
@@ -165,7 +179,7 @@ static cudaError_t launch_ranked_t(const SweepParams &prm, int nwarps, int nsm, 
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     const uint32_t nTl = prm.t1 - prm.t0;
-    const uint64_t items = (uint64_t)((prm.nQ + PPP_QTILE - 1) / PPP_QTILE) * ((nTl + nwarps - 1) / nwarps);
+    const uint64_t items = (uint64_t)((prm.nQ + PPP_QTILE - 1) / PPP_QTILE) * ((nTl + PPP_SB - 1) / PPP_SB);
     uint64_t grid = (uint64_t)nsm * per_sm;
     if (grid > items) grid = items;
     if (grid < 1) grid = 1;

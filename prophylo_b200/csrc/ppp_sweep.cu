@@ -352,7 +352,12 @@ __global__ void __launch_bounds__(512) ppp_refine_kernel(const SweepParams prm, 
     const unsigned long long n = min(*surv_count, surv_cap);
     const uint32_t nTl = prm.t1 - prm.t0;
     WarpCounters wc;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * nwarps + warp; i < n; i += (unsigned long long)gridDim.x * nwarps) {
+    (void)nwarps;
+    for (;;) { /* survivors are drawn one at a time from a global counter: their costs differ by orders of magnitude */
+        unsigned long long i = 0;
+        if (lane == 0) i = atomicAdd(&prm.counters[CNT_ITEM], 1ull);
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= n) break;
         const uint32_t id = surv[i];
         const uint32_t q = id / nTl, tl = id % nTl, t = prm.t0 + tl;
         uint32_t tw[WPL], pw[WPL], yw[WPL], tp[WPL], ty[WPL];

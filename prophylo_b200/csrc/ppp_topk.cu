@@ -176,6 +176,82 @@ extern "C" cudaError_t ppp_launch_topk_merge(const void *appended, uint32_t *qcn
 
 extern "C" int ppp_topk_max_k(void) { return TOPK_M / 2; }
 
+/* multi-GPU exchange step: merge up to 16 gathered per-rank lists of one query in ONE sort (nlists * k <= TOPK_M) */
+struct MergeOffsets {
+    uint32_t t[16];
+};
+
+__global__ void __launch_bounds__(256) ppp_topk_merge_lists_kernel(const ppp_hit *__restrict__ lists, const uint32_t *__restrict__ counts,
+                                                                   uint32_t nlists, MergeOffsets offs, uint32_t nQ, uint32_t k,
+                                                                   ppp_hit *__restrict__ out, uint32_t *__restrict__ out_cnt)
+{
+    extern __shared__ __align__(16) unsigned char smem_topk[];
+    ppp_hit *rec = reinterpret_cast<ppp_hit *>(smem_topk);
+    __shared__ uint32_t s_base[17];
+    for (uint32_t q = blockIdx.x; q < nQ; q += gridDim.x) {
+        if (threadIdx.x == 0) {
+            uint32_t b = 0;
+            for (uint32_t l = 0; l < nlists; ++l) {
+                s_base[l] = b;
+                b += min(counts[(size_t)l * nQ + q], k);
+            }
+            s_base[nlists] = b;
+        }
+        __syncthreads();
+        const uint32_t tot = s_base[nlists];
+        for (uint32_t l = 0; l < nlists; ++l) {
+            const uint32_t c = s_base[l + 1] - s_base[l];
+            for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+                ppp_hit h = lists[((size_t)l * nQ + q) * k + i];
+                h.t += offs.t[l];
+                rec[s_base[l] + i] = h;
+            }
+        }
+        uint32_t n2 = 1;
+        while (n2 < tot) n2 <<= 1;
+        for (uint32_t i = tot + threadIdx.x; i < n2; i += blockDim.x) {
+            rec[i].score = INFINITY;
+            rec[i].t = 0xffffffffu;
+        }
+        __syncthreads();
+        for (uint32_t size = 2; size <= n2; size <<= 1) {
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t i = threadIdx.x; i < (n2 >> 1); i += blockDim.x) {
+                    const uint32_t lo = 2 * i - (i & (stride - 1));
+                    const uint32_t hi = lo + stride;
+                    const bool asc = ((lo & size) == 0);
+                    const ppp_hit a = rec[lo], b = rec[hi];
+                    if (rec_less(b, a) == asc) {
+                        rec[lo] = b;
+                        rec[hi] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        const uint32_t keep = min(tot, k);
+        for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) out[(size_t)q * k + i] = rec[i];
+        if (threadIdx.x == 0) out_cnt[q] = keep;
+        __syncthreads();
+    }
+}
+
+/* returns cudaErrorNotSupported when the lists do not fit one sort (caller falls back to sequential merges) */
+extern "C" cudaError_t ppp_launch_topk_merge_lists(const void *lists, const uint32_t *counts, uint32_t nlists, const uint32_t *t_offsets,
+                                                   uint32_t nQ, uint32_t k, void *out, uint32_t *out_cnt, int nsm, cudaStream_t st)
+{
+    if (nlists > 16 || (size_t)nlists * k > TOPK_M) return cudaErrorNotSupported;
+    MergeOffsets offs;
+    for (uint32_t l = 0; l < 16; ++l) offs.t[l] = l < nlists ? t_offsets[l] : 0u;
+    const int smem = TOPK_M * (int)sizeof(ppp_hit);
+    cudaError_t e = cudaFuncSetAttribute(ppp_topk_merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)min((uint32_t)(nsm * 2), nQ);
+    ppp_topk_merge_lists_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const ppp_hit *>(lists), counts, nlists, offs, nQ, k,
+                                                         reinterpret_cast<ppp_hit *>(out), out_cnt);
+    return cudaGetLastError();
+}
+
 __global__ void ppp_accumulate_kernel(unsigned long long *totals, const unsigned long long *counters, int n)
 {
     if ((int)threadIdx.x < n) totals[threadIdx.x] += counters[threadIdx.x];
