@@ -14,7 +14,10 @@
 
 #define PPP_QTILE 32      /* queries per shared-memory tile = lanes of a warp (lane i keeps query i's result) */
 #define PPP_SB 128       /* targets per work item of the tile kernels (warps draw them dynamically) */
-#define PPP_QCAP 512      /* candidates per warp queue pass */
+#define PPP_QCAP_MAX 512  /* candidates per warp queue pass (G > 1024) */
+/* G <= 1024 (WPL == 1): smaller queues and 64 registers fit two CTAs per SM, which pays for latency-bound sweeps */
+#define PPP_QCAP_OF(WPL) ((WPL) == 1 ? 256 : PPP_QCAP_MAX)
+#define PPP_MINBLOCKS_OF(WPL) ((WPL) == 1 ? 2 : 1)
 #define PPP_K_TERMS 8     /* series terms of the float enclosure tier */
 
 /* per-query flags */

@@ -125,9 +125,9 @@ __device__ __forceinline__ uint32_t evaluate_pair(const uint32_t (&tw)[WPL], con
                                                   const uint16_t *__restrict__ stair, const SweepParams &prm, int lane,
                                                   WarpCounters &wc, PairOut *out)
 {
+    constexpr uint32_t PPP_QCAP = PPP_QCAP_OF(WPL);
     PairOut res;
     res.score = 1.0; res.yes = 0; res.number = 0; res.depth = 0; res.margin = INFINITY;
-    uint32_t flags = 0;
 
     if (qc.flags & PPP_QF_DOMAIN) {
         /* p outside [0,1]: bdtrc -> 0.0 at the first element of the list (ppp.pm:225-241) */

@@ -19,6 +19,7 @@ template <int WPL>
 __global__ void __launch_bounds__(256) ppp_sweep_ranked_kernel(const SweepParams prm)
 {
     constexpr int NW = 32 * WPL; /* list words: up to 1024 * WPL positions */
+    constexpr uint32_t PPP_QCAP = PPP_QCAP_OF(WPL);
     constexpr int GD = 32 * NW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -164,7 +165,7 @@ static size_t ranked_smem_bytes(int wpl, int nwarps, uint32_t Wg)
 {
     const size_t NW = 32 * (size_t)wpl, GD = 32 * NW;
     return 128 + ((((GD + 2) * 8) + 127) & ~(size_t)127) + (size_t)PPP_QTILE * 2 * Wg * 4 + PPP_QTILE * sizeof(QConst) + PPP_QTILE * 4 +
-           (size_t)nwarps * 3 * PPP_QCAP * 4 + 64;
+           (size_t)nwarps * 3 * PPP_QCAP_OF(wpl) * 4 + 64;
 }
 
 template <int WPL>

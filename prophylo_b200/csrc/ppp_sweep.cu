@@ -35,8 +35,9 @@
 /* ---------------------------------------------------------------- tile kernel: every pair of (query tile x targets)
  * One warp owns one target row (registers) and walks a 32-query tile staged in shared memory by TMA. */
 template <int WPL>
-__global__ void __launch_bounds__(512) ppp_sweep_kernel(const SweepParams prm)
+__global__ void __launch_bounds__(512, PPP_MINBLOCKS_OF(WPL)) ppp_sweep_kernel(const SweepParams prm)
 {
+    constexpr uint32_t PPP_QCAP = PPP_QCAP_OF(WPL);
     constexpr int W = 32 * WPL;  /* words per row */
     constexpr int GD = 32 * W;   /* padded genome count */
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -324,9 +325,10 @@ __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams pr
 
 /* ---------------------------------------------------------------- refine kernel: warp per surviving pair */
 template <int WPL>
-__global__ void __launch_bounds__(512) ppp_refine_kernel(const SweepParams prm, const uint32_t *__restrict__ surv,
+__global__ void __launch_bounds__(512, PPP_MINBLOCKS_OF(WPL)) ppp_refine_kernel(const SweepParams prm, const uint32_t *__restrict__ surv,
                                                          const unsigned long long *__restrict__ surv_count, unsigned long long surv_cap)
 {
+    constexpr uint32_t PPP_QCAP = PPP_QCAP_OF(WPL);
     constexpr int W = 32 * WPL;
     constexpr int GD = 32 * W;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -407,12 +409,12 @@ static size_t sweep_smem_bytes(int wpl, int nwarps)
 {
     const size_t W = 32 * (size_t)wpl, GD = 32 * W;
     return 128 + ((((GD + 2) * 8) + 127) & ~(size_t)127) + PPP_QTILE * 2 * W * 4 + PPP_QTILE * sizeof(QConst) + PPP_QTILE * 4 +
-           (size_t)nwarps * 3 * PPP_QCAP * 4 + 64;
+           (size_t)nwarps * 3 * PPP_QCAP_OF(wpl) * 4 + 64;
 }
 static size_t refine_smem_bytes(int wpl, int nwarps)
 {
     const size_t W = 32 * (size_t)wpl, GD = 32 * W;
-    return 128 + ((((GD + 2) * 8) + 127) & ~(size_t)127) + (size_t)nwarps * 3 * PPP_QCAP * 4 + 64;
+    return 128 + ((((GD + 2) * 8) + 127) & ~(size_t)127) + (size_t)nwarps * 3 * PPP_QCAP_OF(wpl) * 4 + 64;
 }
 static size_t prefilter_smem_bytes(int wpl) { return 128 + PPP_QTILE * 2 * 32 * (size_t)wpl * 4 + 2 * PPP_QTILE * 4 + 64; }
 
