@@ -134,7 +134,8 @@ int ppp_get_stats(const ppp_ctx *ctx, ppp_stats *out);
 
 /* Options (tests / diagnostics): "force_exact" (0/1: every pair through the exact tier),
  * "check_bounds" (0/1: verify the fast tier's enclosures against the accurate tier, count violations),
- * "sweep_warps" (warps per CTA).  Unknown names return PPP_ERR_INVALID. */
+ * "sweep_warps" (warps per CTA), "table_mode" (-1 auto / 0 off / 1 on: exact (yes, number) table per query for dense
+ * runs of few queries against many targets).  Unknown names return PPP_ERR_INVALID. */
 int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value);
 int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *value);
 

@@ -37,6 +37,10 @@ extern "C" cudaError_t ppp_launch_staircase(const QConst *qc, const double *lf, 
 extern "C" cudaError_t ppp_launch_topk_merge(const void *appended, uint32_t *qcnt, uint32_t qcap, void *topk, uint32_t *topk_cnt,
                                              double *kth, uint32_t k, uint32_t nQ, uint32_t t_offset, int nsm, cudaStream_t st);
 extern "C" int ppp_topk_max_k(void);
+extern "C" cudaError_t ppp_launch_table_build(const QConst *qc, const unsigned long long *toff, uint32_t nQ, double *tab, uint32_t *bad,
+                                              int nsm, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_table_sweep(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, const unsigned long long *toff,
+                                              const double *tab, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_topk_merge_lists(const void *lists, const uint32_t *counts, uint32_t nlists, const uint32_t *t_offsets,
                                                    uint32_t nQ, uint32_t k, void *out, uint32_t *out_cnt, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const unsigned long long *counters, int n, cudaStream_t st);
@@ -114,6 +118,17 @@ struct ppp_ctx {
     std::vector<uint32_t> nmax_off_host; /* static staircase offsets: prefix sums of (ny + 1) */
     size_t nmax_entries = 0;
 
+    /* exact table mode (dense runs, few queries x many targets) */
+    std::vector<unsigned long long> toff_host; /* [nQ+1] table offsets: (ny+1) * (npres+1) cells per query */
+    double *d_tab = nullptr;
+    size_t cap_tab = 0;
+    unsigned long long *d_toff = nullptr;
+    size_t cap_toff = 0;
+    uint32_t *d_tbad = nullptr;
+    size_t cap_tbad = 0;
+    bool table_valid = false, table_ok = false;
+    int table_mode = -1; /* -1 auto, 0 off, 1 always (when it fits) */
+    int last_used_table = 0;
     /* options */
     int force_exact = 0, check_bounds = 0, sweep_warps = 8;
     ppp_stats stats;
@@ -224,6 +239,9 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaFree(ctx->d_off);
     cudaFree(ctx->d_nmax);
     cudaFree(ctx->d_topk);
+    cudaFree(ctx->d_tab);
+    cudaFree(ctx->d_toff);
+    cudaFree(ctx->d_tbad);
     cudaFree(ctx->d_mtopk);
     cudaFree(ctx->d_mkth);
     cudaFree(ctx->d_mcnt);
@@ -411,6 +429,10 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
         if (off > 0xfffffff0ull) return fail(ctx, PPP_ERR_INVALID, "ppp_set_queries: staircase tables exceed 4G entries");
         ctx->nmax_entries = off;
     }
+    ctx->toff_host.assign(nQ + 1, 0);
+    for (size_t q = 0; q < nQ; ++q)
+        ctx->toff_host[q + 1] = ctx->toff_host[q] + ((unsigned long long)qc[q].ny + 1) * ((unsigned long long)qc[q].npres + 1);
+    ctx->table_valid = false;
     CU(cudaMemsetAsync(ctx->d_Q, 0, ctx->capQ * 2 * W * 4, ctx->stream));
     CU(cudaMemcpy2DAsync(ctx->d_Q, 2 * W * 4, P, wpr * 4, wpr * 4, nQ, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpy2DAsync(ctx->d_Q + W, 2 * W * 4, Y, wpr * 4, wpr * 4, nQ, cudaMemcpyHostToDevice, ctx->stream));
@@ -572,7 +594,67 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
     ctx->prefilter_pairs = 0;
     ctx->prefilter_us = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-    if (f->mode == PPP_FILTER_ALL) {
+    ctx->last_used_table = 0;
+    bool use_table = false;
+    if (f->mode == PPP_FILTER_ALL && !ctx->ranked && !ctx->force_exact && !ctx->check_bounds && ctx->table_mode != 0) {
+        /* exact table mode pays when one table serves many targets: |Y| x |P| bit-exact evaluations per query against
+         * popc(T&Y) enclosure + series evaluations per pair */
+        const unsigned long long cells = ctx->toff_host[nQ];
+        const bool fits = cells <= ((unsigned long long)1 << 27);
+        const bool pays = nT >= 8192 && cells / 24 <= (unsigned long long)nQ * nT;
+        use_table = fits && (ctx->table_mode == 1 || pays);
+    }
+    if (use_table) {
+        if (!ctx->Tt_valid) {
+            const size_t W = 32 * (size_t)ctx->wpl;
+            if ((rc = grow(ctx, &ctx->d_Tt, &ctx->cap_Tt, nT * W))) return rc;
+            CU(ppp_launch_transpose(ctx->d_T, ctx->d_Tt, (uint32_t)nT, ctx->wpl, ctx->stream));
+            ctx->Tt_valid = true;
+            launches++;
+        }
+        if (!ctx->table_valid) {
+            if ((rc = grow(ctx, &ctx->d_tab, &ctx->cap_tab, (size_t)ctx->toff_host[nQ] + 1))) return rc;
+            if ((rc = grow(ctx, &ctx->d_toff, &ctx->cap_toff, nQ + 1))) return rc;
+            if ((rc = grow(ctx, &ctx->d_tbad, &ctx->cap_tbad, nQ))) return rc;
+            CU(cudaMemcpyAsync(ctx->d_toff, ctx->toff_host.data(), (nQ + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaMemsetAsync(ctx->d_tbad, 0, nQ * sizeof(uint32_t), ctx->stream));
+            CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+            CU(ppp_launch_table_build(ctx->d_qc, ctx->d_toff, (uint32_t)nQ, ctx->d_tab, ctx->d_tbad, ctx->nsm, ctx->stream));
+            CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+            launches += 2;
+            std::vector<uint32_t> bad(nQ);
+            CU(cudaMemcpyAsync(bad.data(), ctx->d_tbad, nQ * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
+            ctx->phase_us[2] += 1e3 * ms; /* reported under "staircase": per-query precomputation */
+            ctx->table_ok = true;
+            for (size_t q = 0; q < nQ; ++q)
+                if (bad[q]) ctx->table_ok = false; /* Cephes rounding broke monotonicity somewhere: use the general sweep */
+            ctx->table_valid = true;
+        }
+        use_table = ctx->table_ok;
+    }
+    if (use_table) {
+        if ((rc = grow(ctx, &ctx->d_hits, &ctx->cap_hits, nQ * nT))) return rc;
+        SweepParams prm;
+        base_params(ctx, &prm);
+        prm.hits = ctx->d_hits;
+        prm.t0 = 0;
+        prm.t1 = (uint32_t)nT;
+        CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+        CU(ppp_launch_table_sweep(&prm, ctx->wpl, ctx->d_Tt, (uint32_t)nT, ctx->d_toff, ctx->d_tab, ctx->nsm, ctx->stream));
+        CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+        sweep_ms += ms;
+        ctx->phase_us[0] += 1e3 * ms;
+        launches++;
+        sweep_launches++;
+        ctx->n_results = nQ * nT;
+        ctx->last_used_table = 1;
+    } else if (f->mode == PPP_FILTER_ALL) {
         /* dense: chunks only bound the launch-local pair ids of the exact-tier list (31 bits) */
         size_t tchunk = std::max<size_t>(1, ((size_t)1 << 30) / nQ);
         if (tchunk > nT) tchunk = nT;
@@ -849,7 +931,10 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
     if (!ctx || !name) return PPP_ERR_INVALID;
     if (!strcmp(name, "force_exact")) ctx->force_exact = value != 0;
     else if (!strcmp(name, "check_bounds")) ctx->check_bounds = value != 0;
-    else if (!strcmp(name, "sweep_warps")) {
+    else if (!strcmp(name, "table_mode")) {
+        if (value < -1 || value > 1) return fail(ctx, PPP_ERR_INVALID, "table_mode must be -1 (auto), 0 (off) or 1 (on)");
+        ctx->table_mode = (int)value;
+    } else if (!strcmp(name, "sweep_warps")) {
         if (value < 1 || value > 16) return fail(ctx, PPP_ERR_INVALID, "sweep_warps must be in [1,16]");
         ctx->sweep_warps = (int)value;
     } else
@@ -868,6 +953,7 @@ extern "C" int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *va
     else if (!strcmp(name, "bound_checks")) i = CNT_CHECKS;
     else if (!strcmp(name, "full_pairs")) i = CNT_FULL;
     else if (!strcmp(name, "num_sms")) { *value = ctx->nsm; return PPP_OK; }
+    else if (!strcmp(name, "used_table")) { *value = ctx->last_used_table; return PPP_OK; }
     else if (!strcmp(name, "us_prefilter")) { *value = (int64_t)ctx->prefilter_us; return PPP_OK; }
     else if (!strcmp(name, "prefilter_pairs")) { *value = (int64_t)ctx->prefilter_pairs; return PPP_OK; }
     else if (!strcmp(name, "survivors")) { *value = (int64_t)ctx->survivors; return PPP_OK; }

@@ -219,7 +219,11 @@ def test_topk_multichunk_matches_dense(ctx, G, kind, nq, nt, k):
     P, Y, p = synth.make_queries(G, nq, 300 + G, kind)
     T = synth.make_targets(G, nt, 400 + G, plant_from=Y, plant_frac=0.02)
     ctx.set_targets_bits(T, G)
-    dense = ctx.score(P, Y, p).reshape(nq, nt)
+    ctx.set_option("table_mode", 0)  # compare like with like: the general sweep on both sides (bit-identical scores)
+    try:
+        dense = ctx.score(P, Y, p).reshape(nq, nt)
+    finally:
+        ctx.set_option("table_mode", -1)
     tk = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
     assert ctx.counter("survivors") > 0 and ctx.counter("full_pairs") < nq * nt
     assert tk.size == nq * k
@@ -425,3 +429,38 @@ def test_topk_ties_at_zero_and_one(ctx):
         got = tk[q * k:(q + 1) * k]
         for f in ("t", "score", "yes", "number", "depth"):
             assert np.array_equal(got[f], exp[f]), (q, f)
+
+
+@pytest.mark.parametrize("G,kind,nq,nt", [(1024, "single", 1, 20000), (1024, "mixed", 24, 9000), (4096, "mixed", 6, 8500), (200, "family", 8, 300)])
+def test_exact_table_mode_is_bit_identical(ctx, G, kind, nq, nt):
+    """Dense runs of few queries x many targets use one bit-exact (yes, number) table per query: counts, cut-offs AND
+    scores must equal the oracle's exactly (1 ulp only on the host-libm expm1 branch: yes == 1 and p < 0.01)."""
+    P, Y, p = synth.make_queries(G, nq, 900 + G, kind)
+    T = synth.make_targets(G, nt, 901 + G, plant_from=Y, plant_frac=0.05)
+    ctx.set_targets_bits(T, G)
+    ctx.set_option("table_mode", 1)
+    try:
+        hits = ctx.score(P, Y, p).reshape(nq, nt)
+        assert ctx.counter("used_table") == 1
+    finally:
+        ctx.set_option("table_mode", -1)
+    sub = slice(0, min(nt, 1500))
+    ref, _ = oracle.score_bits_batch(P, Y, p, T[sub], G, nthreads=os.cpu_count() or 1)
+    h = hits[:, sub]
+    for f in ("yes", "number", "depth"):
+        assert np.array_equal(h[f], ref[f]), f
+    libm = (ref["yes"] == 1) & (p[:, None] < 0.01)
+    assert np.array_equal(h["score"][~libm].view(np.uint64), ref["score"][~libm].view(np.uint64))
+    assert np.all(np.abs(h["score"][libm] - ref["score"][libm]) <= np.spacing(ref["score"][libm]))
+    # and the general sweep agrees with the table on every pair (cut-offs exactly, scores within the stated tolerance)
+    ctx.set_option("table_mode", 0)
+    try:
+        gen = ctx.score(P, Y, p).reshape(nq, nt)
+        assert ctx.counter("used_table") == 0
+    finally:
+        ctx.set_option("table_mode", -1)
+    for f in ("yes", "number", "depth"):
+        assert np.array_equal(gen[f], hits[f]), f
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.abs(np.log(gen["score"]) - np.log(hits["score"])) / np.abs(np.log(hits["score"]))
+    assert np.all((gen["score"] == hits["score"]) | (rel <= REL_TOL_NEGLOG))
