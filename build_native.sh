@@ -10,8 +10,9 @@ nvcc $COMMON -c ppp_sweep.cu -o build/ppp_sweep.o &
 nvcc $COMMON -fmad=false -c ppp_exact.cu -o build/ppp_exact.o &
 nvcc $COMMON -c ppp_topk.cu -o build/ppp_topk.o &
 nvcc $COMMON -c ppp_ranked.cu -o build/ppp_ranked.o &
+nvcc $COMMON -c ppp_prefilter.cu -o build/ppp_prefilter.o &
 nvcc $COMMON -fmad=false -c ppp_table.cu -o build/ppp_table.o &
 nvcc $COMMON -c ppp_capi.cu -o build/ppp_capi.o &
 FAIL=0; for j in $(jobs -p); do wait $j || FAIL=1; done; [ $FAIL = 0 ] || { echo "nvcc failed"; exit 1; }
-nvcc $ARCH -shared -o ../libppp_b200.so build/ppp_sweep.o build/ppp_exact.o build/ppp_topk.o build/ppp_ranked.o build/ppp_table.o build/ppp_capi.o
+nvcc $ARCH -shared -o ../libppp_b200.so build/ppp_sweep.o build/ppp_exact.o build/ppp_topk.o build/ppp_ranked.o build/ppp_prefilter.o build/ppp_table.o build/ppp_capi.o
 echo "built $(cd .. && pwd)/libppp_b200.so"

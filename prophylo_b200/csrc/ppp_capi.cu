@@ -25,6 +25,13 @@ extern "C" cudaError_t ppp_launch_sweep(const SweepParams *prm, int wpl, int nwa
 extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, const uint32_t *qflags, uint32_t *surv,
                                            unsigned long long *surv_count, unsigned long long surv_cap, int nwarps, int nsm,
                                            cudaStream_t st, cudaEvent_t between);
+extern "C" cudaError_t ppp_launch_prefilter2(const SweepParams *prm, int wpl, int pall, const void *Tt, uint32_t ntt, const uint32_t *qorder,
+                                             uint32_t nqk, uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count,
+                                             unsigned long long surv_cap, unsigned long long *stats, int nsm, cudaStream_t st);
+extern "C" uint32_t ppp_prefilter2_max_stair(int wpl, int pall);
+extern "C" uint32_t ppp_prefilter2_tile_queries(int pall);
+extern "C" cudaError_t ppp_launch_refine(const SweepParams *prm, int wpl, const uint32_t *surv, const unsigned long long *surv_count,
+                                         unsigned long long surv_cap, int nwarps, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_transpose(const void *T, void *Tt, uint32_t nT, int wpl, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_exact(const SweepParams *prm, int W, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_sweep_ranked(const SweepParams *prm, int rwpl, int nwarps, int nsm, cudaStream_t st);
@@ -84,6 +91,11 @@ struct ppp_ctx {
     uint32_t *d_Q = nullptr;
     QConst *d_qc = nullptr;
     uint32_t *d_qflags = nullptr; /* bit 0: presence plane is all ones over the G genomes */
+    uint32_t *d_qorder = nullptr; /* query ids: the n_pall queries with an all-ones presence plane first, then the others */
+    size_t n_pall = 0;
+    uint32_t stair_need[2] = {0, 0}; /* largest per-tile staircase footprint (entries) of the general / all-ones launch */
+    unsigned long long *d_pfstats = nullptr;
+    int prefilter_version = 2; /* 2: ppp_prefilter.cu (queued slow path), 1: the in-line screen of ppp_sweep.cu */
     size_t nQ = 0, capQ = 0;
     /* results */
     ppp_hit *d_hits = nullptr;
@@ -229,6 +241,8 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaFree(ctx->d_Q);
     cudaFree(ctx->d_qc);
     cudaFree(ctx->d_qflags);
+    cudaFree(ctx->d_qorder);
+    cudaFree(ctx->d_pfstats);
     cudaFree(ctx->d_hits);
     cudaFree(ctx->d_exact);
     cudaFree(ctx->d_counters);
@@ -309,6 +323,8 @@ static void reset_queries_if_layout_changed(ppp_ctx *ctx, int wpl, uint32_t G)
         cudaFree(ctx->d_Q);
         cudaFree(ctx->d_qc);
         cudaFree(ctx->d_qflags);
+        cudaFree(ctx->d_qorder);
+        ctx->d_qorder = nullptr;
         ctx->d_Q = nullptr;
         ctx->d_qc = nullptr;
         ctx->d_qflags = nullptr;
@@ -405,6 +421,7 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
         CU(cudaMalloc(&ctx->d_Q, cap * 2 * W * 4));
         CU(cudaMalloc(&ctx->d_qc, cap * sizeof(QConst)));
         CU(cudaMalloc(&ctx->d_qflags, cap * sizeof(uint32_t)));
+        CU(cudaMalloc(&ctx->d_qorder, cap * sizeof(uint32_t)));
         ctx->capQ = cap;
     }
     ctx->nQ = 0;
@@ -440,6 +457,28 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
     std::vector<uint32_t> qfl(nQ);
     for (size_t q = 0; q < nQ; ++q) qfl[q] = (qc[q].npres == ctx->G) ? 1u : 0u;
     CU(cudaMemcpyAsync(ctx->d_qflags, qfl.data(), nQ * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        /* processing order of the pre-filter: all-ones presence planes first (number == depth: their own launch) */
+        std::vector<uint32_t> order;
+        order.reserve(nQ);
+        for (size_t q = 0; q < nQ; ++q)
+            if (qfl[q]) order.push_back((uint32_t)q);
+        ctx->n_pall = order.size();
+        for (size_t q = 0; q < nQ; ++q)
+            if (!qfl[q]) order.push_back((uint32_t)q);
+        CU(cudaMemcpyAsync(ctx->d_qorder, order.data(), nQ * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        for (int kind = 0; kind < 2; ++kind) {
+            const size_t b = kind ? 0 : ctx->n_pall, e = kind ? ctx->n_pall : nQ;
+            size_t worst = 0;
+            const size_t qt = ppp_prefilter2_tile_queries(kind);
+            for (size_t i = b; i < e; i += qt) {
+                size_t sum = 1;
+                for (size_t j = i; j < std::min(e, i + qt); ++j) sum += (size_t)qc[order[j]].ny + 1;
+                worst = std::max(worst, sum);
+            }
+            ctx->stair_need[kind] = (uint32_t)std::min<size_t>(worst, 0xffffffffu);
+        }
+    }
     CU(cudaStreamSynchronize(ctx->stream)); /* inputs are copied before returning (Perl SV buffers may move) */
     ctx->nQ = nQ;
     return PPP_OK;
@@ -485,6 +524,35 @@ static int mark(ppp_ctx *ctx, size_t *idx)
     return PPP_OK;
 }
 
+/* pre-filter + refine of one target chunk (bit-plane targets).  Version 2 (ppp_prefilter.cu) needs a tile's staircases
+ * in shared memory; query sets whose staircases do not fit use the in-line screen of ppp_sweep.cu. */
+static bool use_prefilter2(const ppp_ctx *ctx)
+{
+    if (ctx->prefilter_version != 2) return false;
+    for (int kind = 0; kind < 2; ++kind) {
+        const size_t n = kind ? ctx->n_pall : ctx->nQ - ctx->n_pall;
+        if (n && ctx->stair_need[kind] > ppp_prefilter2_max_stair(ctx->wpl, kind)) return false;
+    }
+    return true;
+}
+
+static int launch_prefiltered(ppp_ctx *ctx, SweepParams *prm, cudaEvent_t between)
+{
+    unsigned long long *surv_count = ctx->d_counters + CNT_N;
+    if (!use_prefilter2(ctx)) {
+        CU(ppp_launch_filtered(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qflags, ctx->d_surv, surv_count, ctx->cap_surv,
+                               ctx->sweep_warps, ctx->nsm, ctx->stream, between));
+        return PPP_OK;
+    }
+    CU(ppp_launch_prefilter2(prm, ctx->wpl, 1, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qorder, (uint32_t)ctx->n_pall, ctx->stair_need[1],
+                             ctx->d_surv, surv_count, ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));
+    CU(ppp_launch_prefilter2(prm, ctx->wpl, 0, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qorder + ctx->n_pall, (uint32_t)(ctx->nQ - ctx->n_pall),
+                             ctx->stair_need[0], ctx->d_surv, surv_count, ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));
+    if (between) CU(cudaEventRecord(between, ctx->stream));
+    CU(ppp_launch_refine(prm, ctx->wpl, ctx->d_surv, surv_count, ctx->cap_surv, ctx->sweep_warps, ctx->nsm, ctx->stream));
+    return PPP_OK;
+}
+
 /* one target chunk without any host synchronisation (top-k runs): counters are accumulated on the device, event
  * spans are resolved after the run's final synchronize */
 static int launch_chunk_deferred(ppp_ctx *ctx, SweepParams *prm, uint32_t *launches, bool prefiltered)
@@ -501,9 +569,8 @@ static int launch_chunk_deferred(ppp_ctx *ctx, SweepParams *prm, uint32_t *launc
             ctx->evpool.push_back(e);
         }
         em = ctx->ev_used++;
-        CU(ppp_launch_filtered(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qflags, ctx->d_surv, ctx->d_counters + CNT_N, ctx->cap_surv,
-                               ctx->sweep_warps, ctx->nsm, ctx->stream, ctx->evpool[em]));
-        *launches += 1;
+        if ((rc = launch_prefiltered(ctx, prm, ctx->evpool[em]))) return rc;
+        *launches += 2;
         ctx->spans.push_back({e0, em, 4});
         ctx->prefilter_pairs += (unsigned long long)prm->nQ * (prm->t1 - prm->t0);
     } else if (ctx->ranked) {
@@ -530,9 +597,11 @@ static int run_chunk(ppp_ctx *ctx, SweepParams *prm, unsigned long long *totals,
     CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_SLOTS * sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (prefiltered) {
-        CU(ppp_launch_filtered(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qflags, ctx->d_surv, ctx->d_counters + CNT_N, ctx->cap_surv,
-                               ctx->sweep_warps, ctx->nsm, ctx->stream, ctx->ev[7]));
-        *launches += 1;
+        {
+            const int rc2 = launch_prefiltered(ctx, prm, ctx->ev[7]);
+            if (rc2) return rc2;
+        }
+        *launches += 2;
     } else if (ctx->ranked) {
         CU(ppp_launch_sweep_ranked(prm, ctx->rwpl, ctx->sweep_warps, ctx->nsm, ctx->stream));
     } else {
@@ -919,6 +988,21 @@ extern "C" int ppp_merge_topk_device(ppp_ctx *ctx, const ppp_hit *lists, const u
     return PPP_OK;
 }
 
+/* developer statistics of the queued pre-filter (counted only in a -DPF2_STATS build): pushes, drains, drain
+ * iterations, word-level passes.  The first call arms the counters. */
+extern "C" int ppp_debug_pf2stats(ppp_ctx *ctx, unsigned long long *out8, int reset)
+{
+    if (!ctx || !out8) return PPP_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->d_pfstats) {
+        CU(cudaMalloc(&ctx->d_pfstats, 8 * sizeof(unsigned long long)));
+        CU(cudaMemset(ctx->d_pfstats, 0, 8 * sizeof(unsigned long long)));
+    }
+    CU(cudaMemcpy(out8, ctx->d_pfstats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) CU(cudaMemset(ctx->d_pfstats, 0, 8 * sizeof(unsigned long long)));
+    return PPP_OK;
+}
+
 extern "C" int ppp_get_stats(const ppp_ctx *ctx, ppp_stats *out)
 {
     if (!ctx || !out) return PPP_ERR_INVALID;
@@ -934,6 +1018,9 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
     else if (!strcmp(name, "table_mode")) {
         if (value < -1 || value > 1) return fail(ctx, PPP_ERR_INVALID, "table_mode must be -1 (auto), 0 (off) or 1 (on)");
         ctx->table_mode = (int)value;
+    } else if (!strcmp(name, "prefilter_version")) {
+        if (value != 1 && value != 2) return fail(ctx, PPP_ERR_INVALID, "prefilter_version must be 1 or 2");
+        ctx->prefilter_version = (int)value;
     } else if (!strcmp(name, "sweep_warps")) {
         if (value < 1 || value > 16) return fail(ctx, PPP_ERR_INVALID, "sweep_warps must be in [1,16]");
         ctx->sweep_warps = (int)value;

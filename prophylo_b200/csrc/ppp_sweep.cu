@@ -190,6 +190,14 @@ __device__ __noinline__ bool word_has_passing_candidate(uint32_t a, uint32_t b, 
 #ifndef PF_QG
 #define PF_QG 8 /* queries per unrolled group of the pre-filter */
 #endif
+#ifdef PF_STATS
+__device__ unsigned long long g_pfstats[8][64];
+extern "C" void ppp_debug_pfstats(unsigned long long *out, int reset)
+{
+    cudaMemcpyFromSymbol(out, g_pfstats, sizeof(g_pfstats));
+    if (reset) { static unsigned long long z[8][64]; cudaMemcpyToSymbol(g_pfstats, z, sizeof(z)); }
+}
+#endif
 
 template <int WPL>
 __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams prm, const uint4 *__restrict__ Tt, uint32_t ntt,
@@ -244,6 +252,11 @@ __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams pr
             uint32_t state[PF_QG]; /* yes | number << 16 per query */
 #pragma unroll
             for (int i = 0; i < PF_QG; ++i) state[i] = 0;
+#ifdef PF_STATS
+            uint32_t stp2[PF_QG], stp4[PF_QG];
+#pragma unroll
+            for (int i = 0; i < PF_QG; ++i) stp2[i] = stp4[i] = 0;
+#endif
             for (int c = 0; c < C; ++c) {
                 const uint4 tv = live ? __ldg(Tt + (size_t)c * ntt + t) : make_uint4(0, 0, 0, 0);
                 const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
@@ -273,6 +286,17 @@ __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams pr
                     /* 128-genome screen, one lookup: no candidate of the chunk can pass unless number_before + 1 <=
                      * stair[yes_after]; the rare chunks that survive it are re-screened word by word, then per candidate */
                     const uint32_t lim = (off != PPP_NO_TABLE) ? (uint32_t)__ldg(prm.nmax + off + (st & 0xffffu)) : 0xffffu;
+#ifdef PF_STATS
+                    if (live && off != PPP_NO_TABLE) {
+                        atomicAdd(&g_pfstats[0][c], 1ull);
+                        if (cy && (st0 >> 16) + 1u <= lim) atomicAdd(&g_pfstats[1][c], 1ull);
+                        if ((st0 >> 16) + 1u <= lim) atomicAdd(&g_pfstats[2][c], 1ull);
+                        if ((c & 1) == 0) stp2[qj] = st0;
+                        if ((c & 3) == 0) stp4[qj] = st0;
+                        if ((c & 1) == 1 && (stp2[qj] >> 16) + 1u <= lim) atomicAdd(&g_pfstats[3][c], 1ull);
+                        if ((c & 3) == 3 && (stp4[qj] >> 16) + 1u <= lim) atomicAdd(&g_pfstats[4][c], 1ull);
+                    }
+#endif
                     if (cy && (st0 >> 16) + 1u <= lim) {
                         uint32_t sw = st0;
 #pragma unroll
@@ -283,8 +307,12 @@ __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams pr
                             if (cyw) {
                                 const uint32_t l2 = (off != PPP_NO_TABLE) ? (uint32_t)__ldg(prm.nmax + off + (sw & 0xffffu)) : 0xffffu;
                                 if (nb + 1u <= l2 &&
-                                    (off == PPP_NO_TABLE || word_has_passing_candidate(a[w], b[w], nb, (sw & 0xffffu) - cyw, prm.nmax + off)))
+                                    (off == PPP_NO_TABLE || word_has_passing_candidate(a[w], b[w], nb, (sw & 0xffffu) - cyw, prm.nmax + off))) {
                                     pass |= 1u << qi;
+#ifdef PF_STATS
+                                    if (live) atomicAdd(&g_pfstats[5][c], 1ull);
+#endif
+                                }
                             }
                         }
                     }
@@ -492,6 +520,34 @@ extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, cons
     case 2: return launch_filtered_t<2>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st, between);
     case 4: return launch_filtered_t<4>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st, between);
     case 8: return launch_filtered_t<8>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st, between);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int WPL>
+static cudaError_t launch_refine_t(const SweepParams &prm, const uint32_t *surv, const unsigned long long *surv_count, unsigned long long surv_cap,
+                                   int nwarps, int nsm, cudaStream_t st)
+{
+    const size_t smem = refine_smem_bytes(WPL, nwarps);
+    cudaError_t e = cudaFuncSetAttribute(ppp_refine_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_refine_kernel<WPL>, nwarps * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    ppp_refine_kernel<WPL><<<(unsigned)(nsm * per_sm), nwarps * 32, smem, st>>>(prm, surv, surv_count, surv_cap);
+    return cudaGetLastError();
+}
+
+/* refine only: the survivor list was produced by ppp_launch_prefilter2 (ppp_prefilter.cu) */
+extern "C" cudaError_t ppp_launch_refine(const SweepParams *prm, int wpl, const uint32_t *surv, const unsigned long long *surv_count,
+                                         unsigned long long surv_cap, int nwarps, int nsm, cudaStream_t st)
+{
+    switch (wpl) {
+    case 1: return launch_refine_t<1>(*prm, surv, surv_count, surv_cap, nwarps, nsm, st);
+    case 2: return launch_refine_t<2>(*prm, surv, surv_count, surv_cap, nwarps, nsm, st);
+    case 4: return launch_refine_t<4>(*prm, surv, surv_count, surv_cap, nwarps, nsm, st);
+    case 8: return launch_refine_t<8>(*prm, surv, surv_count, surv_cap, nwarps, nsm, st);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -78,11 +78,17 @@ __global__ void ppp_build_staircase_kernel(const QConst *__restrict__ qc, const 
             tab[y] = (uint16_t)res;
         }
         __syncwarp();
-        if (lane == 0) { /* enforce the staircase's monotonicity in yes (independent searches may differ by rounding) */
-            uint16_t run = 0;
+        if (lane == 0) {
+            /* enforce what the true staircase satisfies (independent searches may differ by rounding; only ever
+             * loosens): non-decreasing in yes, and nmax[y] >= y  =>  nmax[y+1] >= nmax[y] + 1 (one more trial that is a
+             * success cannot raise the tail), i.e. the slack nmax[y] - y is non-decreasing -- the chunk-level screen of
+             * ppp_prefilter.cu tests only a chunk's last candidate on the strength of this */
+            uint32_t run = 0;
             for (int y = 1; y <= ny; ++y) {
-                run = max(run, tab[y]);
-                tab[y] = run;
+                uint32_t v = max(run, (uint32_t)tab[y]);
+                if (y >= 2 && run >= (uint32_t)(y - 1)) v = max(v, run + 1);
+                run = min(v, 65535u);
+                tab[y] = (uint16_t)run;
             }
             active_off[q] = static_off[q];
         }
