@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <new>
 #include <vector>
 
@@ -50,6 +51,11 @@ extern "C" cudaError_t ppp_launch_table_sweep(const SweepParams *prm, int wpl, c
                                               const double *tab, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_topk_merge_lists(const void *lists, const uint32_t *counts, uint32_t nlists, const uint32_t *t_offsets,
                                                    uint32_t nQ, uint32_t k, void *out, uint32_t *out_cnt, int nsm, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_spec_init(const void *topk, const uint32_t *topk_cnt, const double *kth, uint32_t k, uint32_t r, double *kspec,
+                                            double *kspec0, uint32_t nQ, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_spec_update(double *kspec, const double *kth, uint32_t nQ, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_spec_verify(const void *topk, const uint32_t *topk_cnt, const double *kspec0, uint32_t k, double *last_tau,
+                                              uint32_t *failed, uint32_t *nfailed, uint32_t nQ, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const unsigned long long *counters, int n, cudaStream_t st);
 
 struct ppp_ctx {
@@ -96,6 +102,9 @@ struct ppp_ctx {
     uint32_t stair_need[2] = {0, 0}; /* largest per-tile staircase footprint (entries) of the general / all-ones launch */
     unsigned long long *d_pfstats = nullptr;
     int prefilter_version = 2; /* 2: ppp_prefilter.cu (queued slow path), 1: the in-line screen of ppp_sweep.cu */
+    uint32_t stair_need_any = 0; /* staircase footprint of the worst possible general tile (re-scan of arbitrary queries) */
+    int speculate = 1;           /* top-k: screen the bulk of the targets against a speculative, verified threshold */
+    uint32_t spec_rank = 0, spec_failed = 0;
     size_t nQ = 0, capQ = 0;
     /* results */
     ppp_hit *d_hits = nullptr;
@@ -478,6 +487,15 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
             }
             ctx->stair_need[kind] = (uint32_t)std::min<size_t>(worst, 0xffffffffu);
         }
+        {
+            std::vector<uint32_t> lens(nQ);
+            for (size_t q = 0; q < nQ; ++q) lens[q] = qc[q].ny + 1;
+            const size_t qt = std::min<size_t>(ppp_prefilter2_tile_queries(0), nQ);
+            std::partial_sort(lens.begin(), lens.begin() + qt, lens.end(), std::greater<uint32_t>());
+            size_t sum = 1;
+            for (size_t i = 0; i < qt; ++i) sum += lens[i];
+            ctx->stair_need_any = (uint32_t)std::min<size_t>(sum, 0xffffffffu);
+        }
     }
     CU(cudaStreamSynchronize(ctx->stream)); /* inputs are copied before returning (Perl SV buffers may move) */
     ctx->nQ = nQ;
@@ -536,9 +554,16 @@ static bool use_prefilter2(const ppp_ctx *ctx)
     return true;
 }
 
-static int launch_prefiltered(ppp_ctx *ctx, SweepParams *prm, cudaEvent_t between)
+static int launch_prefiltered(ppp_ctx *ctx, SweepParams *prm, cudaEvent_t between, const uint32_t *qlist = nullptr, uint32_t nlist = 0)
 {
     unsigned long long *surv_count = ctx->d_counters + CNT_N;
+    if (qlist) { /* only the listed queries (any presence plane): one general launch */
+        CU(ppp_launch_prefilter2(prm, ctx->wpl, 0, ctx->d_Tt, (uint32_t)ctx->nT, qlist, nlist, ctx->stair_need_any, ctx->d_surv, surv_count,
+                                 ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));
+        if (between) CU(cudaEventRecord(between, ctx->stream));
+        CU(ppp_launch_refine(prm, ctx->wpl, ctx->d_surv, surv_count, ctx->cap_surv, ctx->sweep_warps, ctx->nsm, ctx->stream));
+        return PPP_OK;
+    }
     if (!use_prefilter2(ctx)) {
         CU(ppp_launch_filtered(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qflags, ctx->d_surv, surv_count, ctx->cap_surv,
                                ctx->sweep_warps, ctx->nsm, ctx->stream, between));
@@ -555,7 +580,8 @@ static int launch_prefiltered(ppp_ctx *ctx, SweepParams *prm, cudaEvent_t betwee
 
 /* one target chunk without any host synchronisation (top-k runs): counters are accumulated on the device, event
  * spans are resolved after the run's final synchronize */
-static int launch_chunk_deferred(ppp_ctx *ctx, SweepParams *prm, uint32_t *launches, bool prefiltered)
+static int launch_chunk_deferred(ppp_ctx *ctx, SweepParams *prm, uint32_t *launches, bool prefiltered, const uint32_t *qlist = nullptr,
+                                 uint32_t nlist = 0)
 {
     const int W = 32 * ctx->wpl;
     int rc;
@@ -569,7 +595,7 @@ static int launch_chunk_deferred(ppp_ctx *ctx, SweepParams *prm, uint32_t *launc
             ctx->evpool.push_back(e);
         }
         em = ctx->ev_used++;
-        if ((rc = launch_prefiltered(ctx, prm, ctx->evpool[em]))) return rc;
+        if ((rc = launch_prefiltered(ctx, prm, ctx->evpool[em], qlist, nlist))) return rc;
         *launches += 2;
         ctx->spans.push_back({e0, em, 4});
         ctx->prefilter_pairs += (unsigned long long)prm->nQ * (prm->t1 - prm->t0);
@@ -583,6 +609,16 @@ static int launch_chunk_deferred(ppp_ctx *ctx, SweepParams *prm, uint32_t *launc
     else CU(ppp_launch_exact(prm, W, ctx->nsm, ctx->stream));
     if ((rc = mark(ctx, &e2))) return rc;
     CU(ppp_launch_accumulate(ctx->d_totals, ctx->d_counters, CNT_N + 1, ctx->stream));
+    if (getenv("PPP_B200_DEBUG_CHUNKS")) { /* developer aid: per-chunk counters (synchronises) */
+        unsigned long long c[CNT_SLOTS];
+        CU(cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float m1 = 0.f, m2 = 0.f;
+        cudaEventElapsedTime(&m1, ctx->evpool[e0], ctx->evpool[e1]);
+        cudaEventElapsedTime(&m2, ctx->evpool[e1], ctx->evpool[e2]);
+        fprintf(stderr, "[ppp chunk] t=[%u,%u) mode=%u bounds_only=%u prefiltered=%d: survivors %llu full %llu exact %llu cand %llu  sweep %.3f ms exact %.3f ms\n",
+                prm->t0, prm->t1, prm->accept_mode, prm->bounds_only, (int)prefiltered, c[CNT_N], c[CNT_FULL], c[CNT_EXACT], c[CNT_CAND], m1, m2);
+    }
     *launches += 3;
     ctx->spans.push_back({e0, e1, 0});
     ctx->spans.push_back({e1, e2, 1});
@@ -746,9 +782,11 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         const size_t maxw = std::min<size_t>(nT, std::max<size_t>(256, ((size_t)1 << 29) / nQ));
         if ((rc = grow(ctx, &ctx->d_hits, &ctx->cap_hits, nQ * maxw))) return rc;
         if ((rc = grow(ctx, &ctx->d_exact, &ctx->cap_exact, nQ * maxw))) return rc;
-        if ((rc = grow(ctx, &ctx->d_kth, &ctx->cap_kth, 2 * nQ))) return rc; /* [nQ] k-th scores, [nQ] tau of the resident staircase */
+        /* [nQ] k-th scores, [nQ] tau of the resident staircase, [nQ] speculative thresholds in use, [nQ] their initial values */
+        if ((rc = grow(ctx, &ctx->d_kth, &ctx->cap_kth, 4 * nQ))) return rc;
         if ((rc = grow(ctx, &ctx->d_qcnt, &ctx->cap_qcnt, 2 * nQ))) return rc; /* [nQ] append counters, [nQ] top-k counts */
-        if ((rc = grow(ctx, &ctx->d_off, &ctx->cap_off, 2 * nQ))) return rc;   /* [nQ] static offsets, [nQ] active offsets */
+        /* [nQ] static offsets, [nQ] active offsets, [nQ] queries whose speculative threshold failed, [1] their count */
+        if ((rc = grow(ctx, &ctx->d_off, &ctx->cap_off, 3 * nQ + 4))) return rc;
         if ((rc = grow(ctx, &ctx->d_nmax, &ctx->cap_nmax, ctx->nmax_entries + 8))) return rc;
         if (topk && (rc = grow(ctx, &ctx->d_topk, &ctx->cap_topk, nQ * (size_t)k))) return rc;
         if ((rc = grow(ctx, &ctx->d_surv, &ctx->cap_surv, nQ * maxw))) return rc;
@@ -808,13 +846,38 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                 launches++;
                 seeded_pass = true;
             }
+            double *d_kspec = ctx->d_kth + 2 * nQ, *d_kspec0 = ctx->d_kth + 3 * nQ;
+            uint32_t *d_failed = ctx->d_off + 2 * nQ, *d_nfailed = ctx->d_off + 3 * nQ;
+            const bool spec_ok = ctx->speculate && !ctx->ranked && use_prefilter2(ctx) && !ctx->force_exact &&
+                                 ctx->stair_need_any <= ppp_prefilter2_max_stair(ctx->wpl, 0);
+            bool spec_on = false;
+            size_t spec_start = 0;
+            ctx->spec_rank = 0;
+            ctx->spec_failed = 0;
             while (processed < nT) {
+                if (spec_ok && !spec_on && processed >= 4 * (size_t)k && nT - processed >= 8 * processed) {
+                    /* speculative threshold (ppp_topk.cu): rank r of the list so far, P(Poisson(k processed / nT) >= r) <= 1e-3 */
+                    const double lam = (double)k * (double)processed / (double)nT;
+                    double term = exp(-lam), cdf = term; /* P(X <= 0) */
+                    uint32_t r = 1;
+                    while (1.0 - cdf > 1e-3 && r < k) {
+                        term *= lam / (double)r;
+                        cdf += term;
+                        ++r;
+                    }
+                    CU(ppp_launch_spec_init(ctx->d_topk, d_topk_cnt, ctx->d_kth, k, r, d_kspec, d_kspec0, (uint32_t)nQ, ctx->stream));
+                    launches++;
+                    spec_on = true;
+                    spec_start = processed;
+                    ctx->spec_rank = r;
+                }
                 size_t w = std::min(maxw, nT - processed);
-                w = std::min(w, processed ? 4 * processed : (seeded_pass ? 4 * first : first));
+                if (!spec_on) w = std::min(w, processed ? 4 * processed : (seeded_pass ? 4 * first : first));
+                const double *kth_used = spec_on ? d_kspec : ctx->d_kth;
                 size_t ea, eb;
                 if (processed || seeded_pass) {
                     if ((rc = mark(ctx, &ea))) return rc;
-                    CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 0, 0.0, d_off_static, ctx->d_nmax, d_off_active,
+                    CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, kth_used, 0, 0.0, d_off_static, ctx->d_nmax, d_off_active,
                                             ctx->d_kth + nQ, (uint32_t)nQ, ctx->nsm, ctx->stream));
                     if ((rc = mark(ctx, &eb))) return rc;
                     ctx->spans.push_back({ea, eb, 2});
@@ -822,16 +885,51 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                 }
                 SweepParams prm;
                 fill_filtered(prm, processed, processed + w);
+                prm.kth = kth_used;
                 /* without thresholds (fewer targets than k so far): tile kernel over every pair; otherwise thread-per-pair screen */
                 if ((rc = launch_chunk_deferred(ctx, &prm, &launches, !ctx->ranked && (processed || seeded_pass)))) return rc;
                 sweep_launches++;
                 if ((rc = mark(ctx, &ea))) return rc;
                 CU(ppp_launch_topk_merge(ctx->d_hits, d_qcnt, (uint32_t)maxw, ctx->d_topk, d_topk_cnt, ctx->d_kth, k, (uint32_t)nQ,
                                          0u, ctx->nsm, ctx->stream));
+                if (spec_on) {
+                    CU(ppp_launch_spec_update(d_kspec, ctx->d_kth, (uint32_t)nQ, ctx->stream));
+                    launches++;
+                }
                 if ((rc = mark(ctx, &eb))) return rc;
                 ctx->spans.push_back({ea, eb, 3});
                 launches++;
                 processed += w;
+            }
+            if (spec_on) {
+                /* verify; re-scan the queries whose list is not provably exact with the guaranteed bound */
+                uint32_t nfailed = 0;
+                CU(cudaMemsetAsync(d_nfailed, 0, sizeof(uint32_t), ctx->stream));
+                CU(ppp_launch_spec_verify(ctx->d_topk, d_topk_cnt, d_kspec0, k, ctx->d_kth + nQ, d_failed, d_nfailed, (uint32_t)nQ, ctx->stream));
+                launches++;
+                CU(cudaMemcpyAsync(&nfailed, d_nfailed, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+                ctx->spec_failed = nfailed;
+                for (size_t t0 = spec_start; nfailed && t0 < nT; t0 += maxw) {
+                    size_t ea, eb;
+                    if ((rc = mark(ctx, &ea))) return rc;
+                    CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 0, 0.0, d_off_static, ctx->d_nmax, d_off_active,
+                                            ctx->d_kth + nQ, (uint32_t)nQ, ctx->nsm, ctx->stream));
+                    if ((rc = mark(ctx, &eb))) return rc;
+                    ctx->spans.push_back({ea, eb, 2});
+                    SweepParams prm;
+                    fill_filtered(prm, t0, std::min(nT, t0 + maxw));
+                    prm.accept_mode = 2;
+                    prm.klo = d_kspec0;
+                    if ((rc = launch_chunk_deferred(ctx, &prm, &launches, true, d_failed, nfailed))) return rc;
+                    sweep_launches++;
+                    if ((rc = mark(ctx, &ea))) return rc;
+                    CU(ppp_launch_topk_merge(ctx->d_hits, d_qcnt, (uint32_t)maxw, ctx->d_topk, d_topk_cnt, ctx->d_kth, k, (uint32_t)nQ,
+                                             0u, ctx->nsm, ctx->stream));
+                    if ((rc = mark(ctx, &eb))) return rc;
+                    ctx->spans.push_back({ea, eb, 3});
+                    launches += 2;
+                }
             }
             unsigned long long c[CNT_N + 1];
             CU(cudaMemcpyAsync(c, ctx->d_totals, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1018,6 +1116,8 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
     else if (!strcmp(name, "table_mode")) {
         if (value < -1 || value > 1) return fail(ctx, PPP_ERR_INVALID, "table_mode must be -1 (auto), 0 (off) or 1 (on)");
         ctx->table_mode = (int)value;
+    } else if (!strcmp(name, "speculate")) {
+        ctx->speculate = value != 0;
     } else if (!strcmp(name, "prefilter_version")) {
         if (value != 1 && value != 2) return fail(ctx, PPP_ERR_INVALID, "prefilter_version must be 1 or 2");
         ctx->prefilter_version = (int)value;
@@ -1041,6 +1141,8 @@ extern "C" int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *va
     else if (!strcmp(name, "full_pairs")) i = CNT_FULL;
     else if (!strcmp(name, "num_sms")) { *value = ctx->nsm; return PPP_OK; }
     else if (!strcmp(name, "used_table")) { *value = ctx->last_used_table; return PPP_OK; }
+    else if (!strcmp(name, "spec_rank")) { *value = ctx->spec_rank; return PPP_OK; }
+    else if (!strcmp(name, "spec_failed")) { *value = ctx->spec_failed; return PPP_OK; }
     else if (!strcmp(name, "us_prefilter")) { *value = (int64_t)ctx->prefilter_us; return PPP_OK; }
     else if (!strcmp(name, "prefilter_pairs")) { *value = (int64_t)ctx->prefilter_pairs; return PPP_OK; }
     else if (!strcmp(name, "survivors")) { *value = (int64_t)ctx->survivors; return PPP_OK; }

@@ -58,9 +58,11 @@ struct SweepParams {
     uint32_t check_bounds;
     /* filtered runs (PPP_FILTER_TOPK / PPP_FILTER_THRESH_LOG10) */
     uint32_t append;           /* 0: dense hits[q*nT+t]; 1: per-query append hits[q*qcap + qcnt[q]++]; 2: global append */
-    uint32_t accept_mode;      /* 0: score < kth[q] (top-k, kth = 2.0 while the list is not full); 1: log10(score) < thresh */
+    uint32_t accept_mode;      /* 0: score < kth[q] (top-k, kth = 2.0 while the list is not full); 1: log10(score) < thresh;
+                                  2: klo[q] <= score <= kth[q] (re-scan of queries whose speculative threshold failed) */
     double thresh_log10;
     const double *kth;         /* [nQ] */
+    const double *klo;         /* [nQ] accept_mode 2 */
     const uint16_t *nmax;      /* prefilter staircase: candidate (yes, number) can pass only if number <= nmax[off + yes] */
     const uint32_t *nmax_off;  /* [nQ] offset of query q's staircase, PPP_NO_TABLE = accept every pair */
     uint32_t *qcnt;            /* [nQ] append counters */
@@ -88,6 +90,7 @@ enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_ACCURATE = 2, CNT_VIOL = 3, CNT_CHECKS =
 __device__ __forceinline__ bool ppp_accept(const SweepParams &prm, uint32_t q, double score)
 {
     if (prm.accept_mode == 0) return score < prm.kth[q];
+    if (prm.accept_mode == 2) return score >= prm.klo[q] && score <= prm.kth[q];
     return log10(score) < prm.thresh_log10;
 }
 /* write one result record: dense slot, per-query append or global append */

@@ -188,6 +188,25 @@ __device__ __forceinline__ uint32_t evaluate_pair(const uint32_t (&tw)[WPL], con
         }
         return PF_EXACT;
     }
+    if (prm.bounds_only) {
+        /* threshold seeding needs only SOME valid upper bound of the pair's score: the minimum over a subset of the
+         * candidates.  Each lane evaluates the LAST candidate inside its own words (rank = its inclusive yes count,
+         * number counted up to that genome): one enclosure per lane instead of one per candidate. */
+        float hi = INFINITY;
+        if (cy) {
+            uint32_t nn = excl >> 16, nlast = 0;
+#pragma unroll
+            for (int w = 0; w < WPL; ++w) {
+                if (ty[w]) nlast = nn + __popc(tp[w] & ((2u << (31 - __clz(ty[w]))) - 1u));
+                nn += __popc(tp[w]);
+            }
+            float lo;
+            tier_a((int)(incl & 0xffffu), (int)nlast, qc, s_lf, lo, hi);
+        }
+        res.score = exp((double)warp_min_f(hi));
+        *out = res;
+        return 0;
+    }
 
     /* 2. candidates.  Unfiltered: every set bit of T&Y.  Filtered: only those with number <= stair[yes] -- the
      * pair is only kept if its minimum is below the threshold, and then the minimum (and anything within the

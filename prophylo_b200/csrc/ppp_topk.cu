@@ -268,3 +268,69 @@ extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const u
     ppp_accumulate_kernel<<<1, 32, 0, st>>>(totals, counters, n);
     return cudaGetLastError();
 }
+
+/* ------------------------------------------------------------------------------------------------ speculative thresholds
+ * After the first target chunks of a top-k run a query's list holds its k best pairs of `processed` targets.  Its final
+ * k-th best score over all nT targets is, for exchangeable targets, close to the (k * processed / nT)-th best seen so
+ * far -- far below the guaranteed bound (the k-th best so far).  The remaining targets are therefore screened against
+ * the r-th best score so far (r chosen on the host so that a Poisson(k processed / nT) count reaches r with probability
+ * <= 1e-3), which cuts the pairs that need a full evaluation several-fold, and the result is VERIFIED: every pair below
+ * the speculative threshold was found exactly, so the list is exact iff it is full and its k-th score is strictly
+ * below that threshold.  Queries that fail are re-scanned over the same targets with the guaranteed bound and
+ * klo <= score <= kth acceptance (ppp_capi.cu). */
+__global__ void ppp_spec_init_kernel(const ppp_hit *__restrict__ topk, const uint32_t *__restrict__ topk_cnt, const double *__restrict__ kth,
+                                     uint32_t k, uint32_t r, double *__restrict__ kspec, double *__restrict__ kspec0, uint32_t nQ)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nQ) return;
+    const double g = kth[q];
+    double use = g, s0 = INFINITY;
+    if (topk_cnt[q] >= k && r >= 1 && r <= k) {
+        const double v = topk[(size_t)q * k + (r - 1)].score;
+        if (v > 0.0 && v < g) { /* exact zeros (Cephes underflow) leave nothing below them: keep the guaranteed bound */
+            use = v;
+            s0 = v;
+        }
+    }
+    kspec[q] = use;
+    kspec0[q] = s0;
+}
+
+__global__ void ppp_spec_update_kernel(double *__restrict__ kspec, const double *__restrict__ kth, uint32_t nQ)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nQ) kspec[q] = fmin(kspec[q], kth[q]);
+}
+
+__global__ void ppp_spec_verify_kernel(const ppp_hit *__restrict__ topk, const uint32_t *__restrict__ topk_cnt, const double *__restrict__ kspec0,
+                                       uint32_t k, double *__restrict__ last_tau, uint32_t *__restrict__ failed, uint32_t *__restrict__ nfailed,
+                                       uint32_t nQ)
+{
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nQ) return;
+    const double s0 = kspec0[q];
+    if (!(s0 < INFINITY)) return; /* not speculated */
+    const bool ok = topk_cnt[q] >= k && topk[(size_t)q * k + (k - 1)].score < s0;
+    if (!ok) {
+        failed[atomicAdd(nfailed, 1u)] = q;
+        last_tau[q] = INFINITY; /* force the staircase of this query to be rebuilt for the (looser) guaranteed bound */
+    }
+}
+
+extern "C" cudaError_t ppp_launch_spec_init(const void *topk, const uint32_t *topk_cnt, const double *kth, uint32_t k, uint32_t r, double *kspec,
+                                            double *kspec0, uint32_t nQ, cudaStream_t st)
+{
+    ppp_spec_init_kernel<<<(nQ + 255) / 256, 256, 0, st>>>(reinterpret_cast<const ppp_hit *>(topk), topk_cnt, kth, k, r, kspec, kspec0, nQ);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t ppp_launch_spec_update(double *kspec, const double *kth, uint32_t nQ, cudaStream_t st)
+{
+    ppp_spec_update_kernel<<<(nQ + 255) / 256, 256, 0, st>>>(kspec, kth, nQ);
+    return cudaGetLastError();
+}
+extern "C" cudaError_t ppp_launch_spec_verify(const void *topk, const uint32_t *topk_cnt, const double *kspec0, uint32_t k, double *last_tau,
+                                              uint32_t *failed, uint32_t *nfailed, uint32_t nQ, cudaStream_t st)
+{
+    ppp_spec_verify_kernel<<<(nQ + 255) / 256, 256, 0, st>>>(reinterpret_cast<const ppp_hit *>(topk), topk_cnt, kspec0, k, last_tau, failed, nfailed, nQ);
+    return cudaGetLastError();
+}

@@ -464,3 +464,44 @@ def test_exact_table_mode_is_bit_identical(ctx, G, kind, nq, nt):
     with np.errstate(divide="ignore", invalid="ignore"):
         rel = np.abs(np.log(gen["score"]) - np.log(hits["score"])) / np.abs(np.log(hits["score"]))
     assert np.all((gen["score"] == hits["score"]) | (rel <= REL_TOL_NEGLOG))
+
+
+@pytest.mark.parametrize("front_loaded", [False, True])
+def test_topk_speculative_threshold_is_verified(ctx, front_loaded):
+    """Top-k runs screen the bulk of the targets against a speculative threshold (rank r of the list after the first
+    chunks) and verify the lists afterwards; queries that fail are re-scanned with the guaranteed bound.  Exchangeable
+    targets: (almost) no failures.  Front-loaded targets (every strong match among the first targets, so the
+    speculative threshold is far too tight): the re-scan must run and the lists must still be exactly the dense
+    result's first k rows."""
+    G, nq, nt, k = 2048, 24, 30000, 20
+    P, Y, p = synth.make_queries(G, nq, 77, "mixed")
+    T = synth.make_targets(G, nt, 78, plant_from=Y, plant_frac=0.0)
+    rng = np.random.default_rng(79)
+    Yb = synth.unpack_bits(Y, G)
+    rows = np.arange(0, 600) if front_loaded else rng.choice(nt, 600, replace=False)
+    planted = (Yb[rng.integers(0, nq, size=rows.size)] != 0) ^ (rng.random((rows.size, G)) < 0.03)
+    T[rows] = synth.pack_bits(planted)
+    ctx.set_targets_bits(T, G)
+    ctx.set_option("table_mode", 0)
+    try:
+        dense = ctx.score(P, Y, p).reshape(nq, nt)
+    finally:
+        ctx.set_option("table_mode", -1)
+    tk = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
+    assert ctx.counter("spec_rank") >= 1, "the speculative phase did not run"
+    if front_loaded:
+        assert ctx.counter("spec_failed") > 0, "front-loaded targets must make the verification fail for some query"
+    assert tk.size == nq * k
+    for q in range(nq):
+        exp = np.sort(dense[q], order=["score", "t"])[:k]
+        got = tk[q * k:(q + 1) * k]
+        for f in ("q", "t", "score", "yes", "number", "depth"):
+            assert np.array_equal(got[f], exp[f]), (front_loaded, q, f)
+    ctx.set_option("speculate", 0)
+    try:
+        tk0 = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
+    finally:
+        ctx.set_option("speculate", 1)
+    assert ctx.counter("spec_rank") == 0
+    for f in ("q", "t", "score", "yes", "number", "depth"):
+        assert np.array_equal(tk0[f], tk[f]), f
