@@ -95,7 +95,7 @@ def cpu_reference_throughput(w, budget_s, nthreads):
     t0 = time.perf_counter()
     oracle.score_bits_batch(P[:4], Y[:4], p[:4], T[:32], w["G"], nthreads=nthreads)  # calibration
     rate = 128 / max(time.perf_counter() - t0, 1e-6)
-    npairs = int(min(max(rate * budget_s, 256), 16 * 64 * 64))
+    npairs = int(min(max(rate * budget_s, 256), 16 * 64 * 1024))
     nq = 16
     nt = max(16, npairs // nq)
     T = synth.make_targets(w["G"], nt, synth.SEED_BASE + 103, plant_from=Y, plant_frac=0.01)
@@ -278,22 +278,31 @@ def run_ours(args):
         except OSError:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # Dominant kernel = the thread-per-pair integer pre-filter (ppp_prefilter_kernel).  Its ALGORITHMIC HBM bytes per
-        # step: target planes once, query planes once, survivor ids out; both operands are reused
-        # on chip, so the kernel is bound by the POPC (XU) pipe, not by HBM -- reported as pipe_roofline.
+        # Dominant kernel = the thread-per-pair integer pre-filter (ppp_prefilter2_kernel, ppp_prefilter.cu; two launches
+        # per target chunk: all-ones presence planes / general).  Its ALGORITHMIC HBM bytes per step: target planes once,
+        # query planes once, survivor ids out; both operands are reused on chip, so the kernel is
+        # bound by the integer pipes (POPC on the XU pipe: 16 lanes/clk/SM), not by HBM -- reported as pipe_roofline.
         W_bytes = ((G + 1023) // 1024) * 128
         pf_ms = pf_us_mean * 1e-3
         alg_bytes = nt * W_bytes + nq * 2 * W_bytes + 4 * surv_mean
         achieved = alg_bytes / (pf_ms * 1e-3) / 1e9 if pf_ms > 0 else 0.0
-        # POPC work the pre-filter must do: per pair and 32-bit word one POPC of T&P&Y plus one of T&P (shared by all
-        # queries whose presence plane is all ones: 1/8 per pair in the 8-query groups)
         words = W_bytes // 4
-        frac_all = float(np.mean(np.all(P == P[0], axis=1) & (synth.unpack_bits(P[:1], G).all())))
-        popc_per_pair = words * (1.0 + (1.0 - frac_all) + frac_all / 8.0)
+        frac_all = float(np.mean(synth.unpack_bits(P, G).all(axis=1)))
+        # POPC the kernel EXECUTES per pair: carry-save adders fold a 4-word chunk into 3 POPC (8 words -> 4 at G=8192);
+        # the first chunk is screened word by word; all-ones queries take number from a per-target depth prefix that is
+        # computed once per 32-query tile; general queries count T&P as well.
+        ch = 8 if words == 256 else 4
+        nch, per_chunk = words // ch, (4 if ch == 8 else 3)
+        popc_all = per_chunk * (nch - 1) + ch + ch / 8.0 + per_chunk * nch / 32.0
+        popc_gen = 2 * per_chunk * (nch - 1) + 2 * ch
+        popc_exec = frac_all * popc_all + (1.0 - frac_all) * popc_gen
+        # SURVEY.md section 8(d) counts the straightforward algorithm: 2W POPC per pair when P is all ones, 3W otherwise
+        popc_survey = frac_all * 2 * words + (1.0 - frac_all) * 3 * words
         clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
         nsm = ctx.counter("num_sms")
         popc_peak = nsm * 16 * clk  # POPC issues on the XU pipe: 16 lanes / clk / SM (ncu: sm__inst_executed_pipe_xu)
-        popc_rate = pf_pairs_mean * popc_per_pair / (pf_ms * 1e-3) if pf_ms > 0 else 0.0
+        pairs_rate = pf_pairs_mean / (pf_ms * 1e-3) if pf_ms > 0 else 0.0
+        popc_rate = pairs_rate * popc_exec
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -307,16 +316,22 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "ppp_prefilter_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "ppp_prefilter2_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None,
                          "kernel_ms_per_step": pf_ms, "kernel_share_of_step": pf_ms / step_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                          "note": "operands are reused on chip (targets resident in L2, query tile in shared memory): HBM is not the "
                                  "bound of this kernel, the POPC pipe is -- see pipe_roofline"},
-            "pipe_roofline": {"bound": "xu_popc", "kernel": "ppp_prefilter_kernel", "achieved": popc_rate / 1e12, "peak": popc_peak / 1e12,
-                              "unit": "TPOPC/s", "frac": popc_rate / popc_peak, "popc_per_pair": popc_per_pair,
-                              "pairs_per_s_in_kernel": pf_pairs_mean / (pf_ms * 1e-3) if pf_ms > 0 else 0.0,
-                              "peak_source": f"{nsm} SMs x 16 POPC/clk/SM x {clk / 1e6:.0f} MHz (sampled SM clock)"},
+            "pipe_roofline": {"bound": "xu_popc", "kernel": "ppp_prefilter2_kernel", "achieved": popc_rate / 1e12, "peak": popc_peak / 1e12,
+                              "unit": "TPOPC/s", "frac": popc_rate / popc_peak, "popc_executed_per_pair": popc_exec,
+                              "popc_per_pair_survey_8d": popc_survey, "frac_vs_survey_count": pairs_rate * popc_survey / popc_peak,
+                              "pairs_per_s_in_kernel": pairs_rate, "all_ones_presence_fraction": frac_all,
+                              "peak_source": f"{nsm} SMs x 16 POPC/clk/SM x {clk / 1e6:.0f} MHz (sampled SM clock)",
+                              "note": "frac = executed POPC / pipe peak (a utilisation); frac_vs_survey_count uses the straightforward "
+                                      "algorithm's POPC count and can exceed 1 because carry-save adders and the shared depth prefix "
+                                      "remove POPCs"},
+            "topk_schedule": {"speculative_rank": ctx.counter("spec_rank"), "queries_rescanned": ctx.counter("spec_failed"),
+                              "survivors_fully_evaluated": int(surv_mean)},
         }
         if world == 1:
             info, _ = cpu_reference_throughput(w, 15.0, os.cpu_count() or 1)

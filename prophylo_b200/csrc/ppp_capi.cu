@@ -105,6 +105,7 @@ struct ppp_ctx {
     uint32_t stair_need_any = 0; /* staircase footprint of the worst possible general tile (re-scan of arbitrary queries) */
     int speculate = 1;           /* top-k: screen the bulk of the targets against a speculative, verified threshold */
     uint32_t spec_rank = 0, spec_failed = 0;
+    int seed_mult = 9, chunk1_mult = 24, spec_eps_ppm = 5000; /* top-k schedule: seeding targets / k, first chunk / k, P(spec fails) */
     size_t nQ = 0, capQ = 0;
     /* results */
     ppp_hit *d_hits = nullptr;
@@ -598,7 +599,7 @@ static int launch_chunk_deferred(ppp_ctx *ctx, SweepParams *prm, uint32_t *launc
         if ((rc = launch_prefiltered(ctx, prm, ctx->evpool[em], qlist, nlist))) return rc;
         *launches += 2;
         ctx->spans.push_back({e0, em, 4});
-        ctx->prefilter_pairs += (unsigned long long)prm->nQ * (prm->t1 - prm->t0);
+        ctx->prefilter_pairs += (unsigned long long)(qlist ? nlist : prm->nQ) * (prm->t1 - prm->t0);
     } else if (ctx->ranked) {
         CU(ppp_launch_sweep_ranked(prm, ctx->rwpl, ctx->sweep_warps, ctx->nsm, ctx->stream));
     } else {
@@ -829,7 +830,8 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         };
         if (topk) {
             /* ---- top-k: no host synchronisation until the lists are final ---- */
-            const size_t first = std::max<size_t>(256, 3 * (size_t)k);
+            const size_t first = std::max<size_t>(256, (size_t)ctx->seed_mult * k);             /* targets of the seeding pass */
+            const size_t chunk1 = std::max<size_t>(4 * 256, (size_t)ctx->chunk1_mult * k);      /* first exact chunk */
             const size_t w0 = std::min<size_t>(std::min(maxw, nT), first);
             if (w0 >= (size_t)k) {
                 /* Seeding pass: the k-th smallest UPPER bound (float enclosure only, no series, no exact tier) over the
@@ -860,7 +862,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                     const double lam = (double)k * (double)processed / (double)nT;
                     double term = exp(-lam), cdf = term; /* P(X <= 0) */
                     uint32_t r = 1;
-                    while (1.0 - cdf > 1e-3 && r < k) {
+                    while (1.0 - cdf > 1e-6 * ctx->spec_eps_ppm && r < k) {
                         term *= lam / (double)r;
                         cdf += term;
                         ++r;
@@ -872,7 +874,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                     ctx->spec_rank = r;
                 }
                 size_t w = std::min(maxw, nT - processed);
-                if (!spec_on) w = std::min(w, processed ? 4 * processed : (seeded_pass ? 4 * first : first));
+                if (!spec_on) w = std::min(w, processed ? 4 * processed : (seeded_pass ? chunk1 : first));
                 const double *kth_used = spec_on ? d_kspec : ctx->d_kth;
                 size_t ea, eb;
                 if (processed || seeded_pass) {
@@ -1116,6 +1118,9 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
     else if (!strcmp(name, "table_mode")) {
         if (value < -1 || value > 1) return fail(ctx, PPP_ERR_INVALID, "table_mode must be -1 (auto), 0 (off) or 1 (on)");
         ctx->table_mode = (int)value;
+    } else if (!strcmp(name, "seed_mult") || !strcmp(name, "chunk1_mult") || !strcmp(name, "spec_eps_ppm")) {
+        if (value < 1 || value > 1000000) return fail(ctx, PPP_ERR_INVALID, "%s out of range", name);
+        (name[1] == 'e' ? ctx->seed_mult : name[0] == 'c' ? ctx->chunk1_mult : ctx->spec_eps_ppm) = (int)value;
     } else if (!strcmp(name, "speculate")) {
         ctx->speculate = value != 0;
     } else if (!strcmp(name, "prefilter_version")) {
