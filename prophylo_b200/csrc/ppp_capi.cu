@@ -476,6 +476,20 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
         ctx->n_pall = order.size();
         for (size_t q = 0; q < nQ; ++q)
             if (!qfl[q]) order.push_back((uint32_t)q);
+        /* deal the queries of each kind over its tiles by descending |Y| (tile i takes the i-th, (i + ntiles)-th ...
+         * largest): every tile then holds about the same staircase footprint, which is what sizes the kernel's shared
+         * memory (and hence its occupancy), and about the same amount of slow-path work */
+        for (int kind = 0; kind < 2; ++kind) {
+            const size_t b = kind ? 0 : ctx->n_pall, e = kind ? ctx->n_pall : nQ, n = e - b;
+            const size_t qt = ppp_prefilter2_tile_queries(kind);
+            if (n <= qt) continue;
+            std::vector<uint32_t> sorted(order.begin() + b, order.begin() + e);
+            std::stable_sort(sorted.begin(), sorted.end(), [&](uint32_t x, uint32_t y) { return qc[x].ny > qc[y].ny; });
+            const size_t ntiles = (n + qt - 1) / qt;
+            size_t o = b;
+            for (size_t tile = 0; tile < ntiles; ++tile)
+                for (size_t j = 0; j * ntiles + tile < n && j < qt; ++j) order[o++] = sorted[j * ntiles + tile];
+        }
         CU(cudaMemcpyAsync(ctx->d_qorder, order.data(), nQ * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         for (int kind = 0; kind < 2; ++kind) {
             const size_t b = kind ? 0 : ctx->n_pall, e = kind ? ctx->n_pall : nQ;

@@ -134,7 +134,8 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
     uint32_t *s_sbase = s_qid + 32;                                  /* [40] doubled staircase index of slot i's entry 0 */
     uint32_t *s_misc = s_sbase + 40;                                 /* [0] nact, [1] inactive count */
     uint32_t *s_inact = s_misc + 8;                                  /* [32] query ids that accept every pair */
-    uint32_t *s_y = reinterpret_cast<uint32_t *>(smem_raw + 1024);   /* [NSLOT][W] yes planes of the compact slots */
+    uint32_t *s_pass = reinterpret_cast<uint32_t *>(smem_raw + 1024); /* [THREADS] per target: compact slots with a passing candidate */
+    uint32_t *s_y = s_pass + PF2_THREADS;                            /* [NSLOT][W] yes planes of the compact slots */
     uint32_t *s_p = s_y + NSLOT * W;                                 /* [NSLOT][W] presence planes (general launch) */
     uint16_t *s_pref = reinterpret_cast<uint16_t *>(s_y + (PALL ? 1 : 2) * NSLOT * W); /* [NCH][THREADS] doubled number before chunk */
     uint32_t *s_queue = reinterpret_cast<uint32_t *>(s_pref + (PALL ? NCH * PF2_THREADS : 0)); /* [QCAP][QW][THREADS] */
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
         const uint32_t tl = tb * PF2_THREADS + tid;
         const bool live = tl < a.nTl;
         const uint32_t t = a.t0 + (live ? tl : 0);
-        uint32_t passbits = 0; /* by compact slot */
+        s_pass[tid] = 0; /* by compact slot; written by whichever lane of the warp re-screens this target's entries */
 
         if (PALL && npad) { /* doubled number (= depth) before every chunk of this thread's target row */
             uint32_t run = 0;
@@ -243,24 +244,47 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
         uint32_t *qp = qbase;
 
         /* Slow path, all lanes of the warp together: re-screen the queued chunks word by word, then candidate by
-         * candidate (number at the candidate <= nmax[its rank]). */
+         * candidate (number at the candidate <= nmax[its rank]).  The warp's entries are POOLED: lane i takes the
+         * i-th, (i+32)-th ... entry of the concatenated queues whoever pushed it (queue lengths differ a lot between
+         * dense and sparse targets), so a drain costs ceil(total / 32) rounds instead of the longest queue. */
         auto drain = [&]() {
 #ifdef PF2_NODRAIN
             qp = qbase;
             return;
 #endif
             PF2_STAT(st_drain += 1;)
-            for (;;) {
-                const bool have = qp != qbase;
-                if (!__any_sync(FULL, have)) break;
+            __syncwarp(); /* the other lanes' pushes are read below */
+            const uint32_t cnt = (uint32_t)(qp - qbase) / QSTRIDE;
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t excl = incl - cnt, total = __shfl_sync(FULL, incl, 31);
+            const uint32_t wbase = (uint32_t)tid & ~31u; /* first thread of this warp */
+            for (uint32_t base = 0; base < total; base += 32) {
                 PF2_STAT(st_iter += 1;)
-                if (have) {
-                    qp -= QSTRIDE;
-                    const uint32_t e = qp[0];
+                const uint32_t g = base + lane;
+                /* owner = the last lane whose exclusive prefix is <= g (lanes with empty queues share their successor's) */
+                uint32_t own = 0;
+#pragma unroll
+                for (int step = 16; step; step >>= 1) {
+                    const uint32_t cand = own + step;
+                    const uint32_t ex = __shfl_sync(FULL, excl, cand & 31);
+                    if (ex <= g) own = cand;
+                }
+                const uint32_t oex = __shfl_sync(FULL, excl, own);
+                if (g < total) {
+                    const uint32_t otid = wbase + own, kq = g - oex;
+                    const uint32_t *qe = s_queue + (kq * QW) * PF2_THREADS + otid;
+                    const uint32_t e = qe[0];
                     const uint32_t sl = (e >> 24) & 31u, c = (e >> 16) & 31u;
-                    if (!((passbits >> sl) & 1u)) {
+                    if (!((s_pass[otid] >> sl) & 1u)) {
+                        const uint32_t otl = tb * PF2_THREADS + otid;
+                        const bool olive = otl < a.nTl;
                         uint32_t tw[CH], aw[CH], bw[CH];
-                        load_chunk<CH>(a.Tt, a.ntt, t, (int)c, live, tw);
+                        load_chunk<CH>(a.Tt, a.ntt, a.t0 + (olive ? otl : 0), (int)c, olive, tw);
                         load_words<CH>(s_y + sl * W + c * CH, bw);
                         if (PALL) {
 #pragma unroll
@@ -284,7 +308,7 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
                         }
                         /* state before the chunk: the entry carries the state after its chunk (or word) */
                         uint32_t yb = (e & 0xffffu) - cys;
-                        uint32_t nb = PALL ? (uint32_t)s_pref[c * PF2_THREADS + tid] : qp[PF2_THREADS] - cns;
+                        uint32_t nb = PALL ? (uint32_t)s_pref[c * PF2_THREADS + otid] : qe[PF2_THREADS] - cns;
                         const uint32_t wlo = (e & PF2_E_WORD) ? wsel : 0u;
                         bool ok = false;
 #pragma unroll
@@ -303,10 +327,12 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
                             yb += cyw[w];
                             nb += cnw[w];
                         }
-                        if (ok) passbits |= 1u << sl;
+                        if (ok) atomicOr(&s_pass[otid], 1u << sl);
                     }
                 }
             }
+            __syncwarp();
+            qp = qbase;
         };
 
         for (uint32_t g0 = 0; g0 < npad; g0 += PF2_QG) {
@@ -411,6 +437,8 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
         drain();
 
         /* ---- survivors: compact slots with a passing candidate + every query without a staircase (live threads) */
+        __syncwarp();
+        const uint32_t passbits = s_pass[tid];
         const uint32_t mycnt = live ? (__popc(passbits) + ninact) : 0;
         uint32_t incl = mycnt;
 #pragma unroll
@@ -458,7 +486,7 @@ static size_t pf2_smem_bytes(int wpl, bool pall, uint32_t stair_cap)
 {
     const size_t W = 32 * (size_t)wpl, CH = (wpl == 8 || PF2_CH == 8) ? 8 : 4, NCH = W / CH;
     const size_t nslot = PF2_QT(pall) + PF2_QG;
-    size_t b = 1024 + (pall ? 1 : 2) * nslot * W * 4;
+    size_t b = 1024 + PF2_THREADS * 4 + (pall ? 1 : 2) * nslot * W * 4;
     if (pall) b += NCH * PF2_THREADS * 2;
     b += (size_t)PF2_QCAP * (pall ? 1 : 2) * PF2_THREADS * 4;
     b += ((size_t)stair_cap * 2 + 15) & ~(size_t)15;
