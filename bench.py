@@ -202,17 +202,19 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def merge_global(hits):
-        """optional global top-k merge over ranks (the path's only exchange step): NCCL all-gather + k-way merge"""
+    def collect():
+        """results of the last run on the host.  One GPU: the device top-k lists are copied into the pinned buffer.
+        N GPUs: the path's only exchange step, the global top-k merge -- NCCL all-gather of the device-resident per-rank
+        lists + one device merge, result on every rank (the per-rank lists are not fetched separately)."""
         if world == 1:
-            return hits
+            return ctx.fetch(out_np)
         out, cnt = parallel.global_topk_device(ctx, lambda r: r * nt, k, nq, torch.device("cuda", local_rank))
         return out
 
     # ---- resident-input steps (value)
     for _ in range(args.warmup):
         ctx.run(flt)
-        merge_global(ctx.fetch(out_np))
+        collect()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -224,7 +226,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ctx.run(flt)
-        res = merge_global(ctx.fetch(out_np))
+        res = collect()
         torch.cuda.synchronize()
         wall += time.perf_counter() - t0
         st = ctx.stats()
@@ -260,7 +262,8 @@ def run_ours(args):
         t0 = time.perf_counter()
         ctx.set_targets_bits(Tp, G)
         hits = ctx.score(Pp, Yp, pp, flt, out=out_np)
-        merge_global(hits)
+        if world > 1:
+            collect()
         torch.cuda.synchronize()
         e2e_wall += time.perf_counter() - t0
     barrier()

@@ -142,6 +142,24 @@ int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *value);
 /* Row length in uint32 words of the bit-plane layout for G genomes: ceil(G/128)*4. */
 uint32_t ppp_words_per_row(uint32_t G);
 
+/* Host-side reader of the reference's per-gene BLAST caches (`.bla`: query, subject, e-value, subject taxon; written by
+ * util/cache_blast_result.pl:86 and bin/ppp.pl:1143).  Replaces the per-file Perl parse of bin/ppp.pl:606-673
+ * (get_profile) + BlastResult::get_profile (lib/PhyloProf/BlastResult.pm:192-237) for a whole genome's worth of files:
+ * subjects in first-occurrence order, a subject's last taxon wins, Perl-false taxa ("" / "0") dropped, then taxa
+ * de-duplicated with their raw 1-based list positions kept -- i.e. exactly the arrays ppp_set_targets_ranked() takes,
+ * one target per path.  universe[g] = taxon string of genome index g (taxa outside it map to 0xFFFF).  Needs no GPU and
+ * no ppp_ctx; nthreads <= 0 = all host threads.  On failure returns a negative code and a message in err.  The arrays
+ * are malloc'ed by the library: release them with ppp_free_ranked_lists(). */
+typedef struct ppp_ranked_lists {
+    uint16_t *idx;      /* [n_entries] genome index, 0xFFFF = foreign taxon */
+    uint16_t *rawdepth; /* [n_entries] 1-based raw list position */
+    uint64_t *row_off;  /* [n_targets + 1] */
+    size_t n_targets, n_entries;
+} ppp_ranked_lists;
+int ppp_read_bla(const char *const *paths, size_t n_paths, const char *const *universe, size_t G, int nthreads,
+                 ppp_ranked_lists *out, char *err, size_t errlen);
+void ppp_free_ranked_lists(ppp_ranked_lists *lists);
+
 /* Device-side evaluation of the exact tier's bdtrc (diagnostic; parity tests of cephes_exact.cuh). */
 int ppp_debug_bdtrc(ppp_ctx *ctx, const int32_t *k, const int32_t *n, const double *p, double *out, size_t m);
 

@@ -1,15 +1,22 @@
 # oracle/stubs/DBI.pm -- TEST INFRASTRUCTURE ONLY.
-# Enough of DBI for SeqToolBox::Taxonomy->new and the gi_desc lookup of bin/ppp.pl to run
-# ("no rows"); DBI/DBD::SQLite are not installed in this image.
+# Enough of DBI for SeqToolBox::Taxonomy->new and the gi_desc lookup of bin/ppp.pl to run ("no rows"); DBI/DBD::SQLite
+# are not installed in this image.  If $ENV{PPP_STUB_GI2TAXID} names a two-column TSV (gi, tax_id), every statement
+# answers execute($gi) with that one row -- what SeqToolBox::Taxonomy::get_taxon (lib/SeqToolBox/Taxonomy.pm:362-405)
+# reads from gi_taxid_prot -- so that bin/ppp_cross_score.pl can be run on synthetic BLAST tables.
 package DBI;
+my %map;
+if ( $ENV{PPP_STUB_GI2TAXID} && open( my $fh, '<', $ENV{PPP_STUB_GI2TAXID} ) ) {
+	while (<$fh>) { chomp; my ( $g, $t ) = split /\t/; $map{$g} = $t if defined $t; }
+	close $fh;
+}
 sub connect { bless {}, 'DBI::stubdb' }
 package DBI::stubdb;
-sub prepare    { bless {}, 'DBI::stubst' }
+sub prepare    { bless { row => undef }, 'DBI::stubst' }
 sub disconnect { 1 }
 sub DESTROY    { }
 package DBI::stubst;
-sub execute        { 1 }
-sub fetchrow_array { () }
+sub execute { my ( $s, $id ) = @_; $s->{row} = ( defined $id && exists $map{$id} ) ? [ $map{$id} ] : undef; 1 }
+sub fetchrow_array { my $s = shift; my $r = $s->{row}; $s->{row} = undef; return $r ? @$r : (); }
 sub finish         { 1 }
 sub DESTROY        { }
 1;

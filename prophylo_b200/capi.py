@@ -25,7 +25,8 @@ assert HIT_DTYPE.itemsize == 32
 EXPORTS = [
     "ppp_init", "ppp_destroy", "ppp_last_error", "ppp_abi_version", "ppp_set_targets_bits", "ppp_set_targets_ranked",
     "ppp_set_queries", "ppp_run", "ppp_result_count", "ppp_fetch", "ppp_score", "ppp_get_stats", "ppp_set_option",
-    "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc", "ppp_topk_device", "ppp_merge_topk_device",
+    "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc", "ppp_topk_device", "ppp_merge_topk_device", "ppp_read_bla",
+    "ppp_free_ranked_lists",
 ]
 
 
@@ -45,6 +46,11 @@ class Stats(ctypes.Structure):
         ("exact_pairs", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("sweep_kernel_ms", ctypes.c_float),
         ("total_device_ms", ctypes.c_float), ("sweep_launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
     ]
+
+
+class RankedLists(ctypes.Structure):
+    _fields_ = [("idx", ctypes.POINTER(ctypes.c_uint16)), ("rawdepth", ctypes.POINTER(ctypes.c_uint16)),
+                ("row_off", ctypes.POINTER(ctypes.c_uint64)), ("n_targets", ctypes.c_size_t), ("n_entries", ctypes.c_size_t)]
 
 
 _lib = None
@@ -94,8 +100,35 @@ def load():
     L.ppp_merge_topk_device.argtypes = [vp, vp, vp, u32, vp, sz, u32, vp, vp]
     L.ppp_debug_bdtrc.restype = ctypes.c_int
     L.ppp_debug_bdtrc.argtypes = [vp, vp, vp, vp, vp, sz]
+    L.ppp_read_bla.restype = ctypes.c_int
+    L.ppp_read_bla.argtypes = [ctypes.POINTER(ctypes.c_char_p), sz, ctypes.POINTER(ctypes.c_char_p), sz, ctypes.c_int,
+                               ctypes.POINTER(RankedLists), ctypes.c_char_p, sz]
+    L.ppp_free_ranked_lists.restype = None
+    L.ppp_free_ranked_lists.argtypes = [ctypes.POINTER(RankedLists)]
     _lib = L
     return L
+
+
+def read_bla_files(paths, universe, nthreads: int = 0):
+    """Native reader of `.bla` BLAST caches (ppp_read_bla, prophylo_b200/csrc/ppp_bla.cpp): one ranked target per path,
+    taxa mapped through `universe` (ordered taxon strings).  Returns (idx, rawdepth, row_off) as ppp_set_targets_ranked
+    takes them.  No GPU needed."""
+    L = load()
+    pa = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+    ua = (ctypes.c_char_p * len(universe))(*[str(u).encode() for u in universe])
+    out = RankedLists()
+    err = ctypes.create_string_buffer(512)
+    rc = L.ppp_read_bla(pa, len(paths), ua, len(universe), nthreads, ctypes.byref(out), err, len(err))
+    if rc != PPP_OK:
+        raise PPPError(rc, err.value.decode(errors="replace"))
+    try:
+        n, m = out.n_entries, out.n_targets
+        idx = np.ctypeslib.as_array(out.idx, shape=(max(n, 1),))[:n].copy()
+        raw = np.ctypeslib.as_array(out.rawdepth, shape=(max(n, 1),))[:n].copy()
+        off = np.ctypeslib.as_array(out.row_off, shape=(m + 1,)).copy()
+    finally:
+        L.ppp_free_ranked_lists(ctypes.byref(out))
+    return idx, raw, off
 
 
 def _ptr(a):

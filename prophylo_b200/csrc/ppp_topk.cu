@@ -78,19 +78,37 @@ __global__ void ppp_build_staircase_kernel(const QConst *__restrict__ qc, const 
             tab[y] = (uint16_t)res;
         }
         __syncwarp();
-        if (lane == 0) {
-            /* enforce what the true staircase satisfies (independent searches may differ by rounding; only ever
-             * loosens): non-decreasing in yes, and nmax[y] >= y  =>  nmax[y+1] >= nmax[y] + 1 (one more trial that is a
-             * success cannot raise the tail), i.e. the slack nmax[y] - y is non-decreasing -- the chunk-level screen of
-             * ppp_prefilter.cu tests only a chunk's last candidate on the strength of this */
-            uint32_t run = 0;
-            for (int y = 1; y <= ny; ++y) {
-                uint32_t v = max(run, (uint32_t)tab[y]);
-                if (y >= 2 && run >= (uint32_t)(y - 1)) v = max(v, run + 1);
-                run = min(v, 65535u);
-                tab[y] = (uint16_t)run;
+        /* enforce what the true staircase satisfies (independent searches may differ by rounding; only ever loosens):
+         * non-decreasing in yes, and nmax[y] >= y  =>  nmax[y+1] >= nmax[y] + 1 (one more trial that is a success cannot
+         * raise the tail), i.e. the slack nmax[y] - y is non-decreasing from the first valid entry on -- the chunk-level
+         * screen of ppp_prefilter.cu tests only a chunk's last candidate on the strength of this.  Two warp prefix-max
+         * scans, 32 entries a round: v1 = running max of the table, then slack = running max of (v1[i] - i) over the
+         * valid entries (v1[i] >= i); result = y + slack where a valid entry precedes, v1 otherwise. */
+        {
+            uint32_t carry_v = 0;
+            int carry_s = -1;
+            for (int y0 = 1; y0 <= ny; y0 += 32) {
+                const int y = y0 + lane;
+                const bool in = y <= ny;
+                uint32_t v = in ? (uint32_t)tab[y] : 0u;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+                    if (lane >= o) v = max(v, u);
+                }
+                v = max(v, carry_v);
+                carry_v = __shfl_sync(0xffffffffu, v, 31);
+                int sl = (in && (int)v >= y) ? (int)v - y : -1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int u = __shfl_up_sync(0xffffffffu, sl, o);
+                    if (lane >= o) sl = max(sl, u);
+                }
+                sl = max(sl, carry_s);
+                carry_s = __shfl_sync(0xffffffffu, sl, 31);
+                if (in) tab[y] = (uint16_t)min((sl >= 0) ? (uint32_t)(y + sl) : v, 65535u);
             }
-            active_off[q] = static_off[q];
+            if (lane == 0) active_off[q] = static_off[q];
         }
         __syncwarp();
     }
@@ -100,7 +118,7 @@ extern "C" cudaError_t ppp_launch_staircase(const QConst *qc, const double *lf, 
                                             const uint32_t *static_off, uint16_t *nmax, uint32_t *active_off, double *last_tau,
                                             uint32_t nQ, int nsm, cudaStream_t st)
 {
-    ppp_build_staircase_kernel<<<nsm * 4, 128, 0, st>>>(qc, lf, kth, accept_mode, thresh_ln, static_off, nmax, active_off, last_tau, nQ);
+    ppp_build_staircase_kernel<<<nsm * 16, 128, 0, st>>>(qc, lf, kth, accept_mode, thresh_ln, static_off, nmax, active_off, last_tau, nQ);
     return cudaGetLastError();
 }
 

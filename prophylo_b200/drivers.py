@@ -23,7 +23,7 @@ def read_bla(path):
     first-occurrence order, a subject's LAST taxon wins, subjects with a false taxon ('' or '0') are dropped,
     different subjects of the same taxon stay as duplicates (they count in the depth)."""
     order, taxon = [], {}
-    with open(path) as fh:
+    with open(path, newline="\n") as fh:  # Perl's chomp removes "\n" only
         for line in fh:
             f = line.rstrip("\n").split("\t")
             if len(f) < 4:
@@ -40,13 +40,18 @@ def ppp_scan(ctx: capi.Context, query: Profile, targets: dict, prob=None):
     targets: {locus: path of a .bla file | ordered taxon list}.  Returns [(locus, score, yes, number, depth, p)]."""
     q = query.get_hash()
     loci = list(targets)
-    lists = [read_bla(t) if isinstance(t, (str, os.PathLike)) else list(t) for t in targets.values()]
     p = float(prob) if prob else query.get_yes() / query.get_total()  # bin/ppp.pl:559-572, ppp.pm:138-142
     if not loci:
         return []
     index = packer.universe_index(list(q.keys()))
     P, Y, _ = packer.pack_queries([q], index)
-    idx, raw, off = packer.pack_ranked_targets(lists, index)
+    if all(isinstance(t, (str, os.PathLike)) for t in targets.values()):
+        # a genome's worth of cache files: the native multi-threaded reader (csrc/ppp_bla.cpp) parses, de-duplicates and
+        # maps them straight into the arrays of ppp_set_targets_ranked
+        idx, raw, off = capi.read_bla_files(list(targets.values()), list(index))
+    else:
+        lists = [read_bla(t) if isinstance(t, (str, os.PathLike)) else list(t) for t in targets.values()]
+        idx, raw, off = packer.pack_ranked_targets(lists, index)
     ctx.set_targets_ranked(idx, raw, off, len(index))
     hits = ctx.score(P, Y, np.array([p], dtype=np.float64))
     return [(loci[int(h["t"])], float(h["score"]), int(h["yes"]), int(h["number"]), int(h["depth"]), p) for h in hits]
@@ -199,3 +204,118 @@ def ppp2d_scan(ctx: capi.Context, gi: str, bla_path, genome_targets: dict, taxdi
         rows.append((float(score_str), line_count, fields))
     rows.sort(key=lambda r: (r[0], r[1]))
     return header + "".join(f"{lc}\t" + "\t".join(f) + "\n" for _, lc, f in rows)
+
+
+# ------------------------------------------------------------------------------------------------ ppp_cross_score.pl
+def _m8_rows(text: str):
+    """Non-comment, non-empty lines of a BLAST -m 8/9 table as 12-field lists (bin/ppp_cross_score.pl:361-370, 431-442)."""
+    for line in text.split("\n"):
+        if line.startswith("#") or line in ("", "0"):
+            continue
+        f = line.split("\t")
+        if len(f) != 12:
+            raise ValueError("Wrong BLAST result format. You should run BLAST with -m 8/9")
+        yield f
+
+
+def _m8_gi(subject: str) -> str:
+    import re
+
+    m = re.search(r"gi\|(\d+)", subject)
+    if not m:
+        raise ValueError("Could not parse gi from file")
+    return m.group(1)
+
+
+def cross_target_list(m8_text: str, gi2taxon: dict):
+    """bin/ppp_cross_score.pl:350-413 (get_target_profile_blast): one list entry per table row whose subject gi has a
+    taxon -- repeated subjects (HSPs) are NOT merged (the reference's `exists $data{$f[11]}` tests the bit score as a
+    key, so its de-duplication never fires) -- holding the subject's LAST taxon; the scorer then skips repeated taxa but
+    counts their positions in the depth (ppp.pm:189-192)."""
+    order, taxon = [], {}
+    for f in _m8_rows(m8_text):
+        t = gi2taxon.get(_m8_gi(f[1]))
+        if not t:
+            continue
+        order.append(f[1])
+        taxon[f[1]] = t
+    return [taxon[s] for s in order]
+
+
+def cross_prefix_queries(m8_text: str, gi2taxon: dict, n_taxa: int, start=1, end=None, skip=1, scale=1.0):
+    """The depth-prefix queries of bin/ppp_cross_score.pl:415-546 (_evaluate, BLAST mode): at every row that brings a new
+    taxon (subject to --skip / --start-depth / --end-depth) the query profile is {seen taxa: 1} (no zeros) and
+    p = line_count / n_taxa * scale.  Returns [(line_count, gi, seen-taxa tuple, p)]."""
+    out, seen, line_count = [], {}, 0
+    for f in _m8_rows(m8_text):
+        line_count += 1
+        gi = _m8_gi(f[1])
+        t = gi2taxon.get(gi)
+        if not t or t in seen:
+            continue
+        seen[t] = 1
+        if line_count % skip:
+            continue
+        tc = len(seen)
+        if end and tc > end:
+            break
+        if tc >= start:
+            pr = line_count / n_taxa
+            if scale:
+                pr = pr * scale
+            if not pr > 0:
+                raise ValueError("Error in calculating probability")
+            out.append((line_count, gi, tuple(seen), pr))
+    return out
+
+
+def _gpu_list_scorer(ctx: capi.Context):
+    """queries (list of {taxon: 0|1}), ONE ordered target taxon list, p per query -> [(score, yes, number, depth)] in one GPU call."""
+
+    def score(queries, target, probs):
+        universe = {}
+        for q in queries:
+            for t in q:
+                universe.setdefault(t, None)
+        index = packer.universe_index(list(universe))
+        P, Y, _ = packer.pack_queries(queries, index)
+        idx, raw, off = packer.pack_ranked_targets([target], index)
+        ctx.set_targets_ranked(idx, raw, off, len(index))
+        hits = ctx.score(P, Y, np.asarray(probs, dtype=np.float64))
+        return [(float(h["score"]), int(h["yes"]), int(h["number"]), int(h["depth"])) for h in hits]
+
+    return score
+
+
+def _cross_direction(scorer, src_text, dst_text, gi2taxon, n_taxa, start, end, skip, scale):
+    """Every depth prefix of `src` scored against the hit list of `dst` in ONE scorer call; the best depth is the first
+    one whose printed %.3f log-score is strictly lower than the running best (bin/ppp_cross_score.pl:511-538)."""
+    qs = cross_prefix_queries(src_text, gi2taxon, n_taxa, start, end, skip, scale)
+    if not qs:
+        return None
+    target = cross_target_list(dst_text, gi2taxon)
+    res = scorer([{t: 1 for t in q[2]} for q in qs], target, [q[3] for q in qs])
+    best = None
+    for (score, yes, number, depth), (line_count, gi, _, pr) in zip(res, qs):
+        if score <= 0.0:
+            raise ZeroDivisionError("Can't take log of 0")  # bin/ppp_cross_score.pl:511 dies on log(0)
+        row = (_log10_3f(score), yes, number, depth, "%.2f" % pr)
+        if best is None or float(best[2][0]) > float(row[0]):
+            best = (line_count, gi, row)
+    return best
+
+
+def cross_score_blast(ctx, file1: str, text1: str, file2: str, text2: str, gi2taxon: dict, n_taxa: int, start=1, end=None,
+                      skip=1, scale=1.0, scorer=None) -> str:
+    """bin/ppp_cross_score.pl --method1 blast --method2 blast in process: both directions, each one GPU call over all
+    depth prefixes (the reference writes a temporary profile file and runs the Perl sweep per depth).  Returns the
+    script's stdout text (bin/ppp_cross_score.pl:283-292).  n_taxa = non-comment lines of --dist-file (:299-311)."""
+    out = []
+    scorer = scorer or _gpu_list_scorer(ctx)  # tests inject the oracle here; the product path is the GPU
+    for (which, fa, ta, fb, tb, total) in (("File1", file1, text1, file2, text2, "#Total"), ("File2", file2, text2, file1, text1, "#Toal")):
+        best = _cross_direction(scorer, ta, tb, gi2taxon, n_taxa, start, end, skip, scale)
+        if best is None:
+            raise ValueError(f"no depth of {fa} was evaluated")
+        out.append(f"{which}: {fa} Best result in {fb}:\nSource_Line:gi\tScore\t#yes\t{total}\t#Depth\t#Prob\n"
+                   f"{best[0]}:{best[1]}\t" + "\t".join(str(x) for x in best[2]) + "\n")
+    return out[0] + "\n" + out[1]

@@ -127,3 +127,40 @@ def test_ppp2d_in_process_matches_oracle_restatement(e2e, tmp_path):
         f"{lc}\t" + "\t".join(f) + "\n" for _, lc, f in rows)
     assert len(rows) > 5
     assert got == exp
+
+
+@pytest.fixture(scope="module")
+def cross_cases(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "ppp_cross_score.json")))["cases"]
+
+
+def test_cross_score_host_logic_matches_reference_with_oracle_scores(cross_cases):
+    """CPU: the depth-prefix construction, the target list, the %.3f ranking and the stdout format of
+    bin/ppp_cross_score.pl (BLAST x BLAST) with the per-pair scores taken from the oracle instead of the GPU."""
+
+    def oracle_scorer(queries, target, probs):
+        return [oracle.score_case(q, target, prob=p)[:4] for q, p in zip(queries, probs)]
+
+    for case in cross_cases:
+        n_taxa = sum(1 for ln in case["dist"].split("\n") if ln and not ln.startswith("#"))
+        got = drivers.cross_score_blast(None, "a.m8", case["file1"], "b.m8", case["file2"], case["gi2taxid"], n_taxa,
+                                        start=case["start"], end=case["end"], skip=case["skip"], scale=case["scale"] or 1.0,
+                                        scorer=oracle_scorer)
+        assert got == case["stdout"], (case["seed"], got, case["stdout"])
+
+
+@pytest.mark.gpu
+def test_cross_score_on_gpu_reproduces_reference_stdout(cross_cases):
+    """bin/ppp_cross_score.pl in process: every depth prefix of one BLAST table against the other's hit list, one GPU
+    call per direction; byte-identical to the stdout of the unmodified reference script (oracle/gen_golden_cross.py)."""
+    from prophylo_b200 import capi
+
+    ctx = capi.Context(0)
+    try:
+        for case in cross_cases:
+            n_taxa = sum(1 for ln in case["dist"].split("\n") if ln and not ln.startswith("#"))
+            got = drivers.cross_score_blast(ctx, "a.m8", case["file1"], "b.m8", case["file2"], case["gi2taxid"], n_taxa,
+                                            start=case["start"], end=case["end"], skip=case["skip"], scale=case["scale"] or 1.0)
+            assert got == case["stdout"], (case["seed"], got, case["stdout"])
+    finally:
+        ctx.close()
