@@ -195,6 +195,8 @@ def run_ours(args):
     ctx.set_queries(Pp, Yp, pp)
     out_t = torch.empty(nq * min(k, nt) * capi.HIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
     out_np = out_t.numpy().view(capi.HIT_DTYPE)
+    cnt_t = torch.empty(nq, dtype=torch.int32).pin_memory()
+    cnt_np = cnt_t.numpy().view(np.uint32)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def barrier():
@@ -208,7 +210,7 @@ def run_ours(args):
         lists + one device merge, result on every rank (the per-rank lists are not fetched separately)."""
         if world == 1:
             return ctx.fetch(out_np)
-        out, cnt = parallel.global_topk_device(ctx, lambda r: r * nt, k, nq, torch.device("cuda", local_rank))
+        out, cnt = parallel.global_topk_device(ctx, lambda r: r * nt, k, nq, torch.device("cuda", local_rank), out=out_np, cnt=cnt_np)
         return out
 
     # ---- resident-input steps (value)

@@ -240,11 +240,15 @@ class Context:
         self._check(self.lib.ppp_topk_device(self._h, ctypes.byref(lp), ctypes.byref(cp), ctypes.byref(k), ctypes.byref(nq)))
         return lp.value, cp.value, k.value, nq.value
 
-    def merge_topk_device(self, lists_ptr: int, counts_ptr: int, nlists: int, t_offsets, n_queries: int, k: int):
-        """Merge `nlists` gathered device lists into the global per-query top-k; returns (hits [nQ*k], counts [nQ]) on the host."""
+    def merge_topk_device(self, lists_ptr: int, counts_ptr: int, nlists: int, t_offsets, n_queries: int, k: int, out=None, cnt=None):
+        """Merge `nlists` gathered device lists into the global per-query top-k; returns (hits [nQ*k], counts [nQ]) on the
+        host (`out` / `cnt`: caller's buffers, e.g. pinned memory)."""
         offs = np.ascontiguousarray(t_offsets, dtype=np.uint32)
-        out = np.empty(n_queries * k, dtype=HIT_DTYPE)
-        cnt = np.empty(n_queries, dtype=np.uint32)
+        if out is None:
+            out = np.empty(n_queries * k, dtype=HIT_DTYPE)
+        if cnt is None:
+            cnt = np.empty(n_queries, dtype=np.uint32)
+        assert out.dtype == HIT_DTYPE and out.size >= n_queries * k and cnt.dtype == np.uint32 and cnt.size >= n_queries
         self._check(self.lib.ppp_merge_topk_device(self._h, ctypes.c_void_p(lists_ptr), ctypes.c_void_p(counts_ptr), nlists, _ptr(offs),
                                                    n_queries, k, _ptr(out), _ptr(cnt)))
         return out, cnt

@@ -446,9 +446,12 @@ static size_t refine_smem_bytes(int wpl, int nwarps)
 }
 static size_t prefilter_smem_bytes(int wpl) { return 128 + PPP_QTILE * 2 * 32 * (size_t)wpl * 4 + 2 * PPP_QTILE * 4 + 64; }
 
+#define PPP_MAX_DYN_SMEM (227 * 1024) /* per-CTA limit of sm_100 */
+
 template <int WPL>
 static cudaError_t launch_t(const SweepParams &prm, int nwarps, int nsm, cudaStream_t st)
 {
+    while (nwarps > 1 && sweep_smem_bytes(WPL, nwarps) > PPP_MAX_DYN_SMEM) --nwarps; /* G = 8192: the tile + table leave room for 15 warps */
     const size_t smem = sweep_smem_bytes(WPL, nwarps);
     cudaError_t e = cudaFuncSetAttribute(ppp_sweep_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -487,6 +490,7 @@ static cudaError_t launch_filtered_t(const SweepParams &prm, const void *Tt, uin
         if (between && (e = cudaEventRecord(between, st)) != cudaSuccess) return e;
     }
     {
+        while (nwarps > 1 && refine_smem_bytes(WPL, nwarps) > PPP_MAX_DYN_SMEM) --nwarps;
         const size_t smem = refine_smem_bytes(WPL, nwarps);
         e = cudaFuncSetAttribute(ppp_refine_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -528,6 +532,7 @@ template <int WPL>
 static cudaError_t launch_refine_t(const SweepParams &prm, const uint32_t *surv, const unsigned long long *surv_count, unsigned long long surv_cap,
                                    int nwarps, int nsm, cudaStream_t st)
 {
+    while (nwarps > 1 && refine_smem_bytes(WPL, nwarps) > PPP_MAX_DYN_SMEM) --nwarps;
     const size_t smem = refine_smem_bytes(WPL, nwarps);
     cudaError_t e = cudaFuncSetAttribute(ppp_refine_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(256) ppp_topk_merge_lists_kernel(const ppp_hit
                                                                    ppp_hit *__restrict__ out, uint32_t *__restrict__ out_cnt)
 {
     extern __shared__ __align__(16) unsigned char smem_topk[];
-    ppp_hit *rec = reinterpret_cast<ppp_hit *>(smem_topk);
+    MKey *key = reinterpret_cast<MKey *>(smem_topk); /* 16-byte keys are sorted, the winners' records gathered afterwards */
     __shared__ uint32_t s_base[17];
     for (uint32_t q = blockIdx.x; q < nQ; q += gridDim.x) {
         if (threadIdx.x == 0) {
@@ -275,17 +275,23 @@ __global__ void __launch_bounds__(256) ppp_topk_merge_lists_kernel(const ppp_hit
         const uint32_t tot = s_base[nlists];
         for (uint32_t l = 0; l < nlists; ++l) {
             const uint32_t c = s_base[l + 1] - s_base[l];
+            const ppp_hit *src = lists + ((size_t)l * nQ + q) * k;
             for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
-                ppp_hit h = lists[((size_t)l * nQ + q) * k + i];
-                h.t += offs.t[l];
-                rec[s_base[l] + i] = h;
+                MKey m;
+                m.score = src[i].score;
+                m.t = src[i].t + offs.t[l];
+                m.idx = (l << 16) | i; /* k <= 2048 */
+                key[s_base[l] + i] = m;
             }
         }
         uint32_t n2 = 1;
         while (n2 < tot) n2 <<= 1;
         for (uint32_t i = tot + threadIdx.x; i < n2; i += blockDim.x) {
-            rec[i].score = INFINITY;
-            rec[i].t = 0xffffffffu;
+            MKey m;
+            m.score = INFINITY;
+            m.t = 0xffffffffu;
+            m.idx = 0xffffffffu;
+            key[i] = m;
         }
         __syncthreads();
         for (uint32_t size = 2; size <= n2; size <<= 1) {
@@ -294,17 +300,22 @@ __global__ void __launch_bounds__(256) ppp_topk_merge_lists_kernel(const ppp_hit
                     const uint32_t lo = 2 * i - (i & (stride - 1));
                     const uint32_t hi = lo + stride;
                     const bool asc = ((lo & size) == 0);
-                    const ppp_hit a = rec[lo], b = rec[hi];
-                    if (rec_less(b, a) == asc) {
-                        rec[lo] = b;
-                        rec[hi] = a;
+                    const MKey a = key[lo], b = key[hi];
+                    if (key_less(b, a) == asc) {
+                        key[lo] = b;
+                        key[hi] = a;
                     }
                 }
                 __syncthreads();
             }
         }
         const uint32_t keep = min(tot, k);
-        for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) out[(size_t)q * k + i] = rec[i];
+        for (uint32_t i = threadIdx.x; i < keep; i += blockDim.x) {
+            const MKey m = key[i];
+            ppp_hit h = lists[((size_t)(m.idx >> 16) * nQ + q) * k + (m.idx & 0xffffu)];
+            h.t = m.t;
+            out[(size_t)q * k + i] = h;
+        }
         if (threadIdx.x == 0) out_cnt[q] = keep;
         __syncthreads();
     }
@@ -317,10 +328,10 @@ extern "C" cudaError_t ppp_launch_topk_merge_lists(const void *lists, const uint
     if (nlists > 16 || (size_t)nlists * k > TOPK_M) return cudaErrorNotSupported;
     MergeOffsets offs;
     for (uint32_t l = 0; l < 16; ++l) offs.t[l] = l < nlists ? t_offsets[l] : 0u;
-    const int smem = TOPK_M * (int)sizeof(ppp_hit);
+    const int smem = TOPK_M * (int)sizeof(MKey);
     cudaError_t e = cudaFuncSetAttribute(ppp_topk_merge_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)min((uint32_t)(nsm * 2), nQ);
+    const unsigned grid = (unsigned)min((uint32_t)(nsm * 3), nQ);
     ppp_topk_merge_lists_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const ppp_hit *>(lists), counts, nlists, offs, nQ, k,
                                                          reinterpret_cast<ppp_hit *>(out), out_cnt);
     return cudaGetLastError();

@@ -73,7 +73,7 @@ class _DevBuf:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
 
 
-def global_topk_device(ctx, t_offset_of_rank, k: int, n_queries: int, device):
+def global_topk_device(ctx, t_offset_of_rank, k: int, n_queries: int, device, out=None, cnt=None):
     """Global top-k over the ranks' target shards without a host round trip: NCCL all-gather of the DEVICE-resident
     per-rank lists (ppp_topk_device), then the library's merge kernel (ppp_merge_topk_device).  Returns (hits, counts)
     on the host, identical on every rank.  t_offset_of_rank(r) = first global target index of rank r's shard."""
@@ -91,4 +91,4 @@ def global_topk_device(ctx, t_offset_of_rank, k: int, n_queries: int, device):
     dist.all_gather_into_tensor(g_counts, counts)
     torch.cuda.synchronize(device)
     offs = [t_offset_of_rank(r) for r in range(world)]
-    return ctx.merge_topk_device(g_lists.data_ptr(), g_counts.data_ptr(), world, offs, n_queries, k)
+    return ctx.merge_topk_device(g_lists.data_ptr(), g_counts.data_ptr(), world, offs, n_queries, k, out=out, cnt=cnt)
