@@ -529,3 +529,71 @@ def test_g8192_with_16_sweep_warps(ctx):
         got = tk[q * k:(q + 1) * k]
         for f in ("t", "score", "yes", "number", "depth"):
             assert np.array_equal(got[f], exp[f]), (q, f)
+
+
+def test_config2_full_size_is_bit_exact_against_oracle(ctx):
+    """BASELINE config 2 at its full size (1 query x 1,000,000 targets x 1024 genomes, dense): EVERY pair against the
+    oracle -- counts and cut-off indices bit-exact, scores bit-identical (exact table mode; 1 ulp only on the
+    host-libm expm1 branch)."""
+    G, nt = 1024, 1_000_000
+    P, Y, p = synth.make_queries(G, 1, synth.SEED_BASE + 2, "single")
+    T = synth.make_targets(G, nt, synth.SEED_BASE + 102, plant_from=Y, plant_frac=0.01)
+    ctx.set_targets_bits(T, G)
+    hits = ctx.score(P, Y, p)
+    assert ctx.counter("used_table") == 1
+    ref, _ = oracle.score_bits_batch(P, Y, p, T, G, nthreads=os.cpu_count() or 1)
+    ref = ref.reshape(-1)
+    for f in ("yes", "number", "depth"):
+        assert np.array_equal(hits[f], ref[f]), f
+    same = hits["score"] == ref["score"]
+    ulp = np.abs(hits["score"].view(np.int64) - ref["score"].view(np.int64))
+    assert np.all(same | ((ulp <= 1) & (hits["yes"] == 1))), int((~same).sum())
+    assert same.mean() > 0.999
+
+
+def test_config3_per_gpu_share_properties_and_sampled_oracle(ctx):
+    """BASELINE config 3's per-GPU share at full size (10,000 queries x 125,000 targets x 4096 genomes, top-100; the
+    bench workload): lists complete and sorted; identical with the speculative threshold switched off; a sample of
+    reported hits equals the oracle's record for that pair; and no target of a dense-scored sample that is missing from
+    a list beats the list's last entry."""
+    G, nq, nt, k = 4096, 10000, 125000, 100
+    P, Y, p = synth.make_queries(G, nq, synth.SEED_BASE + 3, "mixed")
+    T = synth.make_targets(G, nt, synth.SEED_BASE + 103, plant_from=Y, plant_frac=0.01)
+    ctx.set_targets_bits(T, G)
+    flt = capi.make_filter(capi.FILTER_TOPK, k=k)
+    a = ctx.score(P, Y, p, flt).copy()
+    assert ctx.counter("spec_rank") >= 1
+    assert a.size == nq * k and np.array_equal(a["q"], np.repeat(np.arange(nq, dtype=np.uint32), k))
+    sc = a["score"].reshape(nq, k)
+    tt = a["t"].reshape(nq, k)
+    assert np.all(np.diff(sc, axis=1) >= 0) and tt.max() < nt
+    tie = np.diff(sc, axis=1) == 0
+    assert np.all(np.diff(tt.astype(np.int64), axis=1)[tie] > 0)  # ties by ascending target index
+    ctx.set_option("speculate", 0)
+    try:
+        b = ctx.score(P, Y, p, flt).copy()
+    finally:
+        ctx.set_option("speculate", 1)
+    for f in ("q", "t", "score", "yes", "number", "depth"):
+        assert np.array_equal(a[f], b[f]), f
+    rng = np.random.default_rng(3)
+    for i in rng.choice(a.size, 48, replace=False):  # sampled oracle check of reported hits
+        h = a[i]
+        r, _ = oracle.score_bits_batch(P[h["q"]:h["q"] + 1], Y[h["q"]:h["q"] + 1], p[h["q"]:h["q"] + 1], T[h["t"]:h["t"] + 1], G)
+        r = r.reshape(-1)[0]
+        assert (h["yes"], h["number"], h["depth"]) == (r["yes"], r["number"], r["depth"]), i
+        assert h["score"] == r["score"] or abs(np.log(h["score"]) - np.log(r["score"])) <= REL_TOL_NEGLOG * abs(np.log(r["score"])), i
+    qs = rng.choice(nq, 16, replace=False)  # nothing outside the lists beats them (dense sample of targets)
+    ts = np.sort(rng.choice(nt, 3000, replace=False))
+    ctx.set_targets_bits(np.ascontiguousarray(T[ts]), G)
+    ctx.set_option("table_mode", 0)
+    try:
+        d = ctx.score(np.ascontiguousarray(P[qs]), np.ascontiguousarray(Y[qs]), np.ascontiguousarray(p[qs])).reshape(len(qs), len(ts))
+    finally:
+        ctx.set_option("table_mode", -1)
+    for j, q in enumerate(qs):
+        last_s, last_t = sc[q, -1], tt[q, -1]
+        inlist = set(tt[q].tolist())
+        for s, t in zip(d[j]["score"], ts):
+            if int(t) not in inlist:
+                assert (s, t) > (last_s, last_t), (q, t, s, last_s)
