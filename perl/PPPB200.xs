@@ -71,6 +71,34 @@ _set_targets_ranked(h, idx, raw, off, nT, G)
     if (ppp_set_targets_ranked(ctx, (const uint16_t *)ib, (const uint16_t *)rb, (const uint64_t *)ob, (size_t)nT, G) != PPP_OK)
         croak("PhyloProf::B200: %s", ppp_last_error(ctx));
 
+UV
+_set_targets_bla(h, paths, universe, nthreads)
+    IV h
+    AV *paths
+    AV *universe
+    int nthreads
+  CODE:
+    /* a genome's worth of `.bla` caches (bin/ppp.pl:606-673) -> ranked targets, parsed natively by ppp_read_bla */
+    ppp_ctx *ctx = INT2PTR(ppp_ctx *, h);
+    const size_t np = (size_t)(av_len(paths) + 1), G = (size_t)(av_len(universe) + 1);
+    const char **pv = NULL, **uv = NULL;
+    Newx(pv, np ? np : 1, const char *);
+    Newx(uv, G ? G : 1, const char *);
+    for (size_t i = 0; i < np; ++i) pv[i] = SvPVbyte_nolen(*av_fetch(paths, (SSize_t)i, 0));
+    for (size_t i = 0; i < G; ++i) uv[i] = SvPVbyte_nolen(*av_fetch(universe, (SSize_t)i, 0));
+    ppp_ranked_lists l;
+    char err[512];
+    int rc = ppp_read_bla(pv, np, uv, G, nthreads, &l, err, sizeof(err));
+    Safefree(pv);
+    Safefree(uv);
+    if (rc != PPP_OK) croak("PhyloProf::B200: %s", err);
+    rc = ppp_set_targets_ranked(ctx, l.idx, l.rawdepth, l.row_off, l.n_targets, (uint32_t)G);
+    RETVAL = (UV)l.n_entries;
+    ppp_free_ranked_lists(&l);
+    if (rc != PPP_OK) croak("PhyloProf::B200: %s", ppp_last_error(ctx));
+  OUTPUT:
+    RETVAL
+
 void
 _score(h, pplanes, yplanes, probs, nQ, mode, k, thresh)
     IV h

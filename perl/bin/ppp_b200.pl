@@ -1,0 +1,114 @@
+#!/usr/bin/env perl
+# perl/bin/ppp_b200.pl -- command-line drop-in for ProPhylo's bin/ppp.pl on the B200 path.
+#
+# Same options, same database layout (<db>/blast/<taxon>/<gi>.bla), same stdout table as the reference's server mode
+# (/root/reference/bin/ppp.pl:300-515): header `Locus #Yes #Total Depth Prob Score Desc`, rows sorted by raw score,
+# `%.3f` Prob and log10 Score, the optional slope marker line (-m).  What changes is the middle: instead of writing
+# chunk files of 50 cache paths and forking `perl ppp.pl --client` workers that parse every cache and sweep every gene
+# in Perl (:354-430, :519-593, :895-1017), the whole genome is ONE GPU call: the `.bla` caches are parsed natively
+# (ppp_read_bla) and every gene is scored by libppp_b200.so through the XS binding (PhyloProf::B200).
+# There is no CPU fallback.  Written from scratch against the reference's observable behaviour.
+#
+#   perl ppp_b200.pl -d <db dir> -t <taxon> -p <profile> -w <workspace> [--prob P] [-m slope] [--device N]
+#
+# Not supported (the script dies; keep bin/ppp.pl for them): -l/--level (rank collapse needs the SeqToolBox taxonomy
+# database) and --dup (a reference quirk, ppp.pm:189-200).  --threads/--serial/--keep/-c/-o/-r/-n are accepted and
+# ignored (there are no workers, temporary files or grid jobs).
+use strict;
+use warnings;
+use Getopt::Long;
+use File::Spec;
+use FindBin;
+use lib "$FindBin::Bin/../lib";
+use PhyloProf::B200;
+
+my ( $help, $db_dir, $workspace, $taxon, $profile, $level, $probability, $slope, $duplicate, $device ) = ( 0, '', '', 0, '', '', 0, 0, 0, 0 );
+my %ignored;
+GetOptions(
+    'help|h'      => \$help,      'db|d=s'   => \$db_dir, 'workspace|w=s' => \$workspace,   'taxon|t=i' => \$taxon,
+    'profile|p=s' => \$profile,   'level|l=s' => \$level, 'prob=s'        => \$probability, 'slope|m=s' => \$slope,
+    'dup'         => \$duplicate, 'device=i' => \$device,
+    'project|r=i' => \$ignored{r}, 'nodes|n=i' => \$ignored{n}, 'client' => \$ignored{client}, 'copy|c' => \$ignored{c},
+    'output|o=s'  => \$ignored{o}, 'serial'    => \$ignored{serial}, 'threads=i' => \$ignored{threads}, 'gi|g=i' => \$ignored{g},
+    'start-depth|s=i' => \$ignored{s}, 'end-depth|e=i' => \$ignored{e}, 'skip|j=i' => \$ignored{j}, 'keep|k' => \$ignored{k},
+) or die "usage: ppp_b200.pl -d <db> -t <taxon> -p <profile> -w <workspace> [--prob P] [-m slope]\n";
+die "usage: ppp_b200.pl -d <db> -t <taxon> -p <profile> -w <workspace> [--prob P] [-m slope]\n" if $help || !$taxon || !$profile;
+die "File $profile not found\n" unless -s $profile;
+die "Workspace missing\n"       unless $workspace;
+die "ppp_b200.pl: --client is the reference's worker mode; this driver has no workers\n" if $ignored{client};
+die "ppp_b200.pl: -l/--level is not supported on the B200 path (use bin/ppp.pl)\n"       if $level;
+die "ppp_b200.pl: --dup is not supported on the B200 path (use bin/ppp.pl)\n"            if $duplicate;
+
+# ---- the gene caches of the genome (bin/ppp.pl:955-1017 lists them the same way)
+my $blast_dir = File::Spec->catdir( $db_dir, "blast", $taxon );
+opendir( my $dh, $blast_dir ) or die "Can't find blast result. Did you setup the database properly?\n";
+my ( @loci, @paths );
+foreach my $file ( sort readdir($dh) ) {
+    next unless $file =~ /(\S+)\.bla$/;
+    push @loci,  $1;
+    push @paths, File::Spec->catfile( $blast_dir, $file );
+}
+closedir($dh);
+die "Can't find blast result. Did you setup the database properly?\n" unless @paths;
+
+# ---- the query profile: two tab columns taxon, 0/1; '#' comments; on a repeated taxon a non-zero value is never
+# overwritten (lib/PhyloProf/Profile.pm:433-514)
+my %q;
+open( my $pf, "<", $profile ) or die "Can't open $profile\n";
+while ( my $line = <$pf> ) {
+    chomp $line;
+    next if $line =~ /^\#/;
+    my @f = split( /\t/, $line );
+    die "$profile must contain only two fields\n" if scalar(@f) != 2;
+    next unless $f[0];                                   # a false taxon ('' or '0') is skipped
+    next if exists $q{ $f[0] } && $q{ $f[0] } != 0;
+    $q{ $f[0] } = $f[1];
+}
+close($pf);
+my $yes   = grep { $_ != 0 } values %q;
+my $total = scalar keys %q;
+die "Illegal division by zero\n" unless $total || $probability;
+my $p = $probability ? $probability + 0 : $yes / $total;    # ppp.pm:138-142, bin/ppp.pl:559-572
+
+# ---- one GPU call for the whole genome
+my @universe = sort keys %q;
+my $gpu      = PhyloProf::B200->new( -device => $device );
+my $hits     = $gpu->score_bla_files( \@universe, [ \%q ], \@paths, -probs => [$p], -filter => 'all' );
+
+# ---- the table (bin/ppp.pl:443-506).  The reference's clients print score and p with Perl's default %.15g
+# stringification and the server reads them back: reproduce that rounding.
+my ( %score, %yes, %number, %depth );
+foreach my $h (@$hits) {
+    my $locus = $loci[ $h->[1] ];
+    $score{$locus}  = 0 + sprintf( "%.15g", $h->[2] );
+    $yes{$locus}    = $h->[3];
+    $number{$locus} = $h->[4];
+    $depth{$locus}  = $h->[5];
+}
+my $prob = 0 + sprintf( "%.15g", $p );
+my $sth;
+my $desc_db = File::Spec->catfile( $db_dir, "desc", "gi_desc.sqlite3" );
+if ( -s $desc_db && eval { require DBI; 1 } ) {    # descriptions are optional: the column stays empty without the database
+    my $dbh = eval { DBI->connect( "dbi:SQLite:dbname=$desc_db", "", "", { RaiseError => 1, AutoCommit => 0 } ) };
+    $sth = eval { $dbh->prepare('select desc from gi_desc where gi =?') } if $dbh;
+}
+print "Locus\t\#Yes\t#Total\tDepth\tProb\tScore\tDesc\n";
+my ( $last_score, $cutoff_found );
+foreach my $s ( sort { $score{$a} <=> $score{$b} || $a cmp $b } keys %score ) {
+    die "Can't take log of 0\n" if $score{$s} == 0;    # as the reference does (log(0) is fatal, bin/ppp.pl:476)
+    my $log_score = sprintf( "%.3f", log( $score{$s} ) / log(10) );
+    $last_score = $log_score unless $last_score;
+    if ( $slope && $last_score && !$cutoff_found ) {
+        my $pl = $last_score < 0 ? -$last_score : $last_score;
+        my $ps = $log_score < 0  ? -$log_score  : $log_score;
+        if ( ( ( $pl - $ps ) / $pl ) * 100 > $slope ) {
+            print "-------------------------------------------\n";
+            $cutoff_found = 1;
+        }
+    }
+    my $desc = "";
+    if ($sth) { $sth->execute($s); my @row = $sth->fetchrow_array(); $desc = $row[0] if $row[0]; }
+    $log_score = "0.000" if $log_score eq "-0.000";    # handle_negative_zero, bin/ppp.pl:595-604
+    print "$s\t$yes{$s}\t$number{$s}\t$depth{$s}\t", sprintf( "%.3f", $prob ), "\t$log_score\t$desc\n";
+}
+exit(0);

@@ -76,6 +76,15 @@ sub score_ranked {
     return $self->_score_queries( $universe, $idx, $queries, %o );
 }
 
+# score every query against the hit lists cached in `.bla` files (one target per file; bin/ppp.pl:606-673 format): the
+# files are parsed, de-duplicated and mapped to the universe natively (ppp_read_bla), no Perl-side parsing
+sub score_bla_files {
+    my ( $self, $universe, $queries, $paths, %o ) = @_;
+    my $idx = _index($universe);
+    _set_targets_bla( $self->{h}, $paths, $universe, $o{-threads} || 0 );
+    return $self->_score_queries( $universe, $idx, $queries, %o );
+}
+
 # score every query (PhyloProf::Profile or {taxon=>0/1}) against every target ([taxa] in universe order semantics)
 sub score_bits {
     my ( $self, $universe, $queries, $targets, %o ) = @_;

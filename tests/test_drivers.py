@@ -164,3 +164,30 @@ def test_cross_score_on_gpu_reproduces_reference_stdout(cross_cases):
             assert got == case["stdout"], (case["seed"], got, case["stdout"])
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_perl_cli_dropin_reproduces_ppp_pl_stdout(e2e, tmp_path):
+    """perl/bin/ppp_b200.pl -- same options, database layout and stdout table as the reference's bin/ppp.pl, with the
+    chunk files / forked Perl clients replaced by one GPU call through the XS binding and the native `.bla` reader --
+    against the stdout of the unmodified reference script (modulo Perl's hash order inside score ties)."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "perl")], stdout=subprocess.DEVNULL)
+    for case in e2e:
+        d = tmp_path / f"cli{case['seed']}"
+        (d / "db" / "blast" / "1140").mkdir(parents=True)
+        (d / "ws").mkdir()
+        (d / "q.profile").write_text(case["profile"])
+        for gi, txt in case["bla"].items():
+            (d / "db" / "blast" / "1140" / f"{gi}.bla").write_text(txt)
+        cmd = ["perl", os.path.join(root, "perl", "bin", "ppp_b200.pl"), "-d", str(d / "db"), "-t", "1140", "-p", str(d / "q.profile"),
+               "-w", str(d / "ws"), "--threads", "2"]
+        if case["prob"]:
+            cmd += ["--prob", str(case["prob"])]
+        if case["slope"]:
+            cmd += ["-m", str(case["slope"])]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        assert normalise(r.stdout) == normalise(case["ppp_pl_stdout"]), case["seed"]
