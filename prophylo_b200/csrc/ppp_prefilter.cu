@@ -77,6 +77,11 @@ __device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c)
     return r;
 }
 
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 /* popcount of CH words through carry-save adders: CH = 4 -> 3 POPC, CH = 8 -> 4 POPC */
 template <int CH>
 __device__ __forceinline__ uint32_t popc_csa(const uint32_t (&b)[CH])
@@ -240,8 +245,10 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
             }
         }
 
-        uint32_t *const qbase = s_queue + tid; /* this thread's queue: entry i at qbase[i * QSTRIDE (+ THREADS)] */
-        uint32_t *qp = qbase;
+        /* this thread's queue: entry i at s_queue[i * QSTRIDE + tid] (+ THREADS for the second word); qa is the 32-bit
+         * shared-memory address of the next free entry (a 64-bit generic pointer costs two instructions per bump) */
+        const uint32_t qa0 = smem_u32(s_queue) + 4u * (uint32_t)tid;
+        uint32_t qa = qa0;
 
         /* Slow path, all lanes of the warp together: re-screen the queued chunks word by word, then candidate by
          * candidate (number at the candidate <= nmax[its rank]).  The warp's entries are POOLED: lane i takes the
@@ -249,12 +256,12 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
          * dense and sparse targets), so a drain costs ceil(total / 32) rounds instead of the longest queue. */
         auto drain = [&]() {
 #ifdef PF2_NODRAIN
-            qp = qbase;
+            qa = qa0;
             return;
 #endif
             PF2_STAT(st_drain += 1;)
             __syncwarp(); /* the other lanes' pushes are read below */
-            const uint32_t cnt = (uint32_t)(qp - qbase) / QSTRIDE;
+            const uint32_t cnt = (qa - qa0) / (4u * QSTRIDE);
             uint32_t incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -332,7 +339,7 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
                 }
             }
             __syncwarp();
-            qp = qbase;
+            qa = qa0;
         };
 
         for (uint32_t g0 = 0; g0 < npad; g0 += PF2_QG) {
@@ -380,13 +387,13 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
                             if (!PALL) nbq[j] += 2u * __popc(aw);
                             const int lim = (int)*reinterpret_cast<const int16_t *>(s_stair_b + ys[j]);
                             if ((int)(nb + cy2) <= lim) {
-                                qp[0] = ys[j] | ctag | ((uint32_t)w << 21) | ((uint32_t)j << 24) | PF2_E_WORD;
-                                if (!PALL) qp[PF2_THREADS] = nbq[j];
-                                qp += QSTRIDE;
+                                sts_u32(qa, ys[j] | ctag | ((uint32_t)w << 21) | ((uint32_t)j << 24) | PF2_E_WORD);
+                                if (!PALL) sts_u32(qa + 4u * PF2_THREADS, nbq[j]);
+                                qa += 4u * QSTRIDE;
                                 PF2_STAT(st_push += 1;)
                             }
                         }
-                        if (__any_sync(FULL, qp > qbase + (PF2_QCAP - CH) * QSTRIDE)) drain(); /* room for the next query's CH pushes */
+                        if (__any_sync(FULL, qa > qa0 + 4u * (PF2_QCAP - CH) * QSTRIDE)) drain(); /* room for the next query's CH pushes */
                     }
                 } else {
                     /* phase A: no shared-memory stores, so the eight queries' load/AND/POPC/lookup chains overlap */
@@ -421,9 +428,9 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
 #pragma unroll
                         for (int j = 0; j < PF2_QG; ++j) {
                             if ((flags >> j) & 1u) {
-                                qp[0] = ys[j] | ctag | ((uint32_t)j << 24);
-                                if (!PALL) qp[PF2_THREADS] = nbq[j];
-                                qp += QSTRIDE;
+                                sts_u32(qa, ys[j] | ctag | ((uint32_t)j << 24));
+                                if (!PALL) sts_u32(qa + 4u * PF2_THREADS, nbq[j]);
+                                qa += 4u * QSTRIDE;
                                 PF2_STAT(st_push += 1;)
                             }
                         }
@@ -431,7 +438,7 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
                 }
 #pragma unroll
                 for (int w = 0; w < CH; ++w) tw[w] = tn[w];
-                if (__any_sync(FULL, qp > qbase + (PF2_QCAP - PF2_QG) * QSTRIDE)) drain();
+                if (__any_sync(FULL, qa > qa0 + 4u * (PF2_QCAP - PF2_QG) * QSTRIDE)) drain();
             }
         }
         drain();
