@@ -162,3 +162,39 @@ extern "C" void ppp_free_ranked_lists(ppp_ranked_lists *l)
     free(l->row_off);
     memset(l, 0, sizeof(*l));
 }
+
+/* ---------------------------------------------------------------- host popcounts of the query planes (ppp_set_queries)
+ * |Y| and |P| of every query: Profile::get_yes / get_total (lib/PhyloProf/Profile.pm:342-375).  nvcc's host pass compiles
+ * __builtin_popcount without -mpopcnt into a library call (8 ms for 10,000 queries x 4096 genomes); here the POPCNT
+ * instruction is used when the CPU has it. */
+__attribute__((target("popcnt"))) static void count_rows_hw(const uint32_t *P, const uint32_t *Y, size_t nQ, size_t wpr, uint32_t *ny, uint32_t *np)
+{
+    for (size_t q = 0; q < nQ; ++q) {
+        const uint32_t *pr = P + q * wpr, *yr = Y + q * wpr;
+        uint32_t a = 0, b = 0;
+        for (size_t w = 0; w < wpr; ++w) {
+            a += (uint32_t)__builtin_popcount(pr[w] & yr[w]);
+            b += (uint32_t)__builtin_popcount(pr[w]);
+        }
+        ny[q] = a;
+        np[q] = b;
+    }
+}
+static void count_rows_sw(const uint32_t *P, const uint32_t *Y, size_t nQ, size_t wpr, uint32_t *ny, uint32_t *np)
+{
+    for (size_t q = 0; q < nQ; ++q) {
+        const uint32_t *pr = P + q * wpr, *yr = Y + q * wpr;
+        uint32_t a = 0, b = 0;
+        for (size_t w = 0; w < wpr; ++w) {
+            a += (uint32_t)__builtin_popcount(pr[w] & yr[w]);
+            b += (uint32_t)__builtin_popcount(pr[w]);
+        }
+        ny[q] = a;
+        np[q] = b;
+    }
+}
+extern "C" void ppp_host_count_rows(const uint32_t *P, const uint32_t *Y, size_t nQ, size_t wpr, uint32_t *ny, uint32_t *np)
+{
+    if (__builtin_cpu_supports("popcnt")) count_rows_hw(P, Y, nQ, wpr, ny, np);
+    else count_rows_sw(P, Y, nQ, wpr, ny, np);
+}

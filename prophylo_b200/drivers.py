@@ -319,3 +319,46 @@ def cross_score_blast(ctx, file1: str, text1: str, file2: str, text2: str, gi2ta
         out.append(f"{which}: {fa} Best result in {fb}:\nSource_Line:gi\tScore\t#yes\t{total}\t#Depth\t#Prob\n"
                    f"{best[0]}:{best[1]}\t" + "\t".join(str(x) for x in best[2]) + "\n")
     return out[0] + "\n" + out[1]
+
+
+# ------------------------------------------------------------------------------------------------ profile families
+def _taxon_sort_key(t: str):
+    """ascending numeric taxon id (bin/hmm3profile.pl:175-181 prints `sort { $a <=> $b }`); non-numeric names after, by name"""
+    try:
+        return (0, float(t), t)
+    except ValueError:
+        return (1, 0.0, t)
+
+
+def read_profile_family(paths, header=False):
+    """A set of profile files as the profile builders write them (bin/hmm3profile.pl:175-181, bin/blast2profile.pl,
+    format of lib/PhyloProf/Profile.pm:433-514: `taxon<TAB>0|1`, '#' comments) -> one shared universe (the union of
+    their taxa in canonical ascending-taxon-id order, as data/taxdis.txt lists it) and the packed planes:
+      P, Y, p   every profile as a QUERY (present = taxa listed in the file, yes = value != 0, p = yes / total)
+      T         every profile as a TARGET: its yes taxa as a bit plane, i.e. the list [g : Y[g] = 1] in canonical order
+                (the embedding of SURVEY.md section 8d)
+    Returns (universe list, P, Y, p, T)."""
+    profs = [Profile(file=str(p), header=header).get_hash() for p in paths]
+    taxa = set()
+    for q in profs:
+        taxa.update(q.keys())
+    universe = sorted(taxa, key=_taxon_sort_key)
+    index = packer.universe_index(universe)
+    P, Y, p = packer.pack_queries(profs, index)
+    return universe, P, Y, p, Y.copy()
+
+
+def profile_family_scan(ctx: capi.Context, paths, k=None, thresh_log10=None, header=False):
+    """All-pairs PPP scan of a family of profile files (BASELINE config 5: every profile against every profile's yes set)
+    in one GPU call; `k` = per-query top-k, `thresh_log10` = keep log10(score) < thresh (e.g. -0.0005: every row whose
+    printed %.3f log-score is negative, which is all bin/ppp_cutoff.pl ever reads), neither = every pair.
+    Returns (universe, hits)."""
+    universe, P, Y, p, T = read_profile_family(paths, header)
+    ctx.set_targets_bits(T, len(universe))
+    if k:
+        flt = capi.make_filter(capi.FILTER_TOPK, k=min(int(k), len(paths)))
+    elif thresh_log10 is not None:
+        flt = capi.make_filter(capi.FILTER_THRESH_LOG10, thresh=float(thresh_log10))
+    else:
+        flt = None
+    return universe, ctx.score(P, Y, p, flt)

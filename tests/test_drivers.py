@@ -191,3 +191,67 @@ def test_perl_cli_dropin_reproduces_ppp_pl_stdout(e2e, tmp_path):
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
         assert normalise(r.stdout) == normalise(case["ppp_pl_stdout"]), case["seed"]
+
+
+def _write_family(tmp_path, n=14, ntaxa=260, seed=21):
+    rng = np.random.default_rng(seed)
+    taxa = [str(x) for x in rng.choice(np.arange(100, 90000), ntaxa, replace=False)]
+    paths, profs = [], []
+    for i in range(n):
+        listed = [t for t in taxa if rng.random() < 0.9]
+        dens = float(np.exp(rng.uniform(np.log(0.03), np.log(0.4))))
+        prof = {t: int(rng.random() < dens) for t in listed}
+        if i and i % 5 == 0:  # a near copy of an earlier profile: strong matches
+            prof = {t: (v if rng.random() > 0.05 else 1 - v) for t, v in profs[i - 1].items()}
+        rows = sorted(prof.items(), key=lambda kv: float(kv[0]))
+        p = tmp_path / f"fam{i}.profile"
+        p.write_text("# taxon\tvalue\n" + "".join(f"{t}\t{v}\n" for t, v in rows))
+        paths.append(str(p))
+        profs.append(prof)
+    return paths, profs
+
+
+def test_profile_family_universe_and_planes(tmp_path):
+    """Profile files -> shared universe in ascending numeric taxon order (data/taxdis.txt / hmm3profile.pl order), query
+    planes and target planes; p = yes / total over the file's own taxa (ppp.pm:138-142)."""
+    from prophylo_b200 import synth
+
+    paths, profs = _write_family(tmp_path)
+    universe, P, Y, p, T = drivers.read_profile_family(paths)
+    assert universe == sorted({t for q in profs for t in q}, key=float)
+    G = len(universe)
+    Pb, Yb = synth.unpack_bits(P, G), synth.unpack_bits(Y, G)
+    for i, q in enumerate(profs):
+        assert {universe[g] for g in np.nonzero(Pb[i])[0]} == set(q)
+        assert {universe[g] for g in np.nonzero(Yb[i])[0]} == {t for t, v in q.items() if v}
+        assert p[i] == sum(q.values()) / len(q)
+    assert np.array_equal(T, Y)
+
+
+@pytest.mark.gpu
+def test_profile_family_all_pairs_vs_oracle(tmp_path):
+    """BASELINE config 5 through real profile files: every profile against every profile's yes set (canonical order),
+    dense, top-k and ppp_cutoff threshold -- each pair against the oracle's get_match_score on the same lists."""
+    from prophylo_b200 import capi
+
+    paths, profs = _write_family(tmp_path)
+    ctx = capi.Context(0)
+    try:
+        universe, hits = drivers.profile_family_scan(ctx, paths)
+        n = len(paths)
+        assert hits.size == n * n
+        for h in hits:
+            q, t = profs[int(h["q"])], profs[int(h["t"])]
+            target = [x for x in universe if t.get(x)]
+            s, y, num, d, _ = oracle.score_case({k: v for k, v in q.items()}, target)
+            assert (int(h["yes"]), int(h["number"]), int(h["depth"])) == (y, num, d), (h, y, num, d)
+            assert h["score"] == s or abs(np.log(h["score"]) - np.log(s)) <= 1e-9 * abs(np.log(s))
+        dense = np.sort(hits, order=["q", "score", "t"])
+        _, top = drivers.profile_family_scan(ctx, paths, k=3)
+        exp = np.concatenate([dense[dense["q"] == q][:3] for q in range(n)])
+        assert np.array_equal(top[["q", "t", "yes", "number", "depth"]], exp[["q", "t", "yes", "number", "depth"]])
+        _, th = drivers.profile_family_scan(ctx, paths, thresh_log10=-0.0005)
+        keep = dense[np.log10(dense["score"]) < -0.0005]
+        assert np.array_equal(np.sort(th, order=["q", "score", "t"])[["q", "t", "depth"]], keep[["q", "t", "depth"]])
+    finally:
+        ctx.close()
