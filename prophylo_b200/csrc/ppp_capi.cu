@@ -57,6 +57,7 @@ extern "C" cudaError_t ppp_launch_spec_update(double *kspec, const double *kth, 
 extern "C" cudaError_t ppp_launch_spec_verify(const void *topk, const uint32_t *topk_cnt, const double *kspec0, uint32_t k, double *last_tau,
                                               uint32_t *failed, uint32_t *nfailed, uint32_t nQ, cudaStream_t st);
 extern "C" void ppp_host_count_rows(const uint32_t *P, const uint32_t *Y, size_t nQ, size_t wpr, uint32_t *ny, uint32_t *np);
+extern "C" cudaError_t ppp_launch_seed_kth(const void *scores, uint32_t S, uint32_t k, double *kth, uint32_t nQ, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const unsigned long long *counters, int n, cudaStream_t st);
 
 struct ppp_ctx {
@@ -861,7 +862,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         };
         if (topk) {
             /* ---- top-k: no host synchronisation until the lists are final ---- */
-            const size_t first = std::max<size_t>(256, (size_t)ctx->seed_mult * k);             /* targets of the seeding pass */
+            const size_t first = std::min<size_t>(4096, std::max<size_t>(256, (size_t)ctx->seed_mult * k)); /* targets of the seeding pass */
             const size_t chunk1 = std::max<size_t>(4 * 256, (size_t)ctx->chunk1_mult * k);      /* first exact chunk */
             const size_t w0 = std::min<size_t>(std::min(maxw, nT), first);
             if (w0 >= (size_t)k) {
@@ -871,11 +872,16 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                 SweepParams prm;
                 fill_filtered(prm, 0, w0);
                 prm.bounds_only = 1;
+                prm.append = 3; /* dense matrix of provisional scores in d_hits; nothing is appended, no record is kept */
                 if ((rc = launch_chunk_deferred(ctx, &prm, &launches, false))) return rc;
                 sweep_launches++;
-                CU(ppp_launch_topk_merge(ctx->d_hits, d_qcnt, (uint32_t)maxw, ctx->d_topk, d_topk_cnt, ctx->d_kth, k, (uint32_t)nQ,
-                                         0u, ctx->nsm, ctx->stream));
-                CU(cudaMemsetAsync(d_topk_cnt, 0, nQ * sizeof(uint32_t), ctx->stream)); /* drop the provisional records, keep kth */
+                {
+                    size_t ea, eb;
+                    if ((rc = mark(ctx, &ea))) return rc;
+                    CU(ppp_launch_seed_kth(ctx->d_hits, (uint32_t)w0, k, ctx->d_kth, (uint32_t)nQ, ctx->nsm, ctx->stream));
+                    if ((rc = mark(ctx, &eb))) return rc;
+                    ctx->spans.push_back({ea, eb, 3});
+                }
                 launches++;
                 seeded_pass = true;
             }

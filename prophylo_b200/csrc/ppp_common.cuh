@@ -57,7 +57,8 @@ struct SweepParams {
     uint32_t force_exact;
     uint32_t check_bounds;
     /* filtered runs (PPP_FILTER_TOPK / PPP_FILTER_THRESH_LOG10) */
-    uint32_t append;           /* 0: dense hits[q*nT+t]; 1: per-query append hits[q*qcap + qcnt[q]++]; 2: global append */
+    uint32_t append;           /* 0: dense hits[q*nT+t]; 1: per-query append hits[q*qcap + qcnt[q]++]; 2: global append;
+                                  3: (bounds_only) dense matrix of provisional scores, double[nQ][t1 - t0] */
     uint32_t accept_mode;      /* 0: score < kth[q] (top-k, kth = 2.0 while the list is not full); 1: log10(score) < thresh;
                                   2: klo[q] <= score <= kth[q] (re-scan of queries whose speculative threshold failed) */
     double thresh_log10;
@@ -101,7 +102,13 @@ __device__ __forceinline__ void ppp_emit(const SweepParams &prm, uint32_t q, uin
     size_t idx;
     /* threshold seeding: a provisional score must stay STRICTLY above the real (Cephes-rounded) score of its pair,
      * also when that is exactly 0.0 (underflow), 1.0 (no hit) or a denormal -- acceptance is `score < kth` */
-    if (prm.bounds_only) score = score * (1.0 + 1e-6) + 1e-300;
+    if (prm.bounds_only) {
+        score = score * (1.0 + 1e-6) + 1e-300;
+        if (prm.append == 3) { /* seeding pass: only the bound itself is needed, as a dense [nQ][t1 - t0] matrix of doubles */
+            reinterpret_cast<double *>(prm.hits)[(size_t)q * (prm.t1 - prm.t0) + (t - prm.t0)] = score;
+            return;
+        }
+    }
     if (prm.append == 0) {
         idx = (size_t)q * prm.nT + t;
     } else {

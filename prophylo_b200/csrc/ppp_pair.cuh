@@ -288,7 +288,6 @@ __device__ __forceinline__ uint32_t evaluate_pair(const uint32_t (&tw)[WPL], con
         }
         Ustar = fminf(Ustar, warp_min_f(umin));
         __syncwarp();
-        if (prm.bounds_only) continue; /* threshold seeding: only the enclosure's upper end is needed */
         /* 4. survivors -> tier B (in rank order, so that the earliest minimum wins) */
         const float cut = Ustar + 1e-5f + 1e-6f * fabsf(Ustar);
         for (uint32_t j0 = 0; j0 < cnt; j0 += 32) {
@@ -324,12 +323,6 @@ __device__ __forceinline__ uint32_t evaluate_pair(const uint32_t (&tw)[WPL], con
             }
         }
         __syncwarp();
-    }
-    if (prm.bounds_only) {
-        /* provisional record: score <= exp(U) is guaranteed, which is all the k-th-best seeding needs */
-        res.score = exp((double)Ustar);
-        *out = res;
-        return 0;
     }
     /* 5. decide */
     const double margin = second_lnf - best_lnf;

@@ -190,14 +190,6 @@ __device__ __noinline__ bool word_has_passing_candidate(uint32_t a, uint32_t b, 
 #ifndef PF_QG
 #define PF_QG 8 /* queries per unrolled group of the pre-filter */
 #endif
-#ifdef PF_STATS
-__device__ unsigned long long g_pfstats[8][64];
-extern "C" void ppp_debug_pfstats(unsigned long long *out, int reset)
-{
-    cudaMemcpyFromSymbol(out, g_pfstats, sizeof(g_pfstats));
-    if (reset) { static unsigned long long z[8][64]; cudaMemcpyToSymbol(g_pfstats, z, sizeof(z)); }
-}
-#endif
 
 template <int WPL>
 __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams prm, const uint4 *__restrict__ Tt, uint32_t ntt,
@@ -252,11 +244,6 @@ __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams pr
             uint32_t state[PF_QG]; /* yes | number << 16 per query */
 #pragma unroll
             for (int i = 0; i < PF_QG; ++i) state[i] = 0;
-#ifdef PF_STATS
-            uint32_t stp2[PF_QG], stp4[PF_QG];
-#pragma unroll
-            for (int i = 0; i < PF_QG; ++i) stp2[i] = stp4[i] = 0;
-#endif
             for (int c = 0; c < C; ++c) {
                 const uint4 tv = live ? __ldg(Tt + (size_t)c * ntt + t) : make_uint4(0, 0, 0, 0);
                 const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
@@ -286,17 +273,6 @@ __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams pr
                     /* 128-genome screen, one lookup: no candidate of the chunk can pass unless number_before + 1 <=
                      * stair[yes_after]; the rare chunks that survive it are re-screened word by word, then per candidate */
                     const uint32_t lim = (off != PPP_NO_TABLE) ? (uint32_t)__ldg(prm.nmax + off + (st & 0xffffu)) : 0xffffu;
-#ifdef PF_STATS
-                    if (live && off != PPP_NO_TABLE) {
-                        atomicAdd(&g_pfstats[0][c], 1ull);
-                        if (cy && (st0 >> 16) + 1u <= lim) atomicAdd(&g_pfstats[1][c], 1ull);
-                        if ((st0 >> 16) + 1u <= lim) atomicAdd(&g_pfstats[2][c], 1ull);
-                        if ((c & 1) == 0) stp2[qj] = st0;
-                        if ((c & 3) == 0) stp4[qj] = st0;
-                        if ((c & 1) == 1 && (stp2[qj] >> 16) + 1u <= lim) atomicAdd(&g_pfstats[3][c], 1ull);
-                        if ((c & 3) == 3 && (stp4[qj] >> 16) + 1u <= lim) atomicAdd(&g_pfstats[4][c], 1ull);
-                    }
-#endif
                     if (cy && (st0 >> 16) + 1u <= lim) {
                         uint32_t sw = st0;
 #pragma unroll
@@ -309,9 +285,6 @@ __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams pr
                                 if (nb + 1u <= l2 &&
                                     (off == PPP_NO_TABLE || word_has_passing_candidate(a[w], b[w], nb, (sw & 0xffffu) - cyw, prm.nmax + off))) {
                                     pass |= 1u << qi;
-#ifdef PF_STATS
-                                    if (live) atomicAdd(&g_pfstats[5][c], 1ull);
-#endif
                                 }
                             }
                         }
@@ -383,34 +356,54 @@ __global__ void __launch_bounds__(512, PPP_MINBLOCKS_OF(WPL)) ppp_refine_kernel(
     const uint32_t nTl = prm.t1 - prm.t0;
     WarpCounters wc;
     (void)nwarps;
-    for (;;) { /* survivors are drawn one at a time from a global counter: their costs differ by orders of magnitude */
-        unsigned long long i = 0;
-        if (lane == 0) i = atomicAdd(&prm.counters[CNT_ITEM], 1ull);
-        i = __shfl_sync(FULL, i, 0);
-        if (i >= n) break;
-        const uint32_t id = surv[i];
-        const uint32_t q = id / nTl, tl = id % nTl, t = prm.t0 + tl;
-        uint32_t tw[WPL], pw[WPL], yw[WPL], tp[WPL], ty[WPL];
-        load_row<WPL>(prm.T + (size_t)t * W + lane * WPL, tw);
-        load_row<WPL>(prm.Q + (size_t)q * 2 * W + lane * WPL, pw);
-        load_row<WPL>(prm.Q + (size_t)q * 2 * W + W + lane * WPL, yw);
-        uint32_t dlane = 0;
-#pragma unroll
-        for (int w = 0; w < WPL; ++w) {
-            tp[w] = tw[w] & pw[w];
-            ty[w] = tp[w] & yw[w];
-            dlane += __popc(tw[w]);
+    /* Survivors are drawn from a global counter (their costs differ by orders of magnitude), 8 at a time: one atomic
+     * and one coalesced load of the ids per batch, and the rows of the whole batch (target, presence and yes planes) are
+     * prefetched into L1 before the first pair is evaluated -- the kernel runs at 16 warps per SM, so the row loads'
+     * latency is otherwise exposed at the start of every pair. */
+    constexpr uint32_t BATCH = 8;
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&prm.counters[CNT_ITEM], (unsigned long long)BATCH);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= n) break;
+        const uint32_t m = (uint32_t)min((unsigned long long)BATCH, n - base);
+        const uint32_t myid = ((uint32_t)lane < m) ? surv[base + lane] : 0u;
+        for (uint32_t e0 = 0; e0 < m; e0 += 32 / WPL) { /* one 128-byte line per lane: WPL lines per row */
+            const uint32_t e = e0 + (uint32_t)lane / WPL, line = (uint32_t)lane % WPL;
+            const uint32_t pid = __shfl_sync(FULL, myid, e & 31);
+            if (e < m) {
+                const uint32_t pq = pid / nTl, pt = prm.t0 + pid % nTl;
+                const uint32_t *rt = prm.T + (size_t)pt * W + line * 32, *rq = prm.Q + (size_t)pq * 2 * W + line * 32;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(rt));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(rq));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(rq + W));
+            }
         }
-        uint32_t dpre, dtotal;
-        depth_prefix(dlane, lane, dpre, dtotal);
-        const QConst qc = prm.qc[q];
-        const uint32_t off = prm.nmax_off[q];
-        const uint16_t *stair = (off != PPP_NO_TABLE) ? prm.nmax + off : nullptr;
-        PairOut res;
-        const uint32_t fl = evaluate_pair<WPL>(tw, tp, ty, dpre, dtotal, qc, s_lf, my_queue, my_y, my_lo, stair, prm, lane, wc, &res);
-        if (lane == 0 && !(fl & PF_REJECTED)) {
-            if (fl & PF_EXACT) push_exact(prm, id, (fl & PF_UNDERFLOW) != 0);
-            else ppp_emit(prm, q, t, res.score, res.yes, res.number, res.depth, res.margin);
+        for (uint32_t j = 0; j < m; ++j) {
+            const uint32_t id = __shfl_sync(FULL, myid, j);
+            const uint32_t q = id / nTl, tl = id % nTl, t = prm.t0 + tl;
+            uint32_t tw[WPL], pw[WPL], yw[WPL], tp[WPL], ty[WPL];
+            load_row<WPL>(prm.T + (size_t)t * W + lane * WPL, tw);
+            load_row<WPL>(prm.Q + (size_t)q * 2 * W + lane * WPL, pw);
+            load_row<WPL>(prm.Q + (size_t)q * 2 * W + W + lane * WPL, yw);
+            uint32_t dlane = 0;
+#pragma unroll
+            for (int w = 0; w < WPL; ++w) {
+                tp[w] = tw[w] & pw[w];
+                ty[w] = tp[w] & yw[w];
+                dlane += __popc(tw[w]);
+            }
+            uint32_t dpre, dtotal;
+            depth_prefix(dlane, lane, dpre, dtotal);
+            const QConst qc = prm.qc[q];
+            const uint32_t off = prm.nmax_off[q];
+            const uint16_t *stair = (off != PPP_NO_TABLE) ? prm.nmax + off : nullptr;
+            PairOut res;
+            const uint32_t fl = evaluate_pair<WPL>(tw, tp, ty, dpre, dtotal, qc, s_lf, my_queue, my_y, my_lo, stair, prm, lane, wc, &res);
+            if (lane == 0 && !(fl & PF_REJECTED)) {
+                if (fl & PF_EXACT) push_exact(prm, id, (fl & PF_UNDERFLOW) != 0);
+                else ppp_emit(prm, q, t, res.score, res.yes, res.number, res.depth, res.margin);
+            }
         }
     }
     flush_counters(prm, wc, lane);

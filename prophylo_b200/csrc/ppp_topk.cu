@@ -413,3 +413,47 @@ extern "C" cudaError_t ppp_launch_spec_verify(const void *topk, const uint32_t *
     ppp_spec_verify_kernel<<<(nQ + 255) / 256, 256, 0, st>>>(reinterpret_cast<const ppp_hit *>(topk), topk_cnt, kspec0, k, last_tau, failed, nfailed, nQ);
     return cudaGetLastError();
 }
+
+/* ------------------------------------------------------------------------------------------------ top-k seeding
+ * k-th smallest of the S provisional upper bounds of every query (dense double[nQ][S] written by the bounds-only pass):
+ * a valid bound on the query's final k-th best score.  Block per query, bitonic sort of S <= 4096 doubles. */
+__global__ void __launch_bounds__(256) ppp_seed_kth_kernel(const double *__restrict__ scores, uint32_t S, uint32_t k, double *__restrict__ kth,
+                                                           uint32_t nQ)
+{
+    extern __shared__ __align__(16) unsigned char smem_topk[];
+    double *v = reinterpret_cast<double *>(smem_topk);
+    uint32_t n2 = 1;
+    while (n2 < S) n2 <<= 1;
+    for (uint32_t q = blockIdx.x; q < nQ; q += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i < n2; i += blockDim.x) v[i] = i < S ? scores[(size_t)q * S + i] : INFINITY;
+        __syncthreads();
+        for (uint32_t size = 2; size <= n2; size <<= 1) {
+            for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                for (uint32_t i = threadIdx.x; i < (n2 >> 1); i += blockDim.x) {
+                    const uint32_t lo = 2 * i - (i & (stride - 1));
+                    const uint32_t hi = lo + stride;
+                    const bool asc = ((lo & size) == 0);
+                    const double a = v[lo], b = v[hi];
+                    if ((b < a) == asc) {
+                        v[lo] = b;
+                        v[hi] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (threadIdx.x == 0 && S >= k) kth[q] = v[k - 1];
+        __syncthreads();
+    }
+}
+
+extern "C" cudaError_t ppp_launch_seed_kth(const void *scores, uint32_t S, uint32_t k, double *kth, uint32_t nQ, int nsm, cudaStream_t st)
+{
+    if (S > 4096) return cudaErrorInvalidValue;
+    uint32_t n2 = 1;
+    while (n2 < S) n2 <<= 1;
+    const int smem = (int)(n2 * sizeof(double));
+    const unsigned grid = (unsigned)min((uint32_t)(nsm * 4), nQ);
+    ppp_seed_kth_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const double *>(scores), S, k, kth, nQ);
+    return cudaGetLastError();
+}
