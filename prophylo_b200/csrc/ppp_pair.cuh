@@ -80,13 +80,28 @@ __device__ __forceinline__ double tier_b(int y, int n, const QConst &qc, const d
     const double lnr = up ? qc.lntheta : -qc.lntheta;
     const double lead = ((lf[n] - lf[kk]) - lf[n - kk]) + ((double)kk * qc.lnp + (double)(n - kk) * qc.lnq);
     const double base = lf[m] + lf[k];
+    const double r = up ? qc.theta : 1.0 / qc.theta;
     double s = 0.0;
-    for (int i0 = 0; i0 <= m; i0 += 32) {
-        const int i = i0 + lane;
-        double t = 0.0;
-        if (i <= m) t = exp(((base - lf[m - i]) - lf[k + i]) + (double)i * lnr);
+    /* 128 terms a round, 4 consecutive terms per lane: the lane's first term from the log-factorial table (one exp),
+     * the next three by the term ratio (m - i) r / (k + i + 1) in a division-free Horner form -- one exp and one
+     * division per four terms instead of four exps */
+    for (int i0 = 0; i0 <= m; i0 += 128) {
+        const int i = i0 + 4 * lane;
+        double t = 0.0, last = 0.0;
+        if (i <= m) {
+            const double t0 = exp(((base - lf[m - i]) - lf[k + i]) + (double)i * lnr);
+            const double a1 = (double)max(m - i, 0) * r, b1 = (double)(k + i + 1);
+            const double a2 = (double)max(m - i - 1, 0) * r, b2 = b1 + 1.0;
+            const double a3 = (double)max(m - i - 2, 0) * r, b3 = b1 + 2.0;
+            const double a12 = a1 * a2, b23 = b2 * b3;
+            const double num = fma(b1, b23, fma(a1, b23, fma(a12, b3, a12 * a3))); /* b1b2b3 + a1b2b3 + a1a2b3 + a1a2a3 */
+            const double inv = 1.0 / (b1 * b23);
+            t = t0 * num * inv;
+            last = t0 * (a12 * a3) * inv; /* the lane's smallest term (ratios decrease along the series) */
+        }
         s += t;
-        if (!__any_sync(FULL, t > 1e-19)) break;
+        /* terms decrease monotonically beyond the mode, which lies at or before the series' start on both sides */
+        if (!__any_sync(FULL, last > 1e-19)) break;
     }
     s = warp_sum_d(s);
     double lnf, f;

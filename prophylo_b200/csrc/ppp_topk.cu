@@ -36,6 +36,61 @@ __device__ static bool tail_may_be_le(int y, int n, const QConst &qc, const doub
     return !(lo > (float)tau + 1e-3f + 1e-6f * fabsf((float)tau)); /* NaN-safe; margin covers the float cast of tau */
 }
 
+/* One staircase: tab[y] (y = 0..ny) = largest number for which P(X >= y | number, p) can still be <= exp(tau); the whole
+ * warp works on it (bisection per y, then the monotone fix-up).  Requires tau < -0.70 and an ordinary query. */
+__device__ static void build_staircase(const QConst &c, const double *__restrict__ lf, double tau, uint16_t *__restrict__ tab, int lane)
+{
+    const double tau_m = tau + 1e-5 + 1e-9 * fabs(tau); /* safety margin >> series + table error */
+    const int ny = (int)c.ny, np_ = (int)c.npres;
+    if (lane == 0) tab[0] = 0;
+    for (int y = 1 + lane; y <= ny; y += 32) {
+        int res = 0;
+        if (isfinite(tau_m) && tail_may_be_le(y, y, c, lf, tau_m)) {
+            int lo = y, hi = np_; /* invariant: tail_le(lo) true */
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (tail_may_be_le(y, mid, c, lf, tau_m)) lo = mid;
+                else hi = mid - 1;
+            }
+            res = lo;
+        }
+        tab[y] = (uint16_t)res;
+    }
+    __syncwarp();
+    /* enforce what the true staircase satisfies (independent searches may differ by rounding; only ever loosens):
+     * non-decreasing in yes, and nmax[y] >= y  =>  nmax[y+1] >= nmax[y] + 1 (one more trial that is a success cannot
+     * raise the tail), i.e. the slack nmax[y] - y is non-decreasing from the first valid entry on -- the chunk-level
+     * screen of ppp_prefilter.cu tests only a chunk's last candidate on the strength of this.  Two warp prefix-max
+     * scans, 32 entries a round: v1 = running max of the table, then slack = running max of (v1[i] - i) over the
+     * valid entries (v1[i] >= i); result = y + slack where a valid entry precedes, v1 otherwise. */
+    {
+        uint32_t carry_v = 0;
+        int carry_s = -1;
+        for (int y0 = 1; y0 <= ny; y0 += 32) {
+            const int y = y0 + lane;
+            const bool in = y <= ny;
+            uint32_t v = in ? (uint32_t)tab[y] : 0u;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v = max(v, u);
+            }
+            v = max(v, carry_v);
+            carry_v = __shfl_sync(0xffffffffu, v, 31);
+            int sl = (in && (int)v >= y) ? (int)v - y : -1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, sl, o);
+                if (lane >= o) sl = max(sl, u);
+            }
+            sl = max(sl, carry_s);
+            carry_s = __shfl_sync(0xffffffffu, sl, 31);
+            if (in) tab[y] = (uint16_t)min((sl >= 0) ? (uint32_t)(y + sl) : v, 65535u);
+        }
+    }
+    __syncwarp();
+}
+
 __global__ void ppp_build_staircase_kernel(const QConst *__restrict__ qc, const double *__restrict__ lf, const double *__restrict__ kth,
                                            int accept_mode, double thresh_ln, const uint32_t *__restrict__ static_off,
                                            uint16_t *__restrict__ nmax, uint32_t *__restrict__ active_off,
@@ -60,56 +115,8 @@ __global__ void ppp_build_staircase_kernel(const QConst *__restrict__ qc, const 
         /* the k-th score only ever decreases: a staircase built for a slightly larger tau stays valid (just looser) */
         if (active_off[q] != PPP_NO_TABLE && tau > last_tau[q] - 0.05) continue;
         if (lane == 0) last_tau[q] = tau;
-        const double tau_m = tau + 1e-5 + 1e-9 * fabs(tau); /* safety margin >> series + table error */
-        uint16_t *tab = nmax + static_off[q];
-        const int ny = (int)c.ny, np_ = (int)c.npres;
-        if (lane == 0) tab[0] = 0;
-        for (int y = 1 + lane; y <= ny; y += 32) {
-            int res = 0;
-            if (isfinite(tau_m) && tail_may_be_le(y, y, c, lf, tau_m)) {
-                int lo = y, hi = np_; /* invariant: tail_le(lo) true */
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (tail_may_be_le(y, mid, c, lf, tau_m)) lo = mid;
-                    else hi = mid - 1;
-                }
-                res = lo;
-            }
-            tab[y] = (uint16_t)res;
-        }
-        __syncwarp();
-        /* enforce what the true staircase satisfies (independent searches may differ by rounding; only ever loosens):
-         * non-decreasing in yes, and nmax[y] >= y  =>  nmax[y+1] >= nmax[y] + 1 (one more trial that is a success cannot
-         * raise the tail), i.e. the slack nmax[y] - y is non-decreasing from the first valid entry on -- the chunk-level
-         * screen of ppp_prefilter.cu tests only a chunk's last candidate on the strength of this.  Two warp prefix-max
-         * scans, 32 entries a round: v1 = running max of the table, then slack = running max of (v1[i] - i) over the
-         * valid entries (v1[i] >= i); result = y + slack where a valid entry precedes, v1 otherwise. */
-        {
-            uint32_t carry_v = 0;
-            int carry_s = -1;
-            for (int y0 = 1; y0 <= ny; y0 += 32) {
-                const int y = y0 + lane;
-                const bool in = y <= ny;
-                uint32_t v = in ? (uint32_t)tab[y] : 0u;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
-                    if (lane >= o) v = max(v, u);
-                }
-                v = max(v, carry_v);
-                carry_v = __shfl_sync(0xffffffffu, v, 31);
-                int sl = (in && (int)v >= y) ? (int)v - y : -1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int u = __shfl_up_sync(0xffffffffu, sl, o);
-                    if (lane >= o) sl = max(sl, u);
-                }
-                sl = max(sl, carry_s);
-                carry_s = __shfl_sync(0xffffffffu, sl, 31);
-                if (in) tab[y] = (uint16_t)min((sl >= 0) ? (uint32_t)(y + sl) : v, 65535u);
-            }
-            if (lane == 0) active_off[q] = static_off[q];
-        }
+        build_staircase(c, lf, tau, nmax + static_off[q], lane);
+        if (lane == 0) active_off[q] = static_off[q];
         __syncwarp();
     }
 }
