@@ -58,6 +58,9 @@ extern "C" cudaError_t ppp_launch_spec_verify(const void *topk, const uint32_t *
                                               uint32_t *failed, uint32_t *nfailed, uint32_t nQ, cudaStream_t st);
 extern "C" void ppp_host_count_rows(const uint32_t *P, const uint32_t *Y, size_t nQ, size_t wpr, uint32_t *ny, uint32_t *np);
 extern "C" cudaError_t ppp_launch_seed_kth(const void *scores, uint32_t S, uint32_t k, double *kth, uint32_t nQ, int nsm, cudaStream_t st);
+extern "C" size_t ppp_rank_scratch_words(size_t n);
+extern "C" cudaError_t ppp_launch_rank_hits(const ppp_hit *rec, size_t n, uint32_t nQ, uint32_t nT, ppp_hit *out, uint32_t *scratch, int nsm,
+                                            cudaStream_t st, uint32_t *launches);
 extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const unsigned long long *counters, int n, cudaStream_t st);
 
 struct ppp_ctx {
@@ -119,6 +122,12 @@ struct ppp_ctx {
     bool results_on_host = false;
     bool results_topk = false;           /* results are the device top-k lists (d_topk, counts in topk_counts) */
     std::vector<uint32_t> topk_counts;
+    ppp_hit *d_ranked = nullptr; /* threshold runs: the hits in (q, score, t) order (ppp_rank.cu) */
+    size_t cap_ranked = 0;
+    uint32_t *d_rank_tmp = nullptr;
+    size_t cap_rank_tmp = 0;
+    bool results_ranked = false;
+    int device_rank = 1; /* 0: rank threshold results on the host (developer A/B) */
     uint32_t *d_exact = nullptr;
     size_t cap_exact = 0;
     unsigned long long *d_counters = nullptr;
@@ -260,6 +269,8 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaFree(ctx->d_pfstats);
     cudaFree(ctx->d_hits);
     cudaFree(ctx->d_exact);
+    cudaFree(ctx->d_ranked);
+    cudaFree(ctx->d_rank_tmp);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_totals);
     for (cudaEvent_t e : ctx->evpool) cudaEventDestroy(e);
@@ -721,6 +732,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
     ctx->host_results.clear();
     ctx->results_on_host = (f->mode != PPP_FILTER_ALL);
     ctx->results_topk = false;
+    ctx->results_ranked = false;
     ctx->last_topk_k = 0;
     unsigned long long totals[CNT_N];
     memset(totals, 0, sizeof(totals));
@@ -999,6 +1011,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 1, thresh_ln, d_off_static, ctx->d_nmax, d_off_active,
                                     ctx->d_kth + nQ, (uint32_t)nQ, ctx->nsm, ctx->stream));
             launches++;
+            const bool one_chunk = nT <= maxw && ctx->device_rank;
             while (processed < nT) {
                 const size_t w = std::min(maxw, nT - processed);
                 SweepParams prm;
@@ -1006,6 +1019,28 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                 unsigned long long c[CNT_N];
                 if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c, !ctx->ranked))) return rc;
                 sweep_launches++;
+                if (one_chunk) {
+                    /* the whole run is one launch: rank the appended hits by (q, score, t) on the device; they stay there
+                     * until ppp_fetch copies them straight into the caller's buffer */
+                    const size_t n = c[CNT_APPEND];
+                    if (n) {
+                        if ((rc = grow(ctx, &ctx->d_ranked, &ctx->cap_ranked, n))) return rc;
+                        if ((rc = grow(ctx, &ctx->d_rank_tmp, &ctx->cap_rank_tmp, ppp_rank_scratch_words(n)))) return rc;
+                        CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+                        CU(ppp_launch_rank_hits(ctx->d_hits, n, (uint32_t)nQ, (uint32_t)nT, ctx->d_ranked, ctx->d_rank_tmp, ctx->nsm,
+                                                ctx->stream, &launches));
+                        CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+                        CU(cudaStreamSynchronize(ctx->stream));
+                        float ms = 0.f;
+                        cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
+                        ctx->phase_us[3] += 1e3 * ms;
+                    }
+                    ctx->n_results = n;
+                    ctx->results_on_host = false;
+                    ctx->results_ranked = true;
+                    processed += w;
+                    break;
+                }
                 if (c[CNT_APPEND]) {
                     const size_t old = ctx->host_results.size();
                     ctx->host_results.resize(old + c[CNT_APPEND]);
@@ -1015,8 +1050,11 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                 }
                 processed += w;
             }
-            std::sort(ctx->host_results.begin(), ctx->host_results.end(), hit_less); /* presentation order only */
-            ctx->n_results = ctx->host_results.size();
+            if (!ctx->results_ranked) {
+                /* more pairs than one launch covers: chunks were copied out as they came; ordered on the host */
+                std::sort(ctx->host_results.begin(), ctx->host_results.end(), hit_less);
+                ctx->n_results = ctx->host_results.size();
+            }
         }
     }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -1069,7 +1107,8 @@ extern "C" int ppp_fetch(ppp_ctx *ctx, ppp_hit *out, size_t cap, size_t *nout)
     } else if (ctx->results_on_host) {
         memcpy(out, ctx->host_results.data(), ctx->n_results * sizeof(ppp_hit));
     } else {
-        CU(cudaMemcpyAsync(out, ctx->d_hits, ctx->n_results * sizeof(ppp_hit), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(out, ctx->results_ranked ? ctx->d_ranked : ctx->d_hits, ctx->n_results * sizeof(ppp_hit), cudaMemcpyDeviceToHost,
+                           ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return PPP_OK;
@@ -1160,6 +1199,8 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
         (name[1] == 'e' ? ctx->seed_mult : name[0] == 'c' ? ctx->chunk1_mult : ctx->spec_eps_ppm) = (int)value;
     } else if (!strcmp(name, "speculate")) {
         ctx->speculate = value != 0;
+    } else if (!strcmp(name, "device_rank")) {
+        ctx->device_rank = value != 0;
     } else if (!strcmp(name, "prefilter_version")) {
         if (value != 1 && value != 2) return fail(ctx, PPP_ERR_INVALID, "prefilter_version must be 1 or 2");
         ctx->prefilter_version = (int)value;

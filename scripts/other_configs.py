@@ -50,7 +50,10 @@ P, Y, p = synth.make_queries(G, nq, synth.SEED_BASE + 5, "family")
 c.set_targets_bits(Y, G); c.set_queries(P, Y, p)
 s = timed(capi.make_filter(capi.FILTER_THRESH_LOG10, thresh=-0.0005), reps=2)
 out["config5_thresh"] = {"shape": f"{nq} x {nq} x G={G}", "ms": s["total_device_ms"], "pairs_per_s": nq * nq / s["total_device_ms"] * 1e3,
-                         "hits": int(c.result_count()) if hasattr(c, "result_count") else None, "exact_pairs": s["exact_pairs"]}
+                         "hits": int(c.result_count()) if hasattr(c, "result_count") else None, "exact_pairs": s["exact_pairs"],
+                         "prefilter_ms": c.counter("us_prefilter") / 1e3, "sweep_ms": c.counter("us_sweep") / 1e3,
+                         "exact_ms": c.counter("us_exact") / 1e3, "rank_ms": c.counter("us_merge") / 1e3,
+                         "survivors": c.counter("survivors")}
 s = timed(capi.make_filter(capi.FILTER_TOPK, k=100), reps=2)
 out["config5_top100"] = {"ms": s["total_device_ms"], "pairs_per_s": nq * nq / s["total_device_ms"] * 1e3,
                          "prefilter_ms": c.counter("us_prefilter") / 1e3, "survivors": c.counter("survivors")}

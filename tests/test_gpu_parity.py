@@ -250,6 +250,28 @@ def test_threshold_filter_uses_staircase_and_matches_dense(ctx):
             assert np.array_equal(th[f], exp[f]), (thresh, f)
 
 
+def test_threshold_results_ranked_on_device(ctx):
+    """Threshold runs rank their hits by (q, score, t) on the device (ppp_rank.cu: the order bin/ppp.pl:473 prints in).
+    All-pairs family shape with the diagonal (exact 0.0 scores -> ties broken by target index), enough hits for
+    several sort tiles and all 64 score bits: identical, record for record, to the host-ordered result."""
+    G, n = 8192, 700
+    P, Y, p = synth.make_queries(G, n, 77, "family")
+    ctx.set_targets_bits(Y, G)
+    flt = capi.make_filter(capi.FILTER_THRESH_LOG10, thresh=-0.0005)
+    dev = ctx.score(P, Y, p, flt).copy()
+    assert ctx.counter("us_merge") > 0
+    ctx.set_option("device_rank", 0)
+    try:
+        host = ctx.score(P, Y, p, flt).copy()
+    finally:
+        ctx.set_option("device_rank", 1)
+    assert dev.size == host.size and dev.size > 3 * 4096
+    assert dev.tobytes() == host.tobytes()
+    key = np.lexsort((dev["t"], dev["score"], dev["q"]))
+    assert np.array_equal(key, np.arange(dev.size))
+    assert (dev["score"] == 0.0).sum() >= 10  # diagonal pairs of the larger families underflow
+
+
 def test_full_size_properties(ctx):
     """Size-independent properties at BASELINE genome counts: every top-k list is sorted, within range, idempotent
     under a second run, a sub-list of the k+5 list, and each reported hit re-scores to the same record alone."""
