@@ -102,7 +102,8 @@ int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, uint32_t G)
  * the value-sorted HASH of HMMERResult, ppp.pm:147-149).  For target t, entries row_off[t]..row_off[t+1]) give,
  * in list order and ALREADY de-duplicated by the host (ppp.pm:189-192), the genome index idx[] (0..G-1 in the
  * query universe; 0xFFFF = taxon foreign to the universe) and the 1-based raw list position rawdepth[].
- * At most 65535 list positions per target. */
+ * At most 65535 list positions per target.  For -dup the host keeps the list's first repeated entry and ends the list
+ * before the second (ppp_read_bla_flags / PhyloProf::B200 / prophylo_b200.packer) and sets the "dup" option. */
 int ppp_set_targets_ranked(ppp_ctx *ctx, const uint16_t *idx, const uint16_t *rawdepth, const uint64_t *row_off,
                            size_t nT, uint32_t G);
 
@@ -135,7 +136,9 @@ int ppp_get_stats(const ppp_ctx *ctx, ppp_stats *out);
 /* Options (tests / diagnostics): "force_exact" (0/1: every pair through the exact tier),
  * "check_bounds" (0/1: verify the fast tier's enclosures against the accurate tier, count violations),
  * "sweep_warps" (warps per CTA), "table_mode" (-1 auto / 0 off / 1 on: exact (yes, number) table per query for dense
- * runs of few queries against many targets).  Unknown names return PPP_ERR_INVALID. */
+ * runs of few queries against many targets), "dup" (0/1: the resident ranked lists were packed for -dup, see
+ * ppp_read_bla_flags), "device_rank" (1/0: threshold results ranked on the device / on the host).
+ * Unknown names return PPP_ERR_INVALID. */
 int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value);
 int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *value);
 
@@ -158,6 +161,14 @@ typedef struct ppp_ranked_lists {
 } ppp_ranked_lists;
 int ppp_read_bla(const char *const *paths, size_t n_paths, const char *const *universe, size_t G, int nthreads,
                  ppp_ranked_lists *out, char *err, size_t errlen);
+/* Same with flags.  PPP_BLA_DUP packs the lists for the reference's -dup flag (bin/ppp.pl:282 -> ppp.pm:189-200, whose
+ * `$seen{key}` is ONE counter for the whole list): the first repeated taxon of a list is kept as a second entry (counted
+ * again), the list ends before the second repeated entry (`yes` is frozen from there on, so no later step can improve).
+ * Score such lists with ppp_set_option(ctx, "dup", 1): the sweep then drops the candidate that would exceed |Y|
+ * (`last if $yes > $max_yes`, ppp.pm:222-224). */
+#define PPP_BLA_DUP 1u
+int ppp_read_bla_flags(const char *const *paths, size_t n_paths, const char *const *universe, size_t G, int nthreads,
+                       uint32_t flags, ppp_ranked_lists *out, char *err, size_t errlen);
 void ppp_free_ranked_lists(ppp_ranked_lists *lists);
 
 /* Device-side evaluation of the exact tier's bdtrc (diagnostic; parity tests of cephes_exact.cuh). */

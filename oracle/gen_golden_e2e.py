@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("REFERENCE_ROOT", "/root/reference")
 
 
-def make_case(seed, ngenes, ntaxa, prob=None, slope=None):
+def make_case(seed, ngenes, ntaxa, prob=None, slope=None, dup=False):
     rng = np.random.default_rng(seed)
     taxa = [str(1000 + i) for i in range(ntaxa)]
     in_profile = taxa[: int(ntaxa * 0.85)]
@@ -34,7 +34,7 @@ def make_case(seed, ngenes, ntaxa, prob=None, slope=None):
         if not rows:
             rows = [f"{gi}\t{gi}\t0.0\t1140\n"]
         bla[gi] = "".join(rows)
-    return dict(seed=seed, profile=profile, bla=bla, prob=prob, slope=slope)
+    return dict(seed=seed, profile=profile, bla=bla, prob=prob, slope=slope, dup=bool(dup))
 
 
 def run_reference(case):
@@ -53,6 +53,8 @@ def run_reference(case):
             cmd += ["--prob", str(case["prob"])]
         if case["slope"]:
             cmd += ["-m", str(case["slope"])]
+        if case.get("dup"):
+            cmd += ["--dup"]
         r = subprocess.run(cmd, env=env, capture_output=True, text=True, check=True)
         case["ppp_pl_stdout"] = r.stdout
         case["cutoff"] = {}
@@ -65,10 +67,16 @@ def run_reference(case):
 
 def main():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"], stdout=subprocess.DEVNULL)
-    cases = [run_reference(make_case(1, 30, 60, slope=30)), run_reference(make_case(2, 45, 200)),
-             run_reference(make_case(3, 25, 90, prob=0.05, slope=15)), run_reference(make_case(4, 60, 400, slope=40))]
-    json.dump({"generator": "oracle/gen_golden_e2e.py", "reference": "bin/ppp.pl (server+clients), bin/ppp_cutoff.pl", "cases": cases},
-              open(os.path.join(ROOT, "tests", "golden", "ppp_pl_e2e.json"), "w"), separators=(",", ":"))
+    if "--dup" in sys.argv:  # the -dup flag of bin/ppp.pl (:282 -> ppp.pm:189-200), its own fixture file
+        cases = [run_reference(make_case(11, 40, 80, slope=30, dup=True)), run_reference(make_case(12, 50, 250, prob=0.08, dup=True))]
+        name = "ppp_pl_e2e_dup.json"
+    else:
+        cases = [run_reference(make_case(1, 30, 60, slope=30)), run_reference(make_case(2, 45, 200)),
+                 run_reference(make_case(3, 25, 90, prob=0.05, slope=15)), run_reference(make_case(4, 60, 400, slope=40))]
+        name = "ppp_pl_e2e.json"
+    json.dump({"generator": "oracle/gen_golden_e2e.py" + (" --dup" if "--dup" in sys.argv else ""),
+               "reference": "bin/ppp.pl (server+clients), bin/ppp_cutoff.pl", "cases": cases},
+              open(os.path.join(ROOT, "tests", "golden", name), "w"), separators=(",", ":"))
     print(f"{len(cases)} end-to-end cases; rows: {[c['ppp_pl_stdout'].count(chr(10)) for c in cases]}", file=sys.stderr)
 
 

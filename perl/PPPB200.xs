@@ -71,12 +71,22 @@ _set_targets_ranked(h, idx, raw, off, nT, G)
     if (ppp_set_targets_ranked(ctx, (const uint16_t *)ib, (const uint16_t *)rb, (const uint64_t *)ob, (size_t)nT, G) != PPP_OK)
         croak("PhyloProf::B200: %s", ppp_last_error(ctx));
 
+void
+_set_option(h, name, value)
+    IV h
+    const char *name
+    IV value
+  CODE:
+    ppp_ctx *ctx = INT2PTR(ppp_ctx *, h);
+    if (ppp_set_option(ctx, name, (int64_t)value) != PPP_OK) croak("PhyloProf::B200: %s", ppp_last_error(ctx));
+
 UV
-_set_targets_bla(h, paths, universe, nthreads)
+_set_targets_bla(h, paths, universe, nthreads, flags)
     IV h
     AV *paths
     AV *universe
     int nthreads
+    unsigned int flags
   CODE:
     /* a genome's worth of `.bla` caches (bin/ppp.pl:606-673) -> ranked targets, parsed natively by ppp_read_bla */
     ppp_ctx *ctx = INT2PTR(ppp_ctx *, h);
@@ -88,7 +98,7 @@ _set_targets_bla(h, paths, universe, nthreads)
     for (size_t i = 0; i < G; ++i) uv[i] = SvPVbyte_nolen(*av_fetch(universe, (SSize_t)i, 0));
     ppp_ranked_lists l;
     char err[512];
-    int rc = ppp_read_bla(pv, np, uv, G, nthreads, &l, err, sizeof(err));
+    int rc = ppp_read_bla_flags(pv, np, uv, G, nthreads, flags, &l, err, sizeof(err)); /* flags: PPP_BLA_DUP = -dup packing */
     Safefree(pv);
     Safefree(uv);
     if (rc != PPP_OK) croak("PhyloProf::B200: %s", err);

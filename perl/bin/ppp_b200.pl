@@ -9,11 +9,11 @@
 # (ppp_read_bla) and every gene is scored by libppp_b200.so through the XS binding (PhyloProf::B200).
 # There is no CPU fallback.  Written from scratch against the reference's observable behaviour.
 #
-#   perl ppp_b200.pl -d <db dir> -t <taxon> -p <profile> -w <workspace> [--prob P] [-m slope] [--device N]
+#   perl ppp_b200.pl -d <db dir> -t <taxon> -p <profile> -w <workspace> [--prob P] [-m slope] [--dup] [--device N]
 #
-# Not supported (the script dies; keep bin/ppp.pl for them): -l/--level (rank collapse needs the SeqToolBox taxonomy
-# database) and --dup (a reference quirk, ppp.pm:189-200).  --threads/--serial/--keep/-c/-o/-r/-n are accepted and
-# ignored (there are no workers, temporary files or grid jobs).
+# Not supported (the script dies; keep bin/ppp.pl for it): -l/--level (rank collapse needs the SeqToolBox taxonomy
+# database).  --dup (bin/ppp.pl:282 -> ppp.pm:189-200) is packed natively (PPP_BLA_DUP) and scored on the device.
+# --threads/--serial/--keep/-c/-o/-r/-n are accepted and ignored (there are no workers, temporary files or grid jobs).
 use strict;
 use warnings;
 use Getopt::Long;
@@ -37,7 +37,6 @@ die "File $profile not found\n" unless -s $profile;
 die "Workspace missing\n"       unless $workspace;
 die "ppp_b200.pl: --client is the reference's worker mode; this driver has no workers\n" if $ignored{client};
 die "ppp_b200.pl: -l/--level is not supported on the B200 path (use bin/ppp.pl)\n"       if $level;
-die "ppp_b200.pl: --dup is not supported on the B200 path (use bin/ppp.pl)\n"            if $duplicate;
 
 # ---- the gene caches of the genome (bin/ppp.pl:955-1017 lists them the same way)
 my $blast_dir = File::Spec->catdir( $db_dir, "blast", $taxon );
@@ -73,7 +72,7 @@ my $p = $probability ? $probability + 0 : $yes / $total;    # ppp.pm:138-142, bi
 # ---- one GPU call for the whole genome
 my @universe = sort keys %q;
 my $gpu      = PhyloProf::B200->new( -device => $device );
-my $hits     = $gpu->score_bla_files( \@universe, [ \%q ], \@paths, -probs => [$p], -filter => 'all' );
+my $hits     = $gpu->score_bla_files( \@universe, [ \%q ], \@paths, -probs => [$p], -filter => 'all', -dup => $duplicate );
 
 # ---- the table (bin/ppp.pl:443-506).  The reference's clients print score and p with Perl's default %.15g
 # stringification and the server reads them back: reproduce that rounding.

@@ -6,7 +6,8 @@ package PhyloProf::Algorithm::ppp_b200;
 #
 # A single pair is embedded exactly by taking the TARGET's own de-duplicated list as the genome order: the target
 # plane is then a run of ones, the query planes are permuted to match, and the raw list position (duplicates and
-# foreign taxa included, ppp.pm:169,231) is restored from the de-duplicated depth on return.
+# foreign taxa included, ppp.pm:169,231) is restored from the de-duplicated depth on return.  With -dup the pair goes
+# through the ranked-list entry instead (PhyloProf::B200::score_ranked, which keeps the list's first repeated entry).
 use strict;
 use warnings;
 use Carp;
@@ -42,12 +43,21 @@ sub _taxon {    # ppp.pm:328-370: identity unless -rank; collapse, fall back to 
 
 sub get_match_score {
     my $self = shift;
-    croak "PhyloProf::Algorithm::ppp_b200: -dup is not accelerated (reference quirk ppp.pm:189-200); use PhyloProf::Algorithm::ppp"
-        if $self->{_dup};
     my $q = $self->{_prof1}->get_hash();
     my $p = exists $self->{_prob} ? $self->{_prob} : $self->{_prof1}->get_yes() / $self->{_prof1}->get_total();
     my $t = $self->{_prof2}->get_hash();
     my @list = ref($t) eq 'HASH' ? ( sort { $t->{$a} <=> $t->{$b} } keys %$t ) : @{ $t || [] };
+    if ( $self->{_dup} ) {
+        # -dup (ppp.pm:189-200, 222-224): the list keeps its own order and its first repeated entry; ranked-list path
+        my @taxa = map { my $x = $self->_taxon($_); die "Taxon not found" unless $x; $x } @list;
+        return ( 1, 0, 0, 0, $p ) unless @taxa && %$q;
+        my @universe = keys %$q;
+        croak "query profile of " . scalar(@universe) . " taxa exceeds 8192" if @universe > 8192;
+        $GPU ||= PhyloProf::B200->new( -device => $ENV{PPP_B200_DEVICE} || 0 );
+        my $hits = $GPU->score_ranked( \@universe, [$q], [ \@taxa ], -probs => [$p], -dup => 1 );
+        my ( undef, undef, $score, $yes, $number, $depth ) = @{ $hits->[0] };
+        return ( $score, $yes, $number, $depth, $p );
+    }
     my ( %seen, @order, @rawpos );
     for my $i ( 0 .. $#list ) {
         my $taxon = $self->_taxon( $list[$i] );

@@ -58,31 +58,50 @@ sub _plane {
 
 # score every query against every target; targets are ORDERED hit lists in their own order, duplicates and foreign taxa
 # allowed (BlastResult.pm:192-237 / value-sorted HMMERResult hash): de-duplicated here, raw positions kept (ppp.pm:169-231)
+#
+# -dup => 1 is the reference's -dup flag (ppp.pm:189-200, 214-217).  Its `$seen{key}` is ONE literal-key counter for the
+# whole list: the first repeated entry of a list is counted again like a new taxon (kept here as a second entry), and
+# from the second repeated entry on `yes` is frozen while `number` only grows, so no later step can improve and the list
+# ends there.  The device drops the candidate that would exceed |Y| (`last if $yes > $max_yes`, ppp.pm:222-224).
 sub score_ranked {
     my ( $self, $universe, $queries, $lists, %o ) = @_;
     my $idx = _index($universe);
     my ( @gi, @raw, @off ) = ();
     push @off, 0;
     foreach my $l (@$lists) {
-        my %seen;
+        my ( %seen, $repeats );
         for my $i ( 0 .. $#$l ) {
-            next if $seen{ $l->[$i] }++;
+            if ( $seen{ $l->[$i] }++ ) {
+                next unless $o{-dup};
+                last if ++$repeats >= 2;
+            }
             push @gi, ( exists $idx->{ $l->[$i] } ? $idx->{ $l->[$i] } : 0xFFFF );
             push @raw, $i + 1;
         }
         push @off, scalar @gi;
     }
     _set_targets_ranked( $self->{h}, pack( "S*", @gi ), pack( "S*", @raw ), pack( "Q*", @off ), scalar(@$lists), scalar(@$universe) );
-    return $self->_score_queries( $universe, $idx, $queries, %o );
+    return $self->_score_dup( $o{-dup}, $universe, $idx, $queries, %o );
+}
+
+sub _score_dup {
+    my ( $self, $dup, @rest ) = @_;
+    _set_option( $self->{h}, "dup", $dup ? 1 : 0 );
+    my $hits = eval { $self->_score_queries(@rest) };
+    my $err  = $@;
+    _set_option( $self->{h}, "dup", 0 );
+    die $err if $err;
+    return $hits;
 }
 
 # score every query against the hit lists cached in `.bla` files (one target per file; bin/ppp.pl:606-673 format): the
-# files are parsed, de-duplicated and mapped to the universe natively (ppp_read_bla), no Perl-side parsing
+# files are parsed, de-duplicated and mapped to the universe natively (ppp_read_bla_flags), no Perl-side parsing;
+# -dup => 1 as in score_ranked
 sub score_bla_files {
     my ( $self, $universe, $queries, $paths, %o ) = @_;
     my $idx = _index($universe);
-    _set_targets_bla( $self->{h}, $paths, $universe, $o{-threads} || 0 );
-    return $self->_score_queries( $universe, $idx, $queries, %o );
+    _set_targets_bla( $self->{h}, $paths, $universe, $o{-threads} || 0, $o{-dup} ? 1 : 0 );    # 1 = PPP_BLA_DUP
+    return $self->_score_dup( $o{-dup}, $universe, $idx, $queries, %o );
 }
 
 # score every query (PhyloProf::Profile or {taxon=>0/1}) against every target ([taxa] in universe order semantics)

@@ -106,8 +106,6 @@ class ppp:
         return t
 
     def get_match_score(self):
-        if self._dup:
-            raise NotImplementedError("-dup (ppp.pm:189-200 quirk) is not accelerated; see INTEGRATION.md")
         q = self._prof1.get_hash()
         total = self._prof1.get_total()
         if self._prob is None and total == 0:
@@ -130,8 +128,12 @@ class ppp:
         if not index:
             return (1, 0, 0, 0, p)
         P, Y, _ = packer.pack_queries([q], index)
-        idx, raw, off = packer.pack_ranked_targets([lst], index)
+        idx, raw, off = packer.pack_ranked_targets([lst], index, dup=self._dup)
         ctx = context()
         ctx.set_targets_ranked(idx, raw, off, len(index))
-        h = ctx.score(P, Y, np.array([p], dtype=np.float64))[0]
+        ctx.set_option("dup", int(self._dup))  # ppp.pm:189-200, 222-224
+        try:
+            h = ctx.score(P, Y, np.array([p], dtype=np.float64))[0]
+        finally:
+            ctx.set_option("dup", 0)
         return (float(h["score"]), int(h["yes"]), int(h["number"]), int(h["depth"]), p)

@@ -25,7 +25,7 @@ assert HIT_DTYPE.itemsize == 32
 EXPORTS = [
     "ppp_init", "ppp_destroy", "ppp_last_error", "ppp_abi_version", "ppp_set_targets_bits", "ppp_set_targets_ranked",
     "ppp_set_queries", "ppp_run", "ppp_result_count", "ppp_fetch", "ppp_score", "ppp_get_stats", "ppp_set_option",
-    "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc", "ppp_topk_device", "ppp_merge_topk_device", "ppp_read_bla",
+    "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc", "ppp_topk_device", "ppp_merge_topk_device", "ppp_read_bla", "ppp_read_bla_flags",
     "ppp_free_ranked_lists",
 ]
 
@@ -103,22 +103,28 @@ def load():
     L.ppp_read_bla.restype = ctypes.c_int
     L.ppp_read_bla.argtypes = [ctypes.POINTER(ctypes.c_char_p), sz, ctypes.POINTER(ctypes.c_char_p), sz, ctypes.c_int,
                                ctypes.POINTER(RankedLists), ctypes.c_char_p, sz]
+    L.ppp_read_bla_flags.restype = ctypes.c_int
+    L.ppp_read_bla_flags.argtypes = [ctypes.POINTER(ctypes.c_char_p), sz, ctypes.POINTER(ctypes.c_char_p), sz, ctypes.c_int, u32,
+                                     ctypes.POINTER(RankedLists), ctypes.c_char_p, sz]
     L.ppp_free_ranked_lists.restype = None
     L.ppp_free_ranked_lists.argtypes = [ctypes.POINTER(RankedLists)]
     _lib = L
     return L
 
 
-def read_bla_files(paths, universe, nthreads: int = 0):
+BLA_DUP = 1  # PPP_BLA_DUP
+
+
+def read_bla_files(paths, universe, nthreads: int = 0, dup: bool = False):
     """Native reader of `.bla` BLAST caches (ppp_read_bla, prophylo_b200/csrc/ppp_bla.cpp): one ranked target per path,
     taxa mapped through `universe` (ordered taxon strings).  Returns (idx, rawdepth, row_off) as ppp_set_targets_ranked
-    takes them.  No GPU needed."""
+    takes them; dup=True packs for the reference's -dup flag (see packer.pack_ranked_targets).  No GPU needed."""
     L = load()
     pa = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
     ua = (ctypes.c_char_p * len(universe))(*[str(u).encode() for u in universe])
     out = RankedLists()
     err = ctypes.create_string_buffer(512)
-    rc = L.ppp_read_bla(pa, len(paths), ua, len(universe), nthreads, ctypes.byref(out), err, len(err))
+    rc = L.ppp_read_bla_flags(pa, len(paths), ua, len(universe), nthreads, BLA_DUP if dup else 0, ctypes.byref(out), err, len(err))
     if rc != PPP_OK:
         raise PPPError(rc, err.value.decode(errors="replace"))
     try:

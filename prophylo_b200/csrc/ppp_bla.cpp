@@ -48,7 +48,7 @@ bool slurp(const char *path, std::string &buf)
     return ok;
 }
 
-void parse_one(const char *path, const std::unordered_map<std::string_view, uint16_t> &universe, FileLists &out)
+void parse_one(const char *path, const std::unordered_map<std::string_view, uint16_t> &universe, bool dup, FileLists &out)
 {
     std::string buf;
     if (!slurp(path, buf)) {
@@ -82,7 +82,7 @@ void parse_one(const char *path, const std::unordered_map<std::string_view, uint
         }
     }
     std::unordered_set<std::string_view> seen;
-    size_t position = 0;
+    size_t position = 0, repeats = 0;
     for (const std::string_view &s : order) {
         const std::string_view t = taxon_of[s];
         if (t.empty() || t == "0") continue; /* Perl-false taxon: the hit is not part of the list */
@@ -91,7 +91,12 @@ void parse_one(const char *path, const std::unordered_map<std::string_view, uint
             out.err = std::string(path) + ": target list longer than 65535 positions";
             return;
         }
-        if (!seen.insert(t).second) continue;
+        if (!seen.insert(t).second) {
+            /* -dup (ppp.pm:189-200): `$seen{key}` is one counter for the whole list -- the first repeated entry is counted
+             * again like a new taxon, from the second on `yes` is frozen and no later step can improve: the list ends */
+            if (!dup) continue;
+            if (++repeats >= 2) break;
+        }
         const auto u = universe.find(t);
         out.idx.push_back(u == universe.end() ? (uint16_t)0xFFFF : u->second);
         out.raw.push_back((uint16_t)position);
@@ -103,6 +108,13 @@ void parse_one(const char *path, const std::unordered_map<std::string_view, uint
 extern "C" int ppp_read_bla(const char *const *paths, size_t n_paths, const char *const *universe, size_t G, int nthreads,
                             ppp_ranked_lists *out, char *err, size_t errlen)
 {
+    return ppp_read_bla_flags(paths, n_paths, universe, G, nthreads, 0u, out, err, errlen);
+}
+
+extern "C" int ppp_read_bla_flags(const char *const *paths, size_t n_paths, const char *const *universe, size_t G, int nthreads,
+                                  uint32_t flags, ppp_ranked_lists *out, char *err, size_t errlen)
+{
+    const bool dup = (flags & PPP_BLA_DUP) != 0;
     if (err && errlen) err[0] = 0;
     if (!out || (n_paths && !paths) || (G && !universe) || G > 0xFFFF) {
         if (err && errlen) snprintf(err, errlen, "ppp_read_bla: invalid argument");
@@ -115,7 +127,7 @@ extern "C" int ppp_read_bla(const char *const *paths, size_t n_paths, const char
     std::vector<FileLists> per(n_paths);
     std::atomic<size_t> next{0};
     auto work = [&]() {
-        for (size_t i; (i = next.fetch_add(1)) < n_paths;) parse_one(paths[i], uni, per[i]);
+        for (size_t i; (i = next.fetch_add(1)) < n_paths;) parse_one(paths[i], uni, dup, per[i]);
     };
     size_t nt = nthreads > 0 ? (size_t)nthreads : std::max(1u, std::thread::hardware_concurrency());
     if (nt > n_paths) nt = n_paths ? n_paths : 1;

@@ -127,6 +127,7 @@ struct ppp_ctx {
     uint32_t *d_rank_tmp = nullptr;
     size_t cap_rank_tmp = 0;
     bool results_ranked = false;
+    int dup = 0; /* ranked lists were packed for -dup: the sweep drops the candidate that exceeds |Y| (ppp.pm:222-224) */
     int device_rank = 1; /* 0: rank threshold results on the host (developer A/B) */
     uint32_t *d_exact = nullptr;
     size_t cap_exact = 0;
@@ -569,6 +570,7 @@ static void base_params(const ppp_ctx *ctx, SweepParams *prm)
     prm->force_exact = (uint32_t)ctx->force_exact;
     prm->check_bounds = (uint32_t)ctx->check_bounds;
     prm->qwords = 32u * (uint32_t)ctx->wpl;
+    prm->dup = (uint32_t)(ctx->dup && ctx->ranked);
     prm->ridx = ctx->d_ridx;
     prm->rraw = ctx->d_rraw;
     prm->roff = ctx->d_roff;
@@ -1199,6 +1201,8 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
         (name[1] == 'e' ? ctx->seed_mult : name[0] == 'c' ? ctx->chunk1_mult : ctx->spec_eps_ppm) = (int)value;
     } else if (!strcmp(name, "speculate")) {
         ctx->speculate = value != 0;
+    } else if (!strcmp(name, "dup")) {
+        ctx->dup = value != 0;
     } else if (!strcmp(name, "device_rank")) {
         ctx->device_rank = value != 0;
     } else if (!strcmp(name, "prefilter_version")) {

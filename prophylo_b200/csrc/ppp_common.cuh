@@ -70,7 +70,8 @@ struct SweepParams {
     uint32_t qcap;             /* per-query append capacity (>= targets per launch) */
     uint32_t qwords;           /* words per query plane row (universe width; = W for bit-plane targets) */
     uint32_t bounds_only;      /* 1: report exp(min upper enclosure) as a provisional score (threshold seeding); no tier B/C */
-    uint32_t pad3_;
+    uint32_t dup;              /* ranked lists packed for -dup (ppp.pm:189-200): a list may hold ONE repeated taxon, which can push
+                                  yes past |Y| -- the reference stops there (ppp.pm:222-224), so that candidate is dropped */
     /* ranked targets (ppp_set_targets_ranked): per target an ordered, de-duplicated list of genome indices */
     const uint16_t *ridx;      /* genome index in the query universe, 0xFFFF = foreign taxon */
     const uint16_t *rraw;      /* 1-based raw list position of each entry (duplicates counted) */

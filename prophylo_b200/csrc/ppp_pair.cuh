@@ -367,6 +367,31 @@ __device__ __forceinline__ uint32_t evaluate_pair(const uint32_t (&tw)[WPL], con
     return 0;
 }
 
+/* -dup lists (ppp.pm:189-200, 222-224): the one re-counted taxon can make the running yes exceed |Y| = max_yes, at which
+ * step the reference leaves the loop before evaluating.  That step is the LAST yes-increment of the list (every yes taxon
+ * has been seen by then), so dropping the highest set bit of T&Y (list order: lane-major, word, bit) removes exactly it. */
+template <int WPL>
+__device__ __forceinline__ void clip_yes_overflow(uint32_t (&ty)[WPL], uint32_t ny, int lane)
+{
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < WPL; ++w) c += __popc(ty[w]);
+    uint32_t tot = c;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+    if (tot <= ny) return;
+    const uint32_t holders = __ballot_sync(FULL, c != 0);
+    if (lane == 31 - __clz(holders)) {
+#pragma unroll
+        for (int w = WPL - 1; w >= 0; --w) {
+            if (ty[w]) {
+                ty[w] &= ~(0x80000000u >> __clz(ty[w]));
+                break;
+            }
+        }
+    }
+}
+
 template <int WPL>
 __device__ __forceinline__ void load_row(const uint32_t *__restrict__ row, uint32_t (&v)[WPL])
 {

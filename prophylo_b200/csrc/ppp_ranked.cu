@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(256) ppp_sweep_ranked_kernel(const SweepParams
                     ty[j % WPL] = wy;
                 }
             }
+            if (prm.dup) clip_yes_overflow<WPL>(ty, s_qc[qi].ny, lane);
             const uint16_t *stair = nullptr;
             if (prm.append) {
                 const uint32_t off = s_off[qi];

@@ -34,10 +34,11 @@ def read_bla(path):
     return [taxon[s] for s in order if taxon[s] not in ("", "0")]
 
 
-def ppp_scan(ctx: capi.Context, query: Profile, targets: dict, prob=None):
+def ppp_scan(ctx: capi.Context, query: Profile, targets: dict, prob=None, dup=False):
     """Score one query profile against every target hit list in ONE GPU call (replaces the chunk files, forked
     `ppp.pl --client` workers and per-gene Perl sweeps of bin/ppp.pl:354-462, 519-593).
-    targets: {locus: path of a .bla file | ordered taxon list}.  Returns [(locus, score, yes, number, depth, p)]."""
+    targets: {locus: path of a .bla file | ordered taxon list}.  dup: the --dup flag of bin/ppp.pl:282 (ppp.pm:189-200,
+    see packer.pack_ranked_targets).  Returns [(locus, score, yes, number, depth, p)]."""
     q = query.get_hash()
     loci = list(targets)
     p = float(prob) if prob else query.get_yes() / query.get_total()  # bin/ppp.pl:559-572, ppp.pm:138-142
@@ -48,12 +49,16 @@ def ppp_scan(ctx: capi.Context, query: Profile, targets: dict, prob=None):
     if all(isinstance(t, (str, os.PathLike)) for t in targets.values()):
         # a genome's worth of cache files: the native multi-threaded reader (csrc/ppp_bla.cpp) parses, de-duplicates and
         # maps them straight into the arrays of ppp_set_targets_ranked
-        idx, raw, off = capi.read_bla_files(list(targets.values()), list(index))
+        idx, raw, off = capi.read_bla_files(list(targets.values()), list(index), dup=bool(dup))
     else:
         lists = [read_bla(t) if isinstance(t, (str, os.PathLike)) else list(t) for t in targets.values()]
-        idx, raw, off = packer.pack_ranked_targets(lists, index)
+        idx, raw, off = packer.pack_ranked_targets(lists, index, dup=bool(dup))
     ctx.set_targets_ranked(idx, raw, off, len(index))
-    hits = ctx.score(P, Y, np.array([p], dtype=np.float64))
+    ctx.set_option("dup", int(bool(dup)))
+    try:
+        hits = ctx.score(P, Y, np.array([p], dtype=np.float64))
+    finally:
+        ctx.set_option("dup", 0)
     return [(loci[int(h["t"])], float(h["score"]), int(h["yes"]), int(h["number"]), int(h["depth"]), p) for h in hits]
 
 

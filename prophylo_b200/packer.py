@@ -68,19 +68,31 @@ def pack_target_sets(targets, index):
     return pack_bits(Tb)
 
 
-def pack_ranked_targets(target_lists, index):
+def pack_ranked_targets(target_lists, index, dup=False):
     """target_lists: iterable of ordered taxon lists, duplicates and foreign taxa allowed (BLAST hit order).
     De-duplicates keeping the first occurrence (ppp.pm:189-192), keeps the raw 1-based position of every kept entry
     (ppp.pm:169,231) and maps taxa to genome indices (FOREIGN = 0xFFFF for taxa outside the universe).
+
+    dup=True packs for the reference's -dup flag (ppp.pm:189-200, 214-217), whose `$seen{key}` is ONE literal-key
+    counter for the whole list: the first repeated entry of the list is counted again like a new taxon (kept here, with
+    its genome index repeated); from the second repeated entry on `yes` is frozen while `number` can only grow, so no
+    later step can improve the score and the list ends there.  Run the context with set_option("dup", 1): the sweep then
+    drops the candidate that would exceed |Y| (ppp.pm:222-224).  (A taxon literally named "key" would alias the
+    counter in the reference; such ids do not occur and are not modelled.)
     Returns (idx uint16[total], rawdepth uint16[total], row_off uint64[nT+1])."""
     idx, raw, off = [], [], [0]
     for lst in target_lists:
         seen = set()
+        repeats = 0
         if len(lst) > 65535:
             raise ValueError("target list longer than 65535 positions")
         for pos, t in enumerate(lst):
             if t in seen:
-                continue
+                if not dup:
+                    continue
+                repeats += 1
+                if repeats >= 2:
+                    break
             seen.add(t)
             idx.append(index.get(t, FOREIGN))
             raw.append(pos + 1)

@@ -79,6 +79,11 @@ def test_native_bla_reader_matches_python_reader(tmp_path):
         got = capi.read_bla_files(paths, universe, nthreads=nthreads)
         for g, e, name in zip(got, exp, ("idx", "rawdepth", "row_off")):
             assert g.dtype == e.dtype and np.array_equal(g, e), name
+    exp = packer.pack_ranked_targets([drivers.read_bla(p) for p in paths], index, dup=True)  # -dup packing (ppp.pm:189-200)
+    got = capi.read_bla_files(paths, universe, nthreads=3, dup=True)
+    for g, e, name in zip(got, exp, ("idx", "rawdepth", "row_off")):
+        assert g.dtype == e.dtype and np.array_equal(g, e), name
+    assert got[0].size != capi.read_bla_files(paths, universe)[0].size
     import pytest
 
     with pytest.raises(capi.PPPError):

@@ -17,6 +17,12 @@ def e2e(golden_dir):
     return json.load(open(os.path.join(golden_dir, "ppp_pl_e2e.json")))["cases"]
 
 
+@pytest.fixture(scope="module")
+def e2e_dup(golden_dir):
+    """bin/ppp.pl --dup (:282 -> ppp.pm:189-200) run unmodified on the same kind of caches (gen_golden_e2e.py --dup)"""
+    return json.load(open(os.path.join(golden_dir, "ppp_pl_e2e_dup.json")))["cases"]
+
+
 def materialise(case, tmp_path):
     d = tmp_path / f"case{case['seed']}"
     (d / "bla").mkdir(parents=True)
@@ -74,6 +80,20 @@ def test_table_format_matches_reference_with_oracle_scores(e2e, tmp_path):
         assert normalise(got) == normalise(case["ppp_pl_stdout"]), case["seed"]
 
 
+def test_dup_table_matches_reference_with_oracle_scores(e2e_dup, tmp_path):
+    """CPU: the oracle's -dup loop reproduces the stdout of the reference's `ppp.pl --dup`, and the flag matters here."""
+    for case in e2e_dup:
+        prof, paths = materialise(case, tmp_path)
+        qd = {k: int(v) for k, v in Profile(file=prof).get_hash().items()}
+        rows, plain = [], []
+        for gi, path in paths.items():
+            lst = drivers.read_bla(path)
+            rows.append((gi,) + oracle.score_case(qd, lst, case["prob"], True))
+            plain.append((gi,) + oracle.score_case(qd, lst, case["prob"], False))
+        assert normalise(drivers.format_ppp_table(rows, slope=case["slope"])) == normalise(case["ppp_pl_stdout"]), case["seed"]
+        assert normalise(drivers.format_ppp_table(plain, slope=case["slope"])) != normalise(case["ppp_pl_stdout"])
+
+
 @pytest.mark.gpu
 def test_ppp_scan_on_gpu_reproduces_ppp_pl_stdout(e2e, tmp_path):
     """One query profile vs a genome's genes in ONE GPU call (ranked targets), formatted: byte-identical to the stdout of
@@ -87,6 +107,24 @@ def test_ppp_scan_on_gpu_reproduces_ppp_pl_stdout(e2e, tmp_path):
         got = drivers.format_ppp_table(rows, slope=case["slope"])
         assert normalise(got) == normalise(case["ppp_pl_stdout"]), case["seed"]
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_ppp_scan_dup_on_gpu_reproduces_ppp_pl_dup_stdout(e2e_dup, tmp_path):
+    """`ppp.pl --dup`: lists packed for the flag by the native reader (PPP_BLA_DUP) and by the Python packer, scored on the
+    device with the "dup" option; the table equals the unmodified reference script's stdout."""
+    from prophylo_b200 import capi
+
+    ctx = capi.Context(0)
+    try:
+        for case in e2e_dup:
+            prof, paths = materialise(case, tmp_path)
+            for targets in (paths, {gi: drivers.read_bla(p) for gi, p in paths.items()}):
+                rows = drivers.ppp_scan(ctx, Profile(file=prof), targets, prob=case["prob"], dup=True)
+                got = drivers.format_ppp_table(rows, slope=case["slope"])
+                assert normalise(got) == normalise(case["ppp_pl_stdout"]), case["seed"]
+    finally:
+        ctx.close()
 
 
 @pytest.mark.gpu
@@ -167,7 +205,7 @@ def test_cross_score_on_gpu_reproduces_reference_stdout(cross_cases):
 
 
 @pytest.mark.gpu
-def test_perl_cli_dropin_reproduces_ppp_pl_stdout(e2e, tmp_path):
+def test_perl_cli_dropin_reproduces_ppp_pl_stdout(e2e, e2e_dup, tmp_path):
     """perl/bin/ppp_b200.pl -- same options, database layout and stdout table as the reference's bin/ppp.pl, with the
     chunk files / forked Perl clients replaced by one GPU call through the XS binding and the native `.bla` reader --
     against the stdout of the unmodified reference script (modulo Perl's hash order inside score ties)."""
@@ -175,7 +213,7 @@ def test_perl_cli_dropin_reproduces_ppp_pl_stdout(e2e, tmp_path):
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     subprocess.check_call(["make", "-C", os.path.join(root, "perl")], stdout=subprocess.DEVNULL)
-    for case in e2e:
+    for case in e2e + e2e_dup:
         d = tmp_path / f"cli{case['seed']}"
         (d / "db" / "blast" / "1140").mkdir(parents=True)
         (d / "ws").mkdir()
@@ -188,6 +226,8 @@ def test_perl_cli_dropin_reproduces_ppp_pl_stdout(e2e, tmp_path):
             cmd += ["--prob", str(case["prob"])]
         if case["slope"]:
             cmd += ["-m", str(case["slope"])]
+        if case.get("dup"):
+            cmd += ["--dup"]
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, r.stderr
         assert normalise(r.stdout) == normalise(case["ppp_pl_stdout"]), case["seed"]

@@ -343,25 +343,23 @@ def test_device_global_topk_merge_of_two_shards(ctx):
 
 def test_python_operator_mirror_on_golden_list_cases(golden_dir):
     """prophylo_b200.algorithm mirrors PhyloProf::Profile / PhyloProf::Algorithm::ppp; every golden list case from the
-    reference (ARRAY targets with duplicates and foreign taxa, HASH targets, -prob) through the ranked-target path."""
+    reference (ARRAY targets with duplicates and foreign taxa, HASH targets, -prob, -dup) through the ranked-target path."""
     from prophylo_b200.algorithm import Profile, ppp
 
     g = json.load(open(os.path.join(golden_dir, "ppp_list_cases.json")))
     n = 0
     for c in g["known_answers"] + g["fuzz"]:
-        if c.get("dup"):
-            continue
         t = c["target"]
         prof1 = Profile(profile=c["query"])
         prof2 = Profile(raw=t, yes=len(t), no=0)
-        got = ppp(prof1, prof2, prob=c.get("prob")).get_match_score()
+        got = ppp(prof1, prof2, prob=c.get("prob"), dup=c.get("dup")).get_match_score()
         e = c["expect"]
         assert got[1:4] == (e[1], e[2], e[3]), (c["name"], got, e)
         assert got[4] == float(e[4])
         es = float(e[0])
         assert got[0] == es or abs(np.log(got[0]) - np.log(es)) <= REL_TOL_NEGLOG * abs(np.log(es)), (c["name"], got, e)
         n += 1
-    assert n > 500
+    assert n > 600
 
 
 def test_ranked_targets_batch_vs_oracle(ctx):
@@ -417,6 +415,65 @@ def test_ranked_targets_batch_vs_oracle(ctx):
         keep = np.log10(dense["score"]) < -2.5
     e = np.sort(dense[keep], order=["q", "score", "t"])
     assert th.size == e.size and np.array_equal(th["t"], e["t"]) and np.array_equal(th["depth"], e["depth"])
+
+
+def test_ranked_targets_dup_flag_batch_vs_oracle(ctx):
+    """-dup (ppp.pm:189-200: first repeated entry of a list re-counted, `yes` frozen from the second, `last` once yes
+    exceeds |Y|, ppp.pm:222-224) on the device: lists packed with dup=True, sweep run with the "dup" option; every pair
+    against the oracle's own -dup loop; lists that show every yes taxon and then repeat one (yes > max_yes) included."""
+    from prophylo_b200 import packer
+
+    rng = np.random.default_rng(11)
+    G, nq, nt = 300, 33, 200
+    universe = [f"g{i}" for i in range(G)]
+    index = packer.universe_index(universe)
+    queries = []
+    for _ in range(nq):
+        dens = float(np.exp(rng.uniform(np.log(0.01), np.log(0.2))))
+        q = {u: int(rng.random() < dens) for u in universe if rng.random() < 0.8}
+        queries.append(q)
+    lists = []
+    for t in range(nt):
+        L = int(rng.integers(1, 400))
+        lst = [universe[int(g)] for g in rng.permutation(G)[:L]]
+        if t % 3 == 0:  # plant the query's yes taxa first, then repeat one of them: yes would exceed max_yes
+            ys = [k for k, v in queries[t % nq].items() if v]
+            if ys:
+                rest = [x for x in lst if x not in set(ys)]
+                lst = ys + [ys[int(rng.integers(len(ys)))]] + rest
+        for _ in range(int(rng.integers(0, 4))):  # 0..3 repeated entries at random places
+            lst.insert(int(rng.integers(1, len(lst) + 1)), lst[int(rng.integers(len(lst)))])
+        lists.append(lst)
+    P, Y, p = packer.pack_queries(queries, index)
+    idx, raw, off = packer.pack_ranked_targets(lists, index, dup=True)
+    ctx.set_targets_ranked(idx, raw, off, G)
+    ctx.set_option("dup", 1)
+    try:
+        dense = ctx.score(P, Y, p).reshape(nq, nt)
+        k = 5
+        tk = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
+    finally:
+        ctx.set_option("dup", 0)
+    differs = 0
+    for qi, q in enumerate(queries):
+        present = np.zeros(G, dtype=np.uint8)
+        isyes = np.zeros(G, dtype=np.uint8)
+        for kx, v in q.items():
+            present[index[kx]] = 1
+            isyes[index[kx]] = int(v != 0)
+        for ti, lst in enumerate(lists):
+            ids = [index[x] for x in lst]
+            exp = oracle.score_list(present, isyes, int(isyes.sum()), ids, float(p[qi]), True)
+            differs += exp[:4] != oracle.score_list(present, isyes, int(isyes.sum()), ids, float(p[qi]), False)[:4]
+            h = dense[qi, ti]
+            assert (h["yes"], h["number"], h["depth"]) == exp[1:4], (qi, ti, h, exp)
+            assert h["score"] == exp[0] or abs(np.log(h["score"]) - np.log(exp[0])) <= REL_TOL_NEGLOG * abs(np.log(exp[0]))
+    assert differs > 20  # the flag changes results on this input
+    for q in range(nq):
+        e = np.sort(dense[q], order=["score", "t"])[:k]
+        got = tk[q * k:(q + 1) * k]
+        for f in ("t", "score", "yes", "number", "depth"):
+            assert np.array_equal(got[f], e[f]), (q, f)
 
 
 def test_topk_ties_at_zero_and_one(ctx):

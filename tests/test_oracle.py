@@ -70,3 +70,61 @@ def test_bit_cases_match_reference(golden_dir):
                 r = res[q * sp["nt"] + t]
                 o = out[q, t]
                 assert (o["score"], o["yes"], o["number"], o["depth"]) == (float(r[0]), r[1], r[2], r[3]), (sp, q, t)
+
+
+def _dup_by_packed_list(query, tlist, prob):
+    """The -dup result computed the way the GPU path does it: the packer's list (first repeated entry kept, list cut
+    at the second, packer.pack_ranked_targets(dup=True)) scored WITHOUT the flag, the kept repeat standing in as a
+    clone of its taxon; the reference's `last if $yes > $max_yes` (ppp.pm:222-224) is part of the oracle loop."""
+    from prophylo_b200 import packer
+    universe = list(query)
+    index = packer.universe_index(universe)
+    idx, raw, off = packer.pack_ranked_targets([tlist], index, dup=True)
+    isyes = [1 if float(query[t]) != 0 else 0 for t in universe]
+    present = [1] * len(universe)
+    ids, seen = [], set()
+    for g in idx.tolist():
+        if g == packer.FOREIGN:
+            ids.append(len(present) + 100000 + len(ids))  # foreign to the query: never present
+            continue
+        if g in seen:  # the re-counted entry: a clone with the same membership
+            present.append(1)
+            isyes.append(isyes[g])
+            g = len(present) - 1
+        seen.add(g)
+        ids.append(g)
+    yes = sum(isyes[:len(universe)])
+    p = float(prob) if prob else yes / len(universe)
+    r = oracle.score_list(present, isyes, yes, ids, p, False)
+    depth = int(raw[r[3] - 1]) if r[3] else 0
+    return (r[0], r[1], r[2], depth, p)
+
+
+def test_dup_packing_rule_matches_reference(golden_dir):
+    """-dup (ppp.pm:189-200 literal-key quirk) as the packer embeds it == the reference, on every golden -dup case and
+    on random lists with many repeats (oracle with the flag, itself pinned above)."""
+    g = json.load(open(os.path.join(golden_dir, "ppp_list_cases.json")))
+    n = 0
+    for c in g["known_answers"] + g["fuzz"]:
+        if not c.get("dup") or isinstance(c["target"], dict):
+            continue
+        e = c["expect"]
+        got = _dup_by_packed_list(c["query"], c["target"], c.get("prob"))
+        assert got == (float(e[0]), e[1], e[2], e[3], float(e[4])), c["name"]
+        n += 1
+    assert n >= 90
+    rng = np.random.default_rng(5)
+    for _ in range(400):
+        U = int(rng.integers(3, 40))
+        taxa = [f"t{i}" for i in range(U)]
+        query = {t: int(rng.random() < 0.4) for t in taxa}
+        if not any(query.values()):
+            query[taxa[0]] = 1
+        pool = taxa + [f"x{i}" for i in range(4)]
+        tlist = [pool[int(i)] for i in rng.integers(0, len(pool), int(rng.integers(1, 60)))]
+        if rng.random() < 0.3:  # every yes taxon first, then a repeated yes taxon: yes exceeds max_yes
+            ys = [t for t in taxa if query[t]]
+            tlist = ys + [ys[0]] + tlist
+        prob = [None, 0.3, 0.05][int(rng.integers(0, 3))]
+        want = oracle.score_case(query, tlist, prob, True)
+        assert _dup_by_packed_list(query, tlist, prob) == want, (query, tlist, prob)
