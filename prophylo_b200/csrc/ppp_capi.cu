@@ -51,13 +51,14 @@ extern "C" cudaError_t ppp_launch_table_sweep(const SweepParams *prm, int wpl, c
                                               const double *tab, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_topk_merge_lists(const void *lists, const uint32_t *counts, uint32_t nlists, const uint32_t *t_offsets,
                                                    uint32_t nQ, uint32_t k, void *out, uint32_t *out_cnt, int nsm, cudaStream_t st);
-extern "C" cudaError_t ppp_launch_spec_init(const void *topk, const uint32_t *topk_cnt, const double *kth, uint32_t k, uint32_t r, double *kspec,
-                                            double *kspec0, uint32_t nQ, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_spec_init(const void *topk, const uint32_t *topk_cnt, const double *kth, const double *prev, uint32_t k,
+                                            uint32_t r, double *kspec, double *kspec0, uint32_t nQ, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_spec_update(double *kspec, const double *kth, uint32_t nQ, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_spec_verify(const void *topk, const uint32_t *topk_cnt, const double *kspec0, uint32_t k, double *last_tau,
                                               uint32_t *failed, uint32_t *nfailed, uint32_t nQ, cudaStream_t st);
 extern "C" void ppp_host_count_rows(const uint32_t *P, const uint32_t *Y, size_t nQ, size_t wpr, uint32_t *ny, uint32_t *np);
-extern "C" cudaError_t ppp_launch_seed_kth(const void *scores, uint32_t S, uint32_t k, double *kth, uint32_t nQ, int nsm, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_seed_kth(const void *scores, uint32_t S, uint32_t k, double *kth, uint32_t rs, double *kspec_seed, uint32_t nQ,
+                                           int nsm, cudaStream_t st);
 extern "C" size_t ppp_rank_scratch_words(size_t n);
 extern "C" cudaError_t ppp_launch_rank_hits(const ppp_hit *rec, size_t n, uint32_t nQ, uint32_t nT, ppp_hit *out, uint32_t *scratch, int nsm,
                                             cudaStream_t st, uint32_t *launches);
@@ -111,8 +112,10 @@ struct ppp_ctx {
     int prefilter_version = 2; /* 2: ppp_prefilter.cu (queued slow path), 1: the in-line screen of ppp_sweep.cu */
     uint32_t stair_need_any = 0; /* staircase footprint of the worst possible general tile (re-scan of arbitrary queries) */
     int speculate = 1;           /* top-k: screen the bulk of the targets against a speculative, verified threshold */
+    int spec_first = 1;          /* ... and the first chunk against the seeding pass's rs-th smallest bound */
     uint32_t spec_rank = 0, spec_failed = 0;
-    int seed_mult = 9, chunk1_mult = 24, spec_eps_ppm = 5000; /* top-k schedule: seeding targets / k, first chunk / k, P(spec fails) */
+    int chunk0_mult = 4; /* head of the first chunk, in units of k (0 = no split) */
+    int seed_mult = 5, chunk1_mult = 24, spec_eps_ppm = 5000; /* top-k schedule: seeding targets / k, first chunk / k, P(spec fails) */
     size_t nQ = 0, capQ = 0;
     /* results */
     ppp_hit *d_hits = nullptr;
@@ -829,8 +832,9 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         const size_t maxw = std::min<size_t>(nT, std::max<size_t>(256, ((size_t)1 << 29) / nQ));
         if ((rc = grow(ctx, &ctx->d_hits, &ctx->cap_hits, nQ * maxw))) return rc;
         if ((rc = grow(ctx, &ctx->d_exact, &ctx->cap_exact, nQ * maxw))) return rc;
-        /* [nQ] k-th scores, [nQ] tau of the resident staircase, [nQ] speculative thresholds in use, [nQ] their initial values */
-        if ((rc = grow(ctx, &ctx->d_kth, &ctx->cap_kth, 4 * nQ))) return rc;
+        /* [nQ] k-th scores, [nQ] tau of the resident staircase, [nQ] speculative thresholds in use, [nQ] their initial values,
+         * [nQ] speculative thresholds of the first chunk (from the seeding pass), [nQ] the same tightened by the k-th scores */
+        if ((rc = grow(ctx, &ctx->d_kth, &ctx->cap_kth, 6 * nQ))) return rc;
         if ((rc = grow(ctx, &ctx->d_qcnt, &ctx->cap_qcnt, 2 * nQ))) return rc; /* [nQ] append counters, [nQ] top-k counts */
         /* [nQ] static offsets, [nQ] active offsets, [nQ] queries whose speculative threshold failed, [1] their count */
         if ((rc = grow(ctx, &ctx->d_off, &ctx->cap_off, 3 * nQ + 4))) return rc;
@@ -874,11 +878,36 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             prm.qcnt = d_qcnt;
             prm.qcap = (uint32_t)maxw;
         };
+        /* smallest rank r with P(Poisson(k seen / nT) >= r) <= spec_eps: the r-th best score (or bound) over `seen` exchangeable
+         * targets then lies above the final k-th best score except with that probability */
+        auto poisson_rank = [&](size_t seen) {
+            const double lam = (double)k * (double)seen / (double)nT;
+            double term = exp(-lam), cdf = term; /* P(X <= 0) */
+            uint32_t r = 1;
+            while (1.0 - cdf > 1e-6 * ctx->spec_eps_ppm && r < k) {
+                term *= lam / (double)r;
+                cdf += term;
+                ++r;
+            }
+            return r;
+        };
         if (topk) {
             /* ---- top-k: no host synchronisation until the lists are final ---- */
             const size_t first = std::min<size_t>(4096, std::max<size_t>(256, (size_t)ctx->seed_mult * k)); /* targets of the seeding pass */
             const size_t chunk1 = std::max<size_t>(4 * 256, (size_t)ctx->chunk1_mult * k);      /* first exact chunk */
             const size_t w0 = std::min<size_t>(std::min(maxw, nT), first);
+            double *d_kspec = ctx->d_kth + 2 * nQ, *d_kspec0 = ctx->d_kth + 3 * nQ, *d_kseed = ctx->d_kth + 4 * nQ, *d_kseed_use = ctx->d_kth + 5 * nQ;
+            const bool spec_ok = ctx->speculate && !ctx->ranked && use_prefilter2(ctx) && !ctx->force_exact &&
+                                 ctx->stair_need_any <= ppp_prefilter2_max_stair(ctx->wpl, 0);
+            /* The first chunk is speculative as well when the bulk will be (its verification covers both): its thresholds are
+             * the rs-th smallest upper bounds of the seeding pass instead of the k-th -- at config 3 the guaranteed bound lets
+             * 15 % of the first chunk's pairs through to a full evaluation, the speculative one 0.8 %. */
+            const size_t w1 = std::min(std::min(maxw, nT), chunk1);
+            const bool chunk1_spec = spec_ok && ctx->spec_first && w0 >= (size_t)k && w1 >= 4 * (size_t)k && nT - w1 >= 8 * w1;
+            size_t chunk1_end = 0;
+            /* the first chunk runs in two launches: a short head, after which queries whose k best scores are already final
+             * (exact zeros: every later target loses the tie on its index) stop sending pairs to the exact tier */
+            const size_t chunk0 = std::max<size_t>(256, (size_t)ctx->chunk0_mult * k);
             if (w0 >= (size_t)k) {
                 /* Seeding pass: the k-th smallest UPPER bound (float enclosure only, no series, no exact tier) over the
                  * first targets is a valid threshold for the query's k-th best score; the provisional records are then
@@ -892,33 +921,25 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                 {
                     size_t ea, eb;
                     if ((rc = mark(ctx, &ea))) return rc;
-                    CU(ppp_launch_seed_kth(ctx->d_hits, (uint32_t)w0, k, ctx->d_kth, (uint32_t)nQ, ctx->nsm, ctx->stream));
+                    CU(ppp_launch_seed_kth(ctx->d_hits, (uint32_t)w0, k, ctx->d_kth, chunk1_spec ? poisson_rank(w0) : 0u,
+                                           chunk1_spec ? d_kseed : nullptr, (uint32_t)nQ, ctx->nsm, ctx->stream));
                     if ((rc = mark(ctx, &eb))) return rc;
                     ctx->spans.push_back({ea, eb, 3});
                 }
                 launches++;
                 seeded_pass = true;
             }
-            double *d_kspec = ctx->d_kth + 2 * nQ, *d_kspec0 = ctx->d_kth + 3 * nQ;
             uint32_t *d_failed = ctx->d_off + 2 * nQ, *d_nfailed = ctx->d_off + 3 * nQ;
-            const bool spec_ok = ctx->speculate && !ctx->ranked && use_prefilter2(ctx) && !ctx->force_exact &&
-                                 ctx->stair_need_any <= ppp_prefilter2_max_stair(ctx->wpl, 0);
             bool spec_on = false;
             size_t spec_start = 0;
             ctx->spec_rank = 0;
             ctx->spec_failed = 0;
             while (processed < nT) {
-                if (spec_ok && !spec_on && processed >= 4 * (size_t)k && nT - processed >= 8 * processed) {
-                    /* speculative threshold (ppp_topk.cu): rank r of the list so far, P(Poisson(k processed / nT) >= r) <= 1e-3 */
-                    const double lam = (double)k * (double)processed / (double)nT;
-                    double term = exp(-lam), cdf = term; /* P(X <= 0) */
-                    uint32_t r = 1;
-                    while (1.0 - cdf > 1e-6 * ctx->spec_eps_ppm && r < k) {
-                        term *= lam / (double)r;
-                        cdf += term;
-                        ++r;
-                    }
-                    CU(ppp_launch_spec_init(ctx->d_topk, d_topk_cnt, ctx->d_kth, k, r, d_kspec, d_kspec0, (uint32_t)nQ, ctx->stream));
+                if (spec_ok && !spec_on && processed >= 4 * (size_t)k && nT - processed >= 8 * processed && (!chunk1_spec || processed >= w1)) {
+                    /* speculative threshold (ppp_topk.cu): rank r of the list so far */
+                    const uint32_t r = poisson_rank(processed);
+                    CU(ppp_launch_spec_init(ctx->d_topk, d_topk_cnt, ctx->d_kth, chunk1_end ? d_kseed_use : nullptr, k, r, d_kspec, d_kspec0,
+                                            (uint32_t)nQ, ctx->stream));
                     launches++;
                     spec_on = true;
                     spec_start = processed;
@@ -926,7 +947,16 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                 }
                 size_t w = std::min(maxw, nT - processed);
                 if (!spec_on) w = std::min(w, processed ? 4 * processed : (seeded_pass ? chunk1 : first));
-                const double *kth_used = spec_on ? d_kspec : ctx->d_kth;
+                const bool first_spec = chunk1_spec && seeded_pass && processed < w1;
+                if (first_spec) {
+                    chunk1_end = w1;
+                    w = w1 - processed;
+                    if (!processed && ctx->chunk0_mult && chunk0 < w1) w = chunk0;
+                    if (!processed) CU(cudaMemcpyAsync(d_kseed_use, d_kseed, nQ * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+                    else CU(ppp_launch_spec_update(d_kseed_use, ctx->d_kth, (uint32_t)nQ, ctx->stream));
+                    if (processed) launches++;
+                }
+                const double *kth_used = spec_on ? d_kspec : first_spec ? d_kseed_use : ctx->d_kth;
                 size_t ea, eb;
                 if (processed || seeded_pass) {
                     if ((rc = mark(ctx, &ea))) return rc;
@@ -963,7 +993,10 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                 CU(cudaMemcpyAsync(&nfailed, d_nfailed, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
                 CU(cudaStreamSynchronize(ctx->stream));
                 ctx->spec_failed = nfailed;
-                for (size_t t0 = spec_start; nfailed && t0 < nT; t0 += maxw) {
+                /* re-scan: the first chunk's range against its own thresholds (pairs below them are already listed), then the rest */
+                for (size_t t0 = chunk1_end ? 0 : spec_start; nfailed && t0 < nT;) {
+                    const bool in_first = t0 < chunk1_end;
+                    const size_t t1 = in_first ? chunk1_end : std::min(nT, t0 + maxw);
                     size_t ea, eb;
                     if ((rc = mark(ctx, &ea))) return rc;
                     CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 0, 0.0, d_off_static, ctx->d_nmax, d_off_active,
@@ -971,9 +1004,9 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                     if ((rc = mark(ctx, &eb))) return rc;
                     ctx->spans.push_back({ea, eb, 2});
                     SweepParams prm;
-                    fill_filtered(prm, t0, std::min(nT, t0 + maxw));
+                    fill_filtered(prm, t0, t1);
                     prm.accept_mode = 2;
-                    prm.klo = d_kspec0;
+                    prm.klo = in_first ? d_kseed : d_kspec0;
                     if ((rc = launch_chunk_deferred(ctx, &prm, &launches, true, d_failed, nfailed))) return rc;
                     sweep_launches++;
                     if ((rc = mark(ctx, &ea))) return rc;
@@ -982,6 +1015,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                     if ((rc = mark(ctx, &eb))) return rc;
                     ctx->spans.push_back({ea, eb, 3});
                     launches += 2;
+                    t0 = (in_first && spec_start > t1) ? spec_start : t1;
                 }
             }
             unsigned long long c[CNT_N + 1];
@@ -1201,6 +1235,11 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
         (name[1] == 'e' ? ctx->seed_mult : name[0] == 'c' ? ctx->chunk1_mult : ctx->spec_eps_ppm) = (int)value;
     } else if (!strcmp(name, "speculate")) {
         ctx->speculate = value != 0;
+    } else if (!strcmp(name, "chunk0_mult")) {
+        if (value < 0 || value > 1000000) return fail(ctx, PPP_ERR_INVALID, "chunk0_mult out of range");
+        ctx->chunk0_mult = (int)value;
+    } else if (!strcmp(name, "spec_first")) {
+        ctx->spec_first = value != 0;
     } else if (!strcmp(name, "dup")) {
         ctx->dup = value != 0;
     } else if (!strcmp(name, "device_rank")) {

@@ -364,19 +364,27 @@ extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const u
  * the speculative threshold was found exactly, so the list is exact iff it is full and its k-th score is strictly
  * below that threshold.  Queries that fail are re-scanned over the same targets with the guaranteed bound and
  * klo <= score <= kth acceptance (ppp_capi.cu). */
+/* prev != nullptr: the targets processed so far were themselves screened against the speculative thresholds prev[q] (taken
+ * from the seeding pass), so a list holds EVERY processed pair below prev[q] and its r-th entry is the exact r-th best of
+ * the processed targets even when the list is not full; the new threshold never exceeds prev[q] and is always verified. */
 __global__ void ppp_spec_init_kernel(const ppp_hit *__restrict__ topk, const uint32_t *__restrict__ topk_cnt, const double *__restrict__ kth,
-                                     uint32_t k, uint32_t r, double *__restrict__ kspec, double *__restrict__ kspec0, uint32_t nQ)
+                                     const double *__restrict__ prev, uint32_t k, uint32_t r, double *__restrict__ kspec,
+                                     double *__restrict__ kspec0, uint32_t nQ)
 {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nQ) return;
     const double g = kth[q];
     double use = g, s0 = INFINITY;
-    if (topk_cnt[q] >= k && r >= 1 && r <= k) {
+    if (topk_cnt[q] >= (prev ? r : k) && r >= 1 && r <= k) {
         const double v = topk[(size_t)q * k + (r - 1)].score;
         if (v > 0.0 && v < g) { /* exact zeros (Cephes underflow) leave nothing below them: keep the guaranteed bound */
             use = v;
             s0 = v;
         }
+    }
+    if (prev) {
+        use = fmin(use, prev[q]);
+        s0 = use;
     }
     kspec[q] = use;
     kspec0[q] = s0;
@@ -403,10 +411,10 @@ __global__ void ppp_spec_verify_kernel(const ppp_hit *__restrict__ topk, const u
     }
 }
 
-extern "C" cudaError_t ppp_launch_spec_init(const void *topk, const uint32_t *topk_cnt, const double *kth, uint32_t k, uint32_t r, double *kspec,
-                                            double *kspec0, uint32_t nQ, cudaStream_t st)
+extern "C" cudaError_t ppp_launch_spec_init(const void *topk, const uint32_t *topk_cnt, const double *kth, const double *prev, uint32_t k,
+                                            uint32_t r, double *kspec, double *kspec0, uint32_t nQ, cudaStream_t st)
 {
-    ppp_spec_init_kernel<<<(nQ + 255) / 256, 256, 0, st>>>(reinterpret_cast<const ppp_hit *>(topk), topk_cnt, kth, k, r, kspec, kspec0, nQ);
+    ppp_spec_init_kernel<<<(nQ + 255) / 256, 256, 0, st>>>(reinterpret_cast<const ppp_hit *>(topk), topk_cnt, kth, prev, k, r, kspec, kspec0, nQ);
     return cudaGetLastError();
 }
 extern "C" cudaError_t ppp_launch_spec_update(double *kspec, const double *kth, uint32_t nQ, cudaStream_t st)
@@ -425,7 +433,7 @@ extern "C" cudaError_t ppp_launch_spec_verify(const void *topk, const uint32_t *
  * k-th smallest of the S provisional upper bounds of every query (dense double[nQ][S] written by the bounds-only pass):
  * a valid bound on the query's final k-th best score.  Block per query, bitonic sort of S <= 4096 doubles. */
 __global__ void __launch_bounds__(256) ppp_seed_kth_kernel(const double *__restrict__ scores, uint32_t S, uint32_t k, double *__restrict__ kth,
-                                                           uint32_t nQ)
+                                                           uint32_t rs, double *__restrict__ kspec_seed, uint32_t nQ)
 {
     extern __shared__ __align__(16) unsigned char smem_topk[];
     double *v = reinterpret_cast<double *>(smem_topk);
@@ -449,18 +457,22 @@ __global__ void __launch_bounds__(256) ppp_seed_kth_kernel(const double *__restr
                 __syncthreads();
             }
         }
-        if (threadIdx.x == 0 && S >= k) kth[q] = v[k - 1];
+        if (threadIdx.x == 0 && S >= k) {
+            kth[q] = v[k - 1];
+            if (kspec_seed) kspec_seed[q] = v[rs - 1]; /* rs-th smallest bound, rs <= k: speculative threshold of the first chunk */
+        }
         __syncthreads();
     }
 }
 
-extern "C" cudaError_t ppp_launch_seed_kth(const void *scores, uint32_t S, uint32_t k, double *kth, uint32_t nQ, int nsm, cudaStream_t st)
+extern "C" cudaError_t ppp_launch_seed_kth(const void *scores, uint32_t S, uint32_t k, double *kth, uint32_t rs, double *kspec_seed, uint32_t nQ,
+                                           int nsm, cudaStream_t st)
 {
-    if (S > 4096) return cudaErrorInvalidValue;
+    if (S > 4096 || (kspec_seed && (rs < 1 || rs > k))) return cudaErrorInvalidValue;
     uint32_t n2 = 1;
     while (n2 < S) n2 <<= 1;
     const int smem = (int)(n2 * sizeof(double));
     const unsigned grid = (unsigned)min((uint32_t)(nsm * 4), nQ);
-    ppp_seed_kth_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const double *>(scores), S, k, kth, nQ);
+    ppp_seed_kth_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const double *>(scores), S, k, kth, rs, kspec_seed, nQ);
     return cudaGetLastError();
 }

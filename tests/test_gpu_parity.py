@@ -584,6 +584,15 @@ def test_topk_speculative_threshold_is_verified(ctx, front_loaded):
     assert ctx.counter("spec_rank") == 0
     for f in ("q", "t", "score", "yes", "number", "depth"):
         assert np.array_equal(tk0[f], tk[f]), f
+    # the first chunk is speculative too (thresholds = the seeding pass's rs-th smallest bounds): same lists without it
+    ctx.set_option("spec_first", 0)
+    try:
+        tk1 = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
+    finally:
+        ctx.set_option("spec_first", 1)
+    assert ctx.counter("spec_rank") >= 1
+    for f in ("q", "t", "score", "yes", "number", "depth"):
+        assert np.array_equal(tk1[f], tk[f]), f
 
 
 def test_g8192_with_16_sweep_warps(ctx):
