@@ -294,7 +294,7 @@ def run_ours(args):
         # DRAM traffic of the step's pre-filter launches, from the committed ncu capture of exactly this workload (the
         # default arguments); other shapes have no capture -> null
         default_shape = (G, nq, nt, k) == (4096, 10000, 125000, 100)
-        traffic = 248265216 if default_shape else None
+        traffic = 265296128 if default_shape else None
         words = W_bytes // 4
         frac_all = float(np.mean(synth.unpack_bits(P, G).all(axis=1)))
         # POPC the kernel EXECUTES per pair: carry-save adders fold a 4-word chunk into 3 POPC (8 words -> 4 at G=8192);
@@ -328,7 +328,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "ppp_prefilter2_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,
                          "traffic_source": "profiles/r01_ncu_bench_prefilter2_traffic.txt: dram__bytes_read.sum + dram__bytes_write.sum "
-                                           "summed over the 11 ppp_prefilter2 launches of one step of this workload (ncu --set full)"
+                                           "summed over the 14 ppp_prefilter2 launches of one step of this workload (ncu, same command)"
                                            if traffic else None,
                          "kernel_ms_per_step": pf_ms, "kernel_share_of_step": pf_ms / step_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",

@@ -893,17 +893,19 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         };
         if (topk) {
             /* ---- top-k: no host synchronisation until the lists are final ---- */
-            const size_t first = std::min<size_t>(4096, std::max<size_t>(256, (size_t)ctx->seed_mult * k)); /* targets of the seeding pass */
             const size_t chunk1 = std::max<size_t>(4 * 256, (size_t)ctx->chunk1_mult * k);      /* first exact chunk */
-            const size_t w0 = std::min<size_t>(std::min(maxw, nT), first);
-            double *d_kspec = ctx->d_kth + 2 * nQ, *d_kspec0 = ctx->d_kth + 3 * nQ, *d_kseed = ctx->d_kth + 4 * nQ, *d_kseed_use = ctx->d_kth + 5 * nQ;
+            const size_t w1 = std::min(std::min(maxw, nT), chunk1);
             const bool spec_ok = ctx->speculate && !ctx->ranked && use_prefilter2(ctx) && !ctx->force_exact &&
                                  ctx->stair_need_any <= ppp_prefilter2_max_stair(ctx->wpl, 0);
             /* The first chunk is speculative as well when the bulk will be (its verification covers both): its thresholds are
              * the rs-th smallest upper bounds of the seeding pass instead of the k-th -- at config 3 the guaranteed bound lets
              * 15 % of the first chunk's pairs through to a full evaluation, the speculative one 0.8 %. */
-            const size_t w1 = std::min(std::min(maxw, nT), chunk1);
-            const bool chunk1_spec = spec_ok && ctx->spec_first && w0 >= (size_t)k && w1 >= 4 * (size_t)k && nT - w1 >= 8 * w1;
+            const bool may_spec_first = spec_ok && ctx->spec_first && w1 >= 4 * (size_t)k && nT - w1 >= 8 * w1;
+            /* targets of the seeding pass: when only the guaranteed k-th bound is used (no speculation) it pays to seed from more */
+            const size_t first = std::min<size_t>(4096, std::max<size_t>(256, (size_t)(may_spec_first ? ctx->seed_mult : std::max(ctx->seed_mult, 9)) * k));
+            const size_t w0 = std::min<size_t>(std::min(maxw, nT), first);
+            double *d_kspec = ctx->d_kth + 2 * nQ, *d_kspec0 = ctx->d_kth + 3 * nQ, *d_kseed = ctx->d_kth + 4 * nQ, *d_kseed_use = ctx->d_kth + 5 * nQ;
+            const bool chunk1_spec = may_spec_first && w0 >= (size_t)k;
             size_t chunk1_end = 0;
             /* the first chunk runs in two launches: a short head, after which queries whose k best scores are already final
              * (exact zeros: every later target loses the tie on its index) stop sending pairs to the exact tier */
