@@ -131,6 +131,22 @@ int ppp_topk_device(ppp_ctx *ctx, const ppp_hit **lists, const uint32_t **counts
 int ppp_merge_topk_device(ppp_ctx *ctx, const ppp_hit *lists, const uint32_t *counts, uint32_t nlists,
                           const uint32_t *t_offsets, size_t nQ, uint32_t k, ppp_hit *out, uint32_t *out_counts);
 
+/* Printed scores and slope cut-offs of the last PPP_FILTER_THRESH_LOG10 run, computed on the device from the ranked hits
+ * (replaces the per-query Perl sort + scan of bin/ppp.pl:473-506 and bin/ppp_cutoff.pl:130-148).  Host buffers:
+ *   row_off[nQ + 1]   rows of query q = hits row_off[q] .. row_off[q + 1] of ppp_fetch's order (may be NULL)
+ *   milli[n hits]     printed score of each row, sprintf("%.3f", log($score) / log(10)), in thousandths (may be NULL)
+ *   marker[nQ]        ppp.pl -m <slope>: index within the query's rows of the row the marker line precedes, -1 = none among
+ *                     the rows present (rows the filter dropped would print 0.000 and follow them)
+ *   cutoff_milli[nQ]  ppp_cutoff.pl -s <slope>: CUTOFF in thousandths, INT32_MIN = none
+ *   status[nQ]        PPP_CUT_OK, or why the caller must treat the query itself: PPP_CUT_DOUBT (a printed score lies within
+ *                     1e-6 of a rounding boundary, so the device's log cannot guarantee the reference's digit),
+ *                     PPP_CUT_LOG0 (a score is 0: the reference dies "Can't take log of 0"), PPP_CUT_DIV0 (the best row
+ *                     prints 0.000: ppp.pl -m dies dividing by it; cutoff_milli is still valid).
+ * Needs a threshold run whose hits were ranked on the device (one launch); otherwise PPP_ERR_STATE. */
+enum { PPP_CUT_OK = 0, PPP_CUT_DOUBT = 1, PPP_CUT_DIV0 = 2, PPP_CUT_LOG0 = 3 };
+int ppp_printed_cutoffs(ppp_ctx *ctx, double slope, uint64_t *row_off, int32_t *milli, int32_t *marker, int32_t *cutoff_milli,
+                        uint8_t *status);
+
 int ppp_get_stats(const ppp_ctx *ctx, ppp_stats *out);
 
 /* Options (tests / diagnostics): "force_exact" (0/1: every pair through the exact tier),

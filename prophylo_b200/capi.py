@@ -25,7 +25,7 @@ assert HIT_DTYPE.itemsize == 32
 EXPORTS = [
     "ppp_init", "ppp_destroy", "ppp_last_error", "ppp_abi_version", "ppp_set_targets_bits", "ppp_set_targets_ranked",
     "ppp_set_queries", "ppp_run", "ppp_result_count", "ppp_fetch", "ppp_score", "ppp_get_stats", "ppp_set_option",
-    "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc", "ppp_topk_device", "ppp_merge_topk_device", "ppp_read_bla", "ppp_read_bla_flags",
+    "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc", "ppp_topk_device", "ppp_merge_topk_device", "ppp_read_bla", "ppp_read_bla_flags", "ppp_printed_cutoffs",
     "ppp_free_ranked_lists",
 ]
 
@@ -106,6 +106,8 @@ def load():
     L.ppp_read_bla_flags.restype = ctypes.c_int
     L.ppp_read_bla_flags.argtypes = [ctypes.POINTER(ctypes.c_char_p), sz, ctypes.POINTER(ctypes.c_char_p), sz, ctypes.c_int, u32,
                                      ctypes.POINTER(RankedLists), ctypes.c_char_p, sz]
+    L.ppp_printed_cutoffs.restype = ctypes.c_int
+    L.ppp_printed_cutoffs.argtypes = [vp, ctypes.c_double, vp, vp, vp, vp, vp]
     L.ppp_free_ranked_lists.restype = None
     L.ppp_free_ranked_lists.argtypes = [ctypes.POINTER(RankedLists)]
     _lib = L
@@ -113,6 +115,8 @@ def load():
 
 
 BLA_DUP = 1  # PPP_BLA_DUP
+CUT_OK, CUT_DOUBT, CUT_DIV0, CUT_LOG0 = 0, 1, 2, 3
+CUT_NONE = -(2 ** 31)
 
 
 def read_bla_files(paths, universe, nthreads: int = 0, dup: bool = False):
@@ -239,6 +243,20 @@ class Context:
             self._check(rc)
         self.nQ = P.shape[0]
         return out[: got.value]
+
+    def printed_cutoffs(self, slope: float, want_milli: bool = True) -> dict:
+        """Printed scores and slope cut-offs of the last threshold run, computed on the device (ppp_printed_cutoffs):
+        row_off [nQ+1], milli [n hits] (sprintf "%.3f" of log10 score, in thousandths), marker [nQ] (ppp.pl -m, -1 = none),
+        cutoff_milli [nQ] (ppp_cutoff.pl, CUT_NONE = none), status [nQ] (CUT_OK / CUT_DOUBT / CUT_DIV0 / CUT_LOG0)."""
+        n, nq = self.result_count(), self.nQ
+        off = np.empty(nq + 1, dtype=np.uint64)
+        milli = np.empty(n if want_milli else 0, dtype=np.int32)
+        marker = np.empty(nq, dtype=np.int32)
+        cut = np.empty(nq, dtype=np.int32)
+        status = np.empty(nq, dtype=np.uint8)
+        self._check(self.lib.ppp_printed_cutoffs(self._h, float(slope), _ptr(off), _ptr(milli) if want_milli else None, _ptr(marker),
+                                                 _ptr(cut), _ptr(status)))
+        return {"row_off": off, "milli": milli if want_milli else None, "marker": marker, "cutoff_milli": cut, "status": status}
 
     def topk_device(self):
         """(lists_ptr, counts_ptr, k, nQ): device addresses of the last top-k run's [nQ][k] hits and [nQ] counts."""

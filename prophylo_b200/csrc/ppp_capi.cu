@@ -62,6 +62,8 @@ extern "C" cudaError_t ppp_launch_seed_kth(const void *scores, uint32_t S, uint3
 extern "C" size_t ppp_rank_scratch_words(size_t n);
 extern "C" cudaError_t ppp_launch_rank_hits(const ppp_hit *rec, size_t n, uint32_t nQ, uint32_t nT, ppp_hit *out, uint32_t *scratch, int nsm,
                                             cudaStream_t st, uint32_t *launches);
+extern "C" cudaError_t ppp_launch_rank_cutoffs(const ppp_hit *rec, size_t n, uint32_t nQ, double slope, unsigned long long *row_off,
+                                               int32_t *milli, int32_t *marker, int32_t *cutoff_milli, uint8_t *status, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const unsigned long long *counters, int n, cudaStream_t st);
 
 struct ppp_ctx {
@@ -125,12 +127,15 @@ struct ppp_ctx {
     bool results_on_host = false;
     bool results_topk = false;           /* results are the device top-k lists (d_topk, counts in topk_counts) */
     std::vector<uint32_t> topk_counts;
+    ppp_hit *d_acc = nullptr; /* threshold runs of several launches: the launches' hits gathered before ranking */
+    size_t cap_acc = 0;
     ppp_hit *d_ranked = nullptr; /* threshold runs: the hits in (q, score, t) order (ppp_rank.cu) */
     size_t cap_ranked = 0;
     uint32_t *d_rank_tmp = nullptr;
     size_t cap_rank_tmp = 0;
     bool results_ranked = false;
     int dup = 0; /* ranked lists were packed for -dup: the sweep drops the candidate that exceeds |Y| (ppp.pm:222-224) */
+    int launch_pairs_log2 = 29; /* filtered runs: pairs per launch (tests lower it to exercise runs of several launches) */
     int device_rank = 1; /* 0: rank threshold results on the host (developer A/B) */
     uint32_t *d_exact = nullptr;
     size_t cap_exact = 0;
@@ -274,6 +279,7 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaFree(ctx->d_hits);
     cudaFree(ctx->d_exact);
     cudaFree(ctx->d_ranked);
+    cudaFree(ctx->d_acc);
     cudaFree(ctx->d_rank_tmp);
     cudaFree(ctx->d_counters);
     cudaFree(ctx->d_totals);
@@ -829,7 +835,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         /* filtered: per-query staircases prune almost every pair inside the sweep kernel; survivors are appended */
         const bool topk = (f->mode == PPP_FILTER_TOPK);
         const uint32_t k = f->k;
-        const size_t maxw = std::min<size_t>(nT, std::max<size_t>(256, ((size_t)1 << 29) / nQ));
+        const size_t maxw = std::min<size_t>(nT, std::max<size_t>(256, ((size_t)1 << ctx->launch_pairs_log2) / nQ));
         if ((rc = grow(ctx, &ctx->d_hits, &ctx->cap_hits, nQ * maxw))) return rc;
         if ((rc = grow(ctx, &ctx->d_exact, &ctx->cap_exact, nQ * maxw))) return rc;
         /* [nQ] k-th scores, [nQ] tau of the resident staircase, [nQ] speculative thresholds in use, [nQ] their initial values,
@@ -1049,7 +1055,21 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 1, thresh_ln, d_off_static, ctx->d_nmax, d_off_active,
                                     ctx->d_kth + nQ, (uint32_t)nQ, ctx->nsm, ctx->stream));
             launches++;
-            const bool one_chunk = nT <= maxw && ctx->device_rank;
+            /* The hits are ranked by (q, score, t) on the device (ppp_rank.cu) and stay there until ppp_fetch copies them straight
+             * into the caller's buffer.  One launch: ranked where the kernels appended them.  Several launches (more than 2^29
+             * pairs): each launch's hits are first gathered in a device buffer; should that not fit (or exceed the sort's 2^31
+             * records) the chunks go to the host and are ordered there. */
+            const bool one_chunk = nT <= maxw;
+            bool on_device = ctx->device_rank != 0;
+            size_t n_acc = 0;
+            auto spill_to_host = [&](size_t n_dev, const ppp_hit *src) -> int {
+                if (!n_dev) return PPP_OK;
+                const size_t old = ctx->host_results.size();
+                ctx->host_results.resize(old + n_dev);
+                CU(cudaMemcpyAsync(ctx->host_results.data() + old, src, n_dev * sizeof(ppp_hit), cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+                return PPP_OK;
+            };
             while (processed < nT) {
                 const size_t w = std::min(maxw, nT - processed);
                 SweepParams prm;
@@ -1057,39 +1077,59 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                 unsigned long long c[CNT_N];
                 if ((rc = run_chunk(ctx, &prm, totals, &sweep_ms, &launches, c, !ctx->ranked))) return rc;
                 sweep_launches++;
-                if (one_chunk) {
-                    /* the whole run is one launch: rank the appended hits by (q, score, t) on the device; they stay there
-                     * until ppp_fetch copies them straight into the caller's buffer */
-                    const size_t n = c[CNT_APPEND];
-                    if (n) {
-                        if ((rc = grow(ctx, &ctx->d_ranked, &ctx->cap_ranked, n))) return rc;
-                        if ((rc = grow(ctx, &ctx->d_rank_tmp, &ctx->cap_rank_tmp, ppp_rank_scratch_words(n)))) return rc;
-                        CU(cudaEventRecord(ctx->ev[5], ctx->stream));
-                        CU(ppp_launch_rank_hits(ctx->d_hits, n, (uint32_t)nQ, (uint32_t)nT, ctx->d_ranked, ctx->d_rank_tmp, ctx->nsm,
-                                                ctx->stream, &launches));
-                        CU(cudaEventRecord(ctx->ev[6], ctx->stream));
-                        CU(cudaStreamSynchronize(ctx->stream));
-                        float ms = 0.f;
-                        cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
-                        ctx->phase_us[3] += 1e3 * ms;
-                    }
-                    ctx->n_results = n;
-                    ctx->results_on_host = false;
-                    ctx->results_ranked = true;
-                    processed += w;
+                const size_t n = c[CNT_APPEND];
+                processed += w;
+                if (on_device && one_chunk) {
+                    n_acc = n;
                     break;
                 }
-                if (c[CNT_APPEND]) {
-                    const size_t old = ctx->host_results.size();
-                    ctx->host_results.resize(old + c[CNT_APPEND]);
-                    CU(cudaMemcpyAsync(ctx->host_results.data() + old, ctx->d_hits, c[CNT_APPEND] * sizeof(ppp_hit),
-                                       cudaMemcpyDeviceToHost, ctx->stream));
-                    CU(cudaStreamSynchronize(ctx->stream));
+                if (on_device && n) {
+                    if (n_acc + n > ((size_t)1 << 30)) on_device = false;
+                    else if (n_acc + n > ctx->cap_acc) {
+                        /* grow the gathering buffer, keeping what it holds */
+                        const size_t want = std::max(n_acc + n, 2 * ctx->cap_acc);
+                        ppp_hit *bigger = nullptr;
+                        if (cudaMalloc(&bigger, want * sizeof(ppp_hit)) != cudaSuccess) {
+                            (void)cudaGetLastError();
+                            on_device = false;
+                        } else {
+                            if (n_acc) CU(cudaMemcpyAsync(bigger, ctx->d_acc, n_acc * sizeof(ppp_hit), cudaMemcpyDeviceToDevice, ctx->stream));
+                            CU(cudaStreamSynchronize(ctx->stream));
+                            cudaFree(ctx->d_acc);
+                            ctx->d_acc = bigger;
+                            ctx->cap_acc = want;
+                        }
+                    }
+                    if (!on_device) { /* what was gathered so far goes to the host with everything that follows */
+                        if ((rc = spill_to_host(n_acc, ctx->d_acc))) return rc;
+                        n_acc = 0;
+                    }
                 }
-                processed += w;
+                if (on_device) {
+                    if (n) CU(cudaMemcpyAsync(ctx->d_acc + n_acc, ctx->d_hits, n * sizeof(ppp_hit), cudaMemcpyDeviceToDevice, ctx->stream));
+                    n_acc += n;
+                } else if ((rc = spill_to_host(n, ctx->d_hits))) {
+                    return rc;
+                }
             }
-            if (!ctx->results_ranked) {
-                /* more pairs than one launch covers: chunks were copied out as they came; ordered on the host */
+            if (on_device) {
+                const ppp_hit *src = one_chunk ? ctx->d_hits : ctx->d_acc;
+                if (n_acc) {
+                    if ((rc = grow(ctx, &ctx->d_ranked, &ctx->cap_ranked, n_acc))) return rc;
+                    if ((rc = grow(ctx, &ctx->d_rank_tmp, &ctx->cap_rank_tmp, ppp_rank_scratch_words(n_acc)))) return rc;
+                    CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+                    CU(ppp_launch_rank_hits(src, n_acc, (uint32_t)nQ, (uint32_t)nT, ctx->d_ranked, ctx->d_rank_tmp, ctx->nsm, ctx->stream,
+                                            &launches));
+                    CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+                    CU(cudaStreamSynchronize(ctx->stream));
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
+                    ctx->phase_us[3] += 1e3 * ms;
+                }
+                ctx->n_results = n_acc;
+                ctx->results_on_host = false;
+                ctx->results_ranked = true;
+            } else {
                 std::sort(ctx->host_results.begin(), ctx->host_results.end(), hit_less);
                 ctx->n_results = ctx->host_results.size();
             }
@@ -1217,6 +1257,32 @@ extern "C" int ppp_debug_pf2stats(ppp_ctx *ctx, unsigned long long *out8, int re
     return PPP_OK;
 }
 
+extern "C" int ppp_printed_cutoffs(ppp_ctx *ctx, double slope, uint64_t *row_off, int32_t *milli, int32_t *marker, int32_t *cutoff_milli,
+                                   uint8_t *status)
+{
+    if (!ctx || !marker || !cutoff_milli || !status) return PPP_ERR_INVALID;
+    if (!ctx->results_ranked) return fail(ctx, PPP_ERR_STATE, "ppp_printed_cutoffs: the last run was not a threshold run ranked on the device");
+    if (isnan(slope)) return fail(ctx, PPP_ERR_INVALID, "ppp_printed_cutoffs: slope is NaN");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n = ctx->n_results, nQ = ctx->nQ;
+    /* scratch (the sort's buffer is free again): [nQ + 1] u64 row offsets, [n] milli, [nQ] marker, [nQ] cutoff, [nQ] status */
+    const size_t words = 2 * (nQ + 1) + n + 2 * nQ + (nQ + 3) / 4 + 8;
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_rank_tmp, &ctx->cap_rank_tmp, words))) return rc;
+    unsigned long long *d_off = reinterpret_cast<unsigned long long *>(ctx->d_rank_tmp);
+    int32_t *d_milli = reinterpret_cast<int32_t *>(d_off + nQ + 1);
+    int32_t *d_marker = d_milli + n, *d_cut = d_marker + nQ;
+    uint8_t *d_status = reinterpret_cast<uint8_t *>(d_cut + nQ);
+    CU(ppp_launch_rank_cutoffs(ctx->d_ranked, n, (uint32_t)nQ, slope, d_off, d_milli, d_marker, d_cut, d_status, ctx->nsm, ctx->stream));
+    if (row_off) CU(cudaMemcpyAsync(row_off, d_off, (nQ + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (milli && n) CU(cudaMemcpyAsync(milli, d_milli, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(marker, d_marker, nQ * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(cutoff_milli, d_cut, nQ * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(status, d_status, nQ, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PPP_OK;
+}
+
 extern "C" int ppp_get_stats(const ppp_ctx *ctx, ppp_stats *out)
 {
     if (!ctx || !out) return PPP_ERR_INVALID;
@@ -1244,6 +1310,9 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
         ctx->spec_first = value != 0;
     } else if (!strcmp(name, "dup")) {
         ctx->dup = value != 0;
+    } else if (!strcmp(name, "launch_pairs_log2")) {
+        if (value < 12 || value > 29) return fail(ctx, PPP_ERR_INVALID, "launch_pairs_log2 must be in [12, 29]");
+        ctx->launch_pairs_log2 = (int)value;
     } else if (!strcmp(name, "device_rank")) {
         ctx->device_rank = value != 0;
     } else if (!strcmp(name, "prefilter_version")) {

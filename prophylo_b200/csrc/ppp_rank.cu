@@ -226,3 +226,97 @@ extern "C" cudaError_t ppp_launch_rank_hits(const ppp_hit *rec, size_t n, uint32
     ++*launches;
     return cudaGetLastError();
 }
+
+/* ------------------------------------------------------------------------------------------------ printed scores and cut-offs
+ * What the drivers compute from a query's rows once they are sorted, on the ranked hits:
+ *   printed score   sprintf("%.3f", log($score) / log(10))                                  bin/ppp.pl:476-503
+ *   ppp.pl -m       marker before the first row with (|best| - |s|) / |best| * 100 > slope, best = the first row's printed
+ *                   score, never updated                                                      bin/ppp.pl:477-489
+ *   ppp_cutoff.pl   printed scores <= -1 in descending order; the first adjacent pair with |(last - s) / last * 100| > slope
+ *                   gives CUTOFF = last                                                       bin/ppp_cutoff.pl:130-148
+ * Printed scores are kept as integer thousandths.  The device's log is not the host libm's and the reference's clients hand
+ * the score to the server through a %.15g string (bin/ppp.pl:582), so a value is only trusted when it is not within 1e-6
+ * of a rounding boundary (those perturbations move it by < 1e-12); otherwise the query is flagged PPP_CUT_DOUBT and the
+ * caller formats that query's rows itself.  The comparisons use the same IEEE double operations as Perl (no contraction). */
+__device__ __forceinline__ int32_t printed_milli(double score, int *status)
+{
+    if (!(score > 0.0)) {
+        *status = PPP_CUT_LOG0;
+        return 0;
+    }
+    const double t = __dmul_rn(__ddiv_rn(log(score), log(10.0)), 1000.0);
+    const double r = rint(t);
+    if (fabs(t - r) > 0.5 - 1e-6) *status = max(*status, (int)PPP_CUT_DOUBT);
+    return (int32_t)r;
+}
+
+__global__ void __launch_bounds__(256) ppp_rank_row_off_kernel(const ppp_hit *__restrict__ rec, uint32_t n, uint32_t nQ,
+                                                               unsigned long long *__restrict__ row_off)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += stride) {
+        const uint32_t qlo = i ? rec[i - 1].q + 1 : 0u;       /* queries whose rows start at i: (previous row's q, this row's q] */
+        const uint32_t qhi = i < n ? rec[i].q : nQ;           /* i == n: every remaining query, and the end marker row_off[nQ] */
+        for (uint32_t q = qlo; q <= qhi && q <= nQ; ++q) row_off[q] = i;
+    }
+}
+
+/* block per query */
+__global__ void __launch_bounds__(256) ppp_rank_cutoff_kernel(const ppp_hit *__restrict__ rec, const unsigned long long *__restrict__ row_off,
+                                                              uint32_t nQ, double slope, int32_t *__restrict__ milli, int32_t *__restrict__ marker,
+                                                              int32_t *__restrict__ cutoff_milli, uint8_t *__restrict__ status)
+{
+    __shared__ int s_status;
+    __shared__ unsigned long long s_first, s_last;
+    for (uint32_t q = blockIdx.x; q < nQ; q += gridDim.x) {
+        const unsigned long long r0 = row_off[q], r1 = row_off[q + 1];
+        if (threadIdx.x == 0) {
+            s_status = PPP_CUT_OK;
+            s_first = ~0ull;
+            s_last = 0ull;
+        }
+        __syncthreads();
+        int st = PPP_CUT_OK;
+        for (unsigned long long i = r0 + threadIdx.x; i < r1; i += blockDim.x) milli[i] = printed_milli(rec[i].score, &st);
+        if (st) atomicMax(&s_status, st);
+        __syncthreads(); /* milli[] of this query is visible to the block (same-block global writes after a barrier) */
+        if (r1 > r0 && s_status != PPP_CUT_LOG0) {
+            const double pl = fabs(__ddiv_rn((double)milli[r0], 1000.0));
+            if (pl == 0.0) {
+                if (threadIdx.x == 0) s_status = max(s_status, (int)PPP_CUT_DIV0); /* ppp.pl -m: "Illegal division by zero" */
+            } else {
+                /* ppp.pl -m: first row i with (pl - |s_i|) / pl * 100 > slope */
+                for (unsigned long long i = r0 + threadIdx.x; i < r1; i += blockDim.x) {
+                    const double ps = fabs(__ddiv_rn((double)milli[i], 1000.0));
+                    if (__dmul_rn(__ddiv_rn(__dsub_rn(pl, ps), pl), 100.0) > slope) {
+                        atomicMin(&s_first, i - r0);
+                        break; /* later rows of this thread are later in the list */
+                    }
+                }
+            }
+            /* ppp_cutoff.pl: rows with printed score <= -1, weakest first; rows are ranked strongest first, so walking the
+             * list backwards the first violating pair is the one with the LARGEST index: last = row j + 1, s = row j */
+            for (unsigned long long j = r0 + threadIdx.x; j + 1 < r1; j += blockDim.x) {
+                const int32_t ml = milli[j + 1], ms = milli[j];
+                if (ml > -1000) break; /* ranked: every later row is weaker still */
+                const double last = __ddiv_rn((double)ml, 1000.0), s = __ddiv_rn((double)ms, 1000.0);
+                if (fabs(__dmul_rn(__ddiv_rn(__dsub_rn(last, s), last), 100.0)) > slope) atomicMax(&s_last, j - r0 + 1);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            status[q] = (uint8_t)s_status;
+            marker[q] = s_first == ~0ull ? -1 : (int32_t)s_first;
+            cutoff_milli[q] = s_last ? milli[r0 + s_last] : INT32_MIN; /* s_last = (index of `last`), >= 1 when found */
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" cudaError_t ppp_launch_rank_cutoffs(const ppp_hit *rec, size_t n, uint32_t nQ, double slope, unsigned long long *row_off,
+                                               int32_t *milli, int32_t *marker, int32_t *cutoff_milli, uint8_t *status, int nsm, cudaStream_t st)
+{
+    ppp_rank_row_off_kernel<<<nsm * 4, 256, 0, st>>>(rec, (uint32_t)n, nQ, row_off);
+    ppp_rank_cutoff_kernel<<<nsm * 8, 256, 0, st>>>(rec, row_off, nQ, slope, milli, marker, cutoff_milli, status);
+    return cudaGetLastError();
+}

@@ -267,9 +267,67 @@ def test_threshold_results_ranked_on_device(ctx):
         ctx.set_option("device_rank", 1)
     assert dev.size == host.size and dev.size > 3 * 4096
     assert dev.tobytes() == host.tobytes()
+    # the same run cut into several launches: each launch's hits are gathered on the device and ranked once at the end
+    ctx.set_option("launch_pairs_log2", 17)
+    try:
+        multi = ctx.score(P, Y, p, flt).copy()
+        assert ctx.stats()["sweep_launches"] > 2
+        assert ctx.printed_cutoffs(20.0)["row_off"][-1] == multi.size  # still resident and ranked on the device
+    finally:
+        ctx.set_option("launch_pairs_log2", 29)
+    assert multi.tobytes() == host.tobytes()
     key = np.lexsort((dev["t"], dev["score"], dev["q"]))
     assert np.array_equal(key, np.arange(dev.size))
     assert (dev["score"] == 0.0).sum() >= 10  # diagonal pairs of the larger families underflow
+
+
+def test_printed_scores_and_slope_cutoffs_on_device(ctx):
+    """ppp_printed_cutoffs: the per-query tail of the drivers (sort, "%.3f" log10 score, ppp.pl -m marker, ppp_cutoff.pl
+    CUTOFF; bin/ppp.pl:473-506, bin/ppp_cutoff.pl:130-148) on the device, against the host restatements in
+    prophylo_b200.drivers -- which reproduce the unmodified reference scripts byte for byte (tests/test_drivers.py)."""
+    from prophylo_b200 import drivers
+
+    G, nq, nt = 1024, 60, 3000
+    P, Y, p = synth.make_queries(G, nq, 91, "mixed")
+    T = synth.make_targets(G, nt, 92, plant_from=Y, plant_frac=0.05)
+    ctx.set_targets_bits(T, G)
+    hits = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_THRESH_LOG10, thresh=-0.0005)).copy()
+    for slope in (10.0, 30.0):
+        r = ctx.printed_cutoffs(slope)
+        off = r["row_off"].astype(np.int64)
+        assert off[0] == 0 and off[-1] == hits.size and np.all(np.diff(off) >= 0)
+        checked = 0
+        for q in range(nq):
+            rows = hits[off[q]:off[q + 1]]
+            assert np.all(rows["q"] == q)
+            if r["status"][q] == capi.CUT_LOG0:
+                assert (rows["score"] == 0).any()
+                continue
+            assert not (rows["score"] == 0).any()
+            if r["status"][q] == capi.CUT_DOUBT or rows.size == 0:
+                continue
+            # printed scores: the server reads the client's %.15g string back before taking the logarithm (bin/ppp.pl:582)
+            strs = [drivers._log10_3f(drivers._perl_num(float(s))) for s in rows["score"]]
+            assert [int(round(float(x) * 1000)) for x in strs] == r["milli"][off[q]:off[q + 1]].tolist(), q
+            table_rows = [(int(h["t"]), float(h["score"]), int(h["yes"]), int(h["number"]), int(h["depth"]), float(p[q])) for h in rows]
+            if r["status"][q] == capi.CUT_DIV0:
+                with pytest.raises(ZeroDivisionError):
+                    drivers.format_ppp_table(table_rows, slope=slope)
+                text = drivers.format_ppp_table(table_rows)
+            else:
+                text = drivers.format_ppp_table(table_rows, slope=slope)
+                lines = text.split("\n")[1:]
+                exp_marker = next((i for i, ln in enumerate(lines) if ln and set(ln) == {"-"}), -1)
+                assert r["marker"][q] == exp_marker, (q, slope)
+            _, cutoff = drivers.ppp_cutoff(text, slope)
+            got = r["cutoff_milli"][q]
+            assert (cutoff is None and got == capi.CUT_NONE) or (cutoff is not None and got == int(round(cutoff * 1000))), (q, slope, cutoff, got)
+            checked += 1
+        assert checked > nq // 2
+    assert (r["marker"] >= 0).sum() > 5 and (r["cutoff_milli"] != capi.CUT_NONE).sum() > 5
+    ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=5))
+    with pytest.raises(capi.PPPError):
+        ctx.printed_cutoffs(10.0)
 
 
 def test_full_size_properties(ctx):
