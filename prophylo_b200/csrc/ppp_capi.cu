@@ -668,11 +668,12 @@ static int launch_chunk_deferred(ppp_ctx *ctx, SweepParams *prm, uint32_t *launc
         unsigned long long c[CNT_SLOTS];
         CU(cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        float m1 = 0.f, m2 = 0.f;
+        float m1 = 0.f, m2 = 0.f, mp = 0.f;
         cudaEventElapsedTime(&m1, ctx->evpool[e0], ctx->evpool[e1]);
         cudaEventElapsedTime(&m2, ctx->evpool[e1], ctx->evpool[e2]);
-        fprintf(stderr, "[ppp chunk] t=[%u,%u) mode=%u bounds_only=%u prefiltered=%d: survivors %llu full %llu exact %llu cand %llu  sweep %.3f ms exact %.3f ms\n",
-                prm->t0, prm->t1, prm->accept_mode, prm->bounds_only, (int)prefiltered, c[CNT_N], c[CNT_FULL], c[CNT_EXACT], c[CNT_CAND], m1, m2);
+        if (prefiltered) cudaEventElapsedTime(&mp, ctx->evpool[e0], ctx->evpool[em]);
+        fprintf(stderr, "[ppp chunk] t=[%u,%u) mode=%u bounds_only=%u prefiltered=%d: survivors %llu full %llu exact %llu cand %llu  sweep %.3f ms (pre-filter %.3f) exact %.3f ms\n",
+                prm->t0, prm->t1, prm->accept_mode, prm->bounds_only, (int)prefiltered, c[CNT_N], c[CNT_FULL], c[CNT_EXACT], c[CNT_CAND], m1, mp, m2);
     }
     *launches += 3;
     ctx->spans.push_back({e0, e1, 0});

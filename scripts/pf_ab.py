@@ -9,8 +9,10 @@ G = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 nq = int(sys.argv[3]) if len(sys.argv) > 3 else 2048
 nt = int(sys.argv[4]) if len(sys.argv) > 4 else 125000
 kind = sys.argv[5] if len(sys.argv) > 5 else "mixed"
-P, Y, p = synth.make_queries(G, nq, synth.SEED_BASE + 3, kind)
-T = synth.make_targets(G, nt, synth.SEED_BASE + 103, plant_from=Y, plant_frac=0.01)
+k = int(sys.argv[6]) if len(sys.argv) > 6 else 100
+seed = {"prefix": 4, "family": 5, "single": 2}.get(kind, 3)
+P, Y, p = synth.make_queries(G, nq, synth.SEED_BASE + seed, kind)
+T = synth.make_targets(G, nt, synth.SEED_BASE + 100 + seed, plant_from=Y, plant_frac=0.01)
 c = capi.Context(0)
 c.set_option("sweep_warps", 16)
 c.set_option("prefilter_version", ver)
@@ -22,7 +24,7 @@ have_stats = hasattr(lib, "ppp_debug_pf2stats")
 if have_stats:
     lib.ppp_debug_pf2stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
     lib.ppp_debug_pf2stats(c._h, out, 1)
-flt = capi.make_filter(capi.FILTER_TOPK, k=100)
+flt = capi.make_filter(capi.FILTER_TOPK, k=k)
 res = None
 for r in range(3):
     c.run(flt)
