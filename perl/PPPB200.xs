@@ -110,6 +110,39 @@ _set_targets_bla(h, paths, universe, nthreads, flags)
     RETVAL
 
 void
+_printed_cutoffs(h, nQ, slope)
+    IV h
+    UV nQ
+    double slope
+  PPCODE:
+    /* per query of the last threshold run: [first row, rows, marker row or -1, CUTOFF in thousandths or undef, status]
+     * (ppp_printed_cutoffs: bin/ppp.pl:473-506 -m marker, bin/ppp_cutoff.pl:130-148 CUTOFF, computed on the device) */
+    ppp_ctx *ctx = INT2PTR(ppp_ctx *, h);
+    uint64_t *off = NULL;
+    int32_t *marker = NULL, *cut = NULL;
+    uint8_t *status = NULL;
+    Newx(off, nQ + 1, uint64_t);
+    Newx(marker, nQ ? nQ : 1, int32_t);
+    Newx(cut, nQ ? nQ : 1, int32_t);
+    Newx(status, nQ ? nQ : 1, uint8_t);
+    int rc = ppp_printed_cutoffs(ctx, slope, off, NULL, marker, cut, status);
+    if (rc != PPP_OK) {
+        Safefree(off); Safefree(marker); Safefree(cut); Safefree(status);
+        croak("PhyloProf::B200: %s", ppp_last_error(ctx));
+    }
+    EXTEND(SP, (SSize_t)nQ);
+    for (size_t q = 0; q < (size_t)nQ; ++q) {
+        AV *av = newAV();
+        av_push(av, newSVuv((UV)off[q]));
+        av_push(av, newSVuv((UV)(off[q + 1] - off[q])));
+        av_push(av, newSViv(marker[q]));
+        av_push(av, cut[q] == INT32_MIN ? newSV(0) : newSViv(cut[q]));
+        av_push(av, newSVuv(status[q]));
+        PUSHs(sv_2mortal(newRV_noinc((SV *)av)));
+    }
+    Safefree(off); Safefree(marker); Safefree(cut); Safefree(status);
+
+void
 _score(h, pplanes, yplanes, probs, nQ, mode, k, thresh)
     IV h
     SV *pplanes

@@ -116,6 +116,14 @@ sub score_bits {
     return $self->_score_queries( $universe, $idx, $queries, %o );
 }
 
+# after a -filter => 'thresh' call: per query [first row, rows, marker row | -1, CUTOFF in thousandths | undef, status] -- the
+# ppp.pl -m <slope> marker and ppp_cutoff.pl -s <slope> CUTOFF of each query's (already sorted) rows, computed on the device
+# (bin/ppp.pl:473-506, bin/ppp_cutoff.pl:130-148).  status != 0: format that query's rows in Perl (include/ppp_b200.h).
+sub printed_cutoffs {
+    my ( $self, $n_queries, $slope ) = @_;
+    return [ _printed_cutoffs( $self->{h}, $n_queries, $slope ) ];
+}
+
 sub _score_queries {
     my ( $self, $universe, $idx, $queries, %o ) = @_;
     my $G   = scalar @$universe;

@@ -48,5 +48,30 @@ foreach my $c ( @{ $g->{known_answers} }, @{ $g->{fuzz} } ) {
         print "MISMATCH ranked batch: @$h vs @e\n";
     }
 }
+# threshold run + device-side cut-offs through the XS binding: rows arrive sorted, CUTOFF as ppp_cutoff.pl computes it
+{
+    my $ka = $g->{known_answers}[1];
+    my @universe = sort keys %{ $ka->{query} };
+    my $gpu = PhyloProf::B200->new( -device => $ENV{PPP_B200_DEVICE} || 0 );
+    my @t = @{ $ka->{target} };
+    my @lists = map { [ @t[ 0 .. $_ ] ] } ( 2 .. $#t );
+    my $hits = $gpu->score_ranked( \@universe, [ $ka->{query} ], \@lists, -filter => 'thresh', -thresh => -0.0005 );
+    my $cuts = $gpu->printed_cutoffs( 1, 20 );
+    my ( $first, $rows, $marker, $cutoff, $status ) = @{ $cuts->[0] };
+    my @logs = map { sprintf( "%.3f", log( $_->[2] ) / log(10) ) } @$hits;
+    my ( $last, $want );
+    foreach my $s ( sort { $b <=> $a } grep { $_ <= -0.001 } @logs ) {    # bin/ppp_cutoff.pl:130-148
+        next if $s > -1;
+        unless ($last) { $last = $s; next; }
+        if ( abs( ( $last - $s ) / $last * 100 ) > 20 ) { $want = $last; last; }
+        $last = $s;
+    }
+    my $sorted = !grep { $hits->[$_][2] < $hits->[ $_ - 1 ][2] } ( 1 .. $#$hits );
+    my $same = defined($want) ? ( defined($cutoff) && $cutoff == sprintf( "%.0f", $want * 1000 ) ) : !defined($cutoff);
+    unless ( $rows == @$hits && $first == 0 && $sorted && ( $status != 0 || $same ) ) {
+        $bad++;
+        print "MISMATCH printed_cutoffs: rows $rows vs ", scalar(@$hits), " cutoff ", ( $cutoff // 'undef' ), " want ", ( $want // 'undef' ), "\n";
+    }
+}
 print "perl drop-in: $n cases ($skipped with -dup), $bad mismatches\n";
 exit( $bad ? 1 : 0 );

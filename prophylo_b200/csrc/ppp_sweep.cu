@@ -325,8 +325,11 @@ __global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams pr
 }
 
 /* ---------------------------------------------------------------- refine kernel: warp per surviving pair */
+#ifndef PPP_REFINE_WARPS
+#define PPP_REFINE_WARPS 16 /* warps per CTA the refine kernel is compiled for (register budget = 65536 / threads) */
+#endif
 template <int WPL>
-__global__ void __launch_bounds__(512, PPP_MINBLOCKS_OF(WPL)) ppp_refine_kernel(const SweepParams prm, const uint32_t *__restrict__ surv,
+__global__ void __launch_bounds__(PPP_REFINE_WARPS * 32, PPP_MINBLOCKS_OF(WPL)) ppp_refine_kernel(const SweepParams prm, const uint32_t *__restrict__ surv,
                                                          const unsigned long long *__restrict__ surv_count, unsigned long long surv_cap)
 {
     constexpr uint32_t PPP_QCAP = PPP_QCAP_OF(WPL);
@@ -525,6 +528,7 @@ template <int WPL>
 static cudaError_t launch_refine_t(const SweepParams &prm, const uint32_t *surv, const unsigned long long *surv_count, unsigned long long surv_cap,
                                    int nwarps, int nsm, cudaStream_t st)
 {
+    if (nwarps == 16) nwarps = PPP_REFINE_WARPS; /* the tuned setting asks for as many warps as the kernel was compiled for */
     while (nwarps > 1 && refine_smem_bytes(WPL, nwarps) > PPP_MAX_DYN_SMEM) --nwarps;
     const size_t smem = refine_smem_bytes(WPL, nwarps);
     cudaError_t e = cudaFuncSetAttribute(ppp_refine_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
