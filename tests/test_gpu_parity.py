@@ -743,3 +743,41 @@ def test_config3_per_gpu_share_properties_and_sampled_oracle(ctx):
         for s, t in zip(d[j]["score"], ts):
             if int(t) not in inlist:
                 assert (s, t) > (last_s, last_t), (q, t, s, last_s)
+
+
+def test_config5_full_size_threshold_run_ranked_on_device(ctx):
+    """BASELINE config 5 at full size (4,500 x 4,500 profile families x 8192 genomes, the ppp_cutoff.pl filter: every pair
+    whose printed log10 score is < 0): the device-ranked hit list is exactly the dense result's passing pairs -- same
+    records, same count -- in (query, score, target) order, and the device's printed scores / CUTOFFs are consistent."""
+    G, n = 8192, 4500
+    P, Y, p = synth.make_queries(G, n, synth.SEED_BASE + 5, "family")
+    ctx.set_targets_bits(Y, G)
+    dense = ctx.score(P, Y, p).reshape(n, n).copy()
+    hits = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_THRESH_LOG10, thresh=-0.0005))
+    with np.errstate(divide="ignore"):
+        keep = np.log10(dense["score"]) < -0.0005
+    assert hits.size == int(keep.sum()) and hits.size > 10_000_000
+    d = dense[hits["q"], hits["t"]]
+    for f in ("q", "t", "score", "yes", "number", "depth"):
+        assert np.array_equal(d[f], hits[f]), f
+    q, s, t = hits["q"].astype(np.int64), hits["score"], hits["t"].astype(np.int64)
+    same_q = q[1:] == q[:-1]
+    assert np.all(q[1:] >= q[:-1])
+    assert np.all(s[1:][same_q] >= s[:-1][same_q])
+    tie = same_q & (s[1:] == s[:-1])
+    assert np.all(t[1:][tie] > t[:-1][tie])
+    r = ctx.printed_cutoffs(20.0)
+    off = r["row_off"].astype(np.int64)
+    assert np.array_equal(off[1:] - off[:-1], np.bincount(q, minlength=n))
+    ok = r["status"] == capi.CUT_OK
+    assert ok.sum() > n // 4  # the diagonal's exact zeros put the other queries into CUT_LOG0, as the reference would die
+    zero_q = np.unique(q[s == 0.0])
+    assert np.all(r["status"][zero_q] == capi.CUT_LOG0)
+    m = r["milli"]
+    rows_ok = ok[q]
+    with np.errstate(divide="ignore"):
+        exp = np.rint(np.log10(s[rows_ok]) * 1000.0)
+    assert np.max(np.abs(m[rows_ok] - exp)) <= 1  # numpy's log10 is not the reference's log/log(10): one unit at a boundary
+    assert np.all(np.diff(m.astype(np.int64))[same_q & rows_ok[1:] & rows_ok[:-1]] >= 0)
+    cm = r["cutoff_milli"][ok]
+    assert np.all((cm == capi.CUT_NONE) | (cm <= -1000))
