@@ -421,13 +421,16 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
                         const uint32_t cy2 = 2u * popc_csa<CH>(b);
                         ys[j] += cy2;
                         const int lim = (int)*reinterpret_cast<const int16_t *>(s_stair_b + ys[j]);
-                        flags |= ((int)(nb + cy2) <= lim) ? (1u << j) : 0u;
+                        /* d < 0: the chunk cannot pass.  One 3-input add and one funnel shift that moves d's sign bit into the
+                         * flag word (query j ends up at bit QG-1-j) instead of compare + select + or */
+                        const int d = lim - (int)cy2 - (int)nb;
+                        flags = __funnelshift_l((uint32_t)d, flags, 1);
                     }
                     /* phase B: predicated pushes */
-                    if (flags) {
+                    if (flags != (1u << PF2_QG) - 1u) {
 #pragma unroll
                         for (int j = 0; j < PF2_QG; ++j) {
-                            if ((flags >> j) & 1u) {
+                            if (!((flags >> (PF2_QG - 1 - j)) & 1u)) {
                                 sts_u32(qa, ys[j] | ctag | ((uint32_t)j << 24));
                                 if (!PALL) sts_u32(qa + 4u * PF2_THREADS, nbq[j]);
                                 qa += 4u * QSTRIDE;
