@@ -355,11 +355,21 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
 
             uint32_t tw[CH];
             load_chunk<CH>(a.Tt, a.ntt, t, 0, live, tw);
+            /* running pointers instead of per-chunk index arithmetic: the row's next chunk (dead lanes read target t0, whose
+             * words are then ignored -- their passes never reach the survivor list) and the depth prefix of this thread */
+            const uint4 *tnext = a.Tt + t;
+            const uint16_t *pref = s_pref + tid;
 #pragma unroll 1
             for (int c = 0; c < NCH; ++c) {
                 uint32_t tn[CH]; /* prefetch the next chunk of the row */
-                load_chunk<CH>(a.Tt, a.ntt, t, (c + 1 < NCH) ? c + 1 : c, live, tn);
-                const uint32_t nb_all = PALL ? (uint32_t)s_pref[c * PF2_THREADS + tid] : 0u;
+                if (c + 1 < NCH) tnext += (size_t)(CH / 4) * a.ntt;
+#pragma unroll
+                for (int i = 0; i < CH / 4; ++i) {
+                    const uint4 v = __ldg(tnext + (size_t)i * a.ntt);
+                    tn[4 * i + 0] = v.x; tn[4 * i + 1] = v.y; tn[4 * i + 2] = v.z; tn[4 * i + 3] = v.w;
+                }
+                const uint32_t nb_all = PALL ? (uint32_t)*pref : 0u;
+                pref += PF2_THREADS;
                 const uint32_t ctag = ((uint32_t)c << 16) + gtag;
                 if (c < HEAD) {
                     /* head of the row: word-level screen (number is small here, a 128-genome chunk would nearly
