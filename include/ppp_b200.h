@@ -154,8 +154,17 @@ int ppp_get_stats(const ppp_ctx *ctx, ppp_stats *out);
  * "sweep_warps" (warps per CTA), "table_mode" (-1 auto / 0 off / 1 on: exact (yes, number) table per query for dense
  * runs of few queries against many targets), "dup" (0/1: the resident ranked lists were packed for -dup, see
  * ppp_read_bla_flags), "device_rank" (1/0: threshold results ranked on the device / on the host).
+ * Top-k schedule (none of them changes a result, only how many pairs need a full evaluation): "speculate" (0/1: screen the
+ * bulk of the targets against a speculative, verified threshold), "spec_first" (0/1: the first chunk as well, against the
+ * seeding pass's bounds), "spec_eps_ppm" (probability, in ppm, with which a speculative threshold may be too tight and
+ * the query is re-scanned), "seed_mult" / "chunk0_mult" / "chunk1_mult" (targets of the seeding pass, of the first chunk's
+ * head and of the first chunk, in units of k), "prefilter_version" (2 / 1), "launch_pairs_log2" (pairs per launch of a
+ * filtered run, 12..29; tests lower it to exercise runs of several launches).
  * Unknown names return PPP_ERR_INVALID. */
 int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value);
+/* Counters of the last run (diagnostics, bench.py): "candidates", "accurate_evals", "exact_pairs", "full_pairs",
+ * "survivors", "prefilter_pairs", "bound_checks", "bound_violations", "spec_rank", "spec_failed", "used_table", "num_sms",
+ * and the CUDA-event times "us_sweep", "us_prefilter", "us_exact", "us_staircase", "us_merge" (microseconds). */
 int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *value);
 
 /* Row length in uint32 words of the bit-plane layout for G genomes: ceil(G/128)*4. */
