@@ -360,7 +360,7 @@ extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const u
  * k-th best score over all nT targets is, for exchangeable targets, close to the (k * processed / nT)-th best seen so
  * far -- far below the guaranteed bound (the k-th best so far).  The remaining targets are therefore screened against
  * the r-th best score so far (r chosen on the host so that a Poisson(k processed / nT) count reaches r with probability
- * <= 1e-3), which cuts the pairs that need a full evaluation several-fold, and the result is VERIFIED: every pair below
+ * <= spec_eps_ppm, 5e-3 by default), which cuts the pairs that need a full evaluation several-fold, and the result is VERIFIED: every pair below
  * the speculative threshold was found exactly, so the list is exact iff it is full and its k-th score is strictly
  * below that threshold.  Queries that fail are re-scanned over the same targets with the guaranteed bound and
  * klo <= score <= kth acceptance (ppp_capi.cu). */
