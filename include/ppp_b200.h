@@ -156,7 +156,8 @@ int ppp_get_stats(const ppp_ctx *ctx, ppp_stats *out);
  * ppp_read_bla_flags), "device_rank" (1/0: threshold results ranked on the device / on the host).
  * Top-k schedule (none of them changes a result, only how many pairs need a full evaluation): "speculate" (0/1: screen the
  * bulk of the targets against a speculative, verified threshold), "spec_first" (0/1: the first chunk as well, against the
- * seeding pass's bounds), "spec_eps_ppm" (probability, in ppm, with which a speculative threshold may be too tight and
+ * seeding pass's bounds), "respec_mult" (a new, tighter speculation level every time the processed targets have grown this
+ * many times, in runs of at least 2^"respec_min_pairs_log2" pairs; <= 1: one level), "spec_eps_ppm" (probability, in ppm, with which a speculative threshold may be too tight and
  * the query is re-scanned), "seed_mult" / "chunk0_mult" / "chunk1_mult" (targets of the seeding pass, of the first chunk's
  * head and of the first chunk, in units of k), "prefilter_version" (2 / 1), "launch_pairs_log2" (pairs per launch of a
  * filtered run, 12..29; tests lower it to exercise runs of several launches).

@@ -117,6 +117,8 @@ struct ppp_ctx {
     int spec_first = 1;          /* ... and the first chunk against the seeding pass's rs-th smallest bound */
     uint32_t spec_rank = 0, spec_failed = 0;
     int chunk0_mult = 4; /* head of the first chunk, in units of k (0 = no split) */
+    int respec_min_pairs_log2 = 27; /* ... in runs of at least this many pairs */
+    int respec_mult = 8; /* a new speculation level every time the processed targets have grown this many times (<= 1: one level) */
     int seed_mult = 5, chunk1_mult = 24, spec_eps_ppm = 5000; /* top-k schedule: seeding targets / k, first chunk / k, P(spec fails) */
     size_t nQ = 0, capQ = 0;
     /* results */
@@ -556,6 +558,8 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
     return PPP_OK;
 }
 
+#define PPP_MAX_SPEC_LEVELS 6
+
 static bool hit_less(const ppp_hit &a, const ppp_hit &b)
 {
     if (a.q != b.q) return a.q < b.q;
@@ -840,8 +844,9 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         if ((rc = grow(ctx, &ctx->d_hits, &ctx->cap_hits, nQ * maxw))) return rc;
         if ((rc = grow(ctx, &ctx->d_exact, &ctx->cap_exact, nQ * maxw))) return rc;
         /* [nQ] k-th scores, [nQ] tau of the resident staircase, [nQ] speculative thresholds in use, [nQ] their initial values,
-         * [nQ] speculative thresholds of the first chunk (from the seeding pass), [nQ] the same tightened by the k-th scores */
-        if ((rc = grow(ctx, &ctx->d_kth, &ctx->cap_kth, 6 * nQ))) return rc;
+         * [nQ] speculative thresholds of the first chunk (from the seeding pass), [nQ] the same tightened by the k-th scores,
+         * [PPP_MAX_SPEC_LEVELS][nQ] initial thresholds of the later speculation levels */
+        if ((rc = grow(ctx, &ctx->d_kth, &ctx->cap_kth, (6 + PPP_MAX_SPEC_LEVELS) * nQ))) return rc;
         if ((rc = grow(ctx, &ctx->d_qcnt, &ctx->cap_qcnt, 2 * nQ))) return rc; /* [nQ] append counters, [nQ] top-k counts */
         /* [nQ] static offsets, [nQ] active offsets, [nQ] queries whose speculative threshold failed, [1] their count */
         if ((rc = grow(ctx, &ctx->d_off, &ctx->cap_off, 3 * nQ + 4))) return rc;
@@ -911,7 +916,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             /* targets of the seeding pass: when only the guaranteed k-th bound is used (no speculation) it pays to seed from more */
             const size_t first = std::min<size_t>(4096, std::max<size_t>(256, (size_t)(may_spec_first ? ctx->seed_mult : std::max(ctx->seed_mult, 9)) * k));
             const size_t w0 = std::min<size_t>(std::min(maxw, nT), first);
-            double *d_kspec = ctx->d_kth + 2 * nQ, *d_kspec0 = ctx->d_kth + 3 * nQ, *d_kseed = ctx->d_kth + 4 * nQ, *d_kseed_use = ctx->d_kth + 5 * nQ;
+            double *d_kspec = ctx->d_kth + 2 * nQ, *d_kseed = ctx->d_kth + 4 * nQ, *d_kseed_use = ctx->d_kth + 5 * nQ;
             const bool chunk1_spec = may_spec_first && w0 >= (size_t)k;
             size_t chunk1_end = 0;
             /* the first chunk runs in two launches: a short head, after which queries whose k best scores are already final
@@ -941,20 +946,39 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             uint32_t *d_failed = ctx->d_off + 2 * nQ, *d_nfailed = ctx->d_off + 3 * nQ;
             bool spec_on = false;
             size_t spec_start = 0;
+            /* speculation levels of the bulk: level l covers targets [lvl_begin[l], lvl_begin[l + 1]) and was screened against
+             * thresholds whose initial values are kept in d_lvl(l) (the re-scan's lower acceptance bound for that range) */
+            std::vector<size_t> lvl_begin;
+            auto d_lvl = [&](size_t l) { return ctx->d_kth + (6 + l) * nQ; };
             ctx->spec_rank = 0;
             ctx->spec_failed = 0;
             while (processed < nT) {
-                if (spec_ok && !spec_on && processed >= 4 * (size_t)k && nT - processed >= 8 * processed && (!chunk1_spec || processed >= w1)) {
-                    /* speculative threshold (ppp_topk.cu): rank r of the list so far */
+                /* a new level: the first one as soon as the lists can support it, later ones every time the processed targets have
+                 * grown respec_mult-fold (the r-th best of 5 x more targets is a much tighter threshold: at config 3 the pairs that
+                 * need a full evaluation drop from 355 to 165 per query) while enough targets remain to pay for the staircases */
+                const bool first_level = spec_ok && !spec_on && processed >= 4 * (size_t)k && nT - processed >= 8 * processed &&
+                                         (!chunk1_spec || processed >= w1);
+                const bool respec = ctx->respec_mult > 1 && (double)nQ * (double)nT >= ldexp(1.0, ctx->respec_min_pairs_log2); /* small runs: the extra launches cost more */
+                const bool next_level = spec_on && respec && lvl_begin.size() < PPP_MAX_SPEC_LEVELS &&
+                                        processed >= (size_t)ctx->respec_mult * lvl_begin.back() && 2 * (nT - processed) >= processed;
+                if (first_level || next_level) {
+                    /* speculative threshold (ppp_topk.cu): rank r of the list so far, never above the threshold in use */
                     const uint32_t r = poisson_rank(processed);
-                    CU(ppp_launch_spec_init(ctx->d_topk, d_topk_cnt, ctx->d_kth, chunk1_end ? d_kseed_use : nullptr, k, r, d_kspec, d_kspec0,
-                                            (uint32_t)nQ, ctx->stream));
+                    const double *prev = next_level ? d_kspec : (chunk1_end ? d_kseed_use : nullptr);
+                    CU(ppp_launch_spec_init(ctx->d_topk, d_topk_cnt, ctx->d_kth, prev, k, r, d_kspec, d_lvl(lvl_begin.size()), (uint32_t)nQ,
+                                            ctx->stream));
                     launches++;
+                    if (first_level) spec_start = processed;
                     spec_on = true;
-                    spec_start = processed;
+                    lvl_begin.push_back(processed);
                     ctx->spec_rank = r;
                 }
                 size_t w = std::min(maxw, nT - processed);
+                if (spec_on && respec && lvl_begin.size() < PPP_MAX_SPEC_LEVELS) {
+                    /* stop at the next level's boundary if there will be one */
+                    const size_t b = (size_t)ctx->respec_mult * lvl_begin.back();
+                    if (b > processed && b < nT && 2 * (nT - b) >= b) w = std::min(w, b - processed);
+                }
                 if (!spec_on) w = std::min(w, processed ? 4 * processed : (seeded_pass ? chunk1 : first));
                 const bool first_spec = chunk1_spec && seeded_pass && processed < w1;
                 if (first_spec) {
@@ -997,15 +1021,21 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                 /* verify; re-scan the queries whose list is not provably exact with the guaranteed bound */
                 uint32_t nfailed = 0;
                 CU(cudaMemsetAsync(d_nfailed, 0, sizeof(uint32_t), ctx->stream));
-                CU(ppp_launch_spec_verify(ctx->d_topk, d_topk_cnt, d_kspec0, k, ctx->d_kth + nQ, d_failed, d_nfailed, (uint32_t)nQ, ctx->stream));
+                /* the last level's thresholds are the smallest: a full list whose k-th score is below them is exact */
+                CU(ppp_launch_spec_verify(ctx->d_topk, d_topk_cnt, d_lvl(lvl_begin.size() - 1), k, ctx->d_kth + nQ, d_failed, d_nfailed,
+                                          (uint32_t)nQ, ctx->stream));
                 launches++;
                 CU(cudaMemcpyAsync(&nfailed, d_nfailed, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
                 CU(cudaStreamSynchronize(ctx->stream));
                 ctx->spec_failed = nfailed;
-                /* re-scan: the first chunk's range against its own thresholds (pairs below them are already listed), then the rest */
+                /* re-scan: every range against the thresholds it was screened with (pairs below them are already listed): the
+                 * first chunk, then level by level */
+                lvl_begin.push_back(nT);
+                size_t lvl = 0;
                 for (size_t t0 = chunk1_end ? 0 : spec_start; nfailed && t0 < nT;) {
                     const bool in_first = t0 < chunk1_end;
-                    const size_t t1 = in_first ? chunk1_end : std::min(nT, t0 + maxw);
+                    while (!in_first && t0 >= lvl_begin[lvl + 1]) ++lvl;
+                    const size_t t1 = in_first ? chunk1_end : std::min(lvl_begin[lvl + 1], t0 + maxw);
                     size_t ea, eb;
                     if ((rc = mark(ctx, &ea))) return rc;
                     CU(ppp_launch_staircase(ctx->d_qc, ctx->d_lf, ctx->d_kth, 0, 0.0, d_off_static, ctx->d_nmax, d_off_active,
@@ -1015,7 +1045,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                     SweepParams prm;
                     fill_filtered(prm, t0, t1);
                     prm.accept_mode = 2;
-                    prm.klo = in_first ? d_kseed : d_kspec0;
+                    prm.klo = in_first ? d_kseed : d_lvl(lvl);
                     if ((rc = launch_chunk_deferred(ctx, &prm, &launches, true, d_failed, nfailed))) return rc;
                     sweep_launches++;
                     if ((rc = mark(ctx, &ea))) return rc;
@@ -1307,6 +1337,12 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
     } else if (!strcmp(name, "chunk0_mult")) {
         if (value < 0 || value > 1000000) return fail(ctx, PPP_ERR_INVALID, "chunk0_mult out of range");
         ctx->chunk0_mult = (int)value;
+    } else if (!strcmp(name, "respec_min_pairs_log2")) {
+        if (value < 0 || value > 62) return fail(ctx, PPP_ERR_INVALID, "respec_min_pairs_log2 out of range");
+        ctx->respec_min_pairs_log2 = (int)value;
+    } else if (!strcmp(name, "respec_mult")) {
+        if (value < 0 || value > 1000000) return fail(ctx, PPP_ERR_INVALID, "respec_mult out of range");
+        ctx->respec_mult = (int)value;
     } else if (!strcmp(name, "spec_first")) {
         ctx->spec_first = value != 0;
     } else if (!strcmp(name, "dup")) {

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
         s_pass[tid] = 0; /* by compact slot; written by whichever lane of the warp re-screens this target's entries */
 
         if (PALL && npad) { /* doubled number (= depth) before every chunk of this thread's target row */
-            uint32_t run = 0;
+            uint32_t run = live ? 0u : 40000u; /* threads past the last target: a number no staircase admits, so nothing is queued */
 #pragma unroll 4
             for (int c = 0; c < NCH; ++c) {
                 uint32_t tw[CH];
@@ -348,15 +348,15 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
 #pragma unroll
             for (int j = 0; j < PF2_QG; ++j) {
                 ys[j] = s_sbase[g0 + j];
-                nbq[j] = 0;
+                nbq[j] = live ? 0u : 40000u; /* see s_pref: threads past the last target never pass */
             }
             const uint32_t *yg = s_y + g0 * W, *pg = s_p + g0 * W;
             const uint32_t gtag = g0 << 24;
 
             uint32_t tw[CH];
             load_chunk<CH>(a.Tt, a.ntt, t, 0, live, tw);
-            /* running pointers instead of per-chunk index arithmetic: the row's next chunk (dead lanes read target t0, whose
-             * words are then ignored -- their passes never reach the survivor list) and the depth prefix of this thread */
+            /* running pointers instead of per-chunk index arithmetic: the row's next chunk (threads past the last target read
+             * target t0's row, which their impossible `number` keeps out of every queue) and the depth prefix of this thread */
             const uint4 *tnext = a.Tt + t;
             const uint16_t *pref = s_pref + tid;
 #pragma unroll 1

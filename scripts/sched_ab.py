@@ -13,11 +13,13 @@ c.set_queries(P, Y, p)
 flt = capi.make_filter(capi.FILTER_TOPK, k=100)
 ref = None
 import itertools
+respecs = [int(x) for x in os.environ.get("RESPEC", "8").split(",")]
 combos = [(9, 0, 24, 5000), (9, 4, 24, 5000), (9, 2, 24, 5000), (5, 4, 24, 5000), (5, 4, 48, 5000), (9, 4, 48, 5000), (9, 4, 96, 5000),
           (5, 2, 48, 5000), (3, 4, 24, 5000), (5, 4, 48, 20000), (5, 4, 48, 1000), (7, 3, 36, 5000)]
 if len(sys.argv) > 1:
     combos = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]]
-for sm, c0, c1, eps in combos:
+for sm, c0, c1, eps, rs in [(a, b, cc, d, e) for (a, b, cc, d) in combos for e in respecs]:
+    c.set_option("respec_mult", rs)
     c.set_option("seed_mult", sm); c.set_option("chunk0_mult", c0); c.set_option("chunk1_mult", c1); c.set_option("spec_eps_ppm", eps)
     best = None
     for _ in range(2):
@@ -29,5 +31,5 @@ for sm, c0, c1, eps in combos:
     h = c.fetch()
     chk = (int(h["t"].astype(np.uint64).sum()), int(h["depth"].astype(np.uint64).sum()))
     ref = ref or chk
-    print(f"seed {sm}k chunk0 {c0}k chunk1 {c1}k eps {eps}ppm: total {best[0]:.2f} ms sweep {best[1]:.2f} prefilter {best[2]:.2f} exact {best[3]:.2f} stair {best[4]:.2f} "
+    print(f"respec {rs} seed {sm}k chunk0 {c0}k chunk1 {c1}k eps {eps}ppm: total {best[0]:.2f} ms sweep {best[1]:.2f} prefilter {best[2]:.2f} exact {best[3]:.2f} stair {best[4]:.2f} "
           f"merge {best[5]:.2f} surv {best[6]} rank {best[7]} failed {best[8]} same_result {chk == ref}", flush=True)

@@ -642,15 +642,19 @@ def test_topk_speculative_threshold_is_verified(ctx, front_loaded):
     assert ctx.counter("spec_rank") == 0
     for f in ("q", "t", "score", "yes", "number", "depth"):
         assert np.array_equal(tk0[f], tk[f]), f
-    # the first chunk is speculative too (thresholds = the seeding pass's rs-th smallest bounds): same lists without it
-    ctx.set_option("spec_first", 0)
-    try:
-        tk1 = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
-    finally:
-        ctx.set_option("spec_first", 1)
-    assert ctx.counter("spec_rank") >= 1
-    for f in ("q", "t", "score", "yes", "number", "depth"):
-        assert np.array_equal(tk1[f], tk[f]), f
+    # the first chunk is speculative too (thresholds = the seeding pass's rs-th smallest bounds): same lists without it;
+    # and with one / many speculation levels instead of the default schedule
+    ctx.set_option("respec_min_pairs_log2", 0)  # further speculation levels are reserved for large runs by default
+    for opt, val, restore in (("spec_first", 0, 1), ("respec_mult", 0, 8), ("respec_mult", 2, 8), ("respec_mult", 3, 8)):
+        ctx.set_option(opt, val)
+        try:
+            tk1 = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
+        finally:
+            ctx.set_option(opt, restore)
+            ctx.set_option("respec_min_pairs_log2", 0 if opt == "spec_first" or val != 3 else 27)
+        assert ctx.counter("spec_rank") >= 1
+        for f in ("q", "t", "score", "yes", "number", "depth"):
+            assert np.array_equal(tk1[f], tk[f]), (opt, val, f)
 
 
 def test_g8192_with_16_sweep_warps(ctx):
