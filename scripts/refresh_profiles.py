@@ -1,7 +1,8 @@
 """Rebuild the tracked summaries under profiles/ from one measurement run's files in gpurun_out/.
-usage: python scripts/refresh_profiles.py PREFIX COMMIT   (files gpurun_out/PREFIX_*, see the gpurun command in profiles/README)"""
+usage: python scripts/refresh_profiles.py PREFIX COMMIT [PREFILTER_LAUNCHES_PER_STEP]   (files gpurun_out/PREFIX_*, see the gpurun command in profiles/README)"""
 import collections, csv, io, re, shutil, subprocess, sys
 pre, commit = sys.argv[1], sys.argv[2]
+n_step_launches = int(sys.argv[3]) if len(sys.argv) > 3 else None  # pre-filter launches of ONE step (the capture may run into the next)
 G = "gpurun_out/" + pre + "_"
 
 
@@ -62,7 +63,7 @@ with open("profiles/r01_ncu_bench_prefilter2_traffic.txt", "w") as f:
             "# dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:ppp_prefilter2 -c N python bench.py\n"
             f"# --steps 1 --warmup 1 (first run of the command = one step); commit {commit}.  The step's total is bench.py's roofline.traffic.\n"
             "# launch, kernel, ms, DRAM read MB, DRAM write MB, L2 hit %\n")
-    ids = list(per)
+    ids = list(per)[:n_step_launches]
     n_step = len(ids) // 1
     # one step = launches up to (not including) the first repetition of the first launch's duration pattern: the command runs 4 scans,
     # each with the same launch sequence, so one step = len/4 launches when the capture covers whole scans; otherwise all captured
