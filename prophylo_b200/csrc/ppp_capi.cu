@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <functional>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "../../include/ppp_b200.h"
@@ -465,11 +466,39 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
     ctx->nQ = 0;
     if (!nQ) return PPP_OK;
     std::vector<QConst> qc(nQ);
-    {
-        std::vector<uint32_t> cy(nQ), cp(nQ);
-        ppp_host_count_rows(P, Y, nQ, wpr, cy.data(), cp.data()); /* ppp_bla.cpp: POPCNT instruction */
-        for (size_t q = 0; q < nQ; ++q) make_qconst(p[q], cy[q], cp[q], &qc[q]);
+    /* device layout [nQ][2][W]: P and Y rows interleaved (zero padded to W words) in a pinned staging buffer and uploaded with
+     * ONE contiguous copy -- two pitched 2-D copies of 512-byte rows cost ~6 ms for 10,000 queries */
+    const size_t stage_need = ctx->capQ * 2 * W * 4;
+    if (stage_need > ctx->cap_stage) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr;
+        ctx->cap_stage = 0;
+        CU(cudaMallocHost(&ctx->h_stage, stage_need));
+        ctx->cap_stage = stage_need;
     }
+    uint32_t *st = reinterpret_cast<uint32_t *>(ctx->h_stage);
+    if (nQ < ctx->capQ) memset(st + nQ * 2 * W, 0, (ctx->capQ - nQ) * 2 * W * 4); /* rows of the last partial tile */
+    {
+        /* per query: |Y| and |P| (POPCNT, ppp_bla.cpp), the constants (long double logarithms) and the staging copy -- a few
+         * milliseconds for 10,000 queries on one core, so the queries are split over a few host threads */
+        std::vector<uint32_t> cy(nQ), cp(nQ);
+        auto work = [&](size_t q0, size_t q1) {
+            ppp_host_count_rows(P + q0 * wpr, Y + q0 * wpr, q1 - q0, wpr, cy.data() + q0, cp.data() + q0);
+            for (size_t q = q0; q < q1; ++q) {
+                make_qconst(p[q], cy[q], cp[q], &qc[q]);
+                uint32_t *row = st + q * 2 * W;
+                if (wpr < W) memset(row, 0, 2 * W * 4); /* zero padding inside the rows */
+                memcpy(row, P + q * wpr, wpr * 4);
+                memcpy(row + W, Y + q * wpr, wpr * 4);
+            }
+        };
+        const size_t nth = std::min<size_t>(std::min<size_t>(8, std::max(1u, std::thread::hardware_concurrency())), nQ / 1024 + 1);
+        std::vector<std::thread> pool;
+        for (size_t i = 1; i < nth; ++i) pool.emplace_back(work, nQ * i / nth, nQ * (i + 1) / nth);
+        work(0, nQ / nth);
+        for (std::thread &t : pool) t.join();
+    }
+    CU(cudaMemcpyAsync(ctx->d_Q, st, stage_need, cudaMemcpyHostToDevice, ctx->stream)); /* overlaps the host work below */
     ctx->nmax_off_host.resize(nQ);
     {
         size_t off = 0;
@@ -484,26 +513,6 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
     for (size_t q = 0; q < nQ; ++q)
         ctx->toff_host[q + 1] = ctx->toff_host[q] + ((unsigned long long)qc[q].ny + 1) * ((unsigned long long)qc[q].npres + 1);
     ctx->table_valid = false;
-    {
-        /* device layout [nQ][2][W]: interleave P and Y rows (zero padded to W words) in a pinned staging buffer and upload
-         * them with ONE contiguous copy -- two pitched 2-D copies of 512-byte rows cost ~6 ms for 10,000 queries */
-        const size_t need = ctx->capQ * 2 * W * 4;
-        if (need > ctx->cap_stage) {
-            if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-            ctx->h_stage = nullptr;
-            ctx->cap_stage = 0;
-            CU(cudaMallocHost(&ctx->h_stage, need));
-            ctx->cap_stage = need;
-        }
-        uint32_t *st = reinterpret_cast<uint32_t *>(ctx->h_stage);
-        if (wpr < W) memset(st, 0, nQ * 2 * W * 4);                                   /* zero padding inside the rows */
-        if (nQ < ctx->capQ) memset(st + nQ * 2 * W, 0, (ctx->capQ - nQ) * 2 * W * 4); /* rows of the last partial tile */
-        for (size_t q = 0; q < nQ; ++q) {
-            memcpy(st + q * 2 * W, P + q * wpr, wpr * 4);
-            memcpy(st + q * 2 * W + W, Y + q * wpr, wpr * 4);
-        }
-        CU(cudaMemcpyAsync(ctx->d_Q, st, need, cudaMemcpyHostToDevice, ctx->stream));
-    }
     CU(cudaMemcpyAsync(ctx->d_qc, qc.data(), nQ * sizeof(QConst), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<uint32_t> qfl(nQ);
     for (size_t q = 0; q < nQ; ++q) qfl[q] = (qc[q].npres == ctx->G) ? 1u : 0u;
