@@ -914,7 +914,11 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         };
         if (topk) {
             /* ---- top-k: no host synchronisation until the lists are final ---- */
-            const size_t chunk1 = std::max<size_t>(4 * 256, (size_t)ctx->chunk1_mult * k);      /* first exact chunk */
+            /* very short lists (ppp2d keeps the best 2 targets): k-proportional sizes would seed from a few hundred targets, and
+             * thresholds that loose send most chunks of a dense query down the slow path of the screen -- floors measured on
+             * config 4 (2,000 prefix queries x 500,000 targets, k = 2: 55.8 -> 48.4 ms) */
+            const size_t seed_floor = k <= 16 ? 1024 : 256, chunk1_floor = k <= 16 ? 4096 : 1024;
+            const size_t chunk1 = std::max<size_t>(chunk1_floor, (size_t)ctx->chunk1_mult * k);      /* first exact chunk */
             const size_t w1 = std::min(std::min(maxw, nT), chunk1);
             const bool spec_ok = ctx->speculate && !ctx->ranked && use_prefilter2(ctx) && !ctx->force_exact &&
                                  ctx->stair_need_any <= ppp_prefilter2_max_stair(ctx->wpl, 0);
@@ -923,7 +927,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
              * 15 % of the first chunk's pairs through to a full evaluation, the speculative one 0.8 %. */
             const bool may_spec_first = spec_ok && ctx->spec_first && w1 >= 4 * (size_t)k && nT - w1 >= 8 * w1;
             /* targets of the seeding pass: when only the guaranteed k-th bound is used (no speculation) it pays to seed from more */
-            const size_t first = std::min<size_t>(4096, std::max<size_t>(256, (size_t)(may_spec_first ? ctx->seed_mult : std::max(ctx->seed_mult, 9)) * k));
+            const size_t first = std::min<size_t>(4096, std::max<size_t>(seed_floor, (size_t)(may_spec_first ? ctx->seed_mult : std::max(ctx->seed_mult, 9)) * k));
             const size_t w0 = std::min<size_t>(std::min(maxw, nT), first);
             double *d_kspec = ctx->d_kth + 2 * nQ, *d_kseed = ctx->d_kth + 4 * nQ, *d_kseed_use = ctx->d_kth + 5 * nQ;
             const bool chunk1_spec = may_spec_first && w0 >= (size_t)k;
