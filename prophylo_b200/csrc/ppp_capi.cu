@@ -120,7 +120,7 @@ struct ppp_ctx {
     int chunk0_mult = 4; /* head of the first chunk, in units of k (0 = no split) */
     int respec_min_pairs_log2 = 27; /* ... in runs of at least this many pairs */
     int respec_mult = 8; /* a new speculation level every time the processed targets have grown this many times (<= 1: one level) */
-    int seed_mult = 5, chunk1_mult = 24, spec_eps_ppm = 5000; /* top-k schedule: seeding targets / k, first chunk / k, P(spec fails) */
+    int seed_mult = 4, chunk1_mult = 24, spec_eps_ppm = 5000; /* top-k schedule: seeding targets / k, first chunk / k, P(spec fails) */
     size_t nQ = 0, capQ = 0;
     /* results */
     ppp_hit *d_hits = nullptr;
