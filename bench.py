@@ -3,16 +3,18 @@
 
   python bench.py --gpus 1 --steps K --warmup W                 # this framework (CUDA through the C ABI)
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-  python bench.py --impl reference ...                          # the reference's CPU path (oracle port, all host threads)
+  python bench.py --impl reference ...                          # the reference's own Perl path on the host cores
 
-Workload (config 3 of BASELINE.json, the configuration the metric is quoted on: 4096 genomes): 10,000 query
-profiles x 1,000,000 target profiles all-pairs at G = 4096, sharded over the target axis -- 125,000 targets per GPU,
-so N = 8 is the full configuration and N = 1 its per-GPU share ("scaling": "weak").  Filter: per-query top-k, k = 100
-(SURVEY.md section 8d config 3).  A step is one pass of the scan over all resident pairs.
+Workload = config 3 of BASELINE.json, the configuration the metric is quoted on: 10,000 query profiles x 1,000,000 target
+profiles all-pairs at G = 4096 genomes (1e10 pairs), per-query top-k with k = 100.  The target
+set is 8 blocks of 125,000 (block b seeded SEED_BASE + 103 + 1000 b); rank r of an N-GPU run holds blocks
+[8 r / N, 8 (r + 1) / N), so every N scores the SAME million targets: N = 1 is the whole configuration on one GPU, N = 8
+is the configuration as BASELINE names it ("scaling": "strong").  The per-GPU-share form of round 1 (125,000 targets per
+GPU, work growing with N) is reported beside it under "weak_scaling".  A step is one pass of the scan over all pairs.
 
-One JSON line on rank 0; see the task contract for the keys.  `value` is measured with inputs resident in HBM and
-timed with the library's CUDA events on its own stream (max over ranks); `e2e` goes through ppp_score() with pinned
-HOST buffers (targets + queries H2D and hits D2H inside the timed region).
+One JSON line on rank 0; see the task contract for the keys.  `value` is measured with inputs resident in HBM (wall time
+of run + result collection bracketed by synchronizes, max over ranks; the library's CUDA-event time is reported beside
+it); `e2e` goes through ppp_score() with pinned HOST buffers (targets + queries H2D and hits D2H inside the timed region).
 """
 from __future__ import annotations
 
@@ -21,6 +23,7 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -33,16 +36,25 @@ from prophylo_b200 import synth  # noqa: E402
 
 METRIC = "ppp_profile_pairs_per_sec_G4096"
 UNIT = "pairs/s"
+NBLOCKS = 8
 
 
 def workload(args):
-    return dict(G=args.genomes, nq=args.queries, nt_per_gpu=args.targets_per_gpu, k=args.topk)
+    return dict(G=args.genomes, nq=args.queries, nt=args.targets, k=args.topk)
 
 
-def make_inputs(w, rank):
-    P, Y, p = synth.make_queries(w["G"], w["nq"], synth.SEED_BASE + 3, "mixed")
-    T = synth.make_targets(w["G"], w["nt_per_gpu"], synth.SEED_BASE + 103 + 1000 * rank, plant_from=Y, plant_frac=0.01)
-    return P, Y, p, T
+def make_queries(w):
+    return synth.make_queries(w["G"], w["nq"], synth.SEED_BASE + 3, "mixed")
+
+
+def target_block(w, b, Y):
+    return synth.make_targets(w["G"], w["nt"] // NBLOCKS, synth.SEED_BASE + 103 + 1000 * b, plant_from=Y, plant_frac=0.01)
+
+
+def rank_blocks(rank, world):
+    """blocks of the target set held by `rank`: contiguous, NBLOCKS / world each (world must divide NBLOCKS)"""
+    per = NBLOCKS // world
+    return list(range(rank * per, (rank + 1) * per))
 
 
 class ClockSampler:
@@ -85,13 +97,19 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_throughput(w, budget_s, nthreads):
-    """The reference's CPU path for this workload: oracle port (C restatement of ppp.pm:130-245 + Math::Cephes bdtrc,
-    pinned bit-for-bit against the reference run under perl) over a bounded sample of the same pairs, all host threads."""
+# ------------------------------------------------------------------------------------------------ CPU arms
+def _sample_inputs(w, nq, nt):
+    P, Y, p = synth.make_queries(w["G"], nq, synth.SEED_BASE + 3, "mixed")
+    T = synth.make_targets(w["G"], nt, synth.SEED_BASE + 103, plant_from=Y, plant_frac=0.01)
+    return P, Y, p, T
+
+
+def cpu_port_throughput(w, budget_s, nthreads):
+    """The C port of the reference path (oracle/: restatement of ppp.pm:130-245 + Math::Cephes bdtrc, pinned bit-for-bit
+    against the reference run under perl) over a bounded sample of the same synthetic workload, all host threads."""
     from oracle import oracle
 
-    P, Y, p = synth.make_queries(w["G"], 16, synth.SEED_BASE + 3, "mixed")
-    T = synth.make_targets(w["G"], 64, synth.SEED_BASE + 103, plant_from=Y, plant_frac=0.01)
+    P, Y, p, T = _sample_inputs(w, 16, 64)
     t0 = time.perf_counter()
     oracle.score_bits_batch(P[:4], Y[:4], p[:4], T[:32], w["G"], nthreads=nthreads)  # calibration
     rate = 128 / max(time.perf_counter() - t0, 1e-6)
@@ -106,65 +124,153 @@ def cpu_reference_throughput(w, budget_s, nthreads):
                 sample=f"{nq} queries x {nt} targets of the same synthetic workload ({nq * nt} pairs, {steps} bdtrc sweep steps, {dt:.1f} s)"), dt
 
 
+def perl_reference_available():
+    return (os.path.exists(os.path.join(ROOT, "baseline", "_ref", "lib", "PhyloProf", "Algorithm", "ppp.pm"))
+            and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "Cephes_shim.so")) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "Cephes.so")))
+
+
+def perl_reference_throughput(w, budget_s, nproc):
+    """The reference ITSELF: the unmodified lib/PhyloProf/Algorithm/ppp.pm (shipped to the box in git-ignored baseline/_ref/,
+    BASELINE.md section 3) with Math::Cephes::bdtrc bound to the reference's own binary, one forked perl per host core
+    (oracle/time_reference.pl), on a bounded sample of the same synthetic workload.  Every result is cross-checked against
+    the C port: the two CPU baselines are the same function."""
+    from oracle import oracle
+
+    G = w["G"]
+    nq, nt = 8, max(8, 4 * nproc)
+    P, Y, p, T = _sample_inputs(w, nq, nt)
+    Pb, Yb, Tb = synth.unpack_bits(P, G), synth.unpack_bits(Y, G), synth.unpack_bits(T, G)
+    cases = {"queries": [{str(g + 1): int(Yb[q, g]) for g in range(G) if Pb[q, g]} for q in range(nq)], "probs": [float(x) for x in p],
+             "targets": [[str(g + 1) for g in np.nonzero(Tb[t])[0]] for t in range(nt)]}
+    with tempfile.TemporaryDirectory() as d:
+        json.dump(cases, open(f"{d}/cases.json", "w"))
+        env = dict(os.environ, REFERENCE_ROOT=os.path.join(ROOT, "baseline", "_ref"))
+        subprocess.run(["perl", os.path.join(ROOT, "oracle", "time_reference.pl"), f"{d}/cases.json", str(nproc), str(budget_s), f"{d}/out.json"],
+                       env=env, check=True, timeout=budget_s * 6 + 120)
+        out = json.load(open(f"{d}/out.json"))
+    ref, _ = oracle.score_bits_batch(P, Y, p, T, G, nthreads=nproc)
+    bad = 0
+    for key, v in out["results"].items():
+        q, t = (int(x) for x in key.split(","))
+        r = ref[q, t]
+        bad += (float(v[0]), v[1], v[2], v[3]) != (float(r["score"]), int(r["yes"]), int(r["number"]), int(r["depth"]))
+    return dict(value=out["pairs"] / out["seconds"], unit=UNIT, cores=nproc, kind="reference",
+                sample=f"{out['pairs']} (query, target) pairs of the same synthetic workload ({nq} queries x {nt} targets drawn; "
+                       f"{out['seconds']:.1f} s wall; unmodified ppp.pm under perl, {nproc} forked workers)",
+                mismatches_vs_port=int(bad)), out["seconds"]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     w = workload(args)
-    nthreads = os.cpu_count() or 1
+    ncpu = os.cpu_count() or 1
+    use_perl = perl_reference_available()
     vals = []
     info = None
-    budget = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    budget = max(2.0, min(15.0, 100.0 / max(1, args.steps + args.warmup)))
     for i in range(args.warmup + args.steps):
-        info, dt = cpu_reference_throughput(w, budget, nthreads)
+        info, dt = perl_reference_throughput(w, budget, ncpu) if use_perl else cpu_port_throughput(w, budget, ncpu)
         if i >= args.warmup:
             vals.append((info["value"], dt))
     v = float(np.mean([x[0] for x in vals]))
     info["value"] = v
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * float(np.mean([x[1] for x in vals])), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * float(np.mean([x[1] for x in vals])), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config3 sample: {w['nq']} queries x {w['nt_per_gpu']} targets/GPU x G={w['G']} all-pairs, "
-                               f"CPU port timed on a bounded sample (see cpu_baseline.sample)", "genomes": w["G"]},
+        "config": {"workload": f"config3 sample: {w['nq']} queries x {w['nt']} targets x G={w['G']} all-pairs; the reference's CPU path timed on a "
+                               f"bounded sample of the same synthetic pairs (see cpu_baseline.sample)", "genomes": w["G"]},
         "cpu_baseline": info,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if use_perl:  # the C port beside it (the stronger CPU baseline: about 19 x the Perl rate per core)
+        line["cpu_baseline_port"] = cpu_port_throughput(w, 8.0, ncpu)[0]
     print(json.dumps(line), flush=True)
     return 0
 
 
-def config2_dense(ctx, torch, args):
-    """BASELINE config 2 (the single-query ppp.pl shape): 1 query x 1,000,000 targets x 1024 genomes, EVERY pair reported
-    (dense).  Few queries x many targets -> exact table mode: scores bit-identical to the reference.  Extra information
-    beside the headline workload; not part of `value`."""
+# ------------------------------------------------------------------------------------------------ other configurations
+def _timed(ctx, flt, reps=3):
+    best = None
+    for _ in range(reps):
+        ctx.run(flt)
+        s = ctx.stats()
+        if best is None or s["total_device_ms"] < best["total_device_ms"]:
+            best = s
+    return best
+
+
+def other_configs(ctx, torch):
+    """BASELINE configs 2, 4, 5 and the dense (every pair reported) form at G = 4096 on one GPU: device time with inputs
+    resident (library CUDA events, best of 3), plus config 2 end to end through host buffers.  Extra information beside the
+    headline workload; not part of `value`."""
     from prophylo_b200 import capi
 
-    G, nt = 1024, 1000000
+    out = {}
+    # config 2: the single-query ppp.pl shape, 1 query x 1,000,000 targets x 1024 genomes
+    G, nt = 1024, 1_000_000
     P, Y, p = synth.make_queries(G, 1, synth.SEED_BASE + 2, "single")
     T = synth.make_targets(G, nt, synth.SEED_BASE + 102, plant_from=Y, plant_frac=0.01)
     Tt = torch.from_numpy(T).pin_memory()
-    out = torch.empty(nt * capi.HIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(capi.HIT_DTYPE)
+    buf = torch.empty(nt * capi.HIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory().numpy().view(capi.HIT_DTYPE)
     ctx.set_targets_bits(Tt.numpy(), G)
     ctx.set_queries(P, Y, p)
-    for _ in range(2):
-        ctx.run(None)
-    dev = []
-    for _ in range(5):
-        ctx.run(None)
-        dev.append(ctx.stats()["total_device_ms"])
+    s = _timed(ctx, None, 5)
     used = ctx.counter("used_table")
     e2e = []
     for _ in range(3):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ctx.set_targets_bits(Tt.numpy(), G)
-        ctx.score(P, Y, p, None, out=out)
+        ctx.score(P, Y, p, None, out=buf)
         e2e.append(time.perf_counter() - t0)
-    return {"pairs_per_s_resident": nt / (float(np.median(dev)) * 1e-3), "pairs_per_s_e2e_host_buffers": nt / float(np.median(e2e)),
-            "mode": "exact table" if used else "general sweep", "hits_out_bytes": int(out.nbytes), "targets_in_bytes": int(T.nbytes)}
+    alg_bytes = nt * (G // 8 + 24)  # SURVEY.md section 8(d): one target plane + a 24-byte result per pair
+    out["config2_dense_1x1M_G1024"] = {
+        "pairs_per_s_resident": nt / (s["total_device_ms"] * 1e-3), "ms": s["total_device_ms"],
+        "pairs_per_s_e2e_host_buffers": nt / float(np.median(e2e)), "mode": "exact table" if used else "general sweep",
+        "hbm_GBps_algorithmic": alg_bytes / (s["total_device_ms"] * 1e-3) / 1e9, "hits_out_bytes": int(buf.nbytes), "targets_in_bytes": int(T.nbytes)}
+    s = _timed(ctx, capi.make_filter(capi.FILTER_TOPK, k=100))
+    out["config2_top100"] = {"ms": s["total_device_ms"], "pairs_per_s_resident": nt / (s["total_device_ms"] * 1e-3)}
+    # config 4: ppp2d shape, 2,000 nested prefix queries x 500,000 targets x 2048 genomes, best 2 per query
+    G, nq, nt = 2048, 2000, 500_000
+    P, Y, p = synth.make_queries(G, nq, synth.SEED_BASE + 4, "prefix")
+    T = synth.make_targets(G, nt, synth.SEED_BASE + 104, plant_from=Y, plant_frac=0.01)
+    ctx.set_targets_bits(T, G)
+    ctx.set_queries(P, Y, p)
+    s = _timed(ctx, capi.make_filter(capi.FILTER_TOPK, k=2))
+    out["config4_ppp2d_top2"] = {"shape": f"{nq} x {nt} x G={G}", "ms": s["total_device_ms"], "pairs_per_s_resident": nq * nt / (s["total_device_ms"] * 1e-3),
+                                 "prefilter_ms": ctx.counter("us_prefilter") / 1e3, "survivors": ctx.counter("survivors")}
+    # config 5: TIGRFAM-scale all-pairs, 4,500 x 4,500 x 8192 genomes: ppp_cutoff threshold filter and top-100
+    G, nq = 8192, 4500
+    P, Y, p = synth.make_queries(G, nq, synth.SEED_BASE + 5, "family")
+    ctx.set_targets_bits(Y, G)
+    ctx.set_queries(P, Y, p)
+    s = _timed(ctx, capi.make_filter(capi.FILTER_THRESH_LOG10, thresh=-0.0005), 2)
+    out["config5_thresh"] = {"shape": f"{nq} x {nq} x G={G}", "ms": s["total_device_ms"], "pairs_per_s_resident": nq * nq / (s["total_device_ms"] * 1e-3),
+                             "hits": ctx.result_count(), "rank_ms": ctx.counter("us_merge") / 1e3}
+    s = _timed(ctx, capi.make_filter(capi.FILTER_TOPK, k=100), 2)
+    out["config5_top100"] = {"ms": s["total_device_ms"], "pairs_per_s_resident": nq * nq / (s["total_device_ms"] * 1e-3),
+                             "prefilter_ms": ctx.counter("us_prefilter") / 1e3, "survivors": ctx.counter("survivors")}
+    # dense at G = 4096: every pair's (score, yes, number, depth) produced (no filter), config 3's query mix
+    G, nq, nt = 4096, 1000, 20_000
+    P, Y, p = synth.make_queries(G, nq, synth.SEED_BASE + 3, "mixed")
+    T = synth.make_targets(G, nt, synth.SEED_BASE + 103, plant_from=Y, plant_frac=0.01)
+    ctx.set_targets_bits(T, G)
+    ctx.set_queries(P, Y, p)
+    ctx.set_option("table_mode", 0)
+    try:
+        s = _timed(ctx, None, 2)
+    finally:
+        ctx.set_option("table_mode", -1)
+    out["dense_G4096"] = {"shape": f"{nq} x {nt} x G={G}, every pair reported", "ms": s["total_device_ms"],
+                          "pairs_per_s_resident": nq * nt / (s["total_device_ms"] * 1e-3), "candidates_per_pair": s["candidates"] / (nq * nt),
+                          "exact_pairs": s["exact_pairs"]}
+    return out
 
 
+# ------------------------------------------------------------------------------------------------ this framework
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -174,13 +280,21 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if NBLOCKS % world:
+        raise SystemExit(f"bench.py: the target set is {NBLOCKS} blocks; --gpus must divide it")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     w = workload(args)
-    G, nq, nt, k = w["G"], w["nq"], w["nt_per_gpu"], w["k"]
-    P, Y, p, T = make_inputs(w, rank)
+    G, nq, nt_total, k = w["G"], w["nq"], w["nt"], w["k"]
+    P, Y, p = make_queries(w)
+    blocks = rank_blocks(rank, world)
+    T = np.concatenate([target_block(w, b, Y) for b in blocks])
+    nt = T.shape[0]
+    t_off = blocks[0] * (nt_total // NBLOCKS)
+    block_nt = nt_total // NBLOCKS
 
     def pinned(a):
         t = torch.from_numpy(a).pin_memory()
@@ -191,12 +305,8 @@ def run_ours(args):
     ctx = capi.Context(local_rank)
     ctx.set_option("sweep_warps", args.sweep_warps)
     flt = capi.make_filter(capi.FILTER_TOPK, k=k)
-    ctx.set_targets_bits(Tp, G)
-    ctx.set_queries(Pp, Yp, pp)
     out_t = torch.empty(nq * min(k, nt) * capi.HIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
     out_np = out_t.numpy().view(capi.HIT_DTYPE)
-    cnt_t = torch.empty(nq, dtype=torch.int32).pin_memory()
-    cnt_np = cnt_t.numpy().view(np.uint32)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
     def barrier():
@@ -204,102 +314,114 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def collect():
+    merger = parallel.SlicedTopkMerge(ctx, nq, k, world, rank, dev) if world > 1 else None
+
+    def collect(offset_of_rank):
         """results of the last run on the host.  One GPU: the device top-k lists are copied into the pinned buffer.
-        N GPUs: the path's only exchange step, the global top-k merge -- NCCL all-gather of the device-resident per-rank
-        lists + one device merge, result on every rank (the per-rank lists are not fetched separately)."""
+        N GPUs: the path's only exchange step, the global top-k merge -- rank r receives every rank's device-resident lists of
+        ITS slice of the queries (NCCL all-to-all over NVLink), merges them on the device and copies its slice of the global
+        lists to its host buffer (the result of an N-process job is the N slices)."""
         if world == 1:
             return ctx.fetch(out_np)
-        out, cnt = parallel.global_topk_device(ctx, lambda r: r * nt, k, nq, torch.device("cuda", local_rank), out=out_np, cnt=cnt_np)
-        return out
+        return merger.run(offset_of_rank)
 
-    # ---- resident-input steps (value)
+    def timed_steps(nsteps, offset_of_rank, sample_clocks):
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        r = dict(dev_ms=[], sweep_ms=[], launches=0, wall=0.0, pf_us=[], pf_pairs=[], survs=[])
+        for _ in range(nsteps):
+            flush.zero_()  # flush L2 between timed iterations (untimed)
+            barrier()
+            t0 = time.perf_counter()
+            ctx.run(flt)
+            collect(offset_of_rank)
+            torch.cuda.synchronize()
+            r["wall"] += time.perf_counter() - t0
+            st = ctx.stats()
+            r["dev_ms"].append(st["total_device_ms"])
+            r["sweep_ms"].append(st["sweep_kernel_ms"])
+            r["launches"] += st["kernel_launches"] + (merger.launches_per_run if merger else 0)
+            r["pf_us"].append(ctx.counter("us_prefilter"))
+            r["pf_pairs"].append(ctx.counter("prefilter_pairs"))
+            r["survs"].append(ctx.counter("survivors"))
+        barrier()
+        r["clocks"] = sampler.stop() if sampler else None
+        t = torch.tensor([1e3 * r["wall"] / nsteps, float(np.mean(r["dev_ms"])), float(np.mean(r["sweep_ms"]))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        r["step_ms"], r["dev_ms_mean"], r["sweep_ms_mean"] = [float(x) for x in t.cpu()]
+        return r
+
+    # ---- the headline: the whole configuration over the N GPUs (resident inputs)
+    ctx.set_targets_bits(Tp, G)
+    ctx.set_queries(Pp, Yp, pp)
+    strong_off = lambda r: rank_blocks(r, world)[0] * block_nt  # noqa: E731
     for _ in range(args.warmup):
         ctx.run(flt)
-        collect()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    dev_ms, sweep_ms, launches, wall = [], [], 0, 0.0
-    pf_us, pf_pairs, survs = [], [], []
-    st = None
-    for _ in range(args.steps):
-        flush.zero_()  # flush L2 between timed iterations (resident inputs are smaller than L2), untimed
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ctx.run(flt)
-        res = collect()
-        torch.cuda.synchronize()
-        wall += time.perf_counter() - t0
-        st = ctx.stats()
-        dev_ms.append(st["total_device_ms"])
-        sweep_ms.append(st["sweep_kernel_ms"])
-        launches += st["kernel_launches"]
-        pf_us.append(ctx.counter("us_prefilter"))
-        pf_pairs.append(ctx.counter("prefilter_pairs"))
-        survs.append(ctx.counter("survivors"))
-    barrier()
-    clocks = sampler.stop()
+        collect(strong_off)
+    main = timed_steps(args.steps, strong_off, True)
+    clocks = main["clocks"]
+    value = nq * nt_total / (main["step_ms"] * 1e-3)
     full_pairs = ctx.counter("full_pairs")
     phase = {n: ctx.counter("us_" + n) for n in ("sweep", "prefilter", "exact", "staircase", "merge")}
-    pf_us_mean, pf_pairs_mean, surv_mean = float(np.mean(pf_us)), float(np.mean(pf_pairs)), float(np.mean(survs))
-    # the step time is the wall time of run+fetch(+merge) bracketed by synchronizes: it contains the device-event time
-    step_ms = 1e3 * wall / args.steps
-    t = torch.tensor([step_ms, float(np.mean(dev_ms)), float(np.mean(sweep_ms))], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, dev_ms_mean, sweep_ms_mean = [float(x) for x in t.cpu()]
-    pairs_per_gpu = nq * nt
-    value = world * pairs_per_gpu / (step_ms * 1e-3)
+    spec = {"speculative_rank": ctx.counter("spec_rank"), "queries_rescanned": ctx.counter("spec_failed")}
 
-    # ---- end-to-end steps through the one-call C ABI entry with host buffers (targets + queries H2D, hits D2H)
+    # ---- N > 1: the merged global lists of 64 queries equal one GPU scoring the concatenated shards (after the timing)
+    selfcheck = None
+    if world > 1:
+        selfcheck = parallel.check_global_lists(ctx, merger, strong_off, Pp, Yp, pp, Tp, G, k, rank, world, dev, n_check=64)
+        ctx.set_targets_bits(Tp, G)
+        ctx.set_queries(Pp, Yp, pp)
+
+    # ---- end to end through the one-call C ABI entry with host buffers (targets + queries H2D, hits D2H)
     e2e_wall = 0.0
     nsteps_e2e = max(1, min(args.steps, 3))
     ctx.set_targets_bits(Tp, G)
     ctx.score(Pp, Yp, pp, flt, out=out_np)
-    barrier()
     for _ in range(nsteps_e2e):
         flush.zero_()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         ctx.set_targets_bits(Tp, G)
         hits = ctx.score(Pp, Yp, pp, flt, out=out_np)
         if world > 1:
-            collect()
+            collect(strong_off)
         torch.cuda.synchronize()
         e2e_wall += time.perf_counter() - t0
     barrier()
     e2e_ms = torch.tensor([1e3 * e2e_wall / nsteps_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = world * pairs_per_gpu / (float(e2e_ms.item()) * 1e-3)
+    e2e_value = nq * nt_total / (float(e2e_ms.item()) * 1e-3)
     h2d = int(Tp.nbytes + Pp.nbytes + Yp.nbytes + pp.nbytes)
-    d2h = int(hits.nbytes)
+    d2h = int(hits.nbytes) if world == 1 else int(merger.d2h_bytes)
+
+    # ---- the per-GPU-share form (round 1's line): 125,000 targets per GPU whatever N is
+    weak = None
+    if world < NBLOCKS:
+        ctx.set_targets_bits(Tp[:block_nt], G)
+        ctx.set_queries(Pp, Yp, pp)
+        weak_off = lambda r: r * block_nt  # noqa: E731
+        for _ in range(2):
+            ctx.run(flt)
+            collect(weak_off)
+        wk = timed_steps(max(2, min(args.steps, 5)), weak_off, False)
+        weak = {"scaling": "weak", "targets_per_gpu": block_nt, "value": world * nq * block_nt / (wk["step_ms"] * 1e-3), "ms_per_step": wk["step_ms"],
+                "device_ms_per_step": wk["dev_ms_mean"]}
+    else:
+        weak = {"scaling": "weak", "targets_per_gpu": block_nt, "value": value, "ms_per_step": main["step_ms"], "device_ms_per_step": main["dev_ms_mean"],
+                "note": "at N = 8 the per-GPU-share workload IS the headline workload"}
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # Dominant kernel = the thread-per-pair integer pre-filter (ppp_prefilter2_kernel, ppp_prefilter.cu; two launches
-        # per target chunk: all-ones presence planes / general).  Its ALGORITHMIC HBM bytes per step: target planes once,
-        # query planes once, survivor ids out (DESIGN.md section 4); both operands are reused on chip, so the kernel is
-        # bound by the integer pipes (POPC on the XU pipe: 16 lanes/clk/SM), not by HBM -- reported as pipe_roofline.
-        W_bytes = ((G + 1023) // 1024) * 128
+        pf_us_mean, pf_pairs_mean, surv_mean = float(np.mean(main["pf_us"])), float(np.mean(main["pf_pairs"])), float(np.mean(main["survs"]))
         pf_ms = pf_us_mean * 1e-3
-        alg_bytes = nt * W_bytes + nq * 2 * W_bytes + 4 * surv_mean
-        achieved = alg_bytes / (pf_ms * 1e-3) / 1e9 if pf_ms > 0 else 0.0
-        # DRAM traffic of the step's pre-filter launches, from the committed ncu capture of exactly this workload (the
-        # default arguments); other shapes have no capture -> null
-        default_shape = (G, nq, nt, k) == (4096, 10000, 125000, 100)
-        traffic = 266082816 if default_shape else None
-        words = W_bytes // 4
+        words = ((G + 1023) // 1024) * 32
         frac_all = float(np.mean(synth.unpack_bits(P, G).all(axis=1)))
-        # POPC the kernel EXECUTES per pair: carry-save adders fold a 4-word chunk into 3 POPC (8 words -> 4 at G=8192);
-        # the first chunk is screened word by word; all-ones queries take number from a per-target depth prefix that is
-        # computed once per 32-query tile; general queries count T&P as well.
+        # POPC the dominant kernel (ppp_prefilter2_kernel, ppp_prefilter.cu) EXECUTES per pair: carry-save adders fold a
+        # 4-word chunk into 3 POPC (8 words -> 4 at G = 8192); the first chunk is screened word by word; all-ones queries take
+        # `number` from a per-target depth prefix computed once per 32-query tile; general queries count T & P as well
         ch = 8 if words == 256 else 4
         nch, per_chunk = words // ch, (4 if ch == 8 else 3)
         popc_all = per_chunk * (nch - 1) + ch + ch / 8.0 + per_chunk * nch / 32.0
@@ -307,51 +429,70 @@ def run_ours(args):
         popc_exec = frac_all * popc_all + (1.0 - frac_all) * popc_gen
         # SURVEY.md section 8(d) counts the straightforward algorithm: 2W POPC per pair when P is all ones, 3W otherwise
         popc_survey = frac_all * 2 * words + (1.0 - frac_all) * 3 * words
-        clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
         nsm = ctx.counter("num_sms")
-        popc_peak = nsm * 16 * clk  # POPC issues on the XU pipe: 16 lanes / clk / SM (ncu: sm__inst_executed_pipe_xu)
+        peaks = {name: ctx.pipe_peak(name) for name in ("popc", "lop3", "iadd", "dfma")}  # measured now, under this run's clocks
+        clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        popc_peak_analytic = nsm * 16 * clk
         pairs_rate = pf_pairs_mean / (pf_ms * 1e-3) if pf_ms > 0 else 0.0
         popc_rate = pairs_rate * popc_exec
+        # DRAM traffic of the dominant kernel per step: from the committed ncu capture of exactly this command, if there is one
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+            if tj.get("workload") == [G, nq, nt_total, k, world]:
+                traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]
+        except (OSError, ValueError, KeyError):
+            pass
+        W_bytes = words * 4
+        alg_bytes = nt * W_bytes + nq * 2 * W_bytes + 4 * surv_mean
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": main["step_ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"config3 (10k x 1M all-pairs at 4096 genomes over 8 GPUs): {nq} queries x {nt} targets per GPU x "
-                                   f"G={G}, per-query top-k k={k}; N GPUs = {world * nt} targets", "genomes": G, "queries": nq,
+            "config": {"workload": f"config3 (BASELINE: 10k x 1M all-pairs at 4096 genomes): {nq} queries x {nt_total} targets x G={G}, per-query "
+                                   f"top-k k={k}; {world} GPU(s) x {nt} targets each", "genomes": G, "queries": nq, "targets": nt_total,
                        "targets_per_gpu": nt, "filter": f"topk{k}", "l2": "flushed between timed iterations (256 MiB write)",
-                       "timing": "wall of run+fetch bracketed by synchronize; device-event time in device_ms_per_step"},
-            "device_ms_per_step": dev_ms_mean, "sweep_kernel_ms_per_step": sweep_ms_mean,
+                       "timing": "wall of run + result collection bracketed by synchronize, max over ranks; CUDA-event time of the library's "
+                                 "stream in device_ms_per_step"},
+            "device_ms_per_step": main["dev_ms_mean"], "sweep_kernel_ms_per_step": main["sweep_ms_mean"],
             "phase_us_last_step": phase, "full_pairs_last_step": full_pairs,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": "ppp_prefilter2_kernel", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "algorithmic_bytes": alg_bytes,
-                         "traffic_source": "profiles/r01_ncu_bench_prefilter2_traffic.txt: dram__bytes_read.sum + dram__bytes_write.sum "
-                                           "summed over the 14 ppp_prefilter2 launches of one step of this workload (ncu, same command)"
-                                           if traffic else None,
-                         "kernel_ms_per_step": pf_ms, "kernel_share_of_step": pf_ms / step_ms,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                         "note": "operands are reused on chip (targets resident in L2, query tile in shared memory): HBM is not the "
-                                 "bound of this kernel, the POPC pipe is -- see pipe_roofline"},
-            "pipe_roofline": {"bound": "xu_popc", "kernel": "ppp_prefilter2_kernel", "achieved": popc_rate / 1e12, "peak": popc_peak / 1e12,
-                              "unit": "TPOPC/s", "frac": popc_rate / popc_peak, "popc_executed_per_pair": popc_exec,
-                              "popc_per_pair_survey_8d": popc_survey, "frac_vs_survey_count": pairs_rate * popc_survey / popc_peak,
-                              "pairs_per_s_in_kernel": pairs_rate, "all_ones_presence_fraction": frac_all,
-                              "peak_source": f"{nsm} SMs x 16 POPC/clk/SM x {clk / 1e6:.0f} MHz (sampled SM clock)",
-                              "note": "frac = executed POPC / pipe peak (a utilisation); frac_vs_survey_count uses the straightforward "
-                                      "algorithm's POPC count and can exceed 1 because carry-save adders and the shared depth prefix "
-                                      "remove POPCs"},
-            "topk_schedule": {"speculative_rank": ctx.counter("spec_rank"), "queries_rescanned": ctx.counter("spec_failed"),
-                              "survivors_fully_evaluated": int(surv_mean)},
+            "gpu_launches": main["launches"],
+            "roofline": {"bound": "int_pipe", "pipe": "xu_popc", "kernel": "ppp_prefilter2_kernel", "achieved": popc_rate / 1e12,
+                         "peak": peaks["popc"] / 1e12, "unit": "TPOPC/s", "frac": popc_rate / peaks["popc"] if peaks["popc"] else None,
+                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_hbm_bytes_per_step": alg_bytes,
+                         "hbm_GBps_algorithmic": alg_bytes / (pf_ms * 1e-3) / 1e9 if pf_ms > 0 else None,
+                         "kernel_ms_per_step": pf_ms, "kernel_share_of_step": pf_ms / main["step_ms"],
+                         "popc_executed_per_pair": popc_exec, "popc_per_pair_survey_8d": popc_survey,
+                         "frac_vs_survey_count": pairs_rate * popc_survey / peaks["popc"] if peaks["popc"] else None,
+                         "pairs_per_s_in_kernel": pairs_rate, "all_ones_presence_fraction": frac_all,
+                         "peak_source": "ppp_pipe_peak microbenchmark run in this process after the timed steps (popc.b32 chains, 64 warps/SM)",
+                         "peak_analytic": popc_peak_analytic / 1e12,
+                         "peak_analytic_source": f"{nsm} SMs x 16 POPC/clk/SM x {clk / 1e6:.0f} MHz (sampled SM clock)",
+                         "note": "both operands are reused on chip (targets in L2, query tiles in shared memory), so the kernel is bound by the "
+                                 "POPC (XU) pipe, not by HBM; frac = executed POPC / measured pipe peak; frac_vs_survey_count uses the "
+                                 "straightforward algorithm's POPC count and can exceed 1 because carry-save adders and the shared depth "
+                                 "prefix remove POPCs"},
+            "pipe_peaks_measured": {name: v / 1e12 for name, v in peaks.items()}, "pipe_peaks_unit": "T lane-ops/s",
+            "topk_schedule": dict(spec, survivors_fully_evaluated=int(surv_mean)),
+            "weak_scaling": weak,
         }
+        if selfcheck is not None:
+            line["multi_gpu_selfcheck"] = selfcheck
         if world == 1:
-            info, _ = cpu_reference_throughput(w, 15.0, os.cpu_count() or 1)
-            line["cpu_baseline"] = info
-            line["other_configs"] = {"config2_dense_1x1M_G1024": config2_dense(ctx, torch, args)}
+            ncpu = os.cpu_count() or 1
+            port, _ = cpu_port_throughput(w, 12.0, ncpu)
+            if perl_reference_available():
+                line["cpu_baseline"], _ = perl_reference_throughput(w, 12.0, ncpu)
+                line["cpu_baseline_port"] = port
+            else:
+                line["cpu_baseline"] = port
+            line["other_configs"] = other_configs(ctx, torch)
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -364,10 +505,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genomes", type=int, default=4096)
     ap.add_argument("--queries", type=int, default=10000)
-    ap.add_argument("--targets-per-gpu", type=int, default=125000)
+    ap.add_argument("--targets", type=int, default=1000000, help="targets of the whole job (8 blocks)")
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--sweep-warps", type=int, default=16)
     args = ap.parse_args()
+    if args.targets % NBLOCKS:
+        raise SystemExit(f"--targets must be a multiple of {NBLOCKS}")
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -148,6 +148,11 @@ int ppp_printed_cutoffs(ppp_ctx *ctx, double slope, uint64_t *row_off, int32_t *
                         uint8_t *status);
 
 int ppp_get_stats(const ppp_ctx *ctx, ppp_stats *out);
+/* Shape of the resident data, for bindings that must size or check caller buffers: number of resident queries (what
+ * ppp_printed_cutoffs writes per-query entries for) and words per plane row of the resident universe (0 before any
+ * ppp_set_targets_* call). */
+int ppp_query_count(const ppp_ctx *ctx, size_t *nQ);
+int ppp_row_words(const ppp_ctx *ctx, size_t *words);
 
 /* Options (tests / diagnostics): "force_exact" (0/1: every pair through the exact tier),
  * "check_bounds" (0/1: verify the fast tier's enclosures against the accurate tier, count violations),
@@ -199,6 +204,17 @@ void ppp_free_ranked_lists(ppp_ranked_lists *lists);
 
 /* Device-side evaluation of the exact tier's bdtrc (diagnostic; parity tests of cephes_exact.cuh). */
 int ppp_debug_bdtrc(ppp_ctx *ctx, const int32_t *k, const int32_t *n, const double *p, double *out, size_t m);
+
+/* Device-side evaluation of the sweep's fast tiers at m points (yes, number, p) with 1 <= yes <= number <= 8192, 0 < p < 1
+ * (diagnostic; parity tests): lo / hi = the float enclosure of ln P(X >= yes | number, p) that the staircase prune and the
+ * candidate selection rely on, lnf = the FP64 series value.  The tests check lo <= ln bdtrc(yes-1, number, p) <= hi. */
+int ppp_debug_enclosure(ppp_ctx *ctx, const int32_t *yes, const int32_t *number, const double *p, float *lo, float *hi, double *lnf,
+                        size_t m);
+
+/* Measured peak rate of one SM issue pipe on this device under its current clocks, in lane-operations per second over
+ * the whole GPU (a microbenchmark of independent dependent-chains, a few milliseconds; prophylo_b200/csrc/ppp_debug.cu):
+ * "popc" (XU pipe), "lop3", "iadd" (ALU), "dfma" (FP64).  bench.py's roofline divides by these. */
+int ppp_pipe_peak(ppp_ctx *ctx, const char *pipe, double *ops_per_s);
 
 #ifdef __cplusplus
 }

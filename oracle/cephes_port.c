@@ -10,9 +10,10 @@
  * prebuilt binary cpan/x86_64-linux-thread-multi/Math-Cephes-0.47-...-5.10.1.par
  * (arch/auto/Math/Cephes/Cephes.so).  This file restates the published Cephes
  * algorithms; it is pinned bit-for-bit against that binary by
- * oracle/check_cephes_port.py (dlopen of the extracted .so, >= 1e6 random
- * (k,n,p) points plus every edge branch), see tests/test_oracle_cephes.py for
- * the committed golden subset.
+ * oracle/check_cephes_port.c (`make -C oracle check`: dlopen of the extracted
+ * .so, 2e6 random bdtrc + 2e6 random incbet points plus every edge branch);
+ * tests/test_oracle.py checks the committed golden subset
+ * (tests/golden/bdtrc_points.json).
  *
  * Build with -O2 -ffp-contract=off (no FMA contraction: the 2011 x86-64
  * binary is plain SSE2).

@@ -64,6 +64,8 @@ def lib():
         L.ppp_oracle_bits.argtypes = [P, P, P, ctypes.c_int32, D, P]
         L.ppp_oracle_bits_batch.restype = ctypes.c_long
         L.ppp_oracle_bits_batch.argtypes = [P, P, P, ctypes.c_int64, P, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, P, I]
+        L.ppp_oracle_bits_batch_memo.restype = ctypes.c_long
+        L.ppp_oracle_bits_batch_memo.argtypes = L.ppp_oracle_bits_batch.argtypes
         _lib = L
     return _lib
 
@@ -97,9 +99,11 @@ def score_list(present, isyes, max_yes: int, target_ids, p: float, dup: bool = F
     return (r.score, r.yes, r.number, r.depth, r.p, steps)
 
 
-def score_case(query: dict, target, prob=None, dup: bool = False):
+def score_case(query: dict, target, prob=None, dup: bool = False, rank=None, collapse=None):
     """Same inputs as oracle/run_reference.pl: query = {taxon: 0|1}, target = ordered list of taxa
-    (ARRAY branch, ppp.pm:151-153) or {taxon: rank} (HASH branch, ppp.pm:147-149; ranks must be distinct)."""
+    (ARRAY branch, ppp.pm:151-153) or {taxon: rank} (HASH branch, ppp.pm:147-149; ranks must be distinct).
+    rank / collapse = {rank: {taxon: collapsed}}: the -rank pre-pass of ppp.pm:328-370 on every list element
+    (collapse_taxon(taxon, rank), else (taxon, "genus"), else the raw id; croak without a taxonomy, :345-349)."""
     taxa = {t: i for i, t in enumerate(query)}
     present = np.ones(len(taxa), dtype=np.uint8)
     isyes = np.array([1 if float(query[t]) != 0 else 0 for t in query], dtype=np.uint8)
@@ -110,6 +114,10 @@ def score_case(query: dict, target, prob=None, dup: bool = False):
         tlist = [k for k, _ in items]
     else:
         tlist = list(target)
+    if rank:
+        if collapse is None:
+            raise RuntimeError("Taxonomy does not exist")  # ppp.pm:348
+        tlist = [collapse.get(rank, {}).get(t) or collapse.get("genus", {}).get(t) or t for t in tlist]
     ids = []
     for t in tlist:
         if t not in taxa:
@@ -132,8 +140,10 @@ def score_bits(P, Y, T, G: int, p: float):
     return (r.score, r.yes, r.number, r.depth, r.p, steps)
 
 
-def score_bits_batch(P, Y, p, T, G: int, nthreads: int = 1):
-    """All pairs: P,Y [nq, wpr] uint32; p [nq] float64; T [nt, wpr] uint32 -> structured array [nq, nt], steps."""
+def score_bits_batch(P, Y, p, T, G: int, nthreads: int = 1, memo: bool = False):
+    """All pairs: P,Y [nq, wpr] uint32; p [nq] float64; T [nt, wpr] uint32 -> structured array [nq, nt], steps.
+    memo=True caches bdtrc(yes-1, number, p) per query (a pure function; same loop, same results -- see
+    ppp_oracle.c::oracle_list_core): for the full-size parity tests only, never for a timed CPU baseline."""
     P = np.ascontiguousarray(P, dtype=np.uint32)
     Y = np.ascontiguousarray(Y, dtype=np.uint32)
     T = np.ascontiguousarray(T, dtype=np.uint32)
@@ -142,5 +152,6 @@ def score_bits_batch(P, Y, p, T, G: int, nthreads: int = 1):
     nt = T.shape[0]
     assert T.shape[1] == wpr and Y.shape == P.shape and p.shape == (nq,)
     out = np.zeros((nq, nt), dtype=RESULT_DTYPE)
-    steps = lib().ppp_oracle_bits_batch(_ptr(P), _ptr(Y), _ptr(p), nq, _ptr(T), nt, int(G), wpr, _ptr(out), int(nthreads))
+    fn = lib().ppp_oracle_bits_batch_memo if memo else lib().ppp_oracle_bits_batch
+    steps = fn(_ptr(P), _ptr(Y), _ptr(p), nq, _ptr(T), nt, int(G), wpr, _ptr(out), int(nthreads))
     return out, steps

@@ -26,8 +26,13 @@
  *   dup                   the -dup flag, with the reference's literal-key quirk (ppp.pm:189-200,214-217)
  * Returns the number of sweep steps that evaluated bdtrc (work counter for benchmarks).
  */
-long ppp_oracle_list(const uint8_t *present, const uint8_t *isyes, int32_t U, int32_t max_yes,
-                     const int32_t *list, int32_t L, double p, int dup, ppp_oracle_result *out)
+/* memo != NULL: bdtrc is a pure function of (yes, number) for a fixed p, so a caller that sweeps MANY targets against
+ * one query may hand in a per-query cache memo[yes * memo_stride + number] (all bytes 0xFF = empty; a stored value is
+ * never that NaN).  The loop, its order of evaluation and every result are unchanged -- the cache only avoids
+ * re-evaluating cp_bdtrc at a point it has already been evaluated at.  Used by the full-size parity tests; the timed
+ * CPU baseline of bench.py never passes a memo (the reference does not cache). */
+static long oracle_list_core(const uint8_t *present, const uint8_t *isyes, int32_t U, int32_t max_yes, const int32_t *list,
+                             int32_t L, double p, int dup, ppp_oracle_result *out, double *memo, int64_t memo_stride)
 {
     double score = 1.0; /* ppp.pm:132 */
     int number = 0, yes = 0;
@@ -62,7 +67,18 @@ long ppp_oracle_list(const uint8_t *present, const uint8_t *isyes, int32_t U, in
         }
         if (yes > max_yes)
             break;                                     /* ppp.pm:222-224 */
-        double answer = cp_bdtrc(yes - 1, number, p); /* ppp.pm:225 */
+        double answer;
+        if (memo) {
+            double *cell = &memo[(int64_t)yes * memo_stride + number];
+            uint64_t bits;
+            memcpy(&bits, cell, 8);
+            if (bits == ~(uint64_t)0) {
+                *cell = cp_bdtrc(yes - 1, number, p);
+            }
+            answer = *cell;
+        } else {
+            answer = cp_bdtrc(yes - 1, number, p); /* ppp.pm:225 */
+        }
         steps++;
         if (answer < score) { /* ppp.pm:228-237: strict <, first minimum wins */
             best_depth = i + 1;
@@ -81,6 +97,12 @@ long ppp_oracle_list(const uint8_t *present, const uint8_t *isyes, int32_t U, in
     out->depth = best_depth;
     out->p = p;
     return steps;
+}
+
+long ppp_oracle_list(const uint8_t *present, const uint8_t *isyes, int32_t U, int32_t max_yes,
+                     const int32_t *list, int32_t L, double p, int dup, ppp_oracle_result *out)
+{
+    return oracle_list_core(present, isyes, U, max_yes, list, L, p, dup, out, NULL, 0);
 }
 
 static inline int getbit(const uint32_t *w, int g) { return (w[g >> 5] >> (g & 31)) & 1; }
@@ -152,6 +174,93 @@ long ppp_oracle_bits_batch(const uint32_t *P, const uint32_t *Y, const double *p
         batch_job j = {P, Y, T, p, nq, nt, G, wpr, out, i, nthreads, 0};
         jobs[i] = j;
         pthread_create(&th[i], NULL, batch_worker, &jobs[i]);
+    }
+    long steps = 0;
+    for (int i = 0; i < nthreads; ++i) {
+        pthread_join(th[i], NULL);
+        steps += jobs[i].steps;
+    }
+    return steps;
+}
+
+/*
+ * The same all-pairs batch with the per-query bdtrc cache of oracle_list_core (see there): identical results, about
+ * 50x faster when one query meets >= 10^5 targets, which is what makes complete top-k lists over BASELINE-size target
+ * sets checkable against the oracle.  Work is split by (query, target block) so that few queries still use all threads.
+ */
+typedef struct {
+    const uint32_t *P, *Y, *T;
+    const double *p;
+    int64_t nq, nt, nblocks;
+    int32_t G, wpr;
+    ppp_oracle_result *out;
+    int64_t *next; /* shared job counter */
+    long steps;
+} memo_job;
+
+static void *memo_worker(void *arg)
+{
+    memo_job *j = (memo_job *)arg;
+    const int32_t G = j->G;
+    uint8_t *present = (uint8_t *)malloc((size_t)G);
+    uint8_t *isyes = (uint8_t *)malloc((size_t)G);
+    int32_t *list = (int32_t *)malloc(sizeof(int32_t) * (size_t)G);
+    long steps = 0;
+    for (;;) {
+        const int64_t job = __atomic_fetch_add(j->next, 1, __ATOMIC_RELAXED);
+        if (job >= j->nq * j->nblocks)
+            break;
+        const int64_t q = job / j->nblocks, b = job % j->nblocks;
+        const int64_t t0 = j->nt * b / j->nblocks, t1 = j->nt * (b + 1) / j->nblocks;
+        const uint32_t *P = j->P + q * j->wpr, *Y = j->Y + q * j->wpr;
+        int32_t max_yes = 0, npres = 0;
+        for (int g = 0; g < G; ++g) {
+            present[g] = (uint8_t)getbit(P, g);
+            isyes[g] = (uint8_t)(getbit(Y, g) & getbit(P, g));
+            max_yes += isyes[g];
+            npres += present[g];
+        }
+        const int64_t stride = (int64_t)npres + 1;
+        const size_t cells = (size_t)(max_yes + 2) * (size_t)stride;
+        double *memo = (double *)malloc(cells * sizeof(double));
+        memset(memo, 0xFF, cells * sizeof(double));
+        for (int64_t t = t0; t < t1; ++t) {
+            const uint32_t *T = j->T + t * j->wpr;
+            int32_t L = 0;
+            for (int w = 0; w * 32 < G; ++w) /* the target's list = its set genomes in index order */
+                for (uint32_t bits = T[w]; bits; bits &= bits - 1) {
+                    const int g = w * 32 + __builtin_ctz(bits);
+                    if (g < G)
+                        list[L++] = g;
+                }
+            steps += oracle_list_core(present, isyes, G, max_yes, list, L, j->p[q], 0, &j->out[q * j->nt + t], memo, stride);
+        }
+        free(memo);
+    }
+    free(present);
+    free(isyes);
+    free(list);
+    j->steps = steps;
+    return NULL;
+}
+
+long ppp_oracle_bits_batch_memo(const uint32_t *P, const uint32_t *Y, const double *p, int64_t nq, const uint32_t *T,
+                                int64_t nt, int32_t G, int32_t wpr, ppp_oracle_result *out, int nthreads)
+{
+    if (nthreads < 1)
+        nthreads = 1;
+    if (nthreads > 256)
+        nthreads = 256;
+    pthread_t th[256];
+    memo_job jobs[256];
+    int64_t next = 0;
+    int64_t nblocks = nq >= 4 * (int64_t)nthreads ? 1 : (4 * (int64_t)nthreads + nq - 1) / (nq > 0 ? nq : 1);
+    if (nblocks > nt)
+        nblocks = nt > 0 ? nt : 1;
+    for (int i = 0; i < nthreads; ++i) {
+        memo_job j = {P, Y, T, p, nq, nt, nblocks, G, wpr, out, &next, 0};
+        jobs[i] = j;
+        pthread_create(&th[i], NULL, memo_worker, &jobs[i]);
     }
     long steps = 0;
     for (int i = 0; i < nthreads; ++i) {

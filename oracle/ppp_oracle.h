@@ -20,6 +20,9 @@ long ppp_oracle_bits(const uint32_t *P, const uint32_t *Y, const uint32_t *T, in
                      ppp_oracle_result *out);
 long ppp_oracle_bits_batch(const uint32_t *P, const uint32_t *Y, const double *p, int64_t nq, const uint32_t *T,
                            int64_t nt, int32_t G, int32_t wpr, ppp_oracle_result *out, int nthreads);
+/* same results as ppp_oracle_bits_batch, with a per-query cache of the pure function bdtrc(yes-1, number, p) */
+long ppp_oracle_bits_batch_memo(const uint32_t *P, const uint32_t *Y, const double *p, int64_t nq, const uint32_t *T,
+                                int64_t nt, int32_t G, int32_t wpr, ppp_oracle_result *out, int nthreads);
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,9 @@
 #
 # input (stdin): JSON array of cases
 #   { "query": {taxon: 0|1, ...}, "target": [taxon, ...] | {taxon: rank, ...},
-#     "prob": optional number, "dup": optional 0|1, "file": optional path of a profile file for the query }
+#     "prob": optional number, "dup": optional 0|1, "file": optional path of a profile file for the query,
+#     "rank": optional rank name (-rank), "collapse": optional {rank: {taxon: collapsed taxon}} served by a mock
+#     -taxonomy object exposing collapse_taxon (what ppp.pm:328-370 calls); "rank" without "collapse" passes no taxonomy }
 # output (file argv[0], else stdout): JSON array of [score, yes, number, depth, p] as strings ("%.17g") / ints
 use strict;
 use warnings;
@@ -22,6 +24,12 @@ BEGIN {
 }
 use PhyloProf::Profile;
 use PhyloProf::Algorithm::ppp;
+
+{
+    package MockTaxonomy;    # stands in for SeqToolBox::Taxonomy: collapse_taxon(id, rank) from a table (Taxonomy.pm:296-360)
+    sub new { my ( $c, $map ) = @_; return bless { map => $map }, $c }
+    sub collapse_taxon { my ( $s, $id, $rank ) = @_; my $v = $s->{map}{$rank}{$id}; return $v ? $v : undef }
+}
 
 my $cases = do { local $/; decode_json(<STDIN>) };
 my @out;
@@ -39,6 +47,8 @@ foreach my $c (@$cases) {
     my @args = ( -prof1 => $prof1, -prof2 => $prof2 );
     push @args, ( -prob => $c->{prob} ) if defined $c->{prob};
     push @args, ( -dup  => 1 )          if $c->{dup};
+    push @args, ( -rank => $c->{rank} ) if $c->{rank};
+    push @args, ( -taxonomy => MockTaxonomy->new( $c->{collapse} ) ) if $c->{collapse};
     my $alg = PhyloProf::Algorithm::ppp->new(@args);
     # Cephes' mtherr prints "bdtrc domain error" on stdout: keep it out of the JSON stream
     open( STDOUT, ">", "/dev/null" ) or die;

@@ -68,6 +68,7 @@ _set_targets_ranked(h, idx, raw, off, nT, G)
     const char *rb = SvPVbyte(raw, lr);   /* pack "S*": 1-based raw list positions                      */
     const char *ob = SvPVbyte(off, lo);   /* pack "Q*": nT + 1 entry offsets                            */
     if (lo < (STRLEN)(nT + 1) * 8 || li != lr) croak("PhyloProf::B200: ranked target buffers inconsistent");
+    if (nT && li < (STRLEN)(((const uint64_t *)ob)[nT] * 2)) croak("PhyloProf::B200: ranked target lists shorter than row_off[nT]");
     if (ppp_set_targets_ranked(ctx, (const uint16_t *)ib, (const uint16_t *)rb, (const uint64_t *)ob, (size_t)nT, G) != PPP_OK)
         croak("PhyloProf::B200: %s", ppp_last_error(ctx));
 
@@ -94,13 +95,21 @@ _set_targets_bla(h, paths, universe, nthreads, flags)
     const char **pv = NULL, **uv = NULL;
     Newx(pv, np ? np : 1, const char *);
     Newx(uv, G ? G : 1, const char *);
-    for (size_t i = 0; i < np; ++i) pv[i] = SvPVbyte_nolen(*av_fetch(paths, (SSize_t)i, 0));
-    for (size_t i = 0; i < G; ++i) uv[i] = SvPVbyte_nolen(*av_fetch(universe, (SSize_t)i, 0));
+    SAVEFREEPV(pv); /* released when the XSUB is left, also through a croak of SvPVbyte_nolen */
+    SAVEFREEPV(uv);
+    for (size_t i = 0; i < np; ++i) {
+        SV **e = av_fetch(paths, (SSize_t)i, 0);
+        if (!e) croak("PhyloProf::B200: undefined path at index %lu", (unsigned long)i);
+        pv[i] = SvPVbyte_nolen(*e);
+    }
+    for (size_t i = 0; i < G; ++i) {
+        SV **e = av_fetch(universe, (SSize_t)i, 0);
+        if (!e) croak("PhyloProf::B200: undefined taxon at index %lu", (unsigned long)i);
+        uv[i] = SvPVbyte_nolen(*e);
+    }
     ppp_ranked_lists l;
     char err[512];
     int rc = ppp_read_bla_flags(pv, np, uv, G, nthreads, flags, &l, err, sizeof(err)); /* flags: PPP_BLA_DUP = -dup packing */
-    Safefree(pv);
-    Safefree(uv);
     if (rc != PPP_OK) croak("PhyloProf::B200: %s", err);
     rc = ppp_set_targets_ranked(ctx, l.idx, l.rawdepth, l.row_off, l.n_targets, (uint32_t)G);
     RETVAL = (UV)l.n_entries;
@@ -121,6 +130,9 @@ _printed_cutoffs(h, nQ, slope)
     uint64_t *off = NULL;
     int32_t *marker = NULL, *cut = NULL;
     uint8_t *status = NULL;
+    size_t ctx_nq = 0;
+    ppp_query_count(ctx, &ctx_nq); /* the library writes one entry per RESIDENT query: the buffers must be that long */
+    if ((size_t)nQ != ctx_nq) croak("PhyloProf::B200: printed_cutoffs asked for %lu queries, the last run had %lu", (unsigned long)nQ, (unsigned long)ctx_nq);
     Newx(off, nQ + 1, uint64_t);
     Newx(marker, nQ ? nQ : 1, int32_t);
     Newx(cut, nQ ? nQ : 1, int32_t);
@@ -159,6 +171,11 @@ _score(h, pplanes, yplanes, probs, nQ, mode, k, thresh)
     const char *yb = SvPVbyte(yplanes, ly);
     const char *qb = SvPVbyte(probs, lq); /* packed native doubles: pack "d*" */
     if (lq < (STRLEN)nQ * sizeof(double) || lp != ly) croak("PhyloProf::B200: query buffers inconsistent");
+    {
+        size_t wpr = 0;
+        ppp_row_words(ctx, &wpr); /* words per plane row of the resident targets' universe */
+        if (lp < (STRLEN)nQ * wpr * 4) croak("PhyloProf::B200: query planes shorter than nQ rows of %lu words", (unsigned long)wpr);
+    }
     ppp_filter f;
     f.mode = mode; f.k = k; f.thresh = thresh;
     if (ppp_set_queries(ctx, (const uint32_t *)pb, (const uint32_t *)yb, (const double *)qb, (size_t)nQ) != PPP_OK)

@@ -37,7 +37,8 @@ sub new {
 
 sub _taxon {    # ppp.pm:328-370: identity unless -rank; collapse, fall back to genus, then to the raw id
     my ( $self, $t ) = @_;
-    return $t unless $self->{_rank} && $self->{_dbh};
+    return $t unless $self->{_rank};
+    croak "Taxonomy does not exist\n" unless exists $self->{_dbh};    # ppp.pm:345-349 (callers may also poke $alg->{_dbh}, bin/ppp.pl:572)
     return $self->{_dbh}->collapse_taxon( $t, $self->{_rank} ) || $self->{_dbh}->collapse_taxon( $t, "genus" ) || $t;
 }
 

@@ -70,6 +70,7 @@ sub score_ranked {
     push @off, 0;
     foreach my $l (@$lists) {
         my ( %seen, $repeats );
+        croak "target list of " . scalar(@$l) . " positions exceeds 65535" if @$l > 65535;    # raw positions are uint16
         for my $i ( 0 .. $#$l ) {
             if ( $seen{ $l->[$i] }++ ) {
                 next unless $o{-dup};
@@ -120,7 +121,7 @@ sub score_bits {
 # ppp.pl -m <slope> marker and ppp_cutoff.pl -s <slope> CUTOFF of each query's (already sorted) rows, computed on the device
 # (bin/ppp.pl:473-506, bin/ppp_cutoff.pl:130-148).  status != 0: format that query's rows in Perl (include/ppp_b200.h).
 sub printed_cutoffs {
-    my ( $self, $n_queries, $slope ) = @_;
+    my ( $self, $n_queries, $slope ) = @_;    # $n_queries is checked against the run's own query count by the XS layer
     return [ _printed_cutoffs( $self->{h}, $n_queries, $slope ) ];
 }
 
@@ -135,8 +136,11 @@ sub _score_queries {
         my @yes     = grep { $h->{$_} != 0 } @present;
         $pb .= _plane( $wpr, $idx, \@present );
         $yb .= _plane( $wpr, $idx, \@yes );
-        my $prob = ref($q) eq 'HASH' ? undef : undef;
-        push @p, defined $o{-prob} ? $o{-prob} : ( @present ? @yes / @present : 0 );    # ppp.pm:138-142
+        # p = get_yes / get_total of the WHOLE profile, taxa outside the universe included (ppp.pm:138-142); a false -prob
+        # counts as absent (ppp.pm:100-102)
+        my ( $yes_all, $total ) = ref($q) eq 'HASH' ? ( scalar( grep { $_ != 0 } values %$h ), scalar( keys %$h ) ) : ( $q->get_yes(), $q->get_total() );
+        croak "Illegal division by zero" unless $o{-prob} || $o{-probs} || $total;    # ppp.pm:141
+        push @p, $o{-prob} ? $o{-prob} : ( $total ? $yes_all / $total : 0 );
     }
     @p = @{ $o{-probs} } if $o{-probs};
     my %mode = ( all => 0, thresh => 1, topk => 2 );

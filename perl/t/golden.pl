@@ -73,5 +73,56 @@ foreach my $c ( @{ $g->{known_answers} }, @{ $g->{fuzz} } ) {
         print "MISMATCH printed_cutoffs: rows $rows vs ", scalar(@$hits), " cutoff ", ( $cutoff // 'undef' ), " want ", ( $want // 'undef' ), "\n";
     }
 }
-print "perl drop-in: $n cases ($skipped with -dup), $bad mismatches\n";
+# -rank (ppp.pm:328-370): the reference run with a mock -taxonomy object (oracle/gen_golden_rank.py); croak without one
+{
+    package MockTaxonomy;
+    sub new { my ( $c, $map ) = @_; return bless { map => $map }, $c }
+    sub collapse_taxon { my ( $s, $id, $rank ) = @_; my $v = $s->{map}{$rank}{$id}; return $v ? $v : undef }
+}
+my $nrank = 0;
+{
+    ( my $rf = $file ) =~ s/ppp_list_cases\.json$/ppp_rank_cases.json/;
+    open( my $rh, "<", $rf ) or die "$rf: $!";
+    my $rg = decode_json( do { local $/; <$rh> } );
+    foreach my $c ( @{ $rg->{cases} } ) {
+        my $t = $c->{target};
+        my $cnt = ref($t) eq 'ARRAY' ? scalar(@$t) : scalar( keys %$t );
+        my @args = ( -prof1 => PhyloProf::Profile->new( -profile => $c->{query} ), -prof2 => PhyloProf::Profile->new( -raw => $t, -yes => $cnt, -no => 0 ),
+                     -rank => $c->{rank}, -taxonomy => MockTaxonomy->new( $c->{collapse} ) );
+        push @args, ( -prob => $c->{prob} ) if defined $c->{prob};
+        push @args, ( -dup => 1 ) if $c->{dup};
+        my @r = PhyloProf::Algorithm::ppp_b200->new(@args)->get_match_score();
+        my @e = @{ $c->{expect} };
+        $nrank++;
+        my $ok = $r[1] == $e[1] && $r[2] == $e[2] && $r[3] == $e[3] && $r[4] == $e[4];
+        if ( $ok && $r[0] != $e[0] + 0 ) {
+            $ok = 0 if $r[0] <= 0 || $e[0] <= 0 || abs( log( $r[0] ) - log( $e[0] ) ) > 1e-9 * abs( log( $e[0] ) );
+        }
+        unless ($ok) { $bad++; print "MISMATCH $c->{name}: got @r expected @e\n" if $bad < 10; }
+    }
+    my $c = $rg->{croak};
+    my $alg = PhyloProf::Algorithm::ppp_b200->new( -prof1 => PhyloProf::Profile->new( -profile => $c->{query} ),
+                                                   -prof2 => PhyloProf::Profile->new( -raw => $c->{target}, -yes => 2, -no => 0 ), -rank => $c->{rank} );
+    eval { $alg->get_match_score() };
+    unless ( $@ =~ /\Q$c->{error}\E/ ) { $bad++; print "MISMATCH: -rank without -taxonomy did not croak ($@)\n"; }
+    # callers also poke the taxonomy in after construction (bin/ppp.pl:572)
+    $alg->{_dbh} = MockTaxonomy->new( {} );
+    my @r = eval { $alg->get_match_score() };
+    if ($@) { $bad++; print "MISMATCH: poked _dbh not honoured ($@)\n"; }
+}
+# p comes from the WHOLE query profile (ppp.pm:138-142) even when some of its taxa lie outside the universe, and a false
+# -prob counts as absent (ppp.pm:100-102)
+{
+    my $gpu = PhyloProf::B200->new( -device => $ENV{PPP_B200_DEVICE} || 0 );
+    my %q = ( a => 1, b => 1, c => 0, d => 0, zz1 => 0, zz2 => 0, zz3 => 1, zz4 => 0 );    # 3 yes of 8
+    my @universe = qw(a b c d);
+    my $ref = $gpu->score_ranked( \@universe, [ \%q ], [ [qw(a b c)] ], -probs => [ 3 / 8 ] );
+    my $got = $gpu->score_ranked( \@universe, [ \%q ], [ [qw(a b c)] ] );
+    my $got0 = $gpu->score_ranked( \@universe, [ \%q ], [ [qw(a b c)] ], -prob => 0 );
+    my $bits = $gpu->score_bits( \@universe, [ \%q ], [ [qw(a b c)] ] );
+    foreach my $h ( $got, $got0, $bits ) {
+        unless ( $h->[0][2] == $ref->[0][2] && $h->[0][3] == 2 ) { $bad++; print "MISMATCH p of a profile with taxa outside the universe: $h->[0][2] vs $ref->[0][2]\n"; }
+    }
+}
+print "perl drop-in: $n cases ($skipped with -dup), $nrank -rank cases, $bad mismatches\n";
 exit( $bad ? 1 : 0 );

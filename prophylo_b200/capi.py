@@ -26,7 +26,7 @@ EXPORTS = [
     "ppp_init", "ppp_destroy", "ppp_last_error", "ppp_abi_version", "ppp_set_targets_bits", "ppp_set_targets_ranked",
     "ppp_set_queries", "ppp_run", "ppp_result_count", "ppp_fetch", "ppp_score", "ppp_get_stats", "ppp_set_option",
     "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc", "ppp_topk_device", "ppp_merge_topk_device", "ppp_read_bla", "ppp_read_bla_flags", "ppp_printed_cutoffs",
-    "ppp_free_ranked_lists",
+    "ppp_free_ranked_lists", "ppp_debug_enclosure", "ppp_query_count", "ppp_row_words", "ppp_pipe_peak",
 ]
 
 
@@ -100,6 +100,10 @@ def load():
     L.ppp_merge_topk_device.argtypes = [vp, vp, vp, u32, vp, sz, u32, vp, vp]
     L.ppp_debug_bdtrc.restype = ctypes.c_int
     L.ppp_debug_bdtrc.argtypes = [vp, vp, vp, vp, vp, sz]
+    L.ppp_debug_enclosure.restype = ctypes.c_int
+    L.ppp_debug_enclosure.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz]
+    L.ppp_pipe_peak.restype = ctypes.c_int
+    L.ppp_pipe_peak.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
     L.ppp_read_bla.restype = ctypes.c_int
     L.ppp_read_bla.argtypes = [ctypes.POINTER(ctypes.c_char_p), sz, ctypes.POINTER(ctypes.c_char_p), sz, ctypes.c_int,
                                ctypes.POINTER(RankedLists), ctypes.c_char_p, sz]
@@ -297,3 +301,20 @@ class Context:
         out = np.empty(k.shape, dtype=np.float64)
         self._check(self.lib.ppp_debug_bdtrc(self._h, _ptr(k), _ptr(n), _ptr(p), _ptr(out), k.size))
         return out
+
+    def debug_enclosure(self, yes, number, p):
+        """(lo, hi, lnf): tier A's float enclosure and tier B's FP64 value of ln P(X >= yes | number, p) at each point."""
+        yes = np.ascontiguousarray(yes, dtype=np.int32)
+        number = np.ascontiguousarray(number, dtype=np.int32)
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        lo = np.empty(yes.shape, dtype=np.float32)
+        hi = np.empty(yes.shape, dtype=np.float32)
+        lnf = np.empty(yes.shape, dtype=np.float64)
+        self._check(self.lib.ppp_debug_enclosure(self._h, _ptr(yes), _ptr(number), _ptr(p), _ptr(lo), _ptr(hi), _ptr(lnf), yes.size))
+        return lo, hi, lnf
+
+    def pipe_peak(self, pipe: str) -> float:
+        """measured lane-operations per second of one issue pipe ("popc", "lop3", "iadd", "dfma") on this GPU"""
+        v = ctypes.c_double()
+        self._check(self.lib.ppp_pipe_peak(self._h, pipe.encode(), ctypes.byref(v)))
+        return v.value

@@ -11,7 +11,8 @@
  * Every operation is IEEE-754 double with round-to-nearest and NO fused multiply-add: the translation unit that
  * includes this header MUST be compiled with -fmad=false (see __graft_entry__.build()); CUDA's double
  * division, floor, frexp and ldexp are exact/IEEE, so results are bit-identical to the x86-64 SSE2 binary
- * (verified on the GPU by tests/test_gpu_exact.py against tests/golden/bdtrc_points.json).
+ * (verified on the GPU by tests/test_gpu_parity.py::test_exact_tier_bdtrc_is_bit_identical against
+ * tests/golden/bdtrc_points.json, and on 200,000 random points against the oracle).
  *
  * One linkage quirk of the reference is mirrored: Cephes.so calls `expm1` through its PLT, which binds to the
  * host libm (glibc) inside perl, so the k == 0, p < 0.01 branch is -expm1_libm(n * log1p(-p)).  glibc's expm1
@@ -22,7 +23,17 @@
 #include <math.h>
 #include <stdint.h>
 
-/* fdlibm s_expm1.c algorithm (what glibc 2.39 sysdeps/ieee754/dbl-64/s_expm1.c implements) */
+/* fdlibm s_expm1.c algorithm (what glibc 2.39 sysdeps/ieee754/dbl-64/s_expm1.c implements), restated for the device.
+ * The algorithm and its constants are from FreeBSD/Sun fdlibm, whose notice reads:
+ *   ====================================================
+ *   Copyright (C) 1993 by Sun Microsystems, Inc. All rights reserved.
+ *
+ *   Developed at SunPro, a Sun Microsystems, Inc. business.
+ *   Permission to use, copy, modify, and distribute this
+ *   software is freely granted, provided that this notice
+ *   is preserved.
+ *   ====================================================
+ */
 __device__ static double dc_fdlibm_expm1(double x)
 {
     const double one = 1.0, tiny = 1.0e-300, o_threshold = 7.09782712893383973096e+02,

@@ -65,6 +65,9 @@ extern "C" cudaError_t ppp_launch_rank_hits(const ppp_hit *rec, size_t n, uint32
                                             cudaStream_t st, uint32_t *launches);
 extern "C" cudaError_t ppp_launch_rank_cutoffs(const ppp_hit *rec, size_t n, uint32_t nQ, double slope, unsigned long long *row_off,
                                                int32_t *milli, int32_t *marker, int32_t *cutoff_milli, uint8_t *status, int nsm, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_debug_enclosure(const QConst *qc, const double *lf, const int32_t *y, const int32_t *n, float *lo, float *hi,
+                                                  double *lnf, size_t m, int nsm, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_pipe_peak(int kind, uint32_t iters, uint32_t *sink, int nsm, cudaStream_t st, double *lane_ops);
 extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const unsigned long long *counters, int n, cudaStream_t st);
 
 struct ppp_ctx {
@@ -178,6 +181,7 @@ struct ppp_ctx {
     int last_used_table = 0;
     /* options */
     int force_exact = 0, check_bounds = 0, sweep_warps = 8;
+    bool debug_chunks = false; /* PPP_B200_DEBUG_CHUNKS was set when the context was created */
     ppp_stats stats;
     unsigned long long last_counters[CNT_N];
 };
@@ -246,17 +250,20 @@ extern "C" int ppp_init(ppp_ctx **out, const int *devices, int ndev)
         delete ctx;
         return PPP_ERR_CUDA;
     }
-    for (int i = 0; i < 8; ++i) cudaEventCreate(&ctx->ev[i]);
-    if ((e = cudaMalloc(&ctx->d_counters, CNT_SLOTS * sizeof(unsigned long long))) != cudaSuccess) {
-        fail(nullptr, PPP_ERR_CUDA, "ppp_init: %s", cudaGetErrorString(e));
-        delete ctx;
-        return PPP_ERR_CUDA;
+    for (int i = 0; i < 8; ++i) {
+        if ((e = cudaEventCreate(&ctx->ev[i])) != cudaSuccess) {
+            fail(nullptr, PPP_ERR_CUDA, "ppp_init: %s", cudaGetErrorString(e));
+            ppp_destroy(ctx); /* releases the stream and the events created so far */
+            return PPP_ERR_CUDA;
+        }
     }
-    if ((e = cudaMalloc(&ctx->d_totals, (CNT_N + 1) * sizeof(unsigned long long))) != cudaSuccess) {
-        fail(nullptr, PPP_ERR_CUDA, "ppp_init: %s", cudaGetErrorString(e));
-        delete ctx;
-        return PPP_ERR_CUDA;
+    if ((e = cudaMalloc(&ctx->d_counters, CNT_SLOTS * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&ctx->d_totals, (CNT_N + 1) * sizeof(unsigned long long))) != cudaSuccess) {
+        fail(nullptr, e == cudaErrorMemoryAllocation ? PPP_ERR_NOMEM : PPP_ERR_CUDA, "ppp_init: %s", cudaGetErrorString(e));
+        ppp_destroy(ctx);
+        return e == cudaErrorMemoryAllocation ? PPP_ERR_NOMEM : PPP_ERR_CUDA;
     }
+    ctx->debug_chunks = getenv("PPP_B200_DEBUG_CHUNKS") != nullptr; /* developer aid, read once */
     *out = ctx;
     return PPP_OK;
 }
@@ -326,6 +333,7 @@ static int pick_wpl(uint32_t G)
     return 0;
 }
 
+static void free_query_buffers(ppp_ctx *ctx);
 static void reset_queries_if_layout_changed(ppp_ctx *ctx, int wpl, uint32_t G);
 
 extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, uint32_t G)
@@ -355,20 +363,23 @@ extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, 
     return PPP_OK;
 }
 
+static void free_query_buffers(ppp_ctx *ctx)
+{
+    cudaFree(ctx->d_Q);
+    cudaFree(ctx->d_qc);
+    cudaFree(ctx->d_qflags);
+    cudaFree(ctx->d_qorder);
+    ctx->d_Q = nullptr;
+    ctx->d_qc = nullptr;
+    ctx->d_qflags = nullptr;
+    ctx->d_qorder = nullptr;
+    ctx->capQ = 0;
+    ctx->nQ = 0;
+}
+
 static void reset_queries_if_layout_changed(ppp_ctx *ctx, int wpl, uint32_t G)
 {
-    if (ctx->wpl != wpl || ctx->G != G) {
-        ctx->nQ = 0; /* queries must be re-uploaded: the row layout changed */
-        cudaFree(ctx->d_Q);
-        cudaFree(ctx->d_qc);
-        cudaFree(ctx->d_qflags);
-        cudaFree(ctx->d_qorder);
-        ctx->d_qorder = nullptr;
-        ctx->d_Q = nullptr;
-        ctx->d_qc = nullptr;
-        ctx->d_qflags = nullptr;
-        ctx->capQ = 0;
-    }
+    if (ctx->wpl != wpl || ctx->G != G) free_query_buffers(ctx); /* queries must be re-uploaded: the row layout changed */
 }
 
 extern "C" int ppp_set_targets_ranked(ppp_ctx *ctx, const uint16_t *idx, const uint16_t *rawdepth, const uint64_t *row_off,
@@ -448,20 +459,17 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
     CU(cudaSetDevice(ctx->device));
     const size_t W = 32 * (size_t)ctx->wpl, wpr = ppp_words_per_row(ctx->G);
     if (nQ > ctx->capQ) {
-        cudaFree(ctx->d_Q);
-        cudaFree(ctx->d_qc);
-        cudaFree(ctx->d_qflags);
-        ctx->d_Q = nullptr;
-        ctx->d_qc = nullptr;
-        ctx->d_qflags = nullptr;
-        ctx->capQ = 0;
+        free_query_buffers(ctx);
         /* round up to a whole tile so that a tile's TMA bulk copy never reads past the allocation */
         const size_t cap = ((nQ + PPP_QTILE - 1) / PPP_QTILE) * PPP_QTILE;
-        CU(cudaMalloc(&ctx->d_Q, cap * 2 * W * 4));
-        CU(cudaMalloc(&ctx->d_qc, cap * sizeof(QConst)));
-        CU(cudaMalloc(&ctx->d_qflags, cap * sizeof(uint32_t)));
-        CU(cudaMalloc(&ctx->d_qorder, cap * sizeof(uint32_t)));
-        ctx->capQ = cap;
+        cudaError_t e;
+        if ((e = cudaMalloc(&ctx->d_Q, cap * 2 * W * 4)) != cudaSuccess || (e = cudaMalloc(&ctx->d_qc, cap * sizeof(QConst))) != cudaSuccess ||
+            (e = cudaMalloc(&ctx->d_qflags, cap * sizeof(uint32_t))) != cudaSuccess ||
+            (e = cudaMalloc(&ctx->d_qorder, cap * sizeof(uint32_t))) != cudaSuccess) {
+            free_query_buffers(ctx); /* no live pointer is left behind a zero capacity */
+            return fail(ctx, e == cudaErrorMemoryAllocation ? PPP_ERR_NOMEM : PPP_ERR_CUDA, "ppp_set_queries: %s", cudaGetErrorString(e));
+        }
+        ctx->capQ = cap; /* only once all four buffers exist */
     }
     ctx->nQ = 0;
     if (!nQ) return PPP_OK;
@@ -506,7 +514,10 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
             ctx->nmax_off_host[q] = (uint32_t)off;
             off += (size_t)qc[q].ny + 1;
         }
-        if (off > 0xfffffff0ull) return fail(ctx, PPP_ERR_INVALID, "ppp_set_queries: staircase tables exceed 4G entries");
+        if (off > 0xfffffff0ull) {
+            cudaStreamSynchronize(ctx->stream); /* the plane upload queued above reads the staging buffer */
+            return fail(ctx, PPP_ERR_INVALID, "ppp_set_queries: staircase tables exceed 4G entries");
+        }
         ctx->nmax_entries = off;
     }
     ctx->toff_host.assign(nQ + 1, 0);
@@ -677,7 +688,7 @@ static int launch_chunk_deferred(ppp_ctx *ctx, SweepParams *prm, uint32_t *launc
     else CU(ppp_launch_exact(prm, W, ctx->nsm, ctx->stream));
     if ((rc = mark(ctx, &e2))) return rc;
     CU(ppp_launch_accumulate(ctx->d_totals, ctx->d_counters, CNT_N + 1, ctx->stream));
-    if (getenv("PPP_B200_DEBUG_CHUNKS")) { /* developer aid: per-chunk counters (synchronises) */
+    if (ctx->debug_chunks) { /* developer aid: per-chunk counters (synchronises) */
         unsigned long long c[CNT_SLOTS];
         CU(cudaMemcpyAsync(c, ctx->d_counters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
@@ -1334,6 +1345,20 @@ extern "C" int ppp_get_stats(const ppp_ctx *ctx, ppp_stats *out)
     return PPP_OK;
 }
 
+extern "C" int ppp_query_count(const ppp_ctx *ctx, size_t *nQ)
+{
+    if (!ctx || !nQ) return PPP_ERR_INVALID;
+    *nQ = ctx->nQ;
+    return PPP_OK;
+}
+
+extern "C" int ppp_row_words(const ppp_ctx *ctx, size_t *words)
+{
+    if (!ctx || !words) return PPP_ERR_INVALID;
+    *words = ctx->G ? ppp_words_per_row(ctx->G) : 0;
+    return PPP_OK;
+}
+
 extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
 {
     if (!ctx || !name) return PPP_ERR_INVALID;
@@ -1409,19 +1434,84 @@ extern "C" int ppp_debug_bdtrc(ppp_ctx *ctx, const int32_t *k, const int32_t *n,
     CU(cudaSetDevice(ctx->device));
     int32_t *dk = nullptr, *dn = nullptr;
     double *dp = nullptr, *dout = nullptr;
-    CU(cudaMalloc(&dk, m * 4));
-    CU(cudaMalloc(&dn, m * 4));
-    CU(cudaMalloc(&dp, m * 8));
-    CU(cudaMalloc(&dout, m * 8));
-    CU(cudaMemcpyAsync(dk, k, m * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dn, n, m * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dp, p, m * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CU(ppp_launch_debug_bdtrc(dk, dn, dp, dout, m, ctx->stream));
-    CU(cudaMemcpyAsync(out, dout, m * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc(&dk, m * 4)) == cudaSuccess && (e = cudaMalloc(&dn, m * 4)) == cudaSuccess && (e = cudaMalloc(&dp, m * 8)) == cudaSuccess &&
+        (e = cudaMalloc(&dout, m * 8)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(dk, k, m * 4, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(dn, n, m * 4, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(dp, p, m * 8, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
+        (e = ppp_launch_debug_bdtrc(dk, dn, dp, dout, m, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(out, dout, m * 8, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess)
+        e = cudaStreamSynchronize(ctx->stream);
     cudaFree(dk);
     cudaFree(dn);
     cudaFree(dp);
     cudaFree(dout);
+    CU(e);
+    return PPP_OK;
+}
+
+extern "C" int ppp_debug_enclosure(ppp_ctx *ctx, const int32_t *y, const int32_t *n, const double *p, float *lo, float *hi, double *lnf,
+                                   size_t m)
+{
+    if (!ctx || !y || !n || !p || !lo || !hi || !lnf) return PPP_ERR_INVALID;
+    if (!m) return PPP_OK;
+    for (size_t i = 0; i < m; ++i)
+        if (y[i] < 1 || n[i] < y[i] || n[i] > 8192 || !(p[i] > 0.0 && p[i] < 1.0))
+            return fail(ctx, PPP_ERR_INVALID, "ppp_debug_enclosure: point %zu outside 1 <= yes <= number <= 8192, 0 < p < 1", i);
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_lf(ctx))) return rc;
+    std::vector<QConst> qc(m);
+    for (size_t i = 0; i < m; ++i) make_qconst(p[i], 0, 0, &qc[i]);
+    QConst *dq = nullptr;
+    int32_t *dy = nullptr, *dn = nullptr;
+    float *dlo = nullptr, *dhi = nullptr;
+    double *dl = nullptr;
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc(&dq, m * sizeof(QConst))) == cudaSuccess && (e = cudaMalloc(&dy, m * 4)) == cudaSuccess &&
+        (e = cudaMalloc(&dn, m * 4)) == cudaSuccess && (e = cudaMalloc(&dlo, m * 4)) == cudaSuccess &&
+        (e = cudaMalloc(&dhi, m * 4)) == cudaSuccess && (e = cudaMalloc(&dl, m * 8)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(dq, qc.data(), m * sizeof(QConst), cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(dy, y, m * 4, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(dn, n, m * 4, cudaMemcpyHostToDevice, ctx->stream)) == cudaSuccess &&
+        (e = ppp_launch_debug_enclosure(dq, ctx->d_lf, dy, dn, dlo, dhi, dl, m, ctx->nsm, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(lo, dlo, m * 4, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(hi, dhi, m * 4, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess &&
+        (e = cudaMemcpyAsync(lnf, dl, m * 8, cudaMemcpyDeviceToHost, ctx->stream)) == cudaSuccess)
+        e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dq);
+    cudaFree(dy);
+    cudaFree(dn);
+    cudaFree(dlo);
+    cudaFree(dhi);
+    cudaFree(dl);
+    CU(e);
+    return PPP_OK;
+}
+
+extern "C" int ppp_pipe_peak(ppp_ctx *ctx, const char *pipe, double *ops_per_s)
+{
+    if (!ctx || !pipe || !ops_per_s) return PPP_ERR_INVALID;
+    int kind = -1;
+    if (!strcmp(pipe, "popc")) kind = 0;
+    else if (!strcmp(pipe, "lop3")) kind = 1;
+    else if (!strcmp(pipe, "iadd")) kind = 2;
+    else if (!strcmp(pipe, "dfma")) kind = 3;
+    if (kind < 0) return fail(ctx, PPP_ERR_INVALID, "ppp_pipe_peak: unknown pipe '%s' (popc, lop3, iadd, dfma)", pipe);
+    CU(cudaSetDevice(ctx->device));
+    /* FP64 and POPC run at 1/8 .. 1/4 of the ALU rate: size every kernel for a few milliseconds */
+    const uint32_t iters = kind == 1 || kind == 2 ? 4096 : 1024;
+    double best = 0.0, lane_ops = 0.0;
+    for (int rep = 0; rep < 4; ++rep) { /* first repetition warms up; best of the rest */
+        CU(cudaEventRecord(ctx->ev[5], ctx->stream));
+        CU(ppp_launch_pipe_peak(kind, iters, reinterpret_cast<uint32_t *>(ctx->d_counters), ctx->nsm, ctx->stream, &lane_ops));
+        CU(cudaEventRecord(ctx->ev[6], ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
+        if (rep && ms > 0.f) best = std::max(best, lane_ops / (1e-3 * (double)ms));
+    }
+    *ops_per_s = best;
     return PPP_OK;
 }

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 from . import capi, packer
-from .algorithm import Profile
+from .algorithm import Profile, perl_num, perl_split_tab
 
 
 def read_bla(path):
@@ -103,6 +103,12 @@ def format_ppp_table(rows, slope=None, desc=None) -> str:
     return "".join(out)
 
 
+def _field5(line: str) -> float:
+    """$f[5] of a table row in numeric context: a missing field is undef = 0 (bin/ppp_cutoff.pl:122, 153)."""
+    f = perl_split_tab(line)
+    return perl_num(f[5]) if len(f) > 5 else 0.0
+
+
 def ppp_cutoff(table_text: str, slope: float):
     """bin/ppp_cutoff.pl:111-162 on the text of a ppp.pl table.  Returns (stdout text, cutoff or None)."""
     lines = table_text.split("\n")
@@ -115,10 +121,10 @@ def ppp_cutoff(table_text: str, slope: float):
             continue
         kept.append(line)
         if not line.startswith("#"):
-            f = line.split("\t")
-            if float(f[5]) > -0.001:
+            v = _field5(line)
+            if v > -0.001:
                 continue
-            scores.append(float(f[5]))
+            scores.append(v)
     cutoff = None
     last = None
     for s in sorted(scores, reverse=True):
@@ -134,8 +140,7 @@ def ppp_cutoff(table_text: str, slope: float):
     out = [header, "Significant hits:\n"]
     marker = False
     for line in kept:
-        f = line.split("\t")
-        v = float(f[5])
+        v = _field5(line)
         if v >= 0:
             continue
         if v > (cutoff if cutoff is not None else 0.0) and not marker:
@@ -195,17 +200,28 @@ def ppp2d_scan(ctx: capi.Context, gi: str, bla_path, genome_targets: dict, taxdi
     ctx.set_targets_ranked(idx, raw, off, len(index))
     k = min(2, len(loci))
     hits = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
+    best = [[(loci[int(h["t"])], float(h["score"]), int(h["yes"]), int(h["number"]), int(h["depth"])) for h in hits[hits["q"] == qi]]
+            for qi in range(len(qs))]
+    return format_ppp2d(gi, qs, best)
+
+
+def format_ppp2d(gi: str, qs, best) -> str:
+    """stdout of bin/ppp2d.pl (:322-364) from the depth-prefix queries `qs` (ppp2d_prefix_queries) and, per query, its best
+    rows [(locus, score, yes, number, depth)] in ppp.pl's order (ascending raw score): the first row that is not the gene
+    itself is kept unless its printed score is 0.000; rows are sorted by printed score."""
+    header = "#Subject_best_depth\tLocus\t#Yes\t#Total\tDepth\tProb\tScore\tDesc\n"
     rows = []
-    for qi, (line_count, tc, _, pq) in enumerate(qs):
-        mine = [h for h in hits[hits["q"] == qi] if loci[int(h["t"])] != gi]
+    for (line_count, tc, _, pq), mine in zip(qs, best):
+        mine = [h for h in mine if h[0] != gi]  # bin/ppp2d.pl:336-338
         if not mine:
             continue
-        h = mine[0]
-        s = _perl_num(float(h["score"]))
-        score_str = _handle_negative_zero(_log10_3f(s))
+        locus, score, yes, number, depth = mine[0]
+        score_str = _handle_negative_zero(_log10_3f(_perl_num(score)))
         if float(score_str) == 0.0:  # bin/ppp2d.pl:340 compares the PRINTED score
             continue
-        fields = [loci[int(h["t"])], str(int(h["yes"])), str(int(h["number"])), str(int(h["depth"])), "%.3f" % _perl_num(pq), score_str, ""]
+        # bin/ppp2d.pl:333-345 splits the ppp.pl row on tabs and joins it again: an empty Desc field (no description
+        # database) is a trailing empty field, which split drops
+        fields = [locus, str(yes), str(number), str(depth), "%.3f" % _perl_num(pq), score_str]
         rows.append((float(score_str), line_count, fields))
     rows.sort(key=lambda r: (r[0], r[1]))
     return header + "".join(f"{lc}\t" + "\t".join(f) + "\n" for _, lc, f in rows)
@@ -310,20 +326,27 @@ def _cross_direction(scorer, src_text, dst_text, gi2taxon, n_taxa, start, end, s
     return best
 
 
-def cross_score_blast(ctx, file1: str, text1: str, file2: str, text2: str, gi2taxon: dict, n_taxa: int, start=1, end=None,
-                      skip=1, scale=1.0, scorer=None) -> str:
-    """bin/ppp_cross_score.pl --method1 blast --method2 blast in process: both directions, each one GPU call over all
-    depth prefixes (the reference writes a temporary profile file and runs the Perl sweep per depth).  Returns the
-    script's stdout text (bin/ppp_cross_score.pl:283-292).  n_taxa = non-comment lines of --dist-file (:299-311)."""
+def format_cross_score(score_lists, file1: str, text1: str, file2: str, text2: str, gi2taxon: dict, n_taxa: int, start=1, end=None,
+                       skip=1, scale=1.0) -> str:
+    """Host logic of bin/ppp_cross_score.pl --method1 blast --method2 blast (:283-292, 415-546) around a list scorer
+    `score_lists(queries, target, probs) -> [(score, yes, number, depth)]`: both directions, depth-prefix queries, the
+    %.3f ranking and the stdout text.  cross_score_blast() below binds it to the GPU."""
     out = []
-    scorer = scorer or _gpu_list_scorer(ctx)  # tests inject the oracle here; the product path is the GPU
     for (which, fa, ta, fb, tb, total) in (("File1", file1, text1, file2, text2, "#Total"), ("File2", file2, text2, file1, text1, "#Toal")):
-        best = _cross_direction(scorer, ta, tb, gi2taxon, n_taxa, start, end, skip, scale)
+        best = _cross_direction(score_lists, ta, tb, gi2taxon, n_taxa, start, end, skip, scale)
         if best is None:
             raise ValueError(f"no depth of {fa} was evaluated")
         out.append(f"{which}: {fa} Best result in {fb}:\nSource_Line:gi\tScore\t#yes\t{total}\t#Depth\t#Prob\n"
                    f"{best[0]}:{best[1]}\t" + "\t".join(str(x) for x in best[2]) + "\n")
     return out[0] + "\n" + out[1]
+
+
+def cross_score_blast(ctx, file1: str, text1: str, file2: str, text2: str, gi2taxon: dict, n_taxa: int, start=1, end=None,
+                      skip=1, scale=1.0) -> str:
+    """bin/ppp_cross_score.pl --method1 blast --method2 blast in process: both directions, each one GPU call over all
+    depth prefixes (the reference writes a temporary profile file and runs the Perl sweep per depth).  Returns the
+    script's stdout text (bin/ppp_cross_score.pl:283-292).  n_taxa = non-comment lines of --dist-file (:299-311)."""
+    return format_cross_score(_gpu_list_scorer(ctx), file1, text1, file2, text2, gi2taxon, n_taxa, start, end, skip, scale)
 
 
 # ------------------------------------------------------------------------------------------------ profile families

@@ -14,6 +14,12 @@ import numpy as np
 
 from .synth import pack_bits, words_per_row
 
+
+def perl_num(v) -> float:
+    from .algorithm import perl_num as f  # the value test of Profile.pm:463 (`!= 0` on Perl scalars)
+
+    return f(v)
+
 FOREIGN = 0xFFFF
 
 
@@ -42,7 +48,7 @@ def pack_queries(queries, index, probs=None):
         yes = total = 0
         for t, v in q.items():
             total += 1
-            isyes = float(v) != 0
+            isyes = perl_num(v) != 0
             yes += isyes
             g = index.get(t)
             if g is not None:

@@ -128,3 +128,32 @@ def test_dup_packing_rule_matches_reference(golden_dir):
         prob = [None, 0.3, 0.05][int(rng.integers(0, 3))]
         want = oracle.score_case(query, tlist, prob, True)
         assert _dup_by_packed_list(query, tlist, prob) == want, (query, tlist, prob)
+
+
+def test_rank_cases_match_reference(golden_dir):
+    """-rank (ppp.pm:328-370): the reference run with a mock -taxonomy object (oracle/gen_golden_rank.py) against the
+    oracle's restatement of the collapse pre-pass; and the croak of ppp.pm:345-349 without a taxonomy."""
+    import pytest
+
+    g = json.load(open(os.path.join(golden_dir, "ppp_rank_cases.json")))
+    assert len(g["cases"]) >= 100
+    differs = 0
+    for c in g["cases"]:
+        got = oracle.score_case(c["query"], c["target"], c.get("prob"), bool(c.get("dup")), rank=c["rank"], collapse=c["collapse"])
+        e = c["expect"]
+        assert got == (float(e[0]), e[1], e[2], e[3], float(e[4])), c["name"]
+        differs += oracle.score_case(c["query"], c["target"], c.get("prob"), bool(c.get("dup")))[:4] != got[:4]
+    assert differs > 50  # the collapse matters in these cases
+    c = g["croak"]
+    with pytest.raises(RuntimeError, match=c["error"]):
+        oracle.score_case(c["query"], c["target"], rank=c["rank"])
+
+
+def test_memoised_batch_equals_plain_batch():
+    """The per-query bdtrc cache of the full-size parity tests changes no result (same loop, pure function)."""
+    for G, kind in ((1024, "mixed"), (4096, "mixed"), (2048, "prefix"), (8192, "family")):
+        P, Y, p = synth.make_queries(G, 5, 300 + G, kind)
+        T = synth.make_targets(G, 150, 400 + G, plant_from=Y, plant_frac=0.1)
+        a, sa = oracle.score_bits_batch(P, Y, p, T, G, nthreads=4)
+        b, sb = oracle.score_bits_batch(P, Y, p, T, G, nthreads=4, memo=True)
+        assert sa == sb and a.tobytes() == b.tobytes(), (G, kind)

@@ -76,3 +76,44 @@ def test_global_topk_two_ranks_gloo(tmp_path):
                         "--master-port", "29611", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_sliced_global_topk_two_ranks_gloo(tmp_path):
+    """The cheap merge: every rank merges only its slice of the queries (all-to-all of the list slices); the slices together
+    equal the global sort.  Uneven query slices (5 queries over 2 ranks) and short lists (counts < k) included."""
+    script = tmp_path / "w2.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np, torch.distributed as dist
+        from prophylo_b200 import parallel
+        from prophylo_b200.capi import HIT_DTYPE
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        nq, k, nt = 5, 6, 9
+        rng = np.random.default_rng(77)
+        h = np.zeros(nq * nt, dtype=HIT_DTYPE)
+        h["q"] = np.repeat(np.arange(nq), nt); h["t"] = np.tile(np.arange(nt), nq)
+        h["score"] = rng.choice([0.0, 1e-9, 0.3, 1.0], size=h.size) * rng.random(h.size).round(1)
+        t0, t1 = parallel.shard_range(nt, rank, world)
+        mine = h[(h["t"] >= t0) & (h["t"] < t1)].copy()
+        mine["t"] -= t0
+        lists = np.zeros((nq, k), dtype=HIT_DTYPE)
+        counts = np.zeros(nq, dtype=np.uint32)
+        for q in range(nq):
+            loc = np.sort(mine[mine["q"] == q], order=["score", "t"])[:k]     # the shard holds fewer than k targets: short lists
+            lists[q, :loc.size] = loc
+            counts[q] = loc.size
+        q0, got = parallel.global_topk_sliced_host(lists, counts, t0, k, nq)
+        a, b = parallel.shard_range(nq, rank, world)
+        assert q0 == a
+        exp = np.concatenate([np.sort(h[h["q"] == q], order=["score", "t"])[:k] for q in range(a, b)])
+        assert np.array_equal(got, exp), (rank, got, exp)
+        dist.barrier(); dist.destroy_process_group()
+        print("ok", rank)
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29613", str(script)], capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("ok") == 2
