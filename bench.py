@@ -137,7 +137,7 @@ def perl_reference_throughput(w, budget_s, nproc):
     from oracle import oracle
 
     G = w["G"]
-    nq, nt = 8, max(8, 4 * nproc)
+    nq, nt = 16, max(16, 32 * nproc)  # more pairs than the budget allows: the workers stop at the budget
     P, Y, p, T = _sample_inputs(w, nq, nt)
     Pb, Yb, Tb = synth.unpack_bits(P, G), synth.unpack_bits(Y, G), synth.unpack_bits(T, G)
     cases = {"queries": [{str(g + 1): int(Yb[q, g]) for g in range(G) if Pb[q, g]} for q in range(nq)], "probs": [float(x) for x in p],

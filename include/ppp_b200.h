@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define PPP_B200_ABI_VERSION 1
+#define PPP_B200_ABI_VERSION 2
 
 typedef struct ppp_ctx ppp_ctx;
 
@@ -84,8 +84,16 @@ typedef struct ppp_stats {
     uint32_t reserved;
 } ppp_stats;
 
-/* Lifetime.  devices/ndev: CUDA ordinals this context may use; this implementation is one process per GPU and
- * uses devices[0] (ndev >= 1).  Returns PPP_OK or a negative code; *out is NULL on failure. */
+/* Lifetime.  devices/ndev: CUDA ordinals this context may use (NULL / 0: device 0).
+ *   ndev == 1  one GPU, one stream: the form a one-process-per-GPU launcher (torchrun + prophylo_b200/parallel.py) uses.
+ *   ndev  > 1  ONE process drives ndev GPUs (replaces the reference's own fan-out, bin/ppp.pl:374-421, 895-922: chunk files
+ *              of 50 targets and forked `ppp.pl --client` workers): the TARGET axis is sharded contiguously over the devices,
+ *              every device keeps its shard resident and receives all queries, the devices score concurrently (one host
+ *              thread and stream each, no exchange), and results are assembled in the caller's buffers exactly as a single
+ *              device would return them -- dense rows by strided copies, threshold hits by a per-query merge, top-k lists
+ *              merged on the devices by query slices over NVLink peer copies.  ppp_printed_cutoffs and ppp_topk_device need
+ *              a single-device context.  A device may be listed more than once (each entry owns a shard).
+ * Returns PPP_OK or a negative code; *out is NULL on failure. */
 int ppp_init(ppp_ctx **out, const int *devices, int ndev);
 void ppp_destroy(ppp_ctx *ctx);
 /* ctx-owned string describing the last failure on ctx (valid until the next call); ctx may be NULL for

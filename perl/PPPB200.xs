@@ -13,13 +13,19 @@ typedef ppp_ctx *PhyloProf__B200__Ctx;
 MODULE = PhyloProf::B200  PACKAGE = PhyloProf::B200
 
 IV
-_init(device)
-    int device
+_init(devices)
+    AV *devices
   CODE:
+    /* one CUDA ordinal = one GPU; several = ONE perl process drives them all (targets sharded by the library) */
     ppp_ctx *ctx = NULL;
-    int dev[1];
-    dev[0] = device;
-    int rc = ppp_init(&ctx, dev, 1);
+    int dev[16];
+    const int n = (int)(av_len(devices) + 1);
+    if (n < 1 || n > 16) croak("PhyloProf::B200: 1 .. 16 devices");
+    for (int i = 0; i < n; ++i) {
+        SV **e = av_fetch(devices, i, 0);
+        dev[i] = e ? (int)SvIV(*e) : 0;
+    }
+    int rc = ppp_init(&ctx, dev, n);
     if (rc != PPP_OK) croak("PhyloProf::B200: %s", ppp_last_error(NULL));
     RETVAL = PTR2IV(ctx);
   OUTPUT:

@@ -9,10 +9,12 @@
 # (ppp_read_bla) and every gene is scored by libppp_b200.so through the XS binding (PhyloProf::B200).
 # There is no CPU fallback.  Written from scratch against the reference's observable behaviour.
 #
-#   perl ppp_b200.pl -d <db dir> -t <taxon> -p <profile> -w <workspace> [--prob P] [-m slope] [--dup] [--device N]
+#   perl ppp_b200.pl -d <db dir> -t <taxon> -p <profile> -w <workspace> [--prob P] [-m slope] [--dup] [--device N | --devices 0-7]
 #
-# Not supported (the script dies; keep bin/ppp.pl for it): -l/--level (rank collapse needs the SeqToolBox taxonomy
-# database).  --dup (bin/ppp.pl:282 -> ppp.pm:189-200) is packed natively (PPP_BLA_DUP) and scored on the device.
+# -l/--level <rank> (bin/ppp.pl:532-547, 566-568): the query profile's taxa and every taxon of every hit list are collapsed
+# to that rank on the host before packing (Profile.pm:516-549, ppp.pm:328-370) through SeqToolBox::Taxonomy, which must be
+# loadable (the reference's lib/ on PERL5LIB and its taxonomy database in place); the caches are then parsed in Perl.
+# --dup (bin/ppp.pl:282 -> ppp.pm:189-200) is packed natively (PPP_BLA_DUP) and scored on the device.
 # --threads/--serial/--keep/-c/-o/-r/-n are accepted and ignored (there are no workers, temporary files or grid jobs).
 use strict;
 use warnings;
@@ -22,12 +24,12 @@ use FindBin;
 use lib "$FindBin::Bin/../lib";
 use PhyloProf::B200;
 
-my ( $help, $db_dir, $workspace, $taxon, $profile, $level, $probability, $slope, $duplicate, $device ) = ( 0, '', '', 0, '', '', 0, 0, 0, 0 );
+my ( $help, $db_dir, $workspace, $taxon, $profile, $level, $probability, $slope, $duplicate, $device, $devices ) = ( 0, '', '', 0, '', '', 0, 0, 0, 0, '' );
 my %ignored;
 GetOptions(
     'help|h'      => \$help,      'db|d=s'   => \$db_dir, 'workspace|w=s' => \$workspace,   'taxon|t=i' => \$taxon,
     'profile|p=s' => \$profile,   'level|l=s' => \$level, 'prob=s'        => \$probability, 'slope|m=s' => \$slope,
-    'dup'         => \$duplicate, 'device=i' => \$device,
+    'dup'         => \$duplicate, 'device=i' => \$device, 'devices=s' => \$devices,
     'project|r=i' => \$ignored{r}, 'nodes|n=i' => \$ignored{n}, 'client' => \$ignored{client}, 'copy|c' => \$ignored{c},
     'output|o=s'  => \$ignored{o}, 'serial'    => \$ignored{serial}, 'threads=i' => \$ignored{threads}, 'gi|g=i' => \$ignored{g},
     'start-depth|s=i' => \$ignored{s}, 'end-depth|e=i' => \$ignored{e}, 'skip|j=i' => \$ignored{j}, 'keep|k' => \$ignored{k},
@@ -36,7 +38,18 @@ die "usage: ppp_b200.pl -d <db> -t <taxon> -p <profile> -w <workspace> [--prob P
 die "File $profile not found\n" unless -s $profile;
 die "Workspace missing\n"       unless $workspace;
 die "ppp_b200.pl: --client is the reference's worker mode; this driver has no workers\n" if $ignored{client};
-die "ppp_b200.pl: -l/--level is not supported on the B200 path (use bin/ppp.pl)\n"       if $level;
+my $collapse = sub { $_[0] };
+if ($level) {
+    eval { require SeqToolBox::Taxonomy; 1 } or die "ppp_b200.pl: -l/--level needs SeqToolBox::Taxonomy on \@INC: $@";
+    my $tax = SeqToolBox::Taxonomy->new();
+    my %memo;
+    $collapse = sub {    # ppp.pm:328-370 / Profile.pm:516-549: the rank, else genus, else the raw id
+        my $t = shift;
+        return $t unless $t;
+        $memo{$t} = $tax->collapse_taxon( $t, $level ) || $tax->collapse_taxon( $t, "genus" ) || $t unless exists $memo{$t};
+        return $memo{$t};
+    };
+}
 
 # ---- the gene caches of the genome (bin/ppp.pl:955-1017 lists them the same way)
 my $blast_dir = File::Spec->catdir( $db_dir, "blast", $taxon );
@@ -59,9 +72,10 @@ while ( my $line = <$pf> ) {
     next if $line =~ /^\#/;
     my @f = split( /\t/, $line );
     die "$profile must contain only two fields\n" if scalar(@f) != 2;
-    next unless $f[0];                                   # a false taxon ('' or '0') is skipped
-    next if exists $q{ $f[0] } && $q{ $f[0] } != 0;
-    $q{ $f[0] } = $f[1];
+    my $taxon = $collapse->( $f[0] );
+    next unless $taxon;                                  # a false taxon ('' or '0') is skipped
+    next if exists $q{$taxon} && $q{$taxon} != 0;
+    $q{$taxon} = $f[1];
 }
 close($pf);
 my $yes   = grep { $_ != 0 } values %q;
@@ -71,8 +85,29 @@ my $p = $probability ? $probability + 0 : $yes / $total;    # ppp.pm:138-142, bi
 
 # ---- one GPU call for the whole genome
 my @universe = sort keys %q;
-my $gpu      = PhyloProf::B200->new( -device => $device );
-my $hits     = $gpu->score_bla_files( \@universe, [ \%q ], \@paths, -probs => [$p], -filter => 'all', -dup => $duplicate );
+my $gpu      = $devices ne '' ? PhyloProf::B200->new( -devices => $devices ) : PhyloProf::B200->new( -device => $device );
+my $hits;
+if ($level) {
+    # rank collapse: the hit lists are read here (bin/ppp.pl:606-673 + BlastResult.pm:192-237: subjects in first-occurrence
+    # order, a subject's last taxon wins, false taxa dropped) and collapsed taxon by taxon before the ranked-list entry
+    my @lists;
+    foreach my $path (@paths) {
+        open( my $bf, "<", $path ) or die "Can't open $path\n";
+        my ( @order, %taxon );
+        while ( my $line = <$bf> ) {
+            chomp $line;
+            my @f = split( /\t/, $line );
+            my $subject = defined $f[1] ? $f[1] : '';
+            push @order, $subject unless exists $taxon{$subject};
+            $taxon{$subject} = $f[3];
+        }
+        close($bf);
+        push @lists, [ map { $collapse->($_) } grep { $_ } map { $taxon{$_} } @order ];
+    }
+    $hits = $gpu->score_ranked( \@universe, [ \%q ], \@lists, -probs => [$p], -filter => 'all', -dup => $duplicate );
+} else {
+    $hits = $gpu->score_bla_files( \@universe, [ \%q ], \@paths, -probs => [$p], -filter => 'all', -dup => $duplicate );
+}
 
 # ---- the table (bin/ppp.pl:443-506).  The reference's clients print score and p with Perl's default %.15g
 # stringification and the server reads them back: reproduce that rounding.

@@ -5,6 +5,7 @@ package PhyloProf::B200;
 # shared objects or without an sm_100 device every entry point croaks.
 #
 #   my $gpu  = PhyloProf::B200->new(-device => 0);                 # after any fork (bin/ppp.pl:910 forks workers)
+#   my $gpu8 = PhyloProf::B200->new(-devices => "0-7");            # one process, eight GPUs
 #   my $hits = $gpu->score_bits(\@universe, \@queries, \@targets, [-filter => 'topk', -k => 100]);
 #
 # Data model (SURVEY.md section 8d): @universe is the ordered taxon list (ascending taxon id as data/taxdis.txt and
@@ -36,8 +37,25 @@ sub _load {
 sub new {
     my ( $class, %a ) = @_;
     _load();
-    my $self = bless { h => _init( $a{-device} || 0 ) }, $class;
+    # -device => N (one GPU) or -devices => [N, M, ...] / "0-3" / "0,2" (one process drives them all: the library shards the
+    # targets over the devices, scores them concurrently and assembles the results; replaces bin/ppp.pl:895-922's forked clients)
+    my $devs = $a{-devices};
+    $devs = parse_devices($devs) if defined $devs && !ref $devs;
+    $devs ||= [ $a{-device} || 0 ];
+    my $self = bless { h => _init($devs), ndev => scalar(@$devs) }, $class;
     return $self;
+}
+
+sub parse_devices {    # "0-7", "0,2,5", "3" -> [ordinals]
+    my $spec = shift;
+    my @d;
+    foreach my $part ( split /,/, $spec ) {
+        if    ( $part =~ /^(\d+)-(\d+)$/ ) { push @d, ( $1 .. $2 ) }
+        elsif ( $part =~ /^\d+$/ )         { push @d, $part + 0 }
+        else                               { croak "PhyloProf::B200: bad device list '$spec'" }
+    }
+    croak "PhyloProf::B200: empty device list" unless @d;
+    return \@d;
 }
 
 sub DESTROY { my $s = shift; _destroy( $s->{h} ) if $s->{h}; $s->{h} = 0 }

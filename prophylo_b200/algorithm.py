@@ -52,6 +52,44 @@ def collapse(taxonomy, rank, taxon, what="Taxonomy does not exist"):
     return taxonomy.collapse_taxon(taxon, rank) or taxonomy.collapse_taxon(taxon, "genus") or taxon
 
 
+class NodesTaxonomy:
+    """collapse_taxon over NCBI `nodes` rows held in memory: {tax_id: (parent_tax_id, rank)} or a 3-column TSV file
+    (tax_id, parent, rank).  Same walk as SeqToolBox::Taxonomy::collapse_taxon (lib/SeqToolBox/Taxonomy.pm:296-360) does
+    against its SQLite copy of nodes.dmp: climb from the id until a node of the wanted rank (case-insensitive) is found;
+    stop at the root (tax_id 1) or at an id with no row -> None."""
+
+    def __init__(self, rows=None, file=None):
+        self.rows = dict(rows or {})
+        if file is not None:
+            with open(file) as fh:
+                for line in fh:
+                    f = line.rstrip("\n").split("\t")
+                    if len(f) >= 3:
+                        self.rows[f[0]] = (f[1], f[2])
+        self._cache = {}
+
+    def collapse_taxon(self, taxon, rank):
+        if not perl_true(taxon):
+            raise ValueError("ERROR: ID not defined")
+        if not rank:
+            raise ValueError("ERROR: RANK not defined")
+        key = (str(taxon), rank.lower())
+        if key in self._cache:
+            return self._cache[key]
+        taxid, found = str(taxon), None
+        while perl_true(taxid) and taxid != "1":
+            row = self.rows.get(taxid)
+            if row is None:
+                break
+            parent, node_rank = row
+            if node_rank is not None and rank.lower() == str(node_rank).lower():
+                found = taxid
+                break
+            taxid = parent
+        self._cache[key] = found
+        return found
+
+
 class Profile:
     """PhyloProf::Profile: a query is a taxon -> 0/1 hash with yes/no counts; a target carrier holds an ordered list
     (ARRAY) or a taxon -> rank hash (HASH) under -raw.  `rank` / `taxonomy` collapse the query's taxa as

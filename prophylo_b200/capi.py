@@ -154,13 +154,15 @@ def make_filter(mode=FILTER_ALL, k=0, thresh=0.0):
 
 
 class Context:
-    """One ppp_ctx = one GPU (one process per GPU). Create after any fork."""
+    """One ppp_ctx.  device = one CUDA ordinal (one GPU, the one-process-per-GPU form) or a list of ordinals (ONE process
+    drives them all: targets sharded over the devices, results assembled by the library).  Create after any fork."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
         self.lib = load()
         self._h = ctypes.c_void_p()
-        dev = (ctypes.c_int * 1)(device)
-        rc = self.lib.ppp_init(ctypes.byref(self._h), dev, 1)
+        devs = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+        dev = (ctypes.c_int * len(devs))(*devs)
+        rc = self.lib.ppp_init(ctypes.byref(self._h), dev, len(devs))
         if rc != PPP_OK:
             raise PPPError(rc, self.lib.ppp_last_error(None).decode())
         self.G = None

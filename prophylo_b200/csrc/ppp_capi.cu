@@ -68,9 +68,17 @@ extern "C" cudaError_t ppp_launch_rank_cutoffs(const ppp_hit *rec, size_t n, uin
 extern "C" cudaError_t ppp_launch_debug_enclosure(const QConst *qc, const double *lf, const int32_t *y, const int32_t *n, float *lo, float *hi,
                                                   double *lnf, size_t m, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_pipe_peak(int kind, uint32_t iters, uint32_t *sink, int nsm, cudaStream_t st, double *lane_ops);
+extern "C" cudaError_t ppp_launch_add_t(void *hits, size_t n, uint32_t off, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const unsigned long long *counters, int n, cudaStream_t st);
 
 struct ppp_ctx {
+    /* multi-device group (ppp_init with ndev > 1): this context owns one single-device context per GPU and shards the
+     * TARGET axis over them; every entry point below dispatches to the group_* functions */
+    std::vector<ppp_ctx *> subs;
+    std::vector<size_t> sub_t0;          /* first global target index of each sub-context's shard, and nT at the end */
+    uint32_t t_base = 0;                 /* (sub-context) added to the target index of every dense / threshold record */
+    uint32_t group_mode = 0, group_k = 0; /* filter mode and k of the group's last run */
+    std::vector<ppp_hit> group_hits;     /* threshold runs of a group: merged on the host */
     int device = 0;
     int nsm = 148;
     cudaStream_t stream = nullptr;
@@ -222,10 +230,20 @@ extern "C" int ppp_abi_version(void) { return PPP_B200_ABI_VERSION; }
 
 extern "C" const char *ppp_last_error(const ppp_ctx *ctx) { return ctx ? ctx->err : g_init_err; }
 
+static int group_init(ppp_ctx **out, const int *devices, int ndev);
+static int group_set_targets_bits(ppp_ctx *g, const uint32_t *T, size_t nT, uint32_t G);
+static int group_set_targets_ranked(ppp_ctx *g, const uint16_t *idx, const uint16_t *rawdepth, const uint64_t *row_off, size_t nT, uint32_t G);
+static int group_set_queries(ppp_ctx *g, const uint32_t *P, const uint32_t *Y, const double *p, size_t nQ);
+static int group_run(ppp_ctx *g, const ppp_filter *f);
+static int group_fetch(ppp_ctx *g, ppp_hit *out, size_t cap, size_t *nout);
+static int group_set_option(ppp_ctx *g, const char *name, int64_t value);
+static int group_get_counter(const ppp_ctx *g, const char *name, int64_t *value);
+
 extern "C" int ppp_init(ppp_ctx **out, const int *devices, int ndev)
 {
     if (!out) return fail(nullptr, PPP_ERR_INVALID, "ppp_init: out is NULL");
     *out = nullptr;
+    if (devices && ndev > 1) return group_init(out, devices, ndev);
     int dev = (devices && ndev > 0) ? devices[0] : 0;
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -271,6 +289,11 @@ extern "C" int ppp_init(ppp_ctx **out, const int *devices, int ndev)
 extern "C" void ppp_destroy(ppp_ctx *ctx)
 {
     if (!ctx) return;
+    if (!ctx->subs.empty()) {
+        for (ppp_ctx *s : ctx->subs) ppp_destroy(s);
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_T);
@@ -338,6 +361,7 @@ static void reset_queries_if_layout_changed(ppp_ctx *ctx, int wpl, uint32_t G);
 
 extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, uint32_t G)
 {
+    if (ctx && !ctx->subs.empty()) return group_set_targets_bits(ctx, T, nT, G);
     if (!ctx) return PPP_ERR_INVALID;
     if (!T && nT) return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_bits: T is NULL");
     if (G == 0 || G > 8192) return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_bits: G = %u outside [1, 8192]", G);
@@ -385,6 +409,7 @@ static void reset_queries_if_layout_changed(ppp_ctx *ctx, int wpl, uint32_t G)
 extern "C" int ppp_set_targets_ranked(ppp_ctx *ctx, const uint16_t *idx, const uint16_t *rawdepth, const uint64_t *row_off,
                                       size_t nT, uint32_t G)
 {
+    if (ctx && !ctx->subs.empty()) return group_set_targets_ranked(ctx, idx, rawdepth, row_off, nT, G);
     if (!ctx) return PPP_ERR_INVALID;
     if (!row_off || (nT && row_off[nT] && (!idx || !rawdepth))) return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_ranked: NULL input");
     if (G == 0 || G > 8192) return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_ranked: G = %u outside [1, 8192]", G);
@@ -452,6 +477,7 @@ static void make_qconst(double p, uint32_t ny, uint32_t npres, QConst *qc)
 
 extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *Y, const double *p, size_t nQ)
 {
+    if (ctx && !ctx->subs.empty()) return group_set_queries(ctx, P, Y, p, nQ);
     if (!ctx) return PPP_ERR_INVALID;
     if (!ctx->wpl) return fail(ctx, PPP_ERR_STATE, "ppp_set_queries: call ppp_set_targets_* first (it fixes G)");
     if (nQ && (!P || !Y || !p)) return fail(ctx, PPP_ERR_INVALID, "ppp_set_queries: NULL input");
@@ -751,6 +777,7 @@ static int run_chunk(ppp_ctx *ctx, SweepParams *prm, unsigned long long *totals,
 
 extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
 {
+    if (ctx && !ctx->subs.empty()) return group_run(ctx, f);
     if (!ctx) return PPP_ERR_INVALID;
     if (!ctx->wpl || !ctx->nT) return fail(ctx, PPP_ERR_STATE, "ppp_run: no targets resident");
     if (!ctx->ranked && !ctx->d_T) return fail(ctx, PPP_ERR_STATE, "ppp_run: no targets resident");
@@ -1190,6 +1217,14 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             }
         }
     }
+    if (ctx->t_base && f->mode != PPP_FILTER_TOPK) { /* sub-context of a group: records carry global target numbers (top-k: the merge adds them) */
+        if (ctx->results_on_host) {
+            for (ppp_hit &h : ctx->host_results) h.t += ctx->t_base;
+        } else {
+            CU(ppp_launch_add_t(ctx->results_ranked ? ctx->d_ranked : ctx->d_hits, ctx->n_results, ctx->t_base, ctx->nsm, ctx->stream));
+            launches++;
+        }
+    }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     float total_ms = 0.f;
@@ -1216,6 +1251,7 @@ extern "C" int ppp_result_count(ppp_ctx *ctx, size_t *nout)
 
 extern "C" int ppp_fetch(ppp_ctx *ctx, ppp_hit *out, size_t cap, size_t *nout)
 {
+    if (ctx && !ctx->subs.empty()) return group_fetch(ctx, out, cap, nout);
     if (!ctx) return PPP_ERR_INVALID;
     if (nout) *nout = ctx->n_results;
     if (cap < ctx->n_results) return fail(ctx, PPP_ERR_CAPACITY, "ppp_fetch: need room for %zu hits, got %zu", ctx->n_results, cap);
@@ -1259,6 +1295,7 @@ extern "C" int ppp_score(ppp_ctx *ctx, const uint32_t *P, const uint32_t *Y, con
 
 extern "C" int ppp_topk_device(ppp_ctx *ctx, const ppp_hit **lists, const uint32_t **counts, uint32_t *k, size_t *nQ)
 {
+    if (ctx && !ctx->subs.empty()) return fail(ctx, PPP_ERR_STATE, "ppp_topk_device: a multi-device context merges its lists itself (ppp_fetch)");
     if (!ctx || !lists || !counts || !k || !nQ) return PPP_ERR_INVALID;
     if (!ctx->last_topk_k) return fail(ctx, PPP_ERR_STATE, "ppp_topk_device: the last run was not a top-k run");
     *lists = ctx->d_topk;
@@ -1268,12 +1305,10 @@ extern "C" int ppp_topk_device(ppp_ctx *ctx, const ppp_hit **lists, const uint32
     return PPP_OK;
 }
 
-extern "C" int ppp_merge_topk_device(ppp_ctx *ctx, const ppp_hit *lists, const uint32_t *counts, uint32_t nlists,
-                                     const uint32_t *t_offsets, size_t nQ, uint32_t k, ppp_hit *out, uint32_t *out_counts)
+/* merge `nlists` device-resident lists into ctx->d_mtopk [nQ][k] / ctx->d_mcnt [nQ] (on ctx's device and stream; no sync) */
+static int merge_lists_on_device(ppp_ctx *ctx, const ppp_hit *lists, const uint32_t *counts, uint32_t nlists, const uint32_t *t_offsets,
+                                 size_t nQ, uint32_t k)
 {
-    if (!ctx || !lists || !counts || !t_offsets || !out || !out_counts || !nlists || !nQ) return PPP_ERR_INVALID;
-    if (k == 0 || (int)k > ppp_topk_max_k()) return fail(ctx, PPP_ERR_INVALID, "ppp_merge_topk_device: k out of range");
-    CU(cudaSetDevice(ctx->device));
     int rc;
     if ((rc = grow(ctx, &ctx->d_mtopk, &ctx->cap_mtopk, nQ * (size_t)k))) return rc;
     if ((rc = grow(ctx, &ctx->d_mkth, &ctx->cap_mkth, nQ))) return rc;
@@ -1291,6 +1326,18 @@ extern "C" int ppp_merge_topk_device(ppp_ctx *ctx, const ppp_hit *lists, const u
     } else {
         CU(me);
     }
+    return PPP_OK;
+}
+
+extern "C" int ppp_merge_topk_device(ppp_ctx *ctx, const ppp_hit *lists, const uint32_t *counts, uint32_t nlists,
+                                     const uint32_t *t_offsets, size_t nQ, uint32_t k, ppp_hit *out, uint32_t *out_counts)
+{
+    if (!ctx || !lists || !counts || !t_offsets || !out || !out_counts || !nlists || !nQ) return PPP_ERR_INVALID;
+    if (!ctx->subs.empty()) ctx = ctx->subs[0];
+    if (k == 0 || (int)k > ppp_topk_max_k()) return fail(ctx, PPP_ERR_INVALID, "ppp_merge_topk_device: k out of range");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = merge_lists_on_device(ctx, lists, counts, nlists, t_offsets, nQ, k))) return rc;
     CU(cudaMemcpyAsync(out, ctx->d_mtopk, nQ * (size_t)k * sizeof(ppp_hit), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaMemcpyAsync(out_counts, ctx->d_mcnt, nQ * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -1301,6 +1348,7 @@ extern "C" int ppp_merge_topk_device(ppp_ctx *ctx, const ppp_hit *lists, const u
  * iterations, word-level passes.  The first call arms the counters. */
 extern "C" int ppp_debug_pf2stats(ppp_ctx *ctx, unsigned long long *out8, int reset)
 {
+    if (ctx && !ctx->subs.empty()) ctx = ctx->subs[0];
     if (!ctx || !out8) return PPP_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     if (!ctx->d_pfstats) {
@@ -1315,6 +1363,7 @@ extern "C" int ppp_debug_pf2stats(ppp_ctx *ctx, unsigned long long *out8, int re
 extern "C" int ppp_printed_cutoffs(ppp_ctx *ctx, double slope, uint64_t *row_off, int32_t *milli, int32_t *marker, int32_t *cutoff_milli,
                                    uint8_t *status)
 {
+    if (ctx && !ctx->subs.empty()) return fail(ctx, PPP_ERR_STATE, "ppp_printed_cutoffs: needs a single-device context (the hits of a group are ranked on the host)");
     if (!ctx || !marker || !cutoff_milli || !status) return PPP_ERR_INVALID;
     if (!ctx->results_ranked) return fail(ctx, PPP_ERR_STATE, "ppp_printed_cutoffs: the last run was not a threshold run ranked on the device");
     if (isnan(slope)) return fail(ctx, PPP_ERR_INVALID, "ppp_printed_cutoffs: slope is NaN");
@@ -1361,6 +1410,7 @@ extern "C" int ppp_row_words(const ppp_ctx *ctx, size_t *words)
 
 extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
 {
+    if (ctx && !ctx->subs.empty()) return group_set_option(ctx, name, value);
     if (!ctx || !name) return PPP_ERR_INVALID;
     if (!strcmp(name, "force_exact")) ctx->force_exact = value != 0;
     else if (!strcmp(name, "check_bounds")) ctx->check_bounds = value != 0;
@@ -1403,6 +1453,7 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
 
 extern "C" int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *value)
 {
+    if (ctx && !ctx->subs.empty()) return group_get_counter(ctx, name, value);
     if (!ctx || !name || !value) return PPP_ERR_INVALID;
     int i = -1;
     if (!strcmp(name, "exact_pairs")) i = CNT_EXACT;
@@ -1429,6 +1480,7 @@ extern "C" int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *va
 
 extern "C" int ppp_debug_bdtrc(ppp_ctx *ctx, const int32_t *k, const int32_t *n, const double *p, double *out, size_t m)
 {
+    if (ctx && !ctx->subs.empty()) ctx = ctx->subs[0];
     if (!ctx || !k || !n || !p || !out) return PPP_ERR_INVALID;
     if (!m) return PPP_OK;
     CU(cudaSetDevice(ctx->device));
@@ -1454,6 +1506,7 @@ extern "C" int ppp_debug_bdtrc(ppp_ctx *ctx, const int32_t *k, const int32_t *n,
 extern "C" int ppp_debug_enclosure(ppp_ctx *ctx, const int32_t *y, const int32_t *n, const double *p, float *lo, float *hi, double *lnf,
                                    size_t m)
 {
+    if (ctx && !ctx->subs.empty()) ctx = ctx->subs[0];
     if (!ctx || !y || !n || !p || !lo || !hi || !lnf) return PPP_ERR_INVALID;
     if (!m) return PPP_OK;
     for (size_t i = 0; i < m; ++i)
@@ -1492,6 +1545,7 @@ extern "C" int ppp_debug_enclosure(ppp_ctx *ctx, const int32_t *y, const int32_t
 
 extern "C" int ppp_pipe_peak(ppp_ctx *ctx, const char *pipe, double *ops_per_s)
 {
+    if (ctx && !ctx->subs.empty()) ctx = ctx->subs[0];
     if (!ctx || !pipe || !ops_per_s) return PPP_ERR_INVALID;
     int kind = -1;
     if (!strcmp(pipe, "popc")) kind = 0;
@@ -1513,5 +1567,305 @@ extern "C" int ppp_pipe_peak(ppp_ctx *ctx, const char *pipe, double *ops_per_s)
         if (rep && ms > 0.f) best = std::max(best, lane_ops / (1e-3 * (double)ms));
     }
     *ops_per_s = best;
+    return PPP_OK;
+}
+
+/* ================================================================================================ multi-device group
+ * ppp_init(devices, ndev > 1): ONE process drives ndev GPUs (replaces the reference's own fan-out over worker processes,
+ * /root/reference/bin/ppp.pl:374-421, 895-922: chunk files of 50 targets and forked `ppp.pl --client` workers).  The group
+ * shards the TARGET axis contiguously over its devices; every device holds its shard resident and receives all queries;
+ * the devices run concurrently, each driven by its own host thread on its own stream, with no exchange while scoring.
+ * Results: dense and threshold hits are assembled on the host (strided D2H copies / per-query merge of the devices' ranked
+ * runs); top-k lists are merged on the devices by QUERY slices -- device d pulls every device's lists of its slice over
+ * NVLink peer copies (cudaMemcpyPeerAsync), merges them with the list-merge kernel and copies its slice of the global
+ * lists straight into the caller's buffer, so the ndev D2H copies use ndev PCIe links at once. */
+template <typename F>
+static int for_each_sub(ppp_ctx *g, F fn)
+{
+    const size_t n = g->subs.size();
+    std::vector<int> rc(n, PPP_OK);
+    std::vector<std::thread> th;
+    for (size_t i = 1; i < n; ++i) th.emplace_back([&, i] { rc[i] = fn(g->subs[i], i); });
+    rc[0] = fn(g->subs[0], 0);
+    for (std::thread &t : th) t.join();
+    for (size_t i = 0; i < n; ++i)
+        if (rc[i]) {
+            snprintf(g->err, sizeof(g->err), "device %d: %.480s", g->subs[i]->device, g->subs[i]->err);
+            return rc[i];
+        }
+    return PPP_OK;
+}
+
+static int group_init(ppp_ctx **out, const int *devices, int ndev)
+{
+    if (ndev > 16) return fail(nullptr, PPP_ERR_INVALID, "ppp_init: at most 16 devices per context");
+    /* a device may be listed more than once: every entry owns its own shard, stream and buffers (that is how the 1-GPU test
+     * box exercises the group code) */
+    ppp_ctx *g = new (std::nothrow) ppp_ctx();
+    if (!g) return fail(nullptr, PPP_ERR_NOMEM, "ppp_init: out of host memory");
+    memset(&g->stats, 0, sizeof(g->stats));
+    memset(g->last_counters, 0, sizeof(g->last_counters));
+    for (int i = 0; i < ndev; ++i) {
+        ppp_ctx *s = nullptr;
+        const int rc = ppp_init(&s, devices + i, 1);
+        if (rc) {
+            ppp_destroy(g);
+            return rc; /* g_init_err holds the message */
+        }
+        g->subs.push_back(s);
+    }
+    /* NVLink / NVSwitch peer access for the list merge (cudaMemcpyPeerAsync falls back to staging through the host without it) */
+    for (int i = 0; i < ndev; ++i)
+        for (int j = 0; j < ndev; ++j) {
+            int can = 0;
+            if (devices[i] != devices[j] && cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) == cudaSuccess && can) {
+                cudaSetDevice(devices[i]);
+                if (cudaDeviceEnablePeerAccess(devices[j], 0) != cudaSuccess) (void)cudaGetLastError(); /* already enabled */
+            }
+        }
+    g->device = devices[0];
+    g->nsm = g->subs[0]->nsm;
+    *out = g;
+    return PPP_OK;
+}
+
+static void group_shard(ppp_ctx *g, size_t nT)
+{
+    const size_t n = g->subs.size(), base = nT / n, rem = nT % n;
+    g->sub_t0.assign(n + 1, 0);
+    for (size_t i = 0; i < n; ++i) g->sub_t0[i + 1] = g->sub_t0[i] + base + (i < rem ? 1 : 0);
+}
+
+static int group_set_targets_bits(ppp_ctx *g, const uint32_t *T, size_t nT, uint32_t G)
+{
+    if (!T && nT) return fail(g, PPP_ERR_INVALID, "ppp_set_targets_bits: T is NULL");
+    if (nT > 0xffffffffull) return fail(g, PPP_ERR_INVALID, "ppp_set_targets_bits: nT too large");
+    group_shard(g, nT);
+    const size_t wpr = ppp_words_per_row(G);
+    g->nT = 0;
+    const int rc = for_each_sub(g, [&](ppp_ctx *s, size_t i) {
+        s->t_base = (uint32_t)g->sub_t0[i];
+        return ppp_set_targets_bits(s, T ? T + g->sub_t0[i] * wpr : nullptr, g->sub_t0[i + 1] - g->sub_t0[i], G);
+    });
+    if (rc) return rc;
+    g->nT = nT;
+    g->G = G;
+    g->wpl = g->subs[0]->wpl;
+    g->ranked = false;
+    g->nQ = g->subs[0]->nQ; /* 0 if the layout changed */
+    return PPP_OK;
+}
+
+static int group_set_targets_ranked(ppp_ctx *g, const uint16_t *idx, const uint16_t *rawdepth, const uint64_t *row_off, size_t nT, uint32_t G)
+{
+    if (!row_off) return fail(g, PPP_ERR_INVALID, "ppp_set_targets_ranked: NULL input");
+    if (nT > 0xffffffffull) return fail(g, PPP_ERR_INVALID, "ppp_set_targets_ranked: nT too large");
+    for (size_t t = 0; t < nT; ++t)
+        if (row_off[t + 1] < row_off[t]) return fail(g, PPP_ERR_INVALID, "ppp_set_targets_ranked: row_off not monotone at %zu", t);
+    group_shard(g, nT);
+    g->nT = 0;
+    const int rc = for_each_sub(g, [&](ppp_ctx *s, size_t i) {
+        const size_t a = g->sub_t0[i], b = g->sub_t0[i + 1];
+        std::vector<uint64_t> off(b - a + 1);
+        for (size_t t = a; t <= b; ++t) off[t - a] = row_off[t] - row_off[a];
+        s->t_base = (uint32_t)a;
+        return ppp_set_targets_ranked(s, idx ? idx + row_off[a] : nullptr, rawdepth ? rawdepth + row_off[a] : nullptr, off.data(), b - a, G);
+    });
+    if (rc) return rc;
+    g->nT = nT;
+    g->G = G;
+    g->wpl = g->subs[0]->wpl;
+    g->ranked = true;
+    g->nQ = g->subs[0]->nQ;
+    return PPP_OK;
+}
+
+static int group_set_queries(ppp_ctx *g, const uint32_t *P, const uint32_t *Y, const double *p, size_t nQ)
+{
+    if (!g->wpl) return fail(g, PPP_ERR_STATE, "ppp_set_queries: call ppp_set_targets_* first (it fixes G)");
+    g->nQ = 0;
+    const int rc = for_each_sub(g, [&](ppp_ctx *s, size_t) { return ppp_set_queries(s, P, Y, p, nQ); });
+    if (rc) return rc;
+    g->nQ = nQ;
+    return PPP_OK;
+}
+
+static int group_run(ppp_ctx *g, const ppp_filter *f)
+{
+    if (!g->wpl || !g->nT) return fail(g, PPP_ERR_STATE, "ppp_run: no targets resident");
+    if (!g->nQ) return fail(g, PPP_ERR_STATE, "ppp_run: no queries resident");
+    ppp_filter all = {PPP_FILTER_ALL, 0, 0.0};
+    if (!f) f = &all;
+    const size_t nQ = g->nQ, nd = g->subs.size();
+    g->group_mode = f->mode;
+    g->group_k = f->k;
+    g->group_hits.clear();
+    g->topk_counts.clear();
+    ppp_filter fs = *f;
+    int rc = for_each_sub(g, [&](ppp_ctx *s, size_t) {
+        if (!s->nT) { /* fewer targets than devices: this device holds none */
+            s->n_results = 0;
+            s->last_topk_k = 0;
+            memset(&s->stats, 0, sizeof(s->stats));
+            return (int)PPP_OK;
+        }
+        return ppp_run(s, &fs);
+    });
+    if (rc) return rc;
+    if (f->mode == PPP_FILTER_ALL) {
+        g->n_results = nQ * g->nT;
+    } else if (f->mode == PPP_FILTER_THRESH_LOG10) {
+        /* every device's hits are ranked by (query, score, target) with global target numbers: merge the runs per query */
+        std::vector<std::vector<ppp_hit>> part(nd);
+        rc = for_each_sub(g, [&](ppp_ctx *s, size_t i) {
+            part[i].resize(s->n_results);
+            size_t n = 0;
+            return s->n_results ? ppp_fetch(s, part[i].data(), part[i].size(), &n) : (int)PPP_OK;
+        });
+        if (rc) return rc;
+        size_t total = 0;
+        for (const auto &v : part) total += v.size();
+        g->group_hits.resize(total);
+        std::vector<size_t> pos(nd, 0);
+        size_t o = 0;
+        for (size_t q = 0; q < nQ; ++q) {
+            const size_t q_begin = o;
+            for (size_t i = 0; i < nd; ++i) { /* shards are in ascending target order: ties on the score stay ordered by target */
+                const size_t a = pos[i];
+                size_t b = a;
+                while (b < part[i].size() && part[i][b].q == q) ++b;
+                if (b > a) {
+                    memcpy(g->group_hits.data() + o, part[i].data() + a, (b - a) * sizeof(ppp_hit));
+                    std::inplace_merge(g->group_hits.begin() + q_begin, g->group_hits.begin() + o, g->group_hits.begin() + o + (b - a), hit_less);
+                    o += b - a;
+                }
+                pos[i] = b;
+            }
+        }
+        g->n_results = total;
+    } else {
+        /* top-k: device d merges the queries [q0, q1) of its slice from every device's lists (peer copies over NVLink) */
+        const uint32_t k = f->k;
+        g->topk_counts.assign(nQ, 0);
+        std::vector<uint32_t> offs(nd);
+        std::vector<size_t> src; /* devices that hold targets */
+        for (size_t i = 0; i < nd; ++i)
+            if (g->subs[i]->nT) {
+                offs[src.size()] = (uint32_t)g->sub_t0[i];
+                src.push_back(i);
+            }
+        rc = for_each_sub(g, [&](ppp_ctx *s, size_t d) {
+            const size_t q0 = nQ * d / nd, q1 = nQ * (d + 1) / nd, ns = q1 - q0;
+            if (!ns) return (int)PPP_OK;
+            ppp_ctx *ctx = s;
+            CU(cudaSetDevice(s->device));
+            int r;
+            /* gathered slices: [src][ns][k] records in d_acc, [src][ns] counts behind them */
+            const size_t rec_words = src.size() * ns * (size_t)k;
+            if ((r = grow(s, &s->d_acc, &s->cap_acc, rec_words + (src.size() * ns * sizeof(uint32_t) + sizeof(ppp_hit) - 1) / sizeof(ppp_hit)))) return r;
+            uint32_t *g_cnt = reinterpret_cast<uint32_t *>(s->d_acc + rec_words);
+            for (size_t j = 0; j < src.size(); ++j) {
+                ppp_ctx *o = g->subs[src[j]];
+                const uint32_t *o_cnt = o->d_qcnt + o->last_topk_nq;
+                CU(cudaMemcpyPeerAsync(s->d_acc + j * ns * k, s->device, o->d_topk + q0 * k, o->device, ns * (size_t)k * sizeof(ppp_hit), s->stream));
+                CU(cudaMemcpyPeerAsync(g_cnt + j * ns, s->device, o_cnt + q0, o->device, ns * sizeof(uint32_t), s->stream));
+            }
+            if ((r = merge_lists_on_device(s, s->d_acc, g_cnt, (uint32_t)src.size(), offs.data(), ns, k))) return r;
+            CU(cudaMemcpyAsync(g->topk_counts.data() + q0, s->d_mcnt, ns * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            return (int)PPP_OK;
+        });
+        if (rc) return rc;
+        size_t n = 0;
+        for (size_t q = 0; q < nQ; ++q) n += g->topk_counts[q];
+        g->n_results = n;
+    }
+    /* statistics: work summed over the devices, times = the slowest device */
+    memset(&g->stats, 0, sizeof(g->stats));
+    memset(g->last_counters, 0, sizeof(g->last_counters));
+    for (ppp_ctx *s : g->subs) {
+        if (!s->nT) continue;
+        g->stats.candidates += s->stats.candidates;
+        g->stats.accurate_evals += s->stats.accurate_evals;
+        g->stats.exact_pairs += s->stats.exact_pairs;
+        g->stats.kernel_launches += s->stats.kernel_launches;
+        g->stats.sweep_launches += s->stats.sweep_launches;
+        g->stats.sweep_kernel_ms = std::max(g->stats.sweep_kernel_ms, s->stats.sweep_kernel_ms);
+        g->stats.total_device_ms = std::max(g->stats.total_device_ms, s->stats.total_device_ms);
+        for (int i = 0; i < CNT_N; ++i) g->last_counters[i] += s->last_counters[i];
+    }
+    g->stats.pairs = (uint64_t)nQ * g->nT;
+    return PPP_OK;
+}
+
+static int group_fetch(ppp_ctx *g, ppp_hit *out, size_t cap, size_t *nout)
+{
+    if (nout) *nout = g->n_results;
+    if (cap < g->n_results) return fail(g, PPP_ERR_CAPACITY, "ppp_fetch: need room for %zu hits, got %zu", g->n_results, cap);
+    if (!g->n_results) return PPP_OK;
+    if (!out) return fail(g, PPP_ERR_INVALID, "ppp_fetch: out is NULL");
+    const size_t nQ = g->nQ, nd = g->subs.size();
+    if (g->group_mode == PPP_FILTER_THRESH_LOG10) {
+        memcpy(out, g->group_hits.data(), g->n_results * sizeof(ppp_hit));
+        return PPP_OK;
+    }
+    if (g->group_mode == PPP_FILTER_ALL) {
+        /* dense out[q * nT + t]: device i's [nQ][nT_i] block goes to columns [t0_i, t0_i + nT_i) of every row */
+        return for_each_sub(g, [&](ppp_ctx *s, size_t i) {
+            ppp_ctx *ctx = s;
+            const size_t w = g->sub_t0[i + 1] - g->sub_t0[i];
+            if (!w) return (int)PPP_OK;
+            CU(cudaSetDevice(s->device));
+            CU(cudaMemcpy2DAsync(out + g->sub_t0[i], g->nT * sizeof(ppp_hit), s->d_hits, w * sizeof(ppp_hit), w * sizeof(ppp_hit), nQ,
+                                 cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            return (int)PPP_OK;
+        });
+    }
+    const size_t k = g->group_k;
+    std::vector<size_t> prefix(nQ + 1, 0);
+    for (size_t q = 0; q < nQ; ++q) prefix[q + 1] = prefix[q] + g->topk_counts[q];
+    return for_each_sub(g, [&](ppp_ctx *s, size_t d) {
+        ppp_ctx *ctx = s;
+        const size_t q0 = nQ * d / nd, q1 = nQ * (d + 1) / nd, ns = q1 - q0;
+        if (!ns) return (int)PPP_OK;
+        CU(cudaSetDevice(s->device));
+        if (prefix[q1] - prefix[q0] == ns * k) { /* every list of the slice is full: straight into the caller's buffer */
+            CU(cudaMemcpyAsync(out + prefix[q0], s->d_mtopk, ns * k * sizeof(ppp_hit), cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+        } else {
+            std::vector<ppp_hit> lists(ns * k);
+            CU(cudaMemcpyAsync(lists.data(), s->d_mtopk, lists.size() * sizeof(ppp_hit), cudaMemcpyDeviceToHost, s->stream));
+            CU(cudaStreamSynchronize(s->stream));
+            for (size_t q = q0; q < q1; ++q) memcpy(out + prefix[q], lists.data() + (q - q0) * k, g->topk_counts[q] * sizeof(ppp_hit));
+        }
+        return (int)PPP_OK;
+    });
+}
+
+static int group_set_option(ppp_ctx *g, const char *name, int64_t value)
+{
+    for (ppp_ctx *s : g->subs) {
+        const int rc = ppp_set_option(s, name, value);
+        if (rc) {
+            snprintf(g->err, sizeof(g->err), "%s", s->err);
+            return rc;
+        }
+    }
+    return PPP_OK;
+}
+
+static int group_get_counter(const ppp_ctx *g, const char *name, int64_t *value)
+{
+    /* times ("us_*") and per-run settings = the maximum over the devices; work counters = the sum */
+    const bool is_max = !strncmp(name, "us_", 3) || !strcmp(name, "num_sms") || !strcmp(name, "used_table") || !strcmp(name, "spec_rank");
+    int64_t acc = 0;
+    for (const ppp_ctx *s : g->subs) {
+        int64_t v = 0;
+        const int rc = ppp_get_counter(s, name, &v);
+        if (rc) return rc;
+        acc = is_max ? std::max(acc, v) : acc + v;
+    }
+    *value = acc;
     return PPP_OK;
 }

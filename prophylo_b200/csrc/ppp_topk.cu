@@ -344,6 +344,19 @@ extern "C" cudaError_t ppp_launch_topk_merge_lists(const void *lists, const uint
     return cudaGetLastError();
 }
 
+/* shift the target index of n records (a sub-context of a multi-device group reports global target numbers) */
+__global__ void ppp_add_t_kernel(ppp_hit *__restrict__ hits, size_t n, uint32_t off)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) hits[i].t += off;
+}
+
+extern "C" cudaError_t ppp_launch_add_t(void *hits, size_t n, uint32_t off, int nsm, cudaStream_t st)
+{
+    if (!n || !off) return cudaSuccess;
+    ppp_add_t_kernel<<<nsm * 8, 256, 0, st>>>(reinterpret_cast<ppp_hit *>(hits), n, off);
+    return cudaGetLastError();
+}
+
 __global__ void ppp_accumulate_kernel(unsigned long long *totals, const unsigned long long *counters, int n)
 {
     if ((int)threadIdx.x < n) totals[threadIdx.x] += counters[threadIdx.x];

@@ -34,11 +34,15 @@ def read_bla(path):
     return [taxon[s] for s in order if taxon[s] not in ("", "0")]
 
 
-def ppp_scan(ctx: capi.Context, query: Profile, targets: dict, prob=None, dup=False):
+def ppp_scan(ctx: capi.Context, query: Profile, targets: dict, prob=None, dup=False, level=None, taxonomy=None):
     """Score one query profile against every target hit list in ONE GPU call (replaces the chunk files, forked
     `ppp.pl --client` workers and per-gene Perl sweeps of bin/ppp.pl:354-462, 519-593).
     targets: {locus: path of a .bla file | ordered taxon list}.  dup: the --dup flag of bin/ppp.pl:282 (ppp.pm:189-200,
-    see packer.pack_ranked_targets).  Returns [(locus, score, yes, number, depth, p)]."""
+    see packer.pack_ranked_targets).  level / taxonomy: the -l <rank> option (bin/ppp.pl:532-547, 566-568): every taxon of
+    every hit list is collapsed to that rank on the host before packing (ppp.pm:328-370); the caller builds `query` with the
+    same rank and taxonomy, as the reference's client does.  Returns [(locus, score, yes, number, depth, p)]."""
+    from .algorithm import collapse
+
     q = query.get_hash()
     loci = list(targets)
     p = float(prob) if prob else query.get_yes() / query.get_total()  # bin/ppp.pl:559-572, ppp.pm:138-142
@@ -46,7 +50,12 @@ def ppp_scan(ctx: capi.Context, query: Profile, targets: dict, prob=None, dup=Fa
         return []
     index = packer.universe_index(list(q.keys()))
     P, Y, _ = packer.pack_queries([q], index)
-    if all(isinstance(t, (str, os.PathLike)) for t in targets.values()):
+    if level:
+        if taxonomy is None:
+            raise RuntimeError("Taxonomy does not exist")  # ppp.pm:345-349
+        lists = [[collapse(taxonomy, level, t) for t in (read_bla(x) if isinstance(x, (str, os.PathLike)) else list(x))] for x in targets.values()]
+        idx, raw, off = packer.pack_ranked_targets(lists, index, dup=bool(dup))
+    elif all(isinstance(t, (str, os.PathLike)) for t in targets.values()):
         # a genome's worth of cache files: the native multi-threaded reader (csrc/ppp_bla.cpp) parses, de-duplicates and
         # maps them straight into the arrays of ppp_set_targets_ranked
         idx, raw, off = capi.read_bla_files(list(targets.values()), list(index), dup=bool(dup))

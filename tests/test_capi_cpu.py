@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), s
     assert set(syms) == set(capi.EXPORTS)
-    assert lib.ppp_abi_version() == 1
+    assert lib.ppp_abi_version() == 2
     assert lib.ppp_words_per_row(1024) == 32 and lib.ppp_words_per_row(1459) == 48 and lib.ppp_words_per_row(1) == 4
 
 

@@ -23,6 +23,24 @@ def e2e_dup(golden_dir):
     return json.load(open(os.path.join(golden_dir, "ppp_pl_e2e_dup.json")))["cases"]
 
 
+@pytest.fixture(scope="module")
+def e2e_level(golden_dir):
+    """bin/ppp.pl -l <rank> run unmodified, SeqToolBox::Taxonomy::collapse_taxon answered from a synthetic NCBI nodes table
+    (gen_golden_e2e.py --level)"""
+    return json.load(open(os.path.join(golden_dir, "ppp_pl_e2e_level.json")))["cases"]
+
+
+def nodes_taxonomy(case):
+    from prophylo_b200.algorithm import NodesTaxonomy
+
+    rows = {}
+    for line in case["nodes"].split("\n"):
+        f = line.split("\t")
+        if len(f) == 3:
+            rows[f[0]] = (f[1], f[2])
+    return NodesTaxonomy(rows)
+
+
 def materialise(case, tmp_path):
     d = tmp_path / f"case{case['seed']}"
     (d / "bla").mkdir(parents=True)
@@ -92,6 +110,66 @@ def test_dup_table_matches_reference_with_oracle_scores(e2e_dup, tmp_path):
             plain.append((gi,) + oracle.score_case(qd, lst, case["prob"], False))
         assert normalise(drivers.format_ppp_table(rows, slope=case["slope"])) == normalise(case["ppp_pl_stdout"]), case["seed"]
         assert normalise(drivers.format_ppp_table(plain, slope=case["slope"])) != normalise(case["ppp_pl_stdout"])
+
+
+def test_level_table_matches_reference_with_oracle_scores(e2e_level, tmp_path):
+    """CPU: `ppp.pl -l <rank>` -- the query profile and every hit list collapsed through the taxonomy (Profile.pm:516-549,
+    ppp.pm:328-370: the rank, else genus, else the raw id), scored by the oracle -- equals the unmodified script's stdout."""
+    from prophylo_b200.algorithm import collapse
+
+    for case in e2e_level:
+        prof, paths = materialise(case, tmp_path)
+        tax = nodes_taxonomy(case)
+        q = Profile(file=prof, rank=case["level"], taxonomy=tax)
+        qd = {k: int(v) for k, v in q.get_hash().items()}
+        rows, raw_rows = [], []
+        for gi, path in paths.items():
+            lst = drivers.read_bla(path)
+            rows.append((gi,) + oracle.score_case(qd, [collapse(tax, case["level"], t) for t in lst], case["prob"], case["dup"]))
+            raw_rows.append((gi,) + oracle.score_case(qd, lst, case["prob"], case["dup"]))
+        assert normalise(drivers.format_ppp_table(rows, slope=case["slope"])) == normalise(case["ppp_pl_stdout"]), case["seed"]
+        assert normalise(drivers.format_ppp_table(raw_rows, slope=case["slope"])) != normalise(case["ppp_pl_stdout"])  # the collapse matters
+
+
+@pytest.mark.gpu
+def test_level_scan_on_gpu_and_perl_cli_reproduce_ppp_pl_stdout(e2e_level, tmp_path):
+    """-l <rank> through both hosts: drivers.ppp_scan(level=, taxonomy=) and `perl/bin/ppp_b200.pl -l <rank>` (with a test stub
+    of SeqToolBox::Taxonomy on PERL5LIB walking the same nodes table) against the unmodified reference script's stdout."""
+    import subprocess
+
+    from prophylo_b200 import capi
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "perl")], stdout=subprocess.DEVNULL)
+    ctx = capi.Context(0)
+    try:
+        for case in e2e_level:
+            prof, paths = materialise(case, tmp_path)
+            tax = nodes_taxonomy(case)
+            q = Profile(file=prof, rank=case["level"], taxonomy=tax)
+            rows = drivers.ppp_scan(ctx, q, paths, prob=case["prob"], dup=case["dup"], level=case["level"], taxonomy=tax)
+            assert normalise(drivers.format_ppp_table(rows, slope=case["slope"])) == normalise(case["ppp_pl_stdout"]), case["seed"]
+            d = tmp_path / f"lvl{case['seed']}"
+            (d / "db" / "blast" / "1140").mkdir(parents=True)
+            (d / "ws").mkdir()
+            (d / "q.profile").write_text(case["profile"])
+            (d / "nodes.tsv").write_text(case["nodes"])
+            for gi, txt in case["bla"].items():
+                (d / "db" / "blast" / "1140" / f"{gi}.bla").write_text(txt)
+            cmd = ["perl", os.path.join(root, "perl", "bin", "ppp_b200.pl"), "-d", str(d / "db"), "-t", "1140", "-p", str(d / "q.profile"),
+                   "-w", str(d / "ws"), "-l", case["level"]]
+            if case["prob"]:
+                cmd += ["--prob", str(case["prob"])]
+            if case["slope"]:
+                cmd += ["-m", str(case["slope"])]
+            if case["dup"]:
+                cmd += ["--dup"]
+            env = dict(os.environ, PERL5LIB=os.path.join(root, "perl", "t", "lib"), PPP_MOCK_NODES=str(d / "nodes.tsv"))
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+            assert r.returncode == 0, r.stderr
+            assert normalise(r.stdout) == normalise(case["ppp_pl_stdout"]), case["seed"]
+    finally:
+        ctx.close()
 
 
 @pytest.mark.gpu
