@@ -386,3 +386,126 @@ def test_profile_family_all_pairs_vs_oracle(tmp_path):
         assert np.array_equal(np.sort(th, order=["q", "score", "t"])[["q", "t", "depth"]], keep[["q", "t", "depth"]])
     finally:
         ctx.close()
+
+
+# ------------------------------------------------------------------------------------------------ the Perl command-line drop-ins
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PERL_BIN = os.path.join(ROOT_DIR, "perl", "bin")
+
+
+def perl_env(tmp, gi2taxid=None, nodes=None):
+    """PERL5LIB with the test stubs of the reference's host modules (SeqToolBox::Taxonomy answering from TSV tables,
+    PhyloProf::Profile) -- on the GPU box the reference tree does not exist; in production its own lib/ is on PERL5LIB."""
+    env = dict(os.environ, PERL5LIB=os.path.join(ROOT_DIR, "perl", "t", "lib"))
+    if gi2taxid is not None:
+        p = os.path.join(str(tmp), "gi2taxid.tsv")
+        open(p, "w").write("".join(f"{g}\t{t}\n" for g, t in gi2taxid.items()))
+        env["PPP_MOCK_GI2TAXID"] = p
+    if nodes is not None:
+        p = os.path.join(str(tmp), "nodes.tsv")
+        open(p, "w").write(nodes)
+        env["PPP_MOCK_NODES"] = p
+    return env
+
+
+def test_perl_cutoff_cli_matches_reference_script(e2e, tmp_path):
+    """perl/bin/ppp_cutoff_b200.pl (pure text filter, no GPU): stdout and the CUTOFF= line identical to the unmodified
+    bin/ppp_cutoff.pl for every golden table and slope, from a file and from stdin."""
+    import subprocess
+
+    n = 0
+    for case in e2e:
+        table = tmp_path / f"table{case['seed']}.txt"
+        table.write_text(case["ppp_pl_stdout"])
+        for slope, ref in case["cutoff"].items():
+            for kw in (dict(args=[str(table)]), dict(args=[], input=case["ppp_pl_stdout"])):
+                r = subprocess.run(["perl", os.path.join(PERL_BIN, "ppp_cutoff_b200.pl"), "-s", slope] + kw["args"], input=kw.get("input"),
+                                   capture_output=True, text=True, timeout=60)
+                assert r.returncode == 0, r.stderr
+                assert r.stdout == ref["stdout"], (case["seed"], slope)
+                assert [ln for ln in r.stderr.split("\n") if ln.startswith("CUTOFF=")] == [ln for ln in ref["stderr"].split("\n") if ln.startswith("CUTOFF=")]
+                n += 1
+    assert n == 24
+
+
+@pytest.mark.gpu
+def test_perl_ppp2d_cli_reproduces_reference_stdout(ppp2d_cases, tmp_path):
+    """perl/bin/ppp2d_b200.pl: same options and stdout as the unmodified bin/ppp2d.pl (which forks bin/ppp.pl per depth); all
+    depths x all genes in one GPU call through XS."""
+    import subprocess
+
+    subprocess.check_call(["make", "-C", os.path.join(ROOT_DIR, "perl")], stdout=subprocess.DEVNULL)
+    for case in ppp2d_cases:
+        d = tmp_path / f"cli2d{case['seed']}"
+        (d / "db" / "blast" / case["genome"]).mkdir(parents=True)
+        (d / "ws").mkdir()
+        for gi, txt in case["bla"].items():
+            (d / "db" / "blast" / case["genome"] / f"{gi}.bla").write_text(txt)
+        (d / "taxdis.txt").write_text("".join(t + "\n" for t in case["taxdis"]))
+        cmd = ["perl", os.path.join(PERL_BIN, "ppp2d_b200.pl"), "-d", str(d / "db"), "-w", str(d / "ws"), "-g", case["gi"], "--start-depth", str(case["start"]),
+               "--skip", str(case["skip"]), "--threads", "2", "--taxdis", str(d / "taxdis.txt")]
+        if case["end"]:
+            cmd += ["--end-depth", str(case["end"])]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=perl_env(d, {case["gi"]: case["genome"]}))
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == case["stdout"], case["seed"]
+
+
+@pytest.fixture(scope="module")
+def cross_hmmer_cases(golden_dir):
+    """stdout of the UNMODIFIED bin/ppp_cross_score.pl with --method hmmer on either or both sides (oracle/gen_golden_hmmer.py)"""
+    return json.load(open(os.path.join(golden_dir, "ppp_cross_score_hmmer.json")))["cases"]
+
+
+@pytest.mark.gpu
+def test_perl_cross_score_cli_reproduces_reference_stdout(cross_cases, cross_hmmer_cases, tmp_path):
+    """perl/bin/ppp_cross_score_b200.pl, BLAST x BLAST, HMMER x HMMER and mixed (bin/ppp_cross_score.pl:415-546, 549-679;
+    target profiles :326-413), with --trusted_cutoff / --start-depth / --end-depth / --skip / --scale: byte-identical to the
+    unmodified reference script's stdout, every direction one GPU call."""
+    import subprocess
+
+    subprocess.check_call(["make", "-C", os.path.join(ROOT_DIR, "perl")], stdout=subprocess.DEVNULL)
+    for case in cross_cases + cross_hmmer_cases:
+        m1, m2 = case.get("method1", "blast"), case.get("method2", "blast")
+        d = tmp_path / f"cross{case['seed']}"
+        d.mkdir()
+        n1, n2 = ("a.m8", "b.m8") if "method1" not in case else ("a.out", "b.out")
+        (d / n1).write_text(case["file1"])
+        (d / n2).write_text(case["file2"])
+        (d / "dist.txt").write_text(case["dist"])
+        cmd = ["perl", os.path.join(PERL_BIN, "ppp_cross_score_b200.pl"), "--file1", n1, "--file2", n2, "--method1", m1, "--method2", m2,
+               "--dist-file", "dist.txt", "--start-depth", str(case["start"]), "--skip", str(case["skip"])]
+        if case["end"]:
+            cmd += ["--end-depth", str(case["end"])]
+        if case["scale"]:
+            cmd += ["--scale", str(case["scale"])]
+        if case.get("cutoff"):
+            cmd += ["--trusted_cutoff", str(case["cutoff"])]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=str(d), env=perl_env(d, case["gi2taxid"]))
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == case["stdout"], (case["seed"], m1, m2, r.stdout, case["stdout"])
+
+
+@pytest.mark.gpu
+def test_perl_hmmer_cli_reproduces_reference_stdout(golden_dir, tmp_path):
+    """perl/bin/ppp_hmmer_b200.pl: one query profile against one hmmsearch 3 report (bin/ppp_hmmer.pl:179-251; full-sequence
+    and --domain scores, -t, --prob): byte-identical to the unmodified reference script's stdout."""
+    import subprocess
+
+    subprocess.check_call(["make", "-C", os.path.join(ROOT_DIR, "perl")], stdout=subprocess.DEVNULL)
+    cases = json.load(open(os.path.join(golden_dir, "ppp_hmmer.json")))["cases"]
+    for case in cases:
+        d = tmp_path / f"hmm{case['seed']}"
+        d.mkdir()
+        (d / "q.profile").write_text(case["profile"])
+        (d / "r.out").write_text(case["hmm"])
+        cmd = ["perl", os.path.join(PERL_BIN, "ppp_hmmer_b200.pl"), "-p", "q.profile", "--hmm", "r.out"]
+        if case["domain"]:
+            cmd += ["--domain"]
+        if case["cutoff"]:
+            cmd += ["-t", str(case["cutoff"])]
+        if case["prob"]:
+            cmd += ["--prob", str(case["prob"])]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=str(d), env=perl_env(d, case["gi2taxid"]))
+        assert r.returncode == 0, r.stderr
+        assert r.stdout == case["stdout"], (case["seed"], r.stdout[:500], case["stdout"][:500])
