@@ -11,11 +11,12 @@ nvcc $COMMON -fmad=false -c ppp_exact.cu -o build/ppp_exact.o &
 nvcc $COMMON -c ppp_topk.cu -o build/ppp_topk.o &
 nvcc $COMMON -c ppp_ranked.cu -o build/ppp_ranked.o &
 nvcc $COMMON -c ppp_prefilter.cu -o build/ppp_prefilter.o &
+nvcc $COMMON -c ppp_prefilter_tc.cu -o build/ppp_prefilter_tc.o &
 nvcc $COMMON -fmad=false -c ppp_table.cu -o build/ppp_table.o &
 nvcc $COMMON -c ppp_rank.cu -o build/ppp_rank.o &
 nvcc $COMMON -c ppp_debug.cu -o build/ppp_debug.o &
 nvcc $COMMON -c ppp_capi.cu -o build/ppp_capi.o &
 g++ -O2 -std=c++17 -fPIC -pthread -c ppp_bla.cpp -o build/ppp_bla.o &
 FAIL=0; for j in $(jobs -p); do wait $j || FAIL=1; done; [ $FAIL = 0 ] || { echo "nvcc failed"; exit 1; }
-nvcc $ARCH -shared -o ../libppp_b200.so build/ppp_sweep.o build/ppp_exact.o build/ppp_topk.o build/ppp_ranked.o build/ppp_prefilter.o build/ppp_table.o build/ppp_rank.o build/ppp_debug.o build/ppp_capi.o build/ppp_bla.o
+nvcc $ARCH -shared -o ../libppp_b200.so build/ppp_sweep.o build/ppp_exact.o build/ppp_topk.o build/ppp_ranked.o build/ppp_prefilter.o build/ppp_prefilter_tc.o build/ppp_table.o build/ppp_rank.o build/ppp_debug.o build/ppp_capi.o build/ppp_bla.o
 echo "built $(cd .. && pwd)/libppp_b200.so"

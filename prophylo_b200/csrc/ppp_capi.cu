@@ -31,6 +31,11 @@ extern "C" cudaError_t ppp_launch_prefilter2(const SweepParams *prm, int wpl, in
                                              uint32_t nqk, uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count,
                                              unsigned long long surv_cap, unsigned long long *stats, int nsm, cudaStream_t st);
 extern "C" uint32_t ppp_prefilter2_max_stair(int wpl, int pall);
+extern "C" cudaError_t ppp_launch_prefilter_tc(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, const uint32_t *qorder, uint32_t nqk,
+                                               uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count, unsigned long long surv_cap,
+                                               int nsm, cudaStream_t st);
+extern "C" uint32_t ppp_prefilter_tc_tile_queries(void);
+extern "C" uint32_t ppp_prefilter_tc_max_stair(int wpl);
 extern "C" uint32_t ppp_prefilter2_tile_queries(int pall);
 extern "C" cudaError_t ppp_launch_refine(const SweepParams *prm, int wpl, const uint32_t *surv, const unsigned long long *surv_count,
                                          unsigned long long surv_cap, int nwarps, int nsm, cudaStream_t st);
@@ -125,6 +130,9 @@ struct ppp_ctx {
     unsigned long long *d_pfstats = nullptr;
     int prefilter_version = 2; /* 2: ppp_prefilter.cu (queued slow path), 1: the in-line screen of ppp_sweep.cu */
     uint32_t stair_need_any = 0; /* staircase footprint of the worst possible general tile (re-scan of arbitrary queries) */
+    uint32_t stair_need_tc = 0;  /* largest staircase footprint of a 128-query tile of the all-ones launch (tensor-core screen) */
+    int prefilter_tc = 0;        /* 1: the all-ones launch of the chunk screen runs on the tensor cores (ppp_prefilter_tc.cu) */
+    unsigned long long tc_launches = 0;
     int speculate = 1;           /* top-k: screen the bulk of the targets against a speculative, verified threshold */
     int spec_first = 1;          /* ... and the first chunk against the seeding pass's rs-th smallest bound */
     uint32_t spec_rank = 0, spec_failed = 0;
@@ -590,6 +598,16 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
             ctx->stair_need[kind] = (uint32_t)std::min<size_t>(worst, 0xffffffffu);
         }
         {
+            const size_t qt = ppp_prefilter_tc_tile_queries();
+            size_t worst = 0;
+            for (size_t i = 0; i < ctx->n_pall; i += qt) {
+                size_t sum = 1;
+                for (size_t j = i; j < std::min(ctx->n_pall, i + qt); ++j) sum += (size_t)qc[order[j]].ny + 1;
+                worst = std::max(worst, sum);
+            }
+            ctx->stair_need_tc = (uint32_t)std::min<size_t>(worst, 0xffffffffu);
+        }
+        {
             std::vector<uint32_t> lens(nQ);
             for (size_t q = 0; q < nQ; ++q) lens[q] = qc[q].ny + 1;
             const size_t qt = std::min<size_t>(ppp_prefilter2_tile_queries(0), nQ);
@@ -674,8 +692,15 @@ static int launch_prefiltered(ppp_ctx *ctx, SweepParams *prm, cudaEvent_t betwee
                                ctx->sweep_warps, ctx->nsm, ctx->stream, between));
         return PPP_OK;
     }
-    CU(ppp_launch_prefilter2(prm, ctx->wpl, 1, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qorder, (uint32_t)ctx->n_pall, ctx->stair_need[1],
-                             ctx->d_surv, surv_count, ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));
+    if (ctx->prefilter_tc && ctx->n_pall && ctx->stair_need_tc <= ppp_prefilter_tc_max_stair(ctx->wpl)) {
+        /* all-ones presence planes: the chunk counts come from the tensor cores (ppp_prefilter_tc.cu) */
+        CU(ppp_launch_prefilter_tc(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qorder, (uint32_t)ctx->n_pall, ctx->stair_need_tc,
+                                   ctx->d_surv, surv_count, ctx->cap_surv, ctx->nsm, ctx->stream));
+        ctx->tc_launches++;
+    } else {
+        CU(ppp_launch_prefilter2(prm, ctx->wpl, 1, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qorder, (uint32_t)ctx->n_pall, ctx->stair_need[1],
+                                 ctx->d_surv, surv_count, ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));
+    }
     CU(ppp_launch_prefilter2(prm, ctx->wpl, 0, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qorder + ctx->n_pall, (uint32_t)(ctx->nQ - ctx->n_pall),
                              ctx->stair_need[0], ctx->d_surv, surv_count, ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));
     if (between) CU(cudaEventRecord(between, ctx->stream));
@@ -806,6 +831,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
     ctx->survivors = 0;
     ctx->prefilter_pairs = 0;
     ctx->prefilter_us = 0;
+    ctx->tc_launches = 0;
     CU(cudaEventRecord(ctx->ev[0], ctx->stream));
     ctx->last_used_table = 0;
     bool use_table = false;
@@ -1440,6 +1466,8 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
         ctx->launch_pairs_log2 = (int)value;
     } else if (!strcmp(name, "device_rank")) {
         ctx->device_rank = value != 0;
+    } else if (!strcmp(name, "prefilter_tc")) {
+        ctx->prefilter_tc = value != 0;
     } else if (!strcmp(name, "prefilter_version")) {
         if (value != 1 && value != 2) return fail(ctx, PPP_ERR_INVALID, "prefilter_version must be 1 or 2");
         ctx->prefilter_version = (int)value;
@@ -1466,6 +1494,7 @@ extern "C" int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *va
     else if (!strcmp(name, "used_table")) { *value = ctx->last_used_table; return PPP_OK; }
     else if (!strcmp(name, "spec_rank")) { *value = ctx->spec_rank; return PPP_OK; }
     else if (!strcmp(name, "spec_failed")) { *value = ctx->spec_failed; return PPP_OK; }
+    else if (!strcmp(name, "tc_launches")) { *value = (int64_t)ctx->tc_launches; return PPP_OK; }
     else if (!strcmp(name, "us_prefilter")) { *value = (int64_t)ctx->prefilter_us; return PPP_OK; }
     else if (!strcmp(name, "prefilter_pairs")) { *value = (int64_t)ctx->prefilter_pairs; return PPP_OK; }
     else if (!strcmp(name, "survivors")) { *value = (int64_t)ctx->survivors; return PPP_OK; }
