@@ -210,6 +210,30 @@ int ppp_read_bla(const char *const *paths, size_t n_paths, const char *const *un
 int ppp_read_bla_flags(const char *const *paths, size_t n_paths, const char *const *universe, size_t G, int nthreads,
                        uint32_t flags, ppp_ranked_lists *out, char *err, size_t errlen);
 void ppp_free_ranked_lists(ppp_ranked_lists *lists);
+/* ppp_read_bla_flags with a persistent packed cache: the parsed lists of the whole path set are kept in
+ * ONE binary file `cache_path`, keyed by the flags, the universe and every path's size and modification time.  A call whose key
+ * matches reads the arrays back without opening a single `.bla` (*from_cache = 1); otherwise the files are parsed and the cache
+ * is (re)written atomically.  cache_path NULL or "" = no cache.  A cache that cannot be written is not an error. */
+int ppp_read_bla_cached(const char *const *paths, size_t n_paths, const char *const *universe, size_t G, int nthreads, uint32_t flags,
+                        const char *cache_path, ppp_ranked_lists *out, int *from_cache, char *err, size_t errlen);
+
+/* Host-side reader and bit-plane packer of a FAMILY of profile files (2 tab columns taxon, 0/1; '#' comments; optional header
+ * line: lib/PhyloProf/Profile.pm:433-514, written by bin/hmm3profile.pl:175-181 / bin/blast2profile.pl): one shared universe --
+ * the union of the files' taxa, numeric ids ascending (data/taxdis.txt order), other names after them -- and the packed presence
+ * (P) and yes (Y) planes of every profile in the row layout of ppp_set_queries / ppp_set_targets_bits, with p = yes / total over
+ * the file's own taxa (ppp.pm:138-142).  Replaces per-file Perl parsing + one hash probe per taxon for TIGRFAM-scale families
+ * (BASELINE config 5).  Needs no GPU; nthreads <= 0 = all host threads; at most 8192 distinct taxa.  Release with
+ * ppp_free_profile_set(). */
+typedef struct ppp_profile_set {
+    char *universe_buf;   /* G NUL-terminated taxon strings, back to back */
+    size_t *universe_off; /* [G] offset of genome g's taxon string in universe_buf */
+    uint32_t *P, *Y;      /* [n][wpr] presence / yes planes */
+    double *p;            /* [n] yes / total */
+    uint32_t *yes, *total; /* [n] Profile::get_yes / get_total */
+    size_t n, G, wpr;
+} ppp_profile_set;
+int ppp_read_profiles(const char *const *paths, size_t n_paths, int header, int nthreads, ppp_profile_set *out, char *err, size_t errlen);
+void ppp_free_profile_set(ppp_profile_set *set);
 
 /* Device-side evaluation of the exact tier's bdtrc (diagnostic; parity tests of cephes_exact.cuh). */
 int ppp_debug_bdtrc(ppp_ctx *ctx, const int32_t *k, const int32_t *n, const double *p, double *out, size_t m);

@@ -26,7 +26,7 @@ EXPORTS = [
     "ppp_init", "ppp_destroy", "ppp_last_error", "ppp_abi_version", "ppp_set_targets_bits", "ppp_set_targets_ranked",
     "ppp_set_queries", "ppp_run", "ppp_result_count", "ppp_fetch", "ppp_score", "ppp_get_stats", "ppp_set_option",
     "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc", "ppp_topk_device", "ppp_merge_topk_device", "ppp_read_bla", "ppp_read_bla_flags", "ppp_printed_cutoffs",
-    "ppp_free_ranked_lists", "ppp_debug_enclosure", "ppp_query_count", "ppp_row_words", "ppp_pipe_peak",
+    "ppp_free_ranked_lists", "ppp_debug_enclosure", "ppp_query_count", "ppp_row_words", "ppp_pipe_peak", "ppp_read_bla_cached", "ppp_read_profiles", "ppp_free_profile_set",
 ]
 
 
@@ -46,6 +46,12 @@ class Stats(ctypes.Structure):
         ("exact_pairs", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("sweep_kernel_ms", ctypes.c_float),
         ("total_device_ms", ctypes.c_float), ("sweep_launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32),
     ]
+
+
+class ProfileSet(ctypes.Structure):
+    _fields_ = [("universe_buf", ctypes.c_void_p), ("universe_off", ctypes.POINTER(ctypes.c_size_t)), ("P", ctypes.POINTER(ctypes.c_uint32)),
+                ("Y", ctypes.POINTER(ctypes.c_uint32)), ("p", ctypes.POINTER(ctypes.c_double)), ("yes", ctypes.POINTER(ctypes.c_uint32)),
+                ("total", ctypes.POINTER(ctypes.c_uint32)), ("n", ctypes.c_size_t), ("G", ctypes.c_size_t), ("wpr", ctypes.c_size_t)]
 
 
 class RankedLists(ctypes.Structure):
@@ -110,6 +116,13 @@ def load():
     L.ppp_read_bla_flags.restype = ctypes.c_int
     L.ppp_read_bla_flags.argtypes = [ctypes.POINTER(ctypes.c_char_p), sz, ctypes.POINTER(ctypes.c_char_p), sz, ctypes.c_int, u32,
                                      ctypes.POINTER(RankedLists), ctypes.c_char_p, sz]
+    L.ppp_read_bla_cached.restype = ctypes.c_int
+    L.ppp_read_bla_cached.argtypes = [ctypes.POINTER(ctypes.c_char_p), sz, ctypes.POINTER(ctypes.c_char_p), sz, ctypes.c_int, u32, ctypes.c_char_p,
+                                      ctypes.POINTER(RankedLists), ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, sz]
+    L.ppp_read_profiles.restype = ctypes.c_int
+    L.ppp_read_profiles.argtypes = [ctypes.POINTER(ctypes.c_char_p), sz, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ProfileSet), ctypes.c_char_p, sz]
+    L.ppp_free_profile_set.restype = None
+    L.ppp_free_profile_set.argtypes = [ctypes.POINTER(ProfileSet)]
     L.ppp_printed_cutoffs.restype = ctypes.c_int
     L.ppp_printed_cutoffs.argtypes = [vp, ctypes.c_double, vp, vp, vp, vp, vp]
     L.ppp_free_ranked_lists.restype = None
@@ -123,16 +136,46 @@ CUT_OK, CUT_DOUBT, CUT_DIV0, CUT_LOG0 = 0, 1, 2, 3
 CUT_NONE = -(2 ** 31)
 
 
-def read_bla_files(paths, universe, nthreads: int = 0, dup: bool = False):
+def read_profile_files(paths, header: bool = False, nthreads: int = 0):
+    """Native reader + bit-plane packer of a family of profile files (ppp_read_profiles, prophylo_b200/csrc/ppp_pack.cpp).
+    Returns (universe list, P, Y, p, yes, total): shared universe in ascending numeric taxon order, packed planes [n, wpr]
+    uint32, p = yes / total per file.  No GPU needed."""
+    L = load()
+    pa = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+    out = ProfileSet()
+    err = ctypes.create_string_buffer(512)
+    rc = L.ppp_read_profiles(pa, len(paths), int(bool(header)), nthreads, ctypes.byref(out), err, len(err))
+    if rc != PPP_OK:
+        raise PPPError(rc, err.value.decode(errors="replace"))
+    try:
+        n, G, wpr = out.n, out.G, out.wpr
+        offs = np.ctypeslib.as_array(out.universe_off, shape=(max(G, 1),))[:G]
+        universe = [ctypes.string_at(out.universe_buf + int(o)).decode() for o in offs]
+        P = np.ctypeslib.as_array(out.P, shape=(max(n * wpr, 1),))[: n * wpr].reshape(n, wpr).copy()
+        Y = np.ctypeslib.as_array(out.Y, shape=(max(n * wpr, 1),))[: n * wpr].reshape(n, wpr).copy()
+        p = np.ctypeslib.as_array(out.p, shape=(max(n, 1),))[:n].copy()
+        yes = np.ctypeslib.as_array(out.yes, shape=(max(n, 1),))[:n].copy()
+        total = np.ctypeslib.as_array(out.total, shape=(max(n, 1),))[:n].copy()
+    finally:
+        L.ppp_free_profile_set(ctypes.byref(out))
+    return universe, P, Y, p, yes, total
+
+
+def read_bla_files(paths, universe, nthreads: int = 0, dup: bool = False, cache: str | None = None, info: dict | None = None):
     """Native reader of `.bla` BLAST caches (ppp_read_bla, prophylo_b200/csrc/ppp_bla.cpp): one ranked target per path,
     taxa mapped through `universe` (ordered taxon strings).  Returns (idx, rawdepth, row_off) as ppp_set_targets_ranked
-    takes them; dup=True packs for the reference's -dup flag (see packer.pack_ranked_targets).  No GPU needed."""
+    takes them; dup=True packs for the reference's -dup flag (see packer.pack_ranked_targets).  cache = path of a persistent
+    packed cache of the whole path set (ppp_read_bla_cached; info["from_cache"] tells whether it was used).  No GPU needed."""
     L = load()
     pa = (ctypes.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
     ua = (ctypes.c_char_p * len(universe))(*[str(u).encode() for u in universe])
     out = RankedLists()
     err = ctypes.create_string_buffer(512)
-    rc = L.ppp_read_bla_flags(pa, len(paths), ua, len(universe), nthreads, BLA_DUP if dup else 0, ctypes.byref(out), err, len(err))
+    hit = ctypes.c_int(0)
+    rc = L.ppp_read_bla_cached(pa, len(paths), ua, len(universe), nthreads, BLA_DUP if dup else 0, os.fsencode(cache) if cache else None,
+                               ctypes.byref(out), ctypes.byref(hit), err, len(err))
+    if info is not None:
+        info["from_cache"] = bool(hit.value)
     if rc != PPP_OK:
         raise PPPError(rc, err.value.decode(errors="replace"))
     try:

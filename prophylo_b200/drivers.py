@@ -367,14 +367,18 @@ def _taxon_sort_key(t: str):
         return (1, 0.0, t)
 
 
-def read_profile_family(paths, header=False):
+def read_profile_family(paths, header=False, native=True):
     """A set of profile files as the profile builders write them (bin/hmm3profile.pl:175-181, bin/blast2profile.pl,
     format of lib/PhyloProf/Profile.pm:433-514: `taxon<TAB>0|1`, '#' comments) -> one shared universe (the union of
     their taxa in canonical ascending-taxon-id order, as data/taxdis.txt lists it) and the packed planes:
       P, Y, p   every profile as a QUERY (present = taxa listed in the file, yes = value != 0, p = yes / total)
       T         every profile as a TARGET: its yes taxa as a bit plane, i.e. the list [g : Y[g] = 1] in canonical order
                 (the embedding of SURVEY.md section 8d)
-    Returns (universe list, P, Y, p, T)."""
+    native=True: the multi-threaded C++ reader and packer (ppp_read_profiles, csrc/ppp_pack.cpp); native=False: the Python
+    restatement of the same rules (kept as its cross-check).  Returns (universe list, P, Y, p, T)."""
+    if native:
+        universe, P, Y, p, _, _ = capi.read_profile_files([str(x) for x in paths], header=header)
+        return universe, P, Y, p, Y.copy()
     profs = [Profile(file=str(p), header=header).get_hash() for p in paths]
     taxa = set()
     for q in profs:
