@@ -31,11 +31,11 @@ extern "C" cudaError_t ppp_launch_prefilter2(const SweepParams *prm, int wpl, in
                                              uint32_t nqk, uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count,
                                              unsigned long long surv_cap, unsigned long long *stats, int nsm, cudaStream_t st);
 extern "C" uint32_t ppp_prefilter2_max_stair(int wpl, int pall);
-extern "C" cudaError_t ppp_launch_prefilter_tc(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, const uint32_t *qorder, uint32_t nqk,
-                                               uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count, unsigned long long surv_cap,
-                                               int nsm, cudaStream_t st);
-extern "C" uint32_t ppp_prefilter_tc_tile_queries(void);
-extern "C" uint32_t ppp_prefilter_tc_max_stair(int wpl);
+extern "C" cudaError_t ppp_launch_prefilter_tc(const SweepParams *prm, int wpl, int pall, const void *Tt, uint32_t ntt, const uint32_t *qorder,
+                                               uint32_t nqk, uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count,
+                                               unsigned long long surv_cap, int exact, int nsm, cudaStream_t st);
+extern "C" uint32_t ppp_prefilter_tc_tile_queries(int pall);
+extern "C" uint32_t ppp_prefilter_tc_max_stair(int wpl, int pall);
 extern "C" uint32_t ppp_prefilter2_tile_queries(int pall);
 extern "C" cudaError_t ppp_launch_refine(const SweepParams *prm, int wpl, const uint32_t *surv, const unsigned long long *surv_count,
                                          unsigned long long surv_cap, int nwarps, int nsm, cudaStream_t st);
@@ -130,8 +130,9 @@ struct ppp_ctx {
     unsigned long long *d_pfstats = nullptr;
     int prefilter_version = 2; /* 2: ppp_prefilter.cu (queued slow path), 1: the in-line screen of ppp_sweep.cu */
     uint32_t stair_need_any = 0; /* staircase footprint of the worst possible general tile (re-scan of arbitrary queries) */
-    uint32_t stair_need_tc = 0;  /* largest staircase footprint of a 128-query tile of the all-ones launch (tensor-core screen) */
-    int prefilter_tc = 0;        /* 1: the all-ones launch of the chunk screen runs on the tensor cores (ppp_prefilter_tc.cu) */
+    uint32_t stair_need_tc[2] = {0, 0}; /* largest staircase footprint of a tile of the tensor-core screen: general (64 queries) / all-ones (128) */
+    int prefilter_tc = 0;        /* bit 0: the all-ones launch of the chunk screen runs on the tensor cores (ppp_prefilter_tc.cu); bit 1: the general one */
+    int tc_exact = 1;            /* the tensor-core screen re-screens chunk-level passes exactly in the kernel (0: superset survivor list) */
     unsigned long long tc_launches = 0;
     int speculate = 1;           /* top-k: screen the bulk of the targets against a speculative, verified threshold */
     int spec_first = 1;          /* ... and the first chunk against the seeding pass's rs-th smallest bound */
@@ -597,15 +598,16 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
             }
             ctx->stair_need[kind] = (uint32_t)std::min<size_t>(worst, 0xffffffffu);
         }
-        {
-            const size_t qt = ppp_prefilter_tc_tile_queries();
+        for (int kind = 0; kind < 2; ++kind) {
+            const size_t b = kind ? 0 : ctx->n_pall, e = kind ? ctx->n_pall : nQ;
+            const size_t qt = ppp_prefilter_tc_tile_queries(kind);
             size_t worst = 0;
-            for (size_t i = 0; i < ctx->n_pall; i += qt) {
+            for (size_t i = b; i < e; i += qt) {
                 size_t sum = 1;
-                for (size_t j = i; j < std::min(ctx->n_pall, i + qt); ++j) sum += (size_t)qc[order[j]].ny + 1;
+                for (size_t j = i; j < std::min(e, i + qt); ++j) sum += (size_t)qc[order[j]].ny + 1;
                 worst = std::max(worst, sum);
             }
-            ctx->stair_need_tc = (uint32_t)std::min<size_t>(worst, 0xffffffffu);
+            ctx->stair_need_tc[kind] = (uint32_t)std::min<size_t>(worst, 0xffffffffu);
         }
         {
             std::vector<uint32_t> lens(nQ);
@@ -692,17 +694,20 @@ static int launch_prefiltered(ppp_ctx *ctx, SweepParams *prm, cudaEvent_t betwee
                                ctx->sweep_warps, ctx->nsm, ctx->stream, between));
         return PPP_OK;
     }
-    if (ctx->prefilter_tc && ctx->n_pall && ctx->stair_need_tc <= ppp_prefilter_tc_max_stair(ctx->wpl)) {
-        /* all-ones presence planes: the chunk counts come from the tensor cores (ppp_prefilter_tc.cu) */
-        CU(ppp_launch_prefilter_tc(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qorder, (uint32_t)ctx->n_pall, ctx->stair_need_tc,
-                                   ctx->d_surv, surv_count, ctx->cap_surv, ctx->nsm, ctx->stream));
-        ctx->tc_launches++;
-    } else {
-        CU(ppp_launch_prefilter2(prm, ctx->wpl, 1, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qorder, (uint32_t)ctx->n_pall, ctx->stair_need[1],
-                                 ctx->d_surv, surv_count, ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));
+    for (int kind = 1; kind >= 0; --kind) { /* all-ones presence planes first, then the general ones */
+        const uint32_t *ql = kind ? ctx->d_qorder : ctx->d_qorder + ctx->n_pall;
+        const uint32_t n = (uint32_t)(kind ? ctx->n_pall : ctx->nQ - ctx->n_pall);
+        if (!n) continue;
+        if (((ctx->prefilter_tc >> (kind ? 0 : 1)) & 1) && ctx->stair_need_tc[kind] <= ppp_prefilter_tc_max_stair(ctx->wpl, kind)) {
+            /* the chunk counts come from the tensor cores (ppp_prefilter_tc.cu) */
+            CU(ppp_launch_prefilter_tc(prm, ctx->wpl, kind, ctx->d_Tt, (uint32_t)ctx->nT, ql, n, ctx->stair_need_tc[kind], ctx->d_surv, surv_count,
+                                       ctx->cap_surv, ctx->tc_exact, ctx->nsm, ctx->stream));
+            ctx->tc_launches++;
+        } else {
+            CU(ppp_launch_prefilter2(prm, ctx->wpl, kind, ctx->d_Tt, (uint32_t)ctx->nT, ql, n, ctx->stair_need[kind], ctx->d_surv, surv_count,
+                                     ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));
+        }
     }
-    CU(ppp_launch_prefilter2(prm, ctx->wpl, 0, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qorder + ctx->n_pall, (uint32_t)(ctx->nQ - ctx->n_pall),
-                             ctx->stair_need[0], ctx->d_surv, surv_count, ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));
     if (between) CU(cudaEventRecord(between, ctx->stream));
     CU(ppp_launch_refine(prm, ctx->wpl, ctx->d_surv, surv_count, ctx->cap_surv, ctx->sweep_warps, ctx->nsm, ctx->stream));
     return PPP_OK;
@@ -1467,7 +1472,10 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
     } else if (!strcmp(name, "device_rank")) {
         ctx->device_rank = value != 0;
     } else if (!strcmp(name, "prefilter_tc")) {
-        ctx->prefilter_tc = value != 0;
+        if (value < 0 || value > 3) return fail(ctx, PPP_ERR_INVALID, "prefilter_tc must be 0 .. 3 (bit 0: all-ones launch, bit 1: general launch)");
+        ctx->prefilter_tc = (int)value;
+    } else if (!strcmp(name, "tc_exact")) {
+        ctx->tc_exact = value != 0;
     } else if (!strcmp(name, "prefilter_version")) {
         if (value != 1 && value != 2) return fail(ctx, PPP_ERR_INVALID, "prefilter_version must be 1 or 2");
         ctx->prefilter_version = (int)value;

@@ -951,3 +951,37 @@ def test_multi_device_context_at_config3_share_equals_single_device(ctx):
     with np.errstate(divide="ignore", invalid="ignore"):
         rel = np.abs(np.log(a["score"]) - np.log(b["score"])) / np.abs(np.log(a["score"]))
     assert np.all((a["score"] == b["score"]) | (rel <= REL_TOL_NEGLOG))
+
+
+@pytest.mark.parametrize("G,kind,nq,nt,k", [(4096, "mixed", 600, 20000, 20), (1024, "mixed", 300, 9000, 10), (8192, "family", 200, 6000, 12),
+                                            (2048, "prefix", 300, 12000, 2)])
+def test_tensor_core_chunk_screen_equals_popc_screen(ctx, G, kind, nq, nt, k):
+    """The tcgen05 chunk screen (option prefilter_tc, ppp_prefilter_tc.cu: T.Y counts per 128-genome chunk accumulated in tensor
+    memory by tcgen05.mma kind::i8) against the POPC screen: identical top-k lists record for record, identical SET of fully
+    evaluated pairs (counter full_pairs), for both launches (all-ones and general presence planes), with the in-kernel exact
+    re-screen and with the pair-level (superset) survivor list."""
+    P, Y, p = synth.make_queries(G, nq, 900 + G, kind)
+    T = synth.make_targets(G, nt, 901 + G, plant_from=Y, plant_frac=0.01)
+    ctx.set_targets_bits(T, G)
+    flt = capi.make_filter(capi.FILTER_TOPK, k=k)
+    try:
+        ctx.set_option("prefilter_tc", 0)
+        base = ctx.score(P, Y, p, flt).copy()
+        full = ctx.counter("full_pairs")
+        surv = ctx.counter("survivors")
+        assert ctx.counter("tc_launches") == 0
+        for tc, exact in ((1, 1), (3, 1), (3, 0)):
+            ctx.set_option("prefilter_tc", tc)
+            ctx.set_option("tc_exact", exact)
+            got = ctx.score(P, Y, p, flt).copy()
+            assert ctx.counter("tc_launches") > 0, (tc, exact)
+            for f in ("q", "t", "score", "yes", "number", "depth"):
+                assert np.array_equal(base[f], got[f]), (tc, exact, f)
+            assert ctx.counter("full_pairs") == full, (tc, exact)
+            if exact:
+                assert ctx.counter("survivors") <= surv * 1.01 + 64  # exact but for queue overflows, which accept unscreened
+            else:
+                assert ctx.counter("survivors") >= surv
+    finally:
+        ctx.set_option("prefilter_tc", 0)
+        ctx.set_option("tc_exact", 1)
