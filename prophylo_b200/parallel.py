@@ -213,10 +213,10 @@ def check_global_lists(ctx, merger: SlicedTopkMerge, t_offset_of_rank, P, Y, p, 
     dist.all_gather(all_rows, rows)
     all_rows = [int(r.item()) for r in all_rows]
     assert len(set(all_rows)) == 1, "check_global_lists expects equal shards"
-    loc = torch.from_numpy(np.ascontiguousarray(T_local)).to(device)
+    loc = torch.from_numpy(np.ascontiguousarray(T_local).view(np.int32)).to(device)  # NCCL has no uint32
     full = torch.empty((world * T_local.shape[0], T_local.shape[1]), dtype=loc.dtype, device=device)
     dist.all_gather_into_tensor(full, loc)
-    full_np = full.cpu().numpy()
+    full_np = full.cpu().numpy().view(np.uint32)
     del full, loc
     order = np.argsort([t_offset_of_rank(r) for r in range(world)], kind="stable")
     if list(order) != list(range(world)):  # shards are gathered in rank order; global target ids follow the offsets
