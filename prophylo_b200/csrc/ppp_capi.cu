@@ -33,7 +33,11 @@ extern "C" cudaError_t ppp_launch_prefilter2(const SweepParams *prm, int wpl, in
 extern "C" uint32_t ppp_prefilter2_max_stair(int wpl, int pall);
 extern "C" cudaError_t ppp_launch_prefilter_tc(const SweepParams *prm, int wpl, int pall, const void *Tt, uint32_t ntt, const uint32_t *qorder,
                                                uint32_t nqk, uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count,
-                                               unsigned long long surv_cap, int exact, int nsm, cudaStream_t st);
+                                               unsigned long long surv_cap, int exact, uint32_t *passmask, int nsm, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_rescreen_masks(const SweepParams *prm, int wpl, int pall, const uint32_t *qorder, uint32_t nqk, uint32_t stair_cap,
+                                                 const uint32_t *masks, uint32_t *out, unsigned long long *out_count, unsigned long long out_cap,
+                                                 int nsm, cudaStream_t st);
+extern "C" uint32_t ppp_rescreen_max_stair(int wpl, int pall);
 extern "C" uint32_t ppp_prefilter_tc_tile_queries(int pall);
 extern "C" uint32_t ppp_prefilter_tc_max_stair(int wpl, int pall);
 extern "C" uint32_t ppp_prefilter2_tile_queries(int pall);
@@ -106,6 +110,8 @@ struct ppp_ctx {
     bool Tt_valid = false;
     uint32_t *d_surv = nullptr;
     size_t cap_surv = 0;
+    uint32_t *d_surv1 = nullptr; /* pair-level column masks of the tensor-core screen ([query tile][target][words]), re-screened into d_surv */
+    size_t cap_surv1 = 0;
     /* ranked targets */
     bool ranked = false;
     int rwpl = 0; /* list words per lane: 1 (<= 1024 entries) or 2 (<= 2048) */
@@ -308,6 +314,7 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaFree(ctx->d_T);
     cudaFree(ctx->d_Tt);
     cudaFree(ctx->d_surv);
+    cudaFree(ctx->d_surv1);
     cudaFree(ctx->d_ridx);
     cudaFree(ctx->d_rraw);
     cudaFree(ctx->d_roff);
@@ -698,11 +705,23 @@ static int launch_prefiltered(ppp_ctx *ctx, SweepParams *prm, cudaEvent_t betwee
         const uint32_t *ql = kind ? ctx->d_qorder : ctx->d_qorder + ctx->n_pall;
         const uint32_t n = (uint32_t)(kind ? ctx->n_pall : ctx->nQ - ctx->n_pall);
         if (!n) continue;
-        if (((ctx->prefilter_tc >> (kind ? 0 : 1)) & 1) && ctx->stair_need_tc[kind] <= ppp_prefilter_tc_max_stair(ctx->wpl, kind)) {
-            /* the chunk counts come from the tensor cores (ppp_prefilter_tc.cu) */
+        if (((ctx->prefilter_tc >> (kind ? 0 : 1)) & 1) && ctx->stair_need_tc[kind] <= ppp_prefilter_tc_max_stair(ctx->wpl, kind) &&
+            (ctx->tc_exact || ctx->stair_need_tc[kind] <= ppp_rescreen_max_stair(ctx->wpl, kind))) {
+            /* the chunk counts come from the tensor cores (ppp_prefilter_tc.cu); in pair-level mode the kernel writes one column
+             * mask per (query tile, target) -- the pairs with a passing CHUNK -- which the re-screen kernel reduces to the pairs
+             * with a passing candidate */
+            const bool pl = !ctx->tc_exact;
+            if (pl) {
+                const size_t nqt = ppp_prefilter_tc_tile_queries(kind), tiles = (n + nqt - 1) / nqt;
+                const int rc = grow(ctx, &ctx->d_surv1, &ctx->cap_surv1, tiles * (size_t)(prm->t1 - prm->t0) * (nqt / 32));
+                if (rc) return rc;
+            }
             CU(ppp_launch_prefilter_tc(prm, ctx->wpl, kind, ctx->d_Tt, (uint32_t)ctx->nT, ql, n, ctx->stair_need_tc[kind], ctx->d_surv, surv_count,
-                                       ctx->cap_surv, ctx->tc_exact, ctx->nsm, ctx->stream));
+                                       ctx->cap_surv, ctx->tc_exact, ctx->d_surv1, ctx->nsm, ctx->stream));
             ctx->tc_launches++;
+            if (pl)
+                CU(ppp_launch_rescreen_masks(prm, ctx->wpl, kind, ql, n, ctx->stair_need_tc[kind], ctx->d_surv1, ctx->d_surv, surv_count, ctx->cap_surv,
+                                             ctx->nsm, ctx->stream));
         } else {
             CU(ppp_launch_prefilter2(prm, ctx->wpl, kind, ctx->d_Tt, (uint32_t)ctx->nT, ql, n, ctx->stair_need[kind], ctx->d_surv, surv_count,
                                      ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));

@@ -84,7 +84,9 @@ enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_ACCURATE = 2, CNT_VIOL = 3, CNT_CHECKS =
        CNT_FULL = 7, CNT_N = 8,
        CNT_SURV = 8, /* survivor count of the pre-filter (slot CNT_N) */
        CNT_ITEM = 9, /* work-item counter of the tile kernels */
-       CNT_SLOTS = 10 };
+       CNT_SURV1 = 10, /* pairs with a passing CHUNK (tensor-core screen, pair-level mode): re-screened into CNT_SURV */
+       CNT_ITEM2 = 11, /* work-item counter of the re-screen kernel */
+       CNT_SLOTS = 12 };
 
 #ifdef __CUDACC__
 #include "../../include/ppp_b200.h"

@@ -70,8 +70,10 @@ struct TcParams {
     unsigned long long surv_cap;
     uint32_t ntt, t0, nTl, nqk;
     uint32_t stair_cap;       /* int16 entries of shared memory reserved for the tile's staircases */
-    uint32_t exact;           /* 1: chunk-level passes are re-screened exactly in the kernel (queue + pooled drain); 0: every pair with a
-                                 passing chunk is a survivor (a superset: the caller re-screens the list, ppp_launch_rescreen) */
+    uint32_t exact;           /* 1: chunk-level passes are re-screened exactly in the kernel (queue + pooled drain); 0: the kernel only
+                                 writes, per (query tile, target), the mask of columns with a passing chunk (passmask) and the caller
+                                 re-screens the flagged pairs (ppp_launch_rescreen_masks) */
+    uint32_t *passmask;       /* exact == 0: [nQtiles][nTl][NQ / 32] column masks */
 };
 
 /* ---------------------------------------------------------------- PTX wrappers */
@@ -183,6 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppp_prefilter_tc_kernel(const T
     uint32_t *s_passw = reinterpret_cast<uint32_t *>(smem_raw + 2048);  /* [2][4][TC_M] pass bits of row r of block b, 32 columns per word */
     uint2 *s_queue = reinterpret_cast<uint2 *>(smem_raw + 2048 + 2 * 4 * TC_M * 4); /* [EPI_WARPS][TC_WQ] */
     uint32_t *s_wqn = s_ninact + 4;                                                  /* [EPI_WARPS] entries queued */
+    uint32_t *s_inactw = s_wqn + TC_EPI_WARPS;                                       /* [4] mask words of the columns without a staircase */
     unsigned char *s_stage = smem_raw + 2048 + 2 * 4 * TC_M * 4 + TC_EPI_WARPS * TC_WQ * 8;
     int16_t *s_stair = reinterpret_cast<int16_t *>(s_stage + TC_STAGES * STAGE_BYTES);
     const unsigned char *s_stair_b = reinterpret_cast<const unsigned char *>(s_stair);
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppp_prefilter_tc_kernel(const T
     const uint64_t span = (nItems + gridDim.x - 1) / gridDim.x;
     const uint64_t i0 = (uint64_t)blockIdx.x * span, i1 = min(nItems, i0 + span);
 
+    if (tid < 4) s_inactw[tid] = 0;
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(&bar_full[s], TC_PROD_WARPS * 32);
@@ -268,6 +272,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppp_prefilter_tc_kernel(const T
                 for (int j = 0; j < 4; ++j)
                     if (qid[j] != 0xffffffffu && !len[j]) s_inact[at++] = qid[j];
                 if (lane == 31) *s_ninact = iin;
+                /* columns that accept every pair, as mask words (pair-level mode flags them for every live target) */
+                uint32_t im = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (qid[j] != 0xffffffffu && !len[j]) im |= 1u << ((4 * lane + j) & 31);
+                im |= __shfl_xor_sync(FULL, im, 1);
+                im |= __shfl_xor_sync(FULL, im, 2);
+                im |= __shfl_xor_sync(FULL, im, 4); /* lanes 8 w .. 8 w + 7 hold word w (columns 32 w .. 32 w + 31) */
+                if ((lane & 7) == 0) s_inactw[lane >> 3] = im;
             }
             __syncthreads();
             if (tid == 0) s_stair[0] = -2;
@@ -489,13 +502,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) ppp_prefilter_tc_kernel(const T
             /* ---- survivors of the two blocks: (query of column, target) for every set pass bit; queries without a staircase
              * accept every live target (emitted once, by the warps of column half 0) */
             const uint32_t ninact = half == 0 ? *s_ninact : 0u;
-            if (!a.exact) {
+            if (!a.exact) { /* pair-level mode: this row's column masks go to the re-screen kernel as they are */
 #pragma unroll
-                for (int b = 0; b < 2; ++b)
-                    for (uint32_t w = 0; w < nwords; ++w) s_passw[(b * 4 + wfirst + w) * TC_M + row] = accw[b][w];
+                for (int b = 0; b < 2; ++b) {
+                    const uint32_t tl = tbase + b * TC_M + row;
+                    if (tl < a.nTl)
+                        for (uint32_t w = 0; w < nwords; ++w)
+                            a.passmask[((size_t)qt * a.nTl + tl) * (NQ / 32) + wfirst + w] = accw[b][w] | s_inactw[wfirst + w];
+                }
             }
 #pragma unroll 1
-            for (int b = 0; b < 2; ++b) {
+            for (int b = 0; a.exact && b < 2; ++b) {
                 const uint32_t tl = tbase + b * TC_M + row;
                 const bool live = tl < a.nTl;
                 uint32_t pb[2] = {0, 0};
@@ -655,7 +672,7 @@ static cudaError_t tc_launch_t(const TcParams &p, int nsm, cudaStream_t st)
  * Appends to the survivor list like ppp_launch_prefilter2 (*surv_count is not reset here). */
 extern "C" cudaError_t ppp_launch_prefilter_tc(const SweepParams *prm, int wpl, int pall, const void *Tt, uint32_t ntt, const uint32_t *qorder,
                                                uint32_t nqk, uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count,
-                                               unsigned long long surv_cap, int exact, int nsm, cudaStream_t st)
+                                               unsigned long long surv_cap, int exact, uint32_t *passmask, int nsm, cudaStream_t st)
 {
     if (!nqk) return cudaSuccess;
     TcParams p;
@@ -674,6 +691,7 @@ extern "C" cudaError_t ppp_launch_prefilter_tc(const SweepParams *prm, int wpl, 
     p.nqk = nqk;
     p.stair_cap = stair_cap;
     p.exact = exact ? 1u : 0u;
+    p.passmask = passmask;
     switch (wpl * 2 + (pall ? 1 : 0)) {
     case 2: return tc_launch_t<1, false>(p, nsm, st);
     case 3: return tc_launch_t<1, true>(p, nsm, st);

@@ -412,6 +412,230 @@ __global__ void __launch_bounds__(PPP_REFINE_WARPS * 32, PPP_MINBLOCKS_OF(WPL)) 
     flush_counters(prm, wc, lane);
 }
 
+/* ---------------------------------------------------------------- re-screen kernel: exact staircase test of the flagged pairs
+ * The tensor-core chunk screen (ppp_prefilter_tc.cu, pair-level mode) flags every pair with a passing 128-genome CHUNK -- a
+ * superset (about 40 x) of the pairs with a passing CANDIDATE -- as one column mask per (query tile, target).  This kernel
+ * applies the candidate-level test of evaluate_pair() to each flagged pair -- number at the candidate <= nmax[its rank] for
+ * some set bit of T & Y (ppp.pm:207-237) -- and appends the pairs that have one to the survivor list of the refine kernel.
+ * One CTA per (query tile, block of targets): the tile's query planes are staged in shared memory once, every warp takes a
+ * target row (registers) and walks the set bits of its mask, so that a flagged pair costs shared-memory reads, a packed warp
+ * scan and a few staircase lookups instead of three row loads from L2. */
+#define PPP_MAX_DYN_SMEM (227 * 1024) /* per-CTA limit of sm_100 */
+#define RS_ROWS 256 /* targets per work item */
+template <int WPL>
+__device__ __forceinline__ void load_words_smem(const uint32_t *src, uint32_t (&v)[WPL])
+{
+    if constexpr (WPL == 4) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(src);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    } else if constexpr (WPL == 8) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(src), b = *(reinterpret_cast<const uint4 *>(src) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else if constexpr (WPL == 2) {
+        const uint2 a = *reinterpret_cast<const uint2 *>(src);
+        v[0] = a.x; v[1] = a.y;
+    } else {
+        v[0] = *src;
+    }
+}
+template <int WPL, int NQ>
+__global__ void __launch_bounds__(512) ppp_rescreen_masks_kernel(const SweepParams prm, const uint32_t *__restrict__ qorder, uint32_t nqk, bool pall,
+                                                                 const uint32_t *__restrict__ masks, uint32_t *__restrict__ out,
+                                                                 unsigned long long *__restrict__ out_count, unsigned long long out_cap)
+{
+    constexpr int W = 32 * WPL;
+    constexpr int MW = NQ / 32;
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint32_t *s_qid = reinterpret_cast<uint32_t *>(rs_smem);   /* [NQ] */
+    uint32_t *s_off = s_qid + NQ;                               /* [NQ] offset of the column's staircase in s_stair, PPP_NO_TABLE = accepts all */
+    uint32_t *s_y = s_off + NQ;                                 /* [NQ][W] yes planes (already ANDed with the presence planes) */
+    uint32_t *s_p = s_y + NQ * W;                               /* [NQ][W] presence planes (general launch only) */
+    uint16_t *s_stair = reinterpret_cast<uint16_t *>(s_p + (pall ? 0 : NQ * W)); /* the tile's staircases, back to back */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const uint32_t nTl = prm.t1 - prm.t0;
+    const uint32_t nTb = (nTl + RS_ROWS - 1) / RS_ROWS, nQt = (nqk + NQ - 1) / NQ;
+    const uint64_t nItems = (uint64_t)nQt * nTb;
+    const uint64_t span = (nItems + gridDim.x - 1) / gridDim.x;
+    const uint64_t i0 = (uint64_t)blockIdx.x * span, i1 = min(nItems, i0 + span);
+    uint32_t cur_qt = 0xffffffffu;
+    for (uint64_t item = i0; item < i1; ++item) {
+        const uint32_t qt = (uint32_t)(item / nTb), tb = (uint32_t)(item % nTb);
+        if (qt != cur_qt) {
+            __syncthreads();
+            const uint32_t nq = min((uint32_t)NQ, nqk - qt * NQ);
+            if (warp == 0) { /* staircase offsets inside shared memory: a warp scan over NQ / 32 columns per lane */
+                uint32_t len[MW], qid[MW], sum = 0;
+#pragma unroll
+                for (int m = 0; m < MW; ++m) {
+                    const uint32_t j = (uint32_t)(MW * lane + m);
+                    qid[m] = j < nq ? qorder[qt * NQ + j] : 0xffffffffu;
+                    const uint32_t off = qid[m] != 0xffffffffu ? prm.nmax_off[qid[m]] : PPP_NO_TABLE;
+                    len[m] = (qid[m] != 0xffffffffu && off != PPP_NO_TABLE) ? prm.qc[qid[m]].ny + 1 : 0;
+                    sum += len[m];
+                }
+                uint32_t incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                uint32_t run = incl - sum;
+#pragma unroll
+                for (int m = 0; m < MW; ++m) {
+                    const uint32_t j = (uint32_t)(MW * lane + m);
+                    s_qid[j] = qid[m];
+                    s_off[j] = len[m] ? run : PPP_NO_TABLE;
+                    run += len[m];
+                }
+            }
+            __syncthreads();
+            for (uint32_t j = warp; j < nq; j += nwarps) {
+                if (s_off[j] == PPP_NO_TABLE) continue;
+                const uint32_t qid = s_qid[j], len = prm.qc[qid].ny + 1;
+                const uint16_t *src = prm.nmax + prm.nmax_off[qid];
+                for (uint32_t i = lane; i < len; i += 32) s_stair[s_off[j] + i] = __ldg(src + i);
+            }
+            for (uint32_t i = threadIdx.x; i < (uint32_t)(NQ * W); i += blockDim.x) {
+                const uint32_t j = i / W, w = i % W;
+                uint32_t y = 0, p = 0;
+                if (j < nq) {
+                    const uint32_t qid = qorder[qt * NQ + j];
+                    p = pall ? 0xffffffffu : __ldg(prm.Q + (size_t)qid * 2 * W + w);
+                    y = __ldg(prm.Q + (size_t)qid * 2 * W + W + w) & p;
+                }
+                s_y[i] = y;
+                if (!pall) s_p[i] = p;
+            }
+            cur_qt = qt;
+            __syncthreads();
+        }
+        for (uint32_t r = warp; r < RS_ROWS; r += nwarps) {
+            const uint32_t tl = tb * RS_ROWS + r;
+            if (tl >= nTl) break;
+            uint32_t mw = lane < MW ? __ldg(masks + ((size_t)qt * nTl + tl) * MW + lane) : 0u;
+            if (!__any_sync(FULL, mw != 0)) continue;
+            uint32_t tw[WPL];
+            load_row<WPL>(prm.T + (size_t)(prm.t0 + tl) * W + lane * WPL, tw);
+            uint32_t passed[MW];
+#pragma unroll
+            for (int m = 0; m < MW; ++m) {
+                uint32_t bits = __shfl_sync(FULL, mw, m);
+                uint32_t okbits = 0;
+                while (bits) { /* warp-uniform walk over the flagged columns of this row */
+                    const uint32_t bit = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const uint32_t j = 32u * m + bit;
+                    const uint32_t off = s_off[j];
+                    const bool real = s_qid[j] != 0xffffffffu;  /* padding columns are never flagged */
+                    bool pass = real && off == PPP_NO_TABLE;    /* a query without a staircase accepts every pair */
+                    if (real && !pass) {
+                        uint32_t aw[WPL], yw[WPL], cy = 0, cn = 0;
+                        load_words_smem<WPL>(s_y + j * W + lane * WPL, yw);
+                        if (!pall) load_words_smem<WPL>(s_p + j * W + lane * WPL, aw);
+#pragma unroll
+                        for (int w = 0; w < WPL; ++w) {
+                            aw[w] = pall ? tw[w] : (tw[w] & aw[w]);
+                            yw[w] &= tw[w];
+                            cy += __popc(yw[w]);
+                            cn += __popc(aw[w]);
+                        }
+                        const uint32_t packed = cy | (cn << 16);
+                        uint32_t incl = packed;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t v = __shfl_up_sync(FULL, incl, o);
+                            if (lane >= o) incl += v;
+                        }
+                        const uint16_t *stair = s_stair + off;
+                        uint32_t yrun = (incl - packed) & 0xffffu, nbase = (incl - packed) >> 16;
+#pragma unroll
+                        for (int w = 0; w < WPL; ++w) {
+                            const uint32_t cyw = __popc(yw[w]);
+                            if (cyw && (nbase + 1u) <= (uint32_t)stair[yrun + cyw]) { /* word-level screen, one lookup */
+                                uint32_t mbits = yw[w], yy = yrun;
+                                while (mbits) {
+                                    const uint32_t b = __ffs(mbits) - 1;
+                                    mbits &= mbits - 1;
+                                    ++yy;
+                                    pass |= nbase + __popc(aw[w] & ((2u << b) - 1u)) <= (uint32_t)stair[yy];
+                                }
+                            }
+                            yrun += cyw;
+                            nbase += __popc(aw[w]);
+                        }
+                        pass = __any_sync(FULL, pass);
+                    }
+                    if (pass) okbits |= 1u << bit;
+                }
+                passed[m] = okbits;
+            }
+            uint32_t total = 0;
+#pragma unroll
+            for (int m = 0; m < MW; ++m) total += __popc(passed[m]);
+            if (total) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(out_count, (unsigned long long)total);
+                base = __shfl_sync(FULL, base, 0);
+                uint32_t before = 0;
+#pragma unroll
+                for (int m = 0; m < MW; ++m) {
+                    if ((passed[m] >> lane) & 1u) {
+                        const unsigned long long slot = base + before + __popc(passed[m] & ((1u << lane) - 1u));
+                        if (slot < out_cap) out[slot] = (uint32_t)((uint64_t)s_qid[32u * m + lane] * nTl + tl);
+                    }
+                    before += __popc(passed[m]);
+                }
+            }
+        }
+    }
+}
+
+static size_t rescreen_fixed_smem(int wpl, int pall)
+{
+    const size_t NQ = pall ? 128 : 64, W = 32 * (size_t)wpl;
+    return 2 * NQ * 4 + (pall ? 1 : 2) * NQ * W * 4;
+}
+/* largest staircase footprint (entries) of a query tile the re-screen kernel can stage */
+extern "C" uint32_t ppp_rescreen_max_stair(int wpl, int pall)
+{
+    const size_t fixed = rescreen_fixed_smem(wpl, pall);
+    if (fixed + 1024 > PPP_MAX_DYN_SMEM) return 0;
+    return (uint32_t)((PPP_MAX_DYN_SMEM - 512 - fixed) / 2);
+}
+
+extern "C" cudaError_t ppp_launch_rescreen_masks(const SweepParams *prm, int wpl, int pall, const uint32_t *qorder, uint32_t nqk, uint32_t stair_cap,
+                                                 const uint32_t *masks, uint32_t *out, unsigned long long *out_count, unsigned long long out_cap,
+                                                 int nsm, cudaStream_t st)
+{
+    if (!nqk) return cudaSuccess;
+    const int NQ = pall ? 128 : 64;
+    const size_t smem = rescreen_fixed_smem(wpl, pall) + (((size_t)stair_cap * 2 + 15) & ~(size_t)15);
+    const uint32_t nTl = prm->t1 - prm->t0;
+    const uint64_t items = (uint64_t)((nqk + NQ - 1) / NQ) * ((nTl + RS_ROWS - 1) / RS_ROWS);
+    const unsigned grid = (unsigned)std::min<uint64_t>(items, (uint64_t)nsm * 2);
+    cudaError_t e = cudaSuccess;
+#define RS_LAUNCH(WPL_, NQ_)                                                                                                                   \
+    do {                                                                                                                                       \
+        e = cudaFuncSetAttribute(ppp_rescreen_masks_kernel<WPL_, NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
+        if (e != cudaSuccess) return e;                                                                                                        \
+        ppp_rescreen_masks_kernel<WPL_, NQ_><<<grid, 512, smem, st>>>(*prm, qorder, nqk, pall != 0, masks, out, out_count, out_cap);           \
+    } while (0)
+    if (smem > PPP_MAX_DYN_SMEM) return cudaErrorInvalidValue;
+    switch (wpl * 2 + (pall ? 1 : 0)) {
+    case 2: RS_LAUNCH(1, 64); break;
+    case 3: RS_LAUNCH(1, 128); break;
+    case 4: RS_LAUNCH(2, 64); break;
+    case 5: RS_LAUNCH(2, 128); break;
+    case 8: RS_LAUNCH(4, 64); break;
+    case 9: RS_LAUNCH(4, 128); break;
+    case 16: RS_LAUNCH(8, 64); break;
+    case 17: RS_LAUNCH(8, 128); break;
+    default: return cudaErrorInvalidValue;
+    }
+#undef RS_LAUNCH
+    return cudaGetLastError();
+}
+
 /* transpose row-major planes T[nT][W] into chunk-major Tt[W/4][nT] of uint4 (coalesced per-thread row streaming) */
 __global__ void ppp_transpose_kernel(const uint4 *__restrict__ T, uint4 *__restrict__ Tt, uint32_t nT, uint32_t C)
 {
@@ -442,7 +666,6 @@ static size_t refine_smem_bytes(int wpl, int nwarps)
 }
 static size_t prefilter_smem_bytes(int wpl) { return 128 + PPP_QTILE * 2 * 32 * (size_t)wpl * 4 + 2 * PPP_QTILE * 4 + 64; }
 
-#define PPP_MAX_DYN_SMEM (227 * 1024) /* per-CTA limit of sm_100 */
 
 template <int WPL>
 static cudaError_t launch_t(const SweepParams &prm, int nwarps, int nsm, cudaStream_t st)
