@@ -7,10 +7,13 @@
 
 Workload = config 3 of BASELINE.json, the configuration the metric is quoted on: 10,000 query profiles x 1,000,000 target
 profiles all-pairs at G = 4096 genomes (1e10 pairs), per-query top-k with k = 100.  The target
-set is 8 blocks of 125,000 (block b seeded SEED_BASE + 103 + 1000 b); rank r of an N-GPU run holds blocks
-[8 r / N, 8 (r + 1) / N), so every N scores the SAME million targets: N = 1 is the whole configuration on one GPU, N = 8
-is the configuration as BASELINE names it ("scaling": "strong").  The per-GPU-share form of round 1 (125,000 targets per
-GPU, work growing with N) is reported beside it under "weak_scaling".  A step is one pass of the scan over all pairs.
+set is 8 blocks of 125,000 (block b seeded SEED_BASE + 103 + 1000 b), so every N scores the SAME million targets: N = 1
+is the whole configuration on one GPU, N = 8 is the configuration as BASELINE names it ("scaling": "strong").  The query x
+target tile partitioner cuts the QUERY axis when there are enough queries per GPU (rank r scores queries [r Q / N,
+(r + 1) Q / N) against all targets: every per-query cost -- threshold seeding, staircases, list merges -- divides by N and
+the ranks' lists are final, no exchange at all) and the TARGET axis otherwise (rank r holds blocks [8 r / N, 8 (r + 1) / N),
+global top-k merged over NVLink).  The per-GPU-share form of round 1 (125,000 targets per GPU, target-sharded, work
+growing with N, merge included) is reported beside it under "weak_scaling".  A step is one pass of the scan over all pairs.
 
 One JSON line on rank 0; see the task contract for the keys.  `value` is measured with inputs resident in HBM (wall time
 of run + result collection bracketed by synchronizes, max over ranks; the library's CUDA-event time is reported beside
@@ -290,18 +293,24 @@ def run_ours(args):
     w = workload(args)
     G, nq, nt_total, k = w["G"], w["nq"], w["nt"], w["k"]
     P, Y, p = make_queries(w)
-    blocks = rank_blocks(rank, world)
+    partition = args.partition if args.partition != "auto" else ("queries" if world > 1 and nq // world >= 512 else "targets")
+    block_nt = nt_total // NBLOCKS
+    if partition == "queries":   # rank r: its slice of the queries against ALL targets
+        blocks = list(range(NBLOCKS))
+        q0, q1 = parallel.shard_range(nq, rank, world)
+    else:                        # rank r: all queries against its blocks of the targets
+        blocks = rank_blocks(rank, world)
+        q0, q1 = 0, nq
     T = np.concatenate([target_block(w, b, Y) for b in blocks])
     nt = T.shape[0]
-    t_off = blocks[0] * (nt_total // NBLOCKS)
-    block_nt = nt_total // NBLOCKS
 
     def pinned(a):
-        t = torch.from_numpy(a).pin_memory()
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t, t.numpy()
 
     hold = [pinned(x) for x in (P, Y, p, T)]
     Pp, Yp, pp, Tp = [h[1] for h in hold]
+    Pq, Yq, pq = Pp[q0:q1], Yp[q0:q1], pp[q0:q1]   # this rank's queries of the headline run
     ctx = capi.Context(local_rank)
     ctx.set_option("sweep_warps", args.sweep_warps)
     flt = capi.make_filter(capi.FILTER_TOPK, k=k)
@@ -317,11 +326,12 @@ def run_ours(args):
     merger = parallel.SlicedTopkMerge(ctx, nq, k, world, rank, dev) if world > 1 else None
 
     def collect(offset_of_rank):
-        """results of the last run on the host.  One GPU: the device top-k lists are copied into the pinned buffer.
-        N GPUs: the path's only exchange step, the global top-k merge -- rank r receives every rank's device-resident lists of
-        ITS slice of the queries (NCCL all-to-all over NVLink), merges them on the device and copies its slice of the global
-        lists to its host buffer (the result of an N-process job is the N slices)."""
-        if world == 1:
+        """results of the last run on the host.  Lists that are final on this rank (one GPU; query-partitioned run): the device
+        top-k lists are copied into the pinned buffer.  Target-partitioned run on N GPUs: the path's only exchange step, the
+        global top-k merge -- rank r receives every rank's device-resident lists of ITS slice of the queries (NCCL all-to-all
+        over NVLink), merges them on the device and copies its slice of the global lists to its host buffer (the result of an
+        N-process job is the N slices)."""
+        if offset_of_rank is None:
             return ctx.fetch(out_np)
         return merger.run(offset_of_rank)
 
@@ -342,7 +352,7 @@ def run_ours(args):
             st = ctx.stats()
             r["dev_ms"].append(st["total_device_ms"])
             r["sweep_ms"].append(st["sweep_kernel_ms"])
-            r["launches"] += st["kernel_launches"] + (merger.launches_per_run if merger else 0)
+            r["launches"] += st["kernel_launches"] + (merger.launches_per_run if offset_of_rank is not None else 0)
             r["pf_us"].append(ctx.counter("us_prefilter"))
             r["pf_pairs"].append(ctx.counter("prefilter_pairs"))
             r["survs"].append(ctx.counter("survivors"))
@@ -356,8 +366,8 @@ def run_ours(args):
 
     # ---- the headline: the whole configuration over the N GPUs (resident inputs)
     ctx.set_targets_bits(Tp, G)
-    ctx.set_queries(Pp, Yp, pp)
-    strong_off = lambda r: rank_blocks(r, world)[0] * block_nt  # noqa: E731
+    ctx.set_queries(Pq, Yq, pq)
+    strong_off = None if (world == 1 or partition == "queries") else (lambda r: rank_blocks(r, world)[0] * block_nt)
     for _ in range(args.warmup):
         ctx.run(flt)
         collect(strong_off)
@@ -368,25 +378,18 @@ def run_ours(args):
     phase = {n: ctx.counter("us_" + n) for n in ("sweep", "prefilter", "exact", "staircase", "merge")}
     spec = {"speculative_rank": ctx.counter("spec_rank"), "queries_rescanned": ctx.counter("spec_failed")}
 
-    # ---- N > 1: the merged global lists of 64 queries equal one GPU scoring the concatenated shards (after the timing)
-    selfcheck = None
-    if world > 1:
-        selfcheck = parallel.check_global_lists(ctx, merger, strong_off, Pp, Yp, pp, Tp, G, k, rank, world, dev, n_check=64)
-        ctx.set_targets_bits(Tp, G)
-        ctx.set_queries(Pp, Yp, pp)
-
     # ---- end to end through the one-call C ABI entry with host buffers (targets + queries H2D, hits D2H)
     e2e_wall = 0.0
     nsteps_e2e = max(1, min(args.steps, 3))
     ctx.set_targets_bits(Tp, G)
-    ctx.score(Pp, Yp, pp, flt, out=out_np)
+    ctx.score(Pq, Yq, pq, flt, out=out_np)
     for _ in range(nsteps_e2e):
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
         ctx.set_targets_bits(Tp, G)
-        hits = ctx.score(Pp, Yp, pp, flt, out=out_np)
-        if world > 1:
+        hits = ctx.score(Pq, Yq, pq, flt, out=out_np)
+        if strong_off is not None:
             collect(strong_off)
         torch.cuda.synchronize()
         e2e_wall += time.perf_counter() - t0
@@ -395,30 +398,33 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_value = nq * nt_total / (float(e2e_ms.item()) * 1e-3)
-    h2d = int(Tp.nbytes + Pp.nbytes + Yp.nbytes + pp.nbytes)
-    d2h = int(hits.nbytes) if world == 1 else int(merger.d2h_bytes)
+    h2d = int(Tp.nbytes + Pq.nbytes + Yq.nbytes + pq.nbytes)
+    d2h = int(hits.nbytes) if strong_off is None else int(merger.d2h_bytes)
 
-    # ---- the per-GPU-share form (round 1's line): 125,000 targets per GPU whatever N is
-    weak = None
-    if world < NBLOCKS:
-        ctx.set_targets_bits(Tp[:block_nt], G)
-        ctx.set_queries(Pp, Yp, pp)
-        weak_off = lambda r: r * block_nt  # noqa: E731
-        for _ in range(2):
-            ctx.run(flt)
-            collect(weak_off)
-        wk = timed_steps(max(2, min(args.steps, 5)), weak_off, False)
-        weak = {"scaling": "weak", "targets_per_gpu": block_nt, "value": world * nq * block_nt / (wk["step_ms"] * 1e-3), "ms_per_step": wk["step_ms"],
-                "device_ms_per_step": wk["dev_ms_mean"]}
-    else:
-        weak = {"scaling": "weak", "targets_per_gpu": block_nt, "value": value, "ms_per_step": main["step_ms"], "device_ms_per_step": main["dev_ms_mean"],
-                "note": "at N = 8 the per-GPU-share workload IS the headline workload"}
+    # ---- the per-GPU-share form (round 1's line): 125,000 targets per GPU whatever N is, target-sharded, global merge included;
+    # N > 1: afterwards the merged global lists of 64 queries are checked against ONE GPU scoring the concatenated shards
+    wb = blocks.index(rank) if partition == "queries" and world > 1 else 0  # a different block on every rank
+    Tw = Tp[wb * block_nt:(wb + 1) * block_nt]
+    ctx.set_targets_bits(Tw, G)
+    ctx.set_queries(Pp, Yp, pp)
+    weak_off = None if world == 1 else (lambda r: r * block_nt)
+    for _ in range(2):
+        ctx.run(flt)
+        collect(weak_off)
+    wk = timed_steps(max(2, min(args.steps, 5)), weak_off, False)
+    weak = {"scaling": "weak", "partition": "targets", "targets_per_gpu": block_nt, "value": world * nq * block_nt / (wk["step_ms"] * 1e-3),
+            "ms_per_step": wk["step_ms"], "device_ms_per_step": wk["dev_ms_mean"]}
+    selfcheck = None
+    if world > 1:
+        selfcheck = parallel.check_global_lists(ctx, merger, weak_off, Pp, Yp, pp, Tw, G, k, rank, world, dev, n_check=64)
+        ctx.set_targets_bits(Tp, G)
+        ctx.set_queries(Pq, Yq, pq)
 
     if rank == 0:
         pf_us_mean, pf_pairs_mean, surv_mean = float(np.mean(main["pf_us"])), float(np.mean(main["pf_pairs"])), float(np.mean(main["survs"]))
         pf_ms = pf_us_mean * 1e-3
         words = ((G + 1023) // 1024) * 32
-        frac_all = float(np.mean(synth.unpack_bits(P, G).all(axis=1)))
+        frac_all = float(np.mean(synth.unpack_bits(Pq, G).all(axis=1)))
         # POPC the dominant kernel (ppp_prefilter2_kernel, ppp_prefilter.cu) EXECUTES per pair: carry-save adders fold a
         # 4-word chunk into 3 POPC (8 words -> 4 at G = 8192); the first chunk is screened word by word; all-ones queries take
         # `number` from a per-target depth prefix computed once per 32-query tile; general queries count T & P as well
@@ -444,14 +450,14 @@ def run_ours(args):
         except (OSError, ValueError, KeyError):
             pass
         W_bytes = words * 4
-        alg_bytes = nt * W_bytes + nq * 2 * W_bytes + 4 * surv_mean
+        alg_bytes = nt * W_bytes + (q1 - q0) * 2 * W_bytes + 4 * surv_mean
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": main["step_ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"config3 (BASELINE: 10k x 1M all-pairs at 4096 genomes): {nq} queries x {nt_total} targets x G={G}, per-query "
-                                   f"top-k k={k}; {world} GPU(s) x {nt} targets each", "genomes": G, "queries": nq, "targets": nt_total,
-                       "targets_per_gpu": nt, "filter": f"topk{k}", "l2": "flushed between timed iterations (256 MiB write)",
+                                   f"top-k k={k}; {world} GPU(s), partition = {partition}: {q1 - q0} queries x {nt} targets each", "genomes": G, "queries": nq,
+                       "targets": nt_total, "partition": partition, "queries_per_gpu": q1 - q0, "targets_per_gpu": nt, "filter": f"topk{k}", "l2": "flushed between timed iterations (256 MiB write)",
                        "timing": "wall of run + result collection bracketed by synchronize, max over ranks; CUDA-event time of the library's "
                                  "stream in device_ms_per_step"},
             "device_ms_per_step": main["dev_ms_mean"], "sweep_kernel_ms_per_step": main["sweep_ms_mean"],
@@ -508,6 +514,8 @@ def main():
     ap.add_argument("--targets", type=int, default=1000000, help="targets of the whole job (8 blocks)")
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--sweep-warps", type=int, default=16)
+    ap.add_argument("--partition", default="auto", choices=["auto", "queries", "targets"],
+                    help="axis the N GPUs split: queries (lists final per rank, no exchange) or targets (global top-k merge); auto = queries when every GPU gets >= 512")
     args = ap.parse_args()
     if args.targets % NBLOCKS:
         raise SystemExit(f"--targets must be a multiple of {NBLOCKS}")
