@@ -105,6 +105,15 @@ int ppp_abi_version(void);
  * genomes in universe order).  T is row-major, nT rows of ppp_words_per_row(G) uint32 words,
  * genome g = bit (g & 31) of word (g >> 5), padding bits zero.  The data is copied before returning. */
 int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, uint32_t G);
+/* The same upload, streamed: returns without copying.  The next ppp_run / ppp_score queues the copies (pieces of 4, 16, then
+ * 32 MiB on a copy stream of the context) at its first launch that reads targets and scans the first rows while the later
+ * pieces are still crossing PCIe: every launch waits only for the pieces it reads.  T should be page-locked (cudaHostAlloc / cudaHostRegister; pageable memory works
+ * but copies synchronously) and MUST stay valid and unchanged until a ppp_run / ppp_score over these targets has returned PPP_OK
+ * or ppp_wait_targets() has returned.  No counterpart in the reference (its targets are Perl values in the worker's memory):
+ * this is the hook for a host that keeps its packed target collection in pinned memory and re-scores it many times. */
+int ppp_set_targets_bits_streamed(ppp_ctx *ctx, const uint32_t *T, size_t nT, uint32_t G);
+/* blocks until a streamed upload is complete on the device (no-op otherwise) */
+int ppp_wait_targets(ppp_ctx *ctx);
 
 /* Targets as ordered hit lists (replaces -prof2 built by BlastResult::get_profile, BlastResult.pm:192-237, or
  * the value-sorted HASH of HMMERResult, ppp.pm:147-149).  For target t, entries row_off[t]..row_off[t+1]) give,

@@ -23,7 +23,7 @@ HIT_DTYPE = np.dtype(
 assert HIT_DTYPE.itemsize == 32
 
 EXPORTS = [
-    "ppp_init", "ppp_destroy", "ppp_last_error", "ppp_abi_version", "ppp_set_targets_bits", "ppp_set_targets_ranked",
+    "ppp_init", "ppp_destroy", "ppp_last_error", "ppp_abi_version", "ppp_set_targets_bits", "ppp_set_targets_bits_streamed", "ppp_wait_targets", "ppp_set_targets_ranked",
     "ppp_set_queries", "ppp_run", "ppp_result_count", "ppp_fetch", "ppp_score", "ppp_get_stats", "ppp_set_option",
     "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc", "ppp_topk_device", "ppp_merge_topk_device", "ppp_read_bla", "ppp_read_bla_flags", "ppp_printed_cutoffs",
     "ppp_free_ranked_lists", "ppp_debug_enclosure", "ppp_query_count", "ppp_row_words", "ppp_pipe_peak", "ppp_read_bla_cached", "ppp_read_profiles", "ppp_free_profile_set",
@@ -80,6 +80,10 @@ def load():
     L.ppp_abi_version.restype = ctypes.c_int
     L.ppp_set_targets_bits.restype = ctypes.c_int
     L.ppp_set_targets_bits.argtypes = [vp, vp, sz, u32]
+    L.ppp_set_targets_bits_streamed.restype = ctypes.c_int
+    L.ppp_set_targets_bits_streamed.argtypes = [vp, vp, sz, u32]
+    L.ppp_wait_targets.restype = ctypes.c_int
+    L.ppp_wait_targets.argtypes = [vp]
     L.ppp_set_targets_ranked.restype = ctypes.c_int
     L.ppp_set_targets_ranked.argtypes = [vp, vp, vp, vp, sz, u32]
     L.ppp_set_queries.restype = ctypes.c_int
@@ -230,11 +234,21 @@ class Context:
     def words_per_row(self, G):
         return int(self.lib.ppp_words_per_row(G))
 
-    def set_targets_bits(self, T: np.ndarray, G: int):
+    def set_targets_bits(self, T: np.ndarray, G: int, streamed: bool = False):
+        """Upload packed target planes.  streamed=True (ppp_set_targets_bits_streamed) only queues the copies: T should be
+        page-locked, is kept referenced by this object, and must not be modified until the next run() / score() returned."""
         T = np.ascontiguousarray(T, dtype=np.uint32)
         assert T.ndim == 2 and T.shape[1] == self.words_per_row(G), (T.shape, G)
-        self._check(self.lib.ppp_set_targets_bits(self._h, _ptr(T), T.shape[0], G))
+        if streamed:
+            self._streamed_T = T  # keeps the host buffer alive while the copies are in flight
+            self._check(self.lib.ppp_set_targets_bits_streamed(self._h, _ptr(T), T.shape[0], G))
+        else:
+            self._check(self.lib.ppp_set_targets_bits(self._h, _ptr(T), T.shape[0], G))
+            self._streamed_T = None
         self.G, self.nT = G, T.shape[0]
+
+    def wait_targets(self):
+        self._check(self.lib.ppp_wait_targets(self._h))
 
     def set_targets_ranked(self, idx, rawdepth, row_off, G: int):
         """Ordered, de-duplicated hit lists (packer.pack_ranked_targets)."""

@@ -44,6 +44,7 @@ extern "C" uint32_t ppp_prefilter2_tile_queries(int pall);
 extern "C" cudaError_t ppp_launch_refine(const SweepParams *prm, int wpl, const uint32_t *surv, const unsigned long long *surv_count,
                                          unsigned long long surv_cap, int nwarps, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_transpose(const void *T, void *Tt, uint32_t nT, int wpl, cudaStream_t st);
+extern "C" cudaError_t ppp_launch_transpose_rows(const void *T, void *Tt, uint32_t nT, int wpl, uint32_t t_begin, uint32_t t_end, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_exact(const SweepParams *prm, int W, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_sweep_ranked(const SweepParams *prm, int rwpl, int nwarps, int nsm, cudaStream_t st);
 extern "C" cudaError_t ppp_launch_exact_ranked(const SweepParams *prm, int rwpl, int nsm, cudaStream_t st);
@@ -108,6 +109,14 @@ struct ppp_ctx {
     uint32_t *d_Tt = nullptr; /* chunk-major transposed planes for the thread-per-pair pre-filter */
     size_t cap_Tt = 0;
     bool Tt_valid = false;
+    /* streamed upload (ppp_set_targets_bits_streamed): pieces of rows copied on copy_stream; a run waits for a piece -- and
+     * transposes it -- right before the first launch that reads it, so the upload hides behind the scan of the earlier pieces */
+    struct Piece { size_t t_end; cudaEvent_t ev; };
+    std::vector<Piece> pieces;
+    size_t pieces_waited = 0;
+    const uint32_t *streamed_src = nullptr; /* host planes of a streamed upload whose copies are not queued yet */
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> piece_evpool;
     uint32_t *d_surv = nullptr;
     size_t cap_surv = 0;
     uint32_t *d_surv1 = nullptr; /* pair-level column masks of the tensor-core screen ([query tile][target][words]), re-screened into d_surv */
@@ -346,6 +355,11 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaFree(ctx->d_mcnt);
     for (int i = 0; i < 8; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
+    for (cudaEvent_t e : ctx->piece_evpool) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -374,6 +388,110 @@ static int pick_wpl(uint32_t G)
 
 static void free_query_buffers(ppp_ctx *ctx);
 static void reset_queries_if_layout_changed(ppp_ctx *ctx, int wpl, uint32_t G);
+static int group_set_targets_bits_streamed(ppp_ctx *g, const uint32_t *T, size_t nT, uint32_t G);
+
+/* a streamed upload that is still in flight is completed before the target buffers are touched again */
+static int drain_streamed_upload(ppp_ctx *ctx)
+{
+    if (ctx->copy_stream && !ctx->pieces.empty()) CU(cudaStreamSynchronize(ctx->copy_stream));
+    ctx->pieces.clear();
+    ctx->pieces_waited = 0;
+    ctx->streamed_src = nullptr;
+    return PPP_OK;
+}
+
+/* Queue the pieces of a streamed upload on the copy stream: 4 MiB, 16 MiB, then 32 MiB each (the first launches of a top-k run
+ * read only a few thousand rows).  Done at the first launch that reads targets, not inside ppp_set_targets_bits_streamed: the
+ * host-to-device copy engine serves its queue in order, and the small uploads of ppp_set_queries and of the run's own set-up
+ * (offsets, initial thresholds) would otherwise sit behind half a gigabyte of planes. */
+static int issue_streamed_upload(ppp_ctx *ctx)
+{
+    const uint32_t *T = ctx->streamed_src;
+    if (!T) return PPP_OK;
+    ctx->streamed_src = nullptr;
+    const size_t nT = ctx->nT, W = 32 * (size_t)ctx->wpl, wpr = ppp_words_per_row(ctx->G), row_bytes = W * 4;
+    if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    /* everything queued on the compute stream so far may still read the old planes */
+    CU(cudaEventRecord(ctx->ev[7], ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[7], 0));
+    size_t done = 0, piece_bytes = (size_t)4 << 20;
+    while (done < nT) {
+        const size_t rows = std::min(nT - done, std::max<size_t>(1024, piece_bytes / row_bytes));
+        if (wpr != W) CU(cudaMemsetAsync(ctx->d_T + done * W, 0, rows * row_bytes, ctx->copy_stream));
+        CU(cudaMemcpy2DAsync(ctx->d_T + done * W, row_bytes, T + done * wpr, wpr * 4, wpr * 4, rows, cudaMemcpyHostToDevice, ctx->copy_stream));
+        const size_t i = ctx->pieces.size();
+        if (i == ctx->piece_evpool.size()) {
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->piece_evpool.push_back(e);
+        }
+        CU(cudaEventRecord(ctx->piece_evpool[i], ctx->copy_stream));
+        done += rows;
+        ctx->pieces.push_back({done, ctx->piece_evpool[i]});
+        piece_bytes = std::min<size_t>((size_t)32 << 20, piece_bytes * 4);
+    }
+    return PPP_OK;
+}
+
+/* make the targets below row t1 usable by the launches that follow on ctx->stream (no-op unless the upload was streamed) */
+static int wait_targets(ppp_ctx *ctx, size_t t1)
+{
+    int rc;
+    if ((rc = issue_streamed_upload(ctx))) return rc;
+    while (ctx->pieces_waited < ctx->pieces.size()) {
+        const size_t i = ctx->pieces_waited, begin = i ? ctx->pieces[i - 1].t_end : 0;
+        if (begin >= t1) break;
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->pieces[i].ev, 0));
+        CU(ppp_launch_transpose_rows(ctx->d_T, ctx->d_Tt, (uint32_t)ctx->nT, ctx->wpl, (uint32_t)begin, (uint32_t)ctx->pieces[i].t_end, ctx->stream));
+        ctx->pieces_waited++;
+    }
+    return PPP_OK;
+}
+
+extern "C" int ppp_set_targets_bits_streamed(ppp_ctx *ctx, const uint32_t *T, size_t nT, uint32_t G)
+{
+    if (ctx && !ctx->subs.empty()) return group_set_targets_bits_streamed(ctx, T, nT, G);
+    if (!ctx) return PPP_ERR_INVALID;
+    if (!T && nT) return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_bits_streamed: T is NULL");
+    if (G == 0 || G > 8192) return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_bits_streamed: G = %u outside [1, 8192]", G);
+    if (nT > 0xffffffffull) return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_bits_streamed: nT too large");
+    CU(cudaSetDevice(ctx->device));
+    const int wpl = pick_wpl(G);
+    const size_t W = 32 * (size_t)wpl;
+    ctx->nT = 0;
+    ctx->Tt_valid = false;
+    int rc;
+    if ((rc = drain_streamed_upload(ctx))) return rc;
+    if ((rc = grow(ctx, &ctx->d_T, &ctx->cap_T, std::max<size_t>(1, nT * W)))) return rc;
+    if ((rc = grow(ctx, &ctx->d_Tt, &ctx->cap_Tt, std::max<size_t>(1, nT * W)))) return rc;
+    if ((rc = ensure_lf(ctx))) return rc;
+    ctx->ranked = false;
+    reset_queries_if_layout_changed(ctx, wpl, G);
+    ctx->nT = nT;
+    ctx->G = G;
+    ctx->wpl = wpl;
+    ctx->streamed_src = nT ? T : nullptr;
+    ctx->Tt_valid = true; /* built piece by piece in wait_targets */
+    return PPP_OK;
+}
+
+extern "C" int ppp_wait_targets(ppp_ctx *ctx)
+{
+    if (!ctx) return PPP_ERR_INVALID;
+    if (!ctx->subs.empty()) {
+        for (ppp_ctx *s : ctx->subs) {
+            const int rc = ppp_wait_targets(s);
+            if (rc) return fail(ctx, rc, "%s", s->err);
+        }
+        return PPP_OK;
+    }
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = wait_targets(ctx, ctx->nT))) return rc;
+    if (ctx->copy_stream) CU(cudaStreamSynchronize(ctx->copy_stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PPP_OK;
+}
 
 extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, uint32_t G)
 {
@@ -388,6 +506,7 @@ extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, 
     ctx->nT = 0;
     ctx->Tt_valid = false;
     int rc;
+    if ((rc = drain_streamed_upload(ctx))) return rc;
     if ((rc = grow(ctx, &ctx->d_T, &ctx->cap_T, std::max<size_t>(1, nT * W)))) return rc; /* buffers are reused across calls */
     if (nT) {
         if (wpr != W) CU(cudaMemsetAsync(ctx->d_T, 0, nT * W * 4, ctx->stream));
@@ -444,6 +563,7 @@ extern "C" int ppp_set_targets_ranked(ppp_ctx *ctx, const uint16_t *idx, const u
     ctx->nT = 0;
     ctx->Tt_valid = false;
     int rc;
+    if ((rc = drain_streamed_upload(ctx))) return rc;
     if ((rc = ensure_lf(ctx))) return rc;
     if ((rc = grow(ctx, &ctx->d_ridx, &ctx->cap_ridx, total + 64))) return rc;
     if ((rc = grow(ctx, &ctx->d_rraw, &ctx->cap_rraw, total + 64))) return rc;
@@ -740,6 +860,7 @@ static int launch_chunk_deferred(ppp_ctx *ctx, SweepParams *prm, uint32_t *launc
     const int W = 32 * ctx->wpl;
     int rc;
     size_t e0, e1, e2, em = 0;
+    if ((rc = wait_targets(ctx, prm->t1))) return rc;
     CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_SLOTS * sizeof(unsigned long long), ctx->stream));
     if ((rc = mark(ctx, &e0))) return rc;
     if (prefiltered) {
@@ -785,6 +906,10 @@ static int run_chunk(ppp_ctx *ctx, SweepParams *prm, unsigned long long *totals,
                      unsigned long long *chunk_counters, bool prefiltered)
 {
     const int W = 32 * ctx->wpl;
+    {
+        const int rcw = wait_targets(ctx, prm->t1);
+        if (rcw) return rcw;
+    }
     CU(cudaMemsetAsync(ctx->d_counters, 0, CNT_SLOTS * sizeof(unsigned long long), ctx->stream));
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     if (prefiltered) {
@@ -868,6 +993,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         use_table = fits && (ctx->table_mode == 1 || pays);
     }
     if (use_table) {
+        if ((rc = wait_targets(ctx, nT))) return rc;
         if (!ctx->Tt_valid) {
             const size_t W = 32 * (size_t)ctx->wpl;
             if ((rc = grow(ctx, &ctx->d_Tt, &ctx->cap_Tt, nT * W))) return rc;
@@ -1709,6 +1835,26 @@ static int group_set_targets_bits(ppp_ctx *g, const uint32_t *T, size_t nT, uint
     g->wpl = g->subs[0]->wpl;
     g->ranked = false;
     g->nQ = g->subs[0]->nQ; /* 0 if the layout changed */
+    return PPP_OK;
+}
+
+static int group_set_targets_bits_streamed(ppp_ctx *g, const uint32_t *T, size_t nT, uint32_t G)
+{
+    if (!T && nT) return fail(g, PPP_ERR_INVALID, "ppp_set_targets_bits_streamed: T is NULL");
+    if (nT > 0xffffffffull) return fail(g, PPP_ERR_INVALID, "ppp_set_targets_bits_streamed: nT too large");
+    group_shard(g, nT);
+    const size_t wpr = ppp_words_per_row(G);
+    g->nT = 0;
+    const int rc = for_each_sub(g, [&](ppp_ctx *s, size_t i) {
+        s->t_base = (uint32_t)g->sub_t0[i];
+        return ppp_set_targets_bits_streamed(s, T ? T + g->sub_t0[i] * wpr : nullptr, g->sub_t0[i + 1] - g->sub_t0[i], G);
+    });
+    if (rc) return rc;
+    g->nT = nT;
+    g->G = G;
+    g->wpl = g->subs[0]->wpl;
+    g->ranked = false;
+    g->nQ = g->subs[0]->nQ;
     return PPP_OK;
 }
 

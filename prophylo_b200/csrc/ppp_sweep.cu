@@ -637,18 +637,19 @@ extern "C" cudaError_t ppp_launch_rescreen_masks(const SweepParams *prm, int wpl
 }
 
 /* transpose row-major planes T[nT][W] into chunk-major Tt[W/4][nT] of uint4 (coalesced per-thread row streaming) */
-__global__ void ppp_transpose_kernel(const uint4 *__restrict__ T, uint4 *__restrict__ Tt, uint32_t nT, uint32_t C)
+__global__ void ppp_transpose_kernel(const uint4 *__restrict__ T, uint4 *__restrict__ Tt, uint32_t nT, uint32_t C, uint32_t t_begin,
+                                     uint32_t t_end)
 {
     __shared__ uint4 tile[32][33];
-    const uint32_t t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const uint32_t t0 = t_begin + blockIdx.x * 32, c0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const uint32_t t = t0 + r, c = c0 + threadIdx.x;
-        if (t < nT && c < C) tile[r][threadIdx.x] = T[(size_t)t * C + c];
+        if (t < t_end && c < C) tile[r][threadIdx.x] = T[(size_t)t * C + c];
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const uint32_t c = c0 + r, t = t0 + threadIdx.x;
-        if (t < nT && c < C) Tt[(size_t)c * nT + t] = tile[threadIdx.x][r];
+        if (t < t_end && c < C) Tt[(size_t)c * nT + t] = tile[threadIdx.x][r];
     }
 }
 
@@ -777,10 +778,15 @@ extern "C" cudaError_t ppp_launch_refine(const SweepParams *prm, int wpl, const 
     }
 }
 
+extern "C" cudaError_t ppp_launch_transpose_rows(const void *T, void *Tt, uint32_t nT, int wpl, uint32_t t_begin, uint32_t t_end, cudaStream_t st)
+{
+    if (t_end <= t_begin) return cudaSuccess;
+    const uint32_t C = 8u * (uint32_t)wpl;
+    dim3 grid((t_end - t_begin + 31) / 32, (C + 31) / 32), block(32, 8);
+    ppp_transpose_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const uint4 *>(T), reinterpret_cast<uint4 *>(Tt), nT, C, t_begin, t_end);
+    return cudaGetLastError();
+}
 extern "C" cudaError_t ppp_launch_transpose(const void *T, void *Tt, uint32_t nT, int wpl, cudaStream_t st)
 {
-    const uint32_t C = 8u * (uint32_t)wpl;
-    dim3 grid((nT + 31) / 32, (C + 31) / 32), block(32, 8);
-    ppp_transpose_kernel<<<grid, block, 0, st>>>(reinterpret_cast<const uint4 *>(T), reinterpret_cast<uint4 *>(Tt), nT, C);
-    return cudaGetLastError();
+    return ppp_launch_transpose_rows(T, Tt, nT, wpl, 0u, nT, st);
 }

@@ -986,3 +986,45 @@ def test_tensor_core_chunk_screen_equals_popc_screen(ctx, G, kind, nq, nt, k):
     finally:
         ctx.set_option("prefilter_tc", 0)
         ctx.set_option("tc_exact", 1)
+
+
+@pytest.mark.parametrize("G,nq,nt,ndev", [(4096, 300, 150000, 1), (1000, 64, 70001, 1), (4096, 200, 150000, 2)])
+def test_streamed_target_upload_equals_plain_upload(ctx, G, nq, nt, ndev):
+    """ppp_set_targets_bits_streamed: the planes cross PCIe in pieces while the scan of the first pieces is already running
+    (every launch waits for -- and transposes -- only the pieces it reads).  Same kernels on the same rows as the plain upload,
+    so every filter mode must return identical records; the host buffer is page-locked once and pageable once; the planes are
+    replaced between runs (the buffers are reused, and an upload still in flight is drained first)."""
+    import torch
+    P, Y, p = synth.make_queries(G, nq, 700 + G, "mixed")
+    T = synth.make_targets(G, nt, 701 + G, plant_from=Y, plant_frac=0.01)
+    T2 = synth.make_targets(G, nt // 3, 702 + G, plant_from=Y, plant_frac=0.01)
+    Tpin = torch.from_numpy(T).pin_memory().numpy()
+    dut = ctx if ndev == 1 else capi.Context(_devices_for_group(ndev))
+    try:
+        filters = [capi.make_filter(capi.FILTER_TOPK, k=50), capi.make_filter(capi.FILTER_THRESH_LOG10, thresh=-6.0)]
+        if nq * nt <= 1 << 23:
+            filters.append(None)
+        for flt in filters:
+            ctx.set_targets_bits(T, G)
+            want = ctx.score(P, Y, p, flt).copy()
+            for host in (Tpin, T):
+                dut.set_targets_bits(host, G, streamed=True)
+                got = dut.score(P, Y, p, flt).copy()
+                assert got.size == want.size and want.size > 0
+                for f in ("q", "t", "yes", "number", "depth") + (("score",) if ndev == 1 else ()):
+                    assert np.array_equal(got[f], want[f]), (flt.mode if flt else 0, f)
+            # replaced while nothing has consumed the previous streamed upload; then a plain upload over a streamed one
+            dut.set_targets_bits(Tpin, G, streamed=True)
+            dut.set_targets_bits(T2, G, streamed=True)
+            a = dut.score(P, Y, p, flt).copy()
+            dut.set_targets_bits(Tpin, G, streamed=True)
+            dut.wait_targets()
+            dut.set_targets_bits(T2, G)
+            b = dut.score(P, Y, p, flt).copy()
+            ctx.set_targets_bits(T2, G)
+            c = ctx.score(P, Y, p, flt).copy()
+            for f in ("q", "t", "yes", "number", "depth"):
+                assert np.array_equal(a[f], c[f]) and np.array_equal(b[f], c[f]), (flt.mode if flt else 0, f)
+    finally:
+        if dut is not ctx:
+            dut.close()
