@@ -140,7 +140,7 @@ def perl_reference_throughput(w, budget_s, nproc):
     from oracle import oracle
 
     G = w["G"]
-    nq, nt = 16, max(16, 32 * nproc)  # more pairs than the budget allows: the workers stop at the budget
+    nq, nt = 16, max(16, 96 * nproc)  # ~6-10 s of wall on the box (16 cores); the workers stop at the budget if it is less
     P, Y, p, T = _sample_inputs(w, nq, nt)
     Pb, Yb, Tb = synth.unpack_bits(P, G), synth.unpack_bits(Y, G), synth.unpack_bits(T, G)
     cases = {"queries": [{str(g + 1): int(Yb[q, g]) for g in range(G) if Pb[q, g]} for q in range(nq)], "probs": [float(x) for x in p],
@@ -371,6 +371,15 @@ def run_ours(args):
     for _ in range(args.warmup):
         ctx.run(flt)
         collect(strong_off)
+    if args.profile_step:
+        flush.zero_()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        ctx.run(flt)
+        collect(strong_off)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     main = timed_steps(args.steps, strong_off, True)
     clocks = main["clocks"]
     value = nq * nt_total / (main["step_ms"] * 1e-3)
@@ -443,11 +452,12 @@ def run_ours(args):
         pairs_rate = pf_pairs_mean / (pf_ms * 1e-3) if pf_ms > 0 else 0.0
         popc_rate = pairs_rate * popc_exec
         # DRAM traffic of the dominant kernel per step: from the committed ncu capture of exactly this command, if there is one
-        traffic, traffic_src = None, None
+        traffic, traffic_step, traffic_src = None, None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
             if tj.get("workload") == [G, nq, nt_total, k, world]:
-                traffic, traffic_src = tj["dram_bytes_per_step"], tj["source"]
+                traffic_step, traffic_src = tj["dram_bytes_per_step"], tj["source"]
+                traffic = traffic_step / tj["launches_per_step"]  # per launch, like the contract's `achieved`
         except (OSError, ValueError, KeyError):
             pass
         W_bytes = words * 4
@@ -468,7 +478,7 @@ def run_ours(args):
             "gpu_launches": main["launches"],
             "roofline": {"bound": "int_pipe", "pipe": "xu_popc", "kernel": "ppp_prefilter2_kernel", "achieved": popc_rate / 1e12,
                          "peak": peaks["popc"] / 1e12, "unit": "TPOPC/s", "frac": popc_rate / peaks["popc"] if peaks["popc"] else None,
-                         "traffic": traffic, "traffic_source": traffic_src, "algorithmic_hbm_bytes_per_step": alg_bytes,
+                         "traffic": traffic, "traffic_per_step": traffic_step, "traffic_source": traffic_src, "algorithmic_hbm_bytes_per_step": alg_bytes,
                          "hbm_GBps_algorithmic": alg_bytes / (pf_ms * 1e-3) / 1e9 if pf_ms > 0 else None,
                          "kernel_ms_per_step": pf_ms, "kernel_share_of_step": pf_ms / main["step_ms"],
                          "popc_executed_per_pair": popc_exec, "popc_per_pair_survey_8d": popc_survey,
@@ -515,6 +525,9 @@ def main():
     ap.add_argument("--targets", type=int, default=1000000, help="targets of the whole job (8 blocks)")
     ap.add_argument("--topk", type=int, default=100)
     ap.add_argument("--sweep-warps", type=int, default=16)
+    ap.add_argument("--profile-step", action="store_true",
+                    help="for ncu --profile-from-start off: after the warm-up, run ONE step between cudaProfilerStart/Stop and exit "
+                         "(no timing, no JSON line)")
     ap.add_argument("--partition", default="auto", choices=["auto", "queries", "targets"],
                     help="axis the N GPUs split: queries (lists final per rank, no exchange) or targets (global top-k merge); auto = queries when every GPU gets >= 512")
     args = ap.parse_args()
