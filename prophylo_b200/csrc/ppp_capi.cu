@@ -993,7 +993,6 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         use_table = fits && (ctx->table_mode == 1 || pays);
     }
     if (use_table) {
-        if ((rc = wait_targets(ctx, nT))) return rc;
         if (!ctx->Tt_valid) {
             const size_t W = 32 * (size_t)ctx->wpl;
             if ((rc = grow(ctx, &ctx->d_Tt, &ctx->cap_Tt, nT * W))) return rc;
@@ -1029,18 +1028,26 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         SweepParams prm;
         base_params(ctx, &prm);
         prm.hits = ctx->d_hits;
-        prm.t0 = 0;
-        prm.t1 = (uint32_t)nT;
         CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-        CU(ppp_launch_table_sweep(&prm, ctx->wpl, ctx->d_Tt, (uint32_t)nT, ctx->d_toff, ctx->d_tab, ctx->nsm, ctx->stream));
+        /* one launch over all targets -- or, while a streamed upload is arriving, one launch per piece: the sweep of a piece
+         * overlaps the copy of the next one (config 2 end to end is then the PCIe time of the planes, not the sum) */
+        if ((rc = issue_streamed_upload(ctx))) return rc;
+        for (size_t tb = 0; tb < nT;) {
+            const size_t te = ctx->pieces_waited < ctx->pieces.size() ? ctx->pieces[ctx->pieces_waited].t_end : nT;
+            if ((rc = wait_targets(ctx, te))) return rc;
+            prm.t0 = (uint32_t)tb;
+            prm.t1 = (uint32_t)te;
+            CU(ppp_launch_table_sweep(&prm, ctx->wpl, ctx->d_Tt, (uint32_t)nT, ctx->d_toff, ctx->d_tab, ctx->nsm, ctx->stream));
+            launches++;
+            sweep_launches++;
+            tb = te;
+        }
         CU(cudaEventRecord(ctx->ev[3], ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
         sweep_ms += ms;
         ctx->phase_us[0] += 1e3 * ms;
-        launches++;
-        sweep_launches++;
         ctx->n_results = nQ * nT;
         ctx->last_used_table = 1;
     } else if (f->mode == PPP_FILTER_ALL) {

@@ -1011,6 +1011,8 @@ def test_streamed_target_upload_equals_plain_upload(ctx, G, nq, nt, ndev):
                 dut.set_targets_bits(host, G, streamed=True)
                 got = dut.score(P, Y, p, flt).copy()
                 assert got.size == want.size and want.size > 0
+                if flt is None and ndev == 1:
+                    assert dut.counter("used_table") == 1  # dense run in exact-table mode: one sweep launch per arriving piece
                 for f in ("q", "t", "yes", "number", "depth") + (("score",) if ndev == 1 else ()):
                     assert np.array_equal(got[f], want[f]), (flt.mode if flt else 0, f)
             # replaced while nothing has consumed the previous streamed upload; then a plain upload over a streamed one
