@@ -295,12 +295,13 @@ def run_ours(args):
     P, Y, p = make_queries(w)
     partition = args.partition if args.partition != "auto" else ("queries" if world > 1 and nq // world >= 512 else "targets")
     block_nt = nt_total // NBLOCKS
-    if partition == "queries":   # rank r: its slice of the queries against ALL targets
+    if partition == "queries":   # rank r: its share of the queries (balanced by presence-plane class and |Y|) against ALL targets
         blocks = list(range(NBLOCKS))
-        q0, q1 = parallel.shard_range(nq, rank, world)
+        qidx = parallel.balanced_query_shards(P, Y, G, world)[rank]
     else:                        # rank r: all queries against its blocks of the targets
         blocks = rank_blocks(rank, world)
-        q0, q1 = 0, nq
+        qidx = np.arange(nq)
+    q0, q1 = 0, len(qidx)
     T = np.concatenate([target_block(w, b, Y) for b in blocks])
     nt = T.shape[0]
 
@@ -308,9 +309,8 @@ def run_ours(args):
         t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
         return t, t.numpy()
 
-    hold = [pinned(x) for x in (P, Y, p, T)]
-    Pp, Yp, pp, Tp = [h[1] for h in hold]
-    Pq, Yq, pq = Pp[q0:q1], Yp[q0:q1], pp[q0:q1]   # this rank's queries of the headline run
+    hold = [pinned(x) for x in (P, Y, p, T, P[qidx], Y[qidx], p[qidx])]
+    Pp, Yp, pp, Tp, Pq, Yq, pq = [h[1] for h in hold]   # ..q: this rank's queries of the headline run
     ctx = capi.Context(local_rank)
     ctx.set_option("sweep_warps", args.sweep_warps)
     flt = capi.make_filter(capi.FILTER_TOPK, k=k)
@@ -468,7 +468,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": f"config3 (BASELINE: 10k x 1M all-pairs at 4096 genomes): {nq} queries x {nt_total} targets x G={G}, per-query "
                                    f"top-k k={k}; {world} GPU(s), partition = {partition}: {q1 - q0} queries x {nt} targets each", "genomes": G, "queries": nq,
-                       "targets": nt_total, "partition": partition, "queries_per_gpu": q1 - q0, "targets_per_gpu": nt, "filter": f"topk{k}", "l2": "flushed between timed iterations (256 MiB write)",
+                       "targets": nt_total, "partition": partition + (" (dealt over the GPUs by presence-plane class and |Y|: parallel.balanced_query_shards)" if partition == "queries" else ""), "queries_per_gpu": q1 - q0, "targets_per_gpu": nt, "filter": f"topk{k}", "l2": "flushed between timed iterations (256 MiB write)",
                        "timing": "wall of run + result collection bracketed by synchronize, max over ranks; CUDA-event time of the library's "
                                  "stream in device_ms_per_step"},
             "device_ms_per_step": main["dev_ms_mean"], "sweep_kernel_ms_per_step": main["sweep_ms_mean"],

@@ -22,6 +22,43 @@ def shard_range(n_targets: int, rank: int, world: int) -> tuple[int, int]:
     return t0, t0 + base + (1 if rank < rem else 0)
 
 
+def balanced_query_shards(P: np.ndarray, Y: np.ndarray, G: int, world: int) -> list[np.ndarray]:
+    """Query-axis partition for `world` GPUs: sorted index arrays, one per rank, covering every query once.
+
+    A query's cost in the scan is set by its presence plane (an all-ones plane takes `number` from the target's depth prefix: 3
+    POPC per 128 genomes; any other plane counts T & P as well: 6) and, to a lesser degree, by |Y| (staircase length, pairs that
+    reach the full evaluation).  Contiguous slices of a random query set differ by a few percent in their number of general
+    planes, and the step time of an N-GPU job is the slowest rank's.  So the queries of each class are dealt over the ranks
+    in descending |Y| order, serpentine (0..N-1, N-1..0, ...) -- the second class continues where the first stopped, so rank sizes
+    differ by at most one query.  The reference has no counterpart (bin/ppp.pl:895-922 forks one client per 50 targets and lets the OS
+    balance them)."""
+    wpr = P.shape[1]
+    full = np.full(wpr, 0xFFFFFFFF, dtype=np.uint32)
+    if G % 32:
+        full[G // 32] = (1 << (G % 32)) - 1
+    full[(G + 31) // 32:] = 0
+    all_ones = (P == full[None, :]).all(axis=1)
+    ny = np.zeros(P.shape[0], dtype=np.int64)
+    for w in range(wpr):  # |Y| per query without unpacking the planes
+        ny += _popcount32(Y[:, w])
+    shards = [[] for _ in range(world)]
+    i = 0
+    for cls in (np.nonzero(~all_ones)[0], np.nonzero(all_ones)[0]):
+        for q in cls[np.argsort(-ny[cls], kind="stable")]:
+            rnd, j = divmod(i, world)
+            shards[j if rnd % 2 == 0 else world - 1 - j].append(int(q))  # serpentine: 0..N-1, N-1..0, ... evens out the |Y| sums
+            i += 1
+    return [np.array(sorted(sh), dtype=np.int64) for sh in shards]
+
+
+def _popcount32(x: np.ndarray) -> np.ndarray:
+    x = x.astype(np.uint32)
+    x = x - ((x >> 1) & 0x55555555)
+    x = (x & 0x33333333) + ((x >> 2) & 0x33333333)
+    x = (x + (x >> 4)) & 0x0F0F0F0F
+    return ((x * 0x01010101) >> 24).astype(np.int64) & 0xFF
+
+
 def merge_topk(parts: list[np.ndarray], k: int, n_queries: int) -> np.ndarray:
     """k-way merge of per-shard top-k hit lists (target indices already global): ascending score, ties by target
     index -- the order of bin/ppp.pl:473-474's sort plus a deterministic tie-break."""

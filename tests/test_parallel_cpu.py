@@ -117,3 +117,27 @@ def test_sliced_global_topk_two_ranks_gloo(tmp_path):
                         "--master-port", "29613", str(script)], capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_balanced_query_shards_cover_and_balance():
+    """parallel.balanced_query_shards: every query exactly once, rank sizes within one, general presence planes (the queries
+    that cost twice as much in the screen) within one per rank, |Y| sums close -- where contiguous slices of the same random
+    set differ by several percent."""
+    from prophylo_b200 import parallel, synth
+
+    for G, nq, world in ((4096, 1000, 8), (1000, 37, 3), (2048, 5, 8)):
+        P, Y, p = synth.make_queries(G, nq, 77 + G, "mixed")
+        shards = parallel.balanced_query_shards(P, Y, G, world)
+        assert len(shards) == world
+        allq = np.concatenate(shards)
+        assert np.array_equal(np.sort(allq), np.arange(nq))
+        assert all(np.all(np.diff(s) > 0) for s in shards if s.size > 1)
+        sizes = [s.size for s in shards]
+        assert max(sizes) - min(sizes) <= 1
+        general = ~(synth.unpack_bits(P, G) == 1).all(axis=1)
+        cnt = [int(general[s].sum()) for s in shards]
+        assert max(cnt) - min(cnt) <= 1, cnt
+        if nq >= 1000:
+            ny = synth.unpack_bits(Y, G).sum(axis=1)
+            tot = np.array([ny[s].sum() for s in shards], dtype=np.float64)
+            assert tot.max() / tot.min() < 1.05
