@@ -1236,6 +1236,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
                 SweepParams prm;
                 fill_filtered(prm, processed, processed + w);
                 prm.kth = kth_used;
+                if (spec_on || first_spec) prm.accept_mode = 3; /* speculative threshold: ties at the threshold are kept */
                 /* without thresholds (fewer targets than k so far): tile kernel over every pair; otherwise thread-per-pair screen */
                 if ((rc = launch_chunk_deferred(ctx, &prm, &launches, !ctx->ranked && (processed || seeded_pass)))) return rc;
                 sweep_launches++;

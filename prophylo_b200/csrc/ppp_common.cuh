@@ -60,7 +60,9 @@ struct SweepParams {
     uint32_t append;           /* 0: dense hits[q*nT+t]; 1: per-query append hits[q*qcap + qcnt[q]++]; 2: global append;
                                   3: (bounds_only) dense matrix of provisional scores, double[nQ][t1 - t0] */
     uint32_t accept_mode;      /* 0: score < kth[q] (top-k, kth = 2.0 while the list is not full); 1: log10(score) < thresh;
-                                  2: klo[q] <= score <= kth[q] (re-scan of queries whose speculative threshold failed) */
+                                  2: klo[q] < score <= kth[q] (re-scan of queries whose speculative threshold failed);
+                                  3: score <= kth[q] (top-k launch screened against a SPECULATIVE threshold: ties at the
+                                     threshold are kept, so the verification may accept a k-th score equal to it) */
     double thresh_log10;
     const double *kth;         /* [nQ] */
     const double *klo;         /* [nQ] accept_mode 2 */
@@ -94,7 +96,8 @@ enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_ACCURATE = 2, CNT_VIOL = 3, CNT_CHECKS =
 __device__ __forceinline__ bool ppp_accept(const SweepParams &prm, uint32_t q, double score)
 {
     if (prm.accept_mode == 0) return score < prm.kth[q];
-    if (prm.accept_mode == 2) return score >= prm.klo[q] && score <= prm.kth[q];
+    if (prm.accept_mode == 3) return score <= prm.kth[q];
+    if (prm.accept_mode == 2) return score > prm.klo[q] && score <= prm.kth[q];
     return log10(score) < prm.thresh_log10;
 }
 /* write one result record: dense slot, per-query append or global append */

@@ -373,10 +373,13 @@ extern "C" cudaError_t ppp_launch_accumulate(unsigned long long *totals, const u
  * k-th best score over all nT targets is, for exchangeable targets, close to the (k * processed / nT)-th best seen so
  * far -- far below the guaranteed bound (the k-th best so far).  The remaining targets are therefore screened against
  * the r-th best score so far (r chosen on the host so that a Poisson(k processed / nT) count reaches r with probability
- * <= spec_eps_ppm, 5e-3 by default), which cuts the pairs that need a full evaluation several-fold, and the result is VERIFIED: every pair below
- * the speculative threshold was found exactly, so the list is exact iff it is full and its k-th score is strictly
- * below that threshold.  Queries that fail are re-scanned over the same targets with the guaranteed bound and
- * klo <= score <= kth acceptance (ppp_capi.cu). */
+ * <= spec_eps_ppm, 5e-3 by default), which cuts the pairs that need a full evaluation several-fold, and the result is VERIFIED: every pair at
+ * or below the speculative threshold was found exactly (acceptance is INCLUSIVE in speculative launches, accept_mode 3), so the
+ * list is exact iff it is full and its k-th score does not exceed that threshold.  Inclusive matters: the scores of a sparse
+ * query are heavily tied (thousands of targets share the score of "one yes at the first position"), the threshold -- an entry
+ * of the list -- is typically one of the tied values, and with a strict rule every such query failed the verification (5 % of
+ * config 3's queries, whatever the Poisson tail) and was scanned twice.  Queries that fail are re-scanned over the same targets
+ * with the guaranteed bound and klo < score <= kth acceptance (ppp_capi.cu). */
 /* prev != nullptr: the targets processed so far were themselves screened against the speculative thresholds prev[q] (taken
  * from the seeding pass), so a list holds EVERY processed pair below prev[q] and its r-th entry is the exact r-th best of
  * the processed targets even when the list is not full; the new threshold never exceeds prev[q] and is always verified. */
@@ -417,7 +420,7 @@ __global__ void ppp_spec_verify_kernel(const ppp_hit *__restrict__ topk, const u
     if (q >= nQ) return;
     const double s0 = kspec0[q];
     if (!(s0 < INFINITY)) return; /* not speculated */
-    const bool ok = topk_cnt[q] >= k && topk[(size_t)q * k + (k - 1)].score < s0;
+    const bool ok = topk_cnt[q] >= k && topk[(size_t)q * k + (k - 1)].score <= s0;
     if (!ok) {
         failed[atomicAdd(nfailed, 1u)] = q;
         last_tau[q] = INFINITY; /* force the staircase of this query to be rebuilt for the (looser) guaranteed bound */

@@ -4,8 +4,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from prophylo_b200 import capi, synth
 G, nq, nt = 4096, 10000, 125000
+NB, NQ = int(os.environ.get("NBLOCKS", "1")), int(os.environ.get("NQ", "10000"))  # bench.py's blocks of 125k targets; queries used
 P, Y, p = synth.make_queries(G, nq, synth.SEED_BASE + 3, "mixed")
-T = synth.make_targets(G, nt, synth.SEED_BASE + 103, plant_from=Y, plant_frac=0.01)
+T = np.concatenate([synth.make_targets(G, nt, synth.SEED_BASE + 103 + 1000 * b, plant_from=Y, plant_frac=0.01) for b in range(NB)])
+P, Y, p = P[:NQ], Y[:NQ], p[:NQ]
 c = capi.Context(0)
 c.set_option("sweep_warps", 16)
 c.set_targets_bits(T, G)
