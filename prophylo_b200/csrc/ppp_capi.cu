@@ -173,7 +173,9 @@ struct ppp_ctx {
     size_t cap_rank_tmp = 0;
     bool results_ranked = false;
     int dup = 0; /* ranked lists were packed for -dup: the sweep drops the candidate that exceeds |Y| (ppp.pm:222-224) */
-    int launch_pairs_log2 = 29; /* filtered runs: pairs per launch (tests lower it to exercise runs of several launches) */
+    int launch_pairs_log2 = 0; /* filtered runs: pairs per launch (0 = chosen from the free device memory; tests lower it to exercise
+                                * runs of several launches) */
+    int auto_pairs_log2 = 0;
     int device_rank = 1; /* 0: rank threshold results on the host (developer A/B) */
     uint32_t *d_exact = nullptr;
     size_t cap_exact = 0;
@@ -1070,7 +1072,23 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         /* filtered: per-query staircases prune almost every pair inside the sweep kernel; survivors are appended */
         const bool topk = (f->mode == PPP_FILTER_TOPK);
         const uint32_t k = f->k;
-        const size_t maxw = std::min<size_t>(nT, std::max<size_t>(256, ((size_t)1 << ctx->launch_pairs_log2) / nQ));
+        /* Pairs per launch.  Every launch pays for a staircase rebuild, a list merge and the tails of its kernels (about 0.5 ms at
+         * config 3), so launches should be as large as the scratch buffers allow: 40 bytes per pair of a launch (append slots,
+         * survivor and exact-tier ids; the pair ids of the exact tier have 31 bits).  Measured on the full config 3: 2^28 pairs
+         * 395.1 ms, 2^29 377.8, 2^30 370.9, 2^31 365.5.  Unless the option fixes it, take the largest of 2^31 / 2^30 / 2^29 whose
+         * scratch stays below 45 % of the memory that is free when the context first needs it (86 GB for 2^31 on a B200). */
+        if (!ctx->launch_pairs_log2 && !ctx->auto_pairs_log2) {
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            ctx->auto_pairs_log2 = 29;
+            for (int l = 31; l > 29; --l)
+                if (40.0 * ldexp(1.0, l) <= 0.45 * (double)free_b) {
+                    ctx->auto_pairs_log2 = l;
+                    break;
+                }
+        }
+        const int pairs_log2 = ctx->launch_pairs_log2 ? ctx->launch_pairs_log2 : ctx->auto_pairs_log2;
+        const size_t maxw = std::min<size_t>(nT, std::max<size_t>(256, ((size_t)1 << pairs_log2) / nQ));
         if ((rc = grow(ctx, &ctx->d_hits, &ctx->cap_hits, nQ * maxw))) return rc;
         if ((rc = grow(ctx, &ctx->d_exact, &ctx->cap_exact, nQ * maxw))) return rc;
         /* [nQ] k-th scores, [nQ] tau of the resident staircase, [nQ] speculative thresholds in use, [nQ] their initial values,
@@ -1122,11 +1140,15 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
         };
         /* smallest rank r with P(Poisson(k seen / nT) >= r) <= spec_eps: the r-th best score (or bound) over `seen` exchangeable
          * targets then lies above the final k-th best score except with that probability */
+        /* a query whose speculation fails is scanned twice over ALL nT targets, while a looser threshold only costs a few more full
+         * evaluations: the tolerated failure probability shrinks with the size of the run (measured at 10,000 x 1,000,000:
+         * 5000 ppm 382.3 ms, 1000 ppm 379.7, 500 ppm 374.4 with no query re-scanned; at 10,000 x 125,000 5000 ppm is best) */
+        const double spec_eps = 1e-6 * ctx->spec_eps_ppm * std::min(1.0, 131072.0 / (double)nT);
         auto poisson_rank = [&](size_t seen) {
             const double lam = (double)k * (double)seen / (double)nT;
             double term = exp(-lam), cdf = term; /* P(X <= 0) */
             uint32_t r = 1;
-            while (1.0 - cdf > 1e-6 * ctx->spec_eps_ppm && r < k) {
+            while (1.0 - cdf > spec_eps && r < k) {
                 term *= lam / (double)r;
                 cdf += term;
                 ++r;
@@ -1620,7 +1642,7 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
     } else if (!strcmp(name, "dup")) {
         ctx->dup = value != 0;
     } else if (!strcmp(name, "launch_pairs_log2")) {
-        if (value < 12 || value > 29) return fail(ctx, PPP_ERR_INVALID, "launch_pairs_log2 must be in [12, 29]");
+        if (value != 0 && (value < 12 || value > 31)) return fail(ctx, PPP_ERR_INVALID, "launch_pairs_log2 must be 0 (automatic) or in [12, 31]");
         ctx->launch_pairs_log2 = (int)value;
     } else if (!strcmp(name, "device_rank")) {
         ctx->device_rank = value != 0;

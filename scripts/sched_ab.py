@@ -10,6 +10,8 @@ T = np.concatenate([synth.make_targets(G, nt, synth.SEED_BASE + 103 + 1000 * b, 
 P, Y, p = P[:NQ], Y[:NQ], p[:NQ]
 c = capi.Context(0)
 c.set_option("sweep_warps", 16)
+if os.environ.get("LPL"):
+    c.set_option("launch_pairs_log2", int(os.environ["LPL"]))
 c.set_targets_bits(T, G)
 c.set_queries(P, Y, p)
 flt = capi.make_filter(capi.FILTER_TOPK, k=100)

@@ -357,7 +357,7 @@ def test_threshold_results_ranked_on_device(ctx):
         assert ctx.stats()["sweep_launches"] > 2
         assert ctx.printed_cutoffs(20.0)["row_off"][-1] == multi.size  # still resident and ranked on the device
     finally:
-        ctx.set_option("launch_pairs_log2", 29)
+        ctx.set_option("launch_pairs_log2", 0)
     assert multi.tobytes() == host.tobytes()
     key = np.lexsort((dev["t"], dev["score"], dev["q"]))
     assert np.array_equal(key, np.arange(dev.size))
