@@ -184,7 +184,7 @@ int ppp_row_words(const ppp_ctx *ctx, size_t *words);
  * head and of the first chunk, in units of k), "prefilter_version" (2 / 1), "prefilter_tc" (bit 0: the chunk screen of the queries
  * with an all-ones presence plane takes its counts from tcgen05.mma instead of POPC, bit 1: that of the other queries too;
  * prophylo_b200/csrc/ppp_prefilter_tc.cu), "launch_pairs_log2" (pairs per launch of a
- * filtered run: 0 = automatic, the largest of 2^31 / 2^30 / 2^29 whose scratch buffers -- 40 bytes per pair -- stay below 45 % of
+ * filtered run: 0 = automatic, the largest of 2^31 / 2^30 / 2^29 whose scratch buffers -- 40 bytes per pair -- stay below half of
  * the free device memory; or 12..31; tests lower it to exercise runs of several launches).  "spec_eps_ppm" is scaled by
  * min(1, 131072 / targets): a failed speculation costs a second scan of all targets.
  * Unknown names return PPP_ERR_INVALID. */

@@ -1076,13 +1076,13 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
          * config 3), so launches should be as large as the scratch buffers allow: 40 bytes per pair of a launch (append slots,
          * survivor and exact-tier ids; the pair ids of the exact tier have 31 bits).  Measured on the full config 3: 2^28 pairs
          * 395.1 ms, 2^29 377.8, 2^30 370.9, 2^31 365.5.  Unless the option fixes it, take the largest of 2^31 / 2^30 / 2^29 whose
-         * scratch stays below 45 % of the memory that is free when the context first needs it (86 GB for 2^31 on a B200). */
+         * scratch stays below half of the memory that is free when the context first needs it (86 GB for 2^31 on a B200). */
         if (!ctx->launch_pairs_log2 && !ctx->auto_pairs_log2) {
             size_t free_b = 0, total_b = 0;
             CU(cudaMemGetInfo(&free_b, &total_b));
             ctx->auto_pairs_log2 = 29;
             for (int l = 31; l > 29; --l)
-                if (40.0 * ldexp(1.0, l) <= 0.45 * (double)free_b) {
+                if (40.0 * ldexp(1.0, l) <= 0.5 * (double)free_b) {
                     ctx->auto_pairs_log2 = l;
                     break;
                 }
