@@ -139,9 +139,10 @@ struct ppp_ctx {
     uint32_t *d_qflags = nullptr; /* bit 0: presence plane is all ones over the G genomes */
     void *h_stage = nullptr; /* pinned staging buffer of ppp_set_queries */
     size_t cap_stage = 0;
-    uint32_t *d_qorder = nullptr; /* query ids: the n_pall queries with an all-ones presence plane first, then the others */
-    size_t n_pall = 0;
-    uint32_t stair_need[2] = {0, 0}; /* largest per-tile staircase footprint (entries) of the general / all-ones launch */
+    uint32_t *d_qorder = nullptr; /* query ids by pre-filter class: the n_pall queries with an all-ones presence plane first, then the
+                                   * n_pyy queries with P == Y (number == yes: one lookup per pair), then the others */
+    size_t n_pall = 0, n_pyy = 0;
+    uint32_t stair_need[3] = {0, 0, 0}; /* largest per-tile staircase footprint (entries) of the general / all-ones / P == Y launch */
     unsigned long long *d_pfstats = nullptr;
     int prefilter_version = 2; /* 2: ppp_prefilter.cu (queued slow path), 1: the in-line screen of ppp_sweep.cu */
     uint32_t stair_need_any = 0; /* staircase footprint of the worst possible general tile (re-scan of arbitrary queries) */
@@ -586,6 +587,21 @@ extern "C" int ppp_set_targets_ranked(ppp_ctx *ctx, const uint16_t *idx, const u
     return PPP_OK;
 }
 
+/* positions [b, e) of pre-filter class `kind` in d_qorder: 1 = all-ones presence plane, 2 = P == Y, 0 = the others */
+static void class_range(const ppp_ctx *ctx, int kind, size_t nQ, size_t *b, size_t *e)
+{
+    if (kind == 1) {
+        *b = 0;
+        *e = ctx->n_pall;
+    } else if (kind == 2) {
+        *b = ctx->n_pall;
+        *e = ctx->n_pall + ctx->n_pyy;
+    } else {
+        *b = ctx->n_pall + ctx->n_pyy;
+        *e = nQ;
+    }
+}
+
 static void make_qconst(double p, uint32_t ny, uint32_t npres, QConst *qc)
 {
     memset(qc, 0, sizeof(*qc));
@@ -693,19 +709,26 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
     for (size_t q = 0; q < nQ; ++q) qfl[q] = (qc[q].npres == ctx->G) ? 1u : 0u;
     CU(cudaMemcpyAsync(ctx->d_qflags, qfl.data(), nQ * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     {
-        /* processing order of the pre-filter: all-ones presence planes first (number == depth: their own launch) */
+        /* processing order of the pre-filter, one launch per class: all-ones presence planes (number == depth), P == Y (number ==
+         * yes; Y is a subset of P, so equal counts mean equal planes), everything else */
         std::vector<uint32_t> order;
         order.reserve(nQ);
+        auto is_pyy = [&](size_t q) { return !qfl[q] && qc[q].ny == qc[q].npres; };
         for (size_t q = 0; q < nQ; ++q)
             if (qfl[q]) order.push_back((uint32_t)q);
         ctx->n_pall = order.size();
         for (size_t q = 0; q < nQ; ++q)
-            if (!qfl[q]) order.push_back((uint32_t)q);
-        /* deal the queries of each kind over its tiles by descending |Y| (tile i takes the i-th, (i + ntiles)-th ...
+            if (is_pyy(q)) order.push_back((uint32_t)q);
+        ctx->n_pyy = order.size() - ctx->n_pall;
+        for (size_t q = 0; q < nQ; ++q)
+            if (!qfl[q] && !is_pyy(q)) order.push_back((uint32_t)q);
+        /* deal the queries of each class over its tiles by descending |Y| (tile i takes the i-th, (i + ntiles)-th ...
          * largest): every tile then holds about the same staircase footprint, which is what sizes the kernel's shared
          * memory (and hence its occupancy), and about the same amount of slow-path work */
-        for (int kind = 0; kind < 2; ++kind) {
-            const size_t b = kind ? 0 : ctx->n_pall, e = kind ? ctx->n_pall : nQ, n = e - b;
+        for (int kind = 0; kind < 3; ++kind) {
+            size_t b, e;
+            class_range(ctx, kind, nQ, &b, &e);
+            const size_t n = e - b;
             const size_t qt = ppp_prefilter2_tile_queries(kind);
             if (n <= qt) continue;
             std::vector<uint32_t> sorted(order.begin() + b, order.begin() + e);
@@ -716,8 +739,9 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
                 for (size_t j = 0; j * ntiles + tile < n && j < qt; ++j) order[o++] = sorted[j * ntiles + tile];
         }
         CU(cudaMemcpyAsync(ctx->d_qorder, order.data(), nQ * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-        for (int kind = 0; kind < 2; ++kind) {
-            const size_t b = kind ? 0 : ctx->n_pall, e = kind ? ctx->n_pall : nQ;
+        for (int kind = 0; kind < 3; ++kind) {
+            size_t b, e;
+            class_range(ctx, kind, nQ, &b, &e);
             size_t worst = 0;
             const size_t qt = ppp_prefilter2_tile_queries(kind);
             for (size_t i = b; i < e; i += qt) {
@@ -728,7 +752,8 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
             ctx->stair_need[kind] = (uint32_t)std::min<size_t>(worst, 0xffffffffu);
         }
         for (int kind = 0; kind < 2; ++kind) {
-            const size_t b = kind ? 0 : ctx->n_pall, e = kind ? ctx->n_pall : nQ;
+            size_t b, e;
+            class_range(ctx, kind, nQ, &b, &e);
             const size_t qt = ppp_prefilter_tc_tile_queries(kind);
             size_t worst = 0;
             for (size_t i = b; i < e; i += qt) {
@@ -801,9 +826,10 @@ static int mark(ppp_ctx *ctx, size_t *idx)
 static bool use_prefilter2(const ppp_ctx *ctx)
 {
     if (ctx->prefilter_version != 2) return false;
-    for (int kind = 0; kind < 2; ++kind) {
-        const size_t n = kind ? ctx->n_pall : ctx->nQ - ctx->n_pall;
-        if (n && ctx->stair_need[kind] > ppp_prefilter2_max_stair(ctx->wpl, kind)) return false;
+    for (int kind = 0; kind < 3; ++kind) {
+        size_t b, e;
+        class_range(ctx, kind, ctx->nQ, &b, &e);
+        if (e > b && ctx->stair_need[kind] > ppp_prefilter2_max_stair(ctx->wpl, kind)) return false;
     }
     return true;
 }
@@ -823,11 +849,13 @@ static int launch_prefiltered(ppp_ctx *ctx, SweepParams *prm, cudaEvent_t betwee
                                ctx->sweep_warps, ctx->nsm, ctx->stream, between));
         return PPP_OK;
     }
-    for (int kind = 1; kind >= 0; --kind) { /* all-ones presence planes first, then the general ones */
-        const uint32_t *ql = kind ? ctx->d_qorder : ctx->d_qorder + ctx->n_pall;
-        const uint32_t n = (uint32_t)(kind ? ctx->n_pall : ctx->nQ - ctx->n_pall);
+    for (int kind : {1, 2, 0}) { /* all-ones presence planes, P == Y, then the general ones */
+        size_t cb, ce;
+        class_range(ctx, kind, ctx->nQ, &cb, &ce);
+        const uint32_t *ql = ctx->d_qorder + cb;
+        const uint32_t n = (uint32_t)(ce - cb);
         if (!n) continue;
-        if (((ctx->prefilter_tc >> (kind ? 0 : 1)) & 1) && ctx->stair_need_tc[kind] <= ppp_prefilter_tc_max_stair(ctx->wpl, kind) &&
+        if (kind != 2 && ((ctx->prefilter_tc >> (kind ? 0 : 1)) & 1) && ctx->stair_need_tc[kind] <= ppp_prefilter_tc_max_stair(ctx->wpl, kind) &&
             (ctx->tc_exact || ctx->stair_need_tc[kind] <= ppp_rescreen_max_stair(ctx->wpl, kind))) {
             /* the chunk counts come from the tensor cores (ppp_prefilter_tc.cu); in pair-level mode the kernel writes one column
              * mask per (query tile, target) -- the pairs with a passing CHUNK -- which the re-screen kernel reduces to the pairs

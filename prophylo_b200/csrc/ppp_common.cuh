@@ -88,8 +88,8 @@ enum { CNT_EXACT = 0, CNT_CAND = 1, CNT_ACCURATE = 2, CNT_VIOL = 3, CNT_CHECKS =
        CNT_ITEM = 9, /* work-item counter of the tile kernels */
        CNT_SURV1 = 10, /* pairs with a passing CHUNK (tensor-core screen, pair-level mode): re-screened into CNT_SURV */
        CNT_ITEM2 = 11, /* work-item counter of the re-screen kernel */
-       CNT_PF_UNIT_GEN = 12, CNT_PF_UNIT_ALL = 13, /* work counters of the pre-filter's general / all-ones launch of a chunk */
-       CNT_SLOTS = 14 };
+       CNT_PF_UNIT_GEN = 12, CNT_PF_UNIT_ALL = 13, CNT_PF_UNIT_PYY = 14, /* work counters of the pre-filter's three launches of a chunk */
+       CNT_SLOTS = 16 };
 
 #ifdef __CUDACC__
 #include "../../include/ppp_b200.h"

@@ -21,6 +21,9 @@
  *               position in the row, which would send nearly every warp down a divergent branch).
  * Queries whose presence plane is all ones (number == depth of the target, the common case) run in their own launch:
  * number_before comes from a per-thread prefix table of the target row, computed once per target block.
+ * Queries with P == Y (the cross-score form: every genome the query knows is a "yes") run in a third one: number == yes
+ * at every candidate, so a candidate passes iff yes <= nmax[yes], the slack nmax[y] - y is non-decreasing, and the pair has a
+ * passing candidate iff its LAST one passes -- one lookup per pair at the row's total popc(T & Y), no queue, no drain.
  *
  * Everything is doubled (stair values, counts) so that the staircase index is a byte offset and no shift is needed.
  */
@@ -42,7 +45,7 @@
 #ifndef PF2_CH
 #define PF2_CH 4
 #endif
-#define PF2_QT(PALL) ((PALL) ? 32 : 16) /* queries per shared-memory tile */
+#define PF2_QT(MODE) ((MODE) ? 32 : 16) /* queries per shared-memory tile (MODE: 0 general, 1 all-ones P, 2 P == Y) */
 #ifdef PF2_STATS
 #define PF2_STAT(x) x
 #else
@@ -123,15 +126,16 @@ __device__ __forceinline__ void load_words(const uint32_t *__restrict__ src, uin
  * query tile, same target), so the queue is only drained when a lane runs out of room and at the end of the item. */
 #define PF2_E_WORD 0x20000000u
 
-template <int WPL, bool PALL>
+template <int WPL, int MODE>
 __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Params a)
 {
+    constexpr bool PALL = MODE == 1, PYY = MODE == 2;
     constexpr int W = 32 * WPL;
     constexpr int CH = (WPL == 8 || PF2_CH == 8) ? 8 : 4; /* words per chunk; at most 32 chunks per row */
     constexpr int NCH = W / CH;
     constexpr int HEAD = (PF2_HEAD < NCH) ? PF2_HEAD : NCH;
-    constexpr int QW = PALL ? 1 : 2;       /* queue words per entry */
-    constexpr int QT = PF2_QT(PALL);
+    constexpr int QW = MODE ? 1 : 2;       /* queue words per entry */
+    constexpr int QT = PF2_QT(MODE);
     constexpr int NSLOT = QT + PF2_QG;     /* compact slots incl. padding of the last register group */
     constexpr int QSTRIDE = QW * PF2_THREADS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -143,9 +147,9 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
     uint32_t *s_pass = reinterpret_cast<uint32_t *>(smem_raw + 1024); /* [THREADS] per target: compact slots with a passing candidate */
     uint32_t *s_y = s_pass + PF2_THREADS;                            /* [NSLOT][W] yes planes of the compact slots */
     uint32_t *s_p = s_y + NSLOT * W;                                 /* [NSLOT][W] presence planes (general launch) */
-    uint16_t *s_pref = reinterpret_cast<uint16_t *>(s_y + (PALL ? 1 : 2) * NSLOT * W); /* [NCH][THREADS] doubled number before chunk */
-    uint32_t *s_queue = reinterpret_cast<uint32_t *>(s_pref + (PALL ? NCH * PF2_THREADS : 0)); /* [QCAP][QW][THREADS] */
-    int16_t *s_stair = reinterpret_cast<int16_t *>(s_queue + PF2_QCAP * QSTRIDE);              /* doubled staircases */
+    uint16_t *s_pref = reinterpret_cast<uint16_t *>(s_y + (MODE ? 1 : 2) * NSLOT * W); /* [NCH][THREADS] doubled number before chunk */
+    uint32_t *s_queue = reinterpret_cast<uint32_t *>(s_pref + (PALL ? NCH * PF2_THREADS : 0)); /* [QCAP][QW][THREADS] (none for P == Y) */
+    int16_t *s_stair = reinterpret_cast<int16_t *>(s_queue + (PYY ? 0 : PF2_QCAP) * QSTRIDE);  /* doubled staircases */
     const unsigned char *s_stair_b = reinterpret_cast<const unsigned char *>(s_stair);
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
                 if (act) {
                     s_qid[slot] = qid;
                     s_sbase[slot] = 2u * (1u + incl - len); /* entry 0 of the shared array is the dummy staircase */
-                    if (!PALL) tma_load_1d(s_p + slot * W, a.Q + (size_t)qid * 2 * W, W * 4, bar);
+                    if (MODE == 0) tma_load_1d(s_p + slot * W, a.Q + (size_t)qid * 2 * W, W * 4, bar);
                     tma_load_1d(s_y + slot * W, a.Q + (size_t)qid * 2 * W + W, W * 4, bar);
                 } else if ((uint32_t)tid < nq) {
                     s_inact[__popc(im & ((1u << tid) - 1u))] = qid;
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
             /* padding slots: all-zero planes */
             for (uint32_t i = nact * W + tid; i < npad * W; i += PF2_THREADS) {
                 s_y[i] = 0;
-                if (!PALL) s_p[i] = 0;
+                if (MODE == 0) s_p[i] = 0;
             }
             if (tid == 0) s_stair[0] = -2;
             /* staircases, doubled; entry 0 of each (no candidate has yes == 0) can never pass */
@@ -236,7 +240,9 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
                 const uint16_t *src = a.nmax + a.nmax_off[qid];
                 const uint32_t len = a.qc[qid].ny + 1;
                 int16_t *dst = s_stair + (s_sbase[s] >> 1);
-                for (uint32_t i = lane; i < len; i += 32) dst[i] = i ? (int16_t)(2 * (int)__ldg(src + i)) : (int16_t)-2;
+                /* P == Y: the doubled SLACK nmax[y] - y instead (number == yes at every candidate: it passes iff this is >= 0) */
+                for (uint32_t i = lane; i < len; i += 32)
+                    dst[i] = i ? (int16_t)(2 * ((int)__ldg(src + i) - (PYY ? (int)i : 0))) : (int16_t)-2;
             }
             mbar_wait(bar, parity);
             parity ^= 1;
@@ -358,6 +364,43 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
             qa = qa0;
         };
 
+        if constexpr (PYY) {
+            /* P == Y: count popc(T & Y) over the whole row, one lookup at the end */
+            uint32_t mypass = 0;
+            for (uint32_t g0 = 0; g0 < npad; g0 += PF2_QG) {
+                uint32_t ys[PF2_QG];
+#pragma unroll
+                for (int j = 0; j < PF2_QG; ++j) ys[j] = s_sbase[g0 + j];
+                const uint32_t *yg = s_y + g0 * W;
+                uint32_t tw[CH];
+                load_chunk<CH>(a.Tt, a.ntt, t, 0, live, tw);
+                const uint4 *tnext = a.Tt + t;
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    uint32_t tn[CH];
+                    if (c + 1 < NCH) tnext += (size_t)(CH / 4) * a.ntt;
+#pragma unroll
+                    for (int i = 0; i < CH / 4; ++i) {
+                        const uint4 v = __ldg(tnext + (size_t)i * a.ntt);
+                        tn[4 * i + 0] = v.x; tn[4 * i + 1] = v.y; tn[4 * i + 2] = v.z; tn[4 * i + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int j = 0; j < PF2_QG; ++j) {
+                        uint32_t b[CH];
+                        load_words<CH>(yg + j * W + c * CH, b);
+#pragma unroll
+                        for (int w = 0; w < CH; ++w) b[w] &= tw[w];
+                        ys[j] += 2u * popc_csa<CH>(b);
+                    }
+#pragma unroll
+                    for (int w = 0; w < CH; ++w) tw[w] = tn[w];
+                }
+#pragma unroll
+                for (int j = 0; j < PF2_QG; ++j)
+                    if ((int)*reinterpret_cast<const int16_t *>(s_stair_b + ys[j]) >= 0) mypass |= 1u << (g0 + j);
+            }
+            s_pass[tid] = mypass; /* threads past the last target are ignored below */
+        } else {
         for (uint32_t g0 = 0; g0 < npad; g0 += PF2_QG) {
             uint32_t ys[PF2_QG];  /* doubled staircase index: base + 2 * yes */
             uint32_t nbq[PF2_QG]; /* doubled number so far (general launch) */
@@ -471,6 +514,7 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
             }
         }
         drain();
+        }
 
         /* ---- survivors: compact slots with a passing candidate + every query without a staircase (live threads) */
         __syncwarp();
@@ -519,47 +563,48 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
 }
 
 /* ---------------------------------------------------------------- host side */
-static size_t pf2_smem_bytes(int wpl, bool pall, uint32_t stair_cap)
+static size_t pf2_smem_bytes(int wpl, int mode, uint32_t stair_cap)
 {
     const size_t W = 32 * (size_t)wpl, CH = (wpl == 8 || PF2_CH == 8) ? 8 : 4, NCH = W / CH;
-    const size_t nslot = PF2_QT(pall) + PF2_QG;
-    size_t b = 1024 + PF2_THREADS * 4 + (pall ? 1 : 2) * nslot * W * 4;
-    if (pall) b += NCH * PF2_THREADS * 2;
-    b += (size_t)PF2_QCAP * (pall ? 1 : 2) * PF2_THREADS * 4;
+    const size_t nslot = PF2_QT(mode) + PF2_QG;
+    size_t b = 1024 + PF2_THREADS * 4 + (mode ? 1 : 2) * nslot * W * 4;
+    if (mode == 1) b += NCH * PF2_THREADS * 2;
+    if (mode != 2) b += (size_t)PF2_QCAP * (mode ? 1 : 2) * PF2_THREADS * 4;
     b += ((size_t)stair_cap * 2 + 15) & ~(size_t)15;
     return b + 64;
 }
 
 /* largest staircase capacity (int16 entries) a tile may use; 0 = this layout cannot run the kernel at all */
-extern "C" uint32_t ppp_prefilter2_tile_queries(int pall) { return PF2_QT(pall != 0); }
+extern "C" uint32_t ppp_prefilter2_tile_queries(int mode) { return PF2_QT(mode); }
 
-extern "C" uint32_t ppp_prefilter2_max_stair(int wpl, int pall)
+extern "C" uint32_t ppp_prefilter2_max_stair(int wpl, int mode)
 {
-    const size_t fixed = pf2_smem_bytes(wpl, pall != 0, 0);
+    const size_t fixed = pf2_smem_bytes(wpl, mode, 0);
     const size_t limit = 220 * 1024;
     if (fixed + 64 > limit) return 0;
     const size_t room = (limit - fixed) / 2;
     return (uint32_t)std::min<size_t>(room, 32767); /* the doubled index must fit 16 bits */
 }
 
-template <int WPL, bool PALL>
+template <int WPL, int MODE>
 static cudaError_t pf2_launch_t(const Pf2Params &p, int nsm, cudaStream_t st)
 {
-    const size_t smem = pf2_smem_bytes(WPL, PALL, p.stair_cap);
-    cudaError_t e = cudaFuncSetAttribute(ppp_prefilter2_kernel<WPL, PALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = pf2_smem_bytes(WPL, MODE, p.stair_cap);
+    cudaError_t e = cudaFuncSetAttribute(ppp_prefilter2_kernel<WPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_prefilter2_kernel<WPL, PALL>, PF2_THREADS, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_prefilter2_kernel<WPL, MODE>, PF2_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    const uint64_t items = (uint64_t)((p.nqk + PF2_QT(PALL) - 1) / PF2_QT(PALL)) * ((p.nTl + PF2_THREADS - 1) / PF2_THREADS);
+    const uint64_t items = (uint64_t)((p.nqk + PF2_QT(MODE) - 1) / PF2_QT(MODE)) * ((p.nTl + PF2_THREADS - 1) / PF2_THREADS);
     uint64_t grid = std::min<uint64_t>((uint64_t)nsm * per_sm, items);
     if (grid < 1) grid = 1;
-    ppp_prefilter2_kernel<WPL, PALL><<<(unsigned)grid, PF2_THREADS, smem, st>>>(p);
+    ppp_prefilter2_kernel<WPL, MODE><<<(unsigned)grid, PF2_THREADS, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-/* One launch over the queries listed in qorder[0..nqk): pall != 0 -> every listed query has an all-ones presence plane.
+/* One launch over the queries listed in qorder[0..nqk): pall = 1 -> every listed query has an all-ones presence plane, 2 -> every
+ * listed query has P == Y, 0 -> any presence plane.
  * *surv_count is NOT reset here (the all-ones and the general launch of a chunk append to the same list). */
 extern "C" cudaError_t ppp_launch_prefilter2(const SweepParams *prm, int wpl, int pall, const void *Tt, uint32_t ntt, const uint32_t *qorder,
                                              uint32_t nqk, uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count,
@@ -577,21 +622,25 @@ extern "C" cudaError_t ppp_launch_prefilter2(const SweepParams *prm, int wpl, in
     p.surv_count = surv_count;
     p.surv_cap = surv_cap;
     p.stats = stats;
-    p.unit_counter = prm->counters + (pall ? CNT_PF_UNIT_ALL : CNT_PF_UNIT_GEN);
+    p.unit_counter = prm->counters + (pall == 1 ? CNT_PF_UNIT_ALL : pall == 2 ? CNT_PF_UNIT_PYY : CNT_PF_UNIT_GEN);
     p.ntt = ntt;
     p.t0 = prm->t0;
     p.nTl = prm->t1 - prm->t0;
     p.nqk = nqk;
     p.stair_cap = stair_cap;
-    switch (wpl * 2 + (pall ? 1 : 0)) {
-    case 2: return pf2_launch_t<1, false>(p, nsm, st);
-    case 3: return pf2_launch_t<1, true>(p, nsm, st);
-    case 4: return pf2_launch_t<2, false>(p, nsm, st);
-    case 5: return pf2_launch_t<2, true>(p, nsm, st);
-    case 8: return pf2_launch_t<4, false>(p, nsm, st);
-    case 9: return pf2_launch_t<4, true>(p, nsm, st);
-    case 16: return pf2_launch_t<8, false>(p, nsm, st);
-    case 17: return pf2_launch_t<8, true>(p, nsm, st);
+    switch (wpl * 4 + pall) {
+    case 4: return pf2_launch_t<1, 0>(p, nsm, st);
+    case 5: return pf2_launch_t<1, 1>(p, nsm, st);
+    case 6: return pf2_launch_t<1, 2>(p, nsm, st);
+    case 8: return pf2_launch_t<2, 0>(p, nsm, st);
+    case 9: return pf2_launch_t<2, 1>(p, nsm, st);
+    case 10: return pf2_launch_t<2, 2>(p, nsm, st);
+    case 16: return pf2_launch_t<4, 0>(p, nsm, st);
+    case 17: return pf2_launch_t<4, 1>(p, nsm, st);
+    case 18: return pf2_launch_t<4, 2>(p, nsm, st);
+    case 32: return pf2_launch_t<8, 0>(p, nsm, st);
+    case 33: return pf2_launch_t<8, 1>(p, nsm, st);
+    case 34: return pf2_launch_t<8, 2>(p, nsm, st);
     default: return cudaErrorInvalidValue;
     }
 }

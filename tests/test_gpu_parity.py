@@ -1030,3 +1030,44 @@ def test_streamed_target_upload_equals_plain_upload(ctx, G, nq, nt, ndev):
     finally:
         if dut is not ctx:
             dut.close()
+
+
+@pytest.mark.parametrize("G,nq,nt,k", [(4096, 90, 9000, 50), (1000, 40, 20000, 10), (8192, 20, 3000, 5)])
+def test_p_equals_y_class_matches_dense(ctx, G, nq, nt, k):
+    """Queries with P == Y (the cross-score form, p = |Y| / G) have their own pre-filter launch: number == yes at every
+    candidate, so the pair is screened with ONE staircase lookup at the row's total popc(T & Y) (ppp_prefilter.cu, MODE 2).  Top-k
+    lists and threshold hits must equal the dense result; a query with P == Y == all ones stays in the all-ones class; queries
+    of the three classes are mixed in one run."""
+    rng = np.random.default_rng(5 + G)
+    P, Y, p = synth.make_queries(G, nq, 600 + G, "family")
+    Yb = synth.unpack_bits(Y, G)
+    Pb = Yb.copy()                        # P == Y ...
+    Pb[::7] = 1                           # ... except every 7th query: all-ones presence plane
+    Pb[3::7] |= rng.random((Pb[3::7].shape[0], G)) < 0.5   # ... and some general planes (Y subset of P, P neither all ones nor Y)
+    Yb[5] = 1
+    Pb[5] = 1                             # P == Y == all ones
+    P, Y = synth.pack_bits(Pb), synth.pack_bits(Yb)
+    p = Yb.sum(axis=1) / np.where((Pb == Yb).all(axis=1), G, Pb.sum(axis=1))
+    p = np.clip(p, 1e-6, 0.999)
+    T = synth.make_targets(G, nt, 601 + G, plant_from=Y, plant_frac=0.03)
+    ctx.set_targets_bits(T, G)
+    ctx.set_option("table_mode", 0)
+    try:
+        dense = ctx.score(P, Y, p).reshape(nq, nt)
+    finally:
+        ctx.set_option("table_mode", -1)
+    tk = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
+    assert tk.size == nq * k and ctx.counter("full_pairs") < nq * nt
+    for q in range(nq):
+        exp = np.sort(dense[q], order=["score", "t"])[:k]
+        got = tk[q * k:(q + 1) * k]
+        for f in ("q", "t", "score", "yes", "number", "depth"):
+            assert np.array_equal(got[f], exp[f]), (q, f)
+    thr = -3.0
+    th = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_THRESH_LOG10, thresh=thr)).copy()
+    with np.errstate(divide="ignore"):
+        keep = np.log10(dense["score"]) < thr
+    exp = np.sort(dense[keep], order=["q", "score", "t"])
+    assert th.size == exp.size and th.size > 0
+    for f in ("q", "t", "score", "yes", "number", "depth"):
+        assert np.array_equal(th[f], exp[f]), f
