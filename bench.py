@@ -438,15 +438,20 @@ def run_ours(args):
         pf_us_mean, pf_pairs_mean, surv_mean = float(np.mean(main["pf_us"])), float(np.mean(main["pf_pairs"])), float(np.mean(main["survs"]))
         pf_ms = pf_us_mean * 1e-3
         words = ((G + 1023) // 1024) * 32
-        frac_all = float(np.mean(synth.unpack_bits(Pq, G).all(axis=1)))
+        Pbits, Ybits = synth.unpack_bits(Pq, G), synth.unpack_bits(Yq, G)
+        is_all = Pbits.all(axis=1)
+        is_pyy = ~is_all & (Pbits == Ybits).all(axis=1)
+        frac_all, frac_pyy = float(np.mean(is_all)), float(np.mean(is_pyy))
         # POPC the dominant kernel (ppp_prefilter2_kernel, ppp_prefilter.cu) EXECUTES per pair: carry-save adders fold a
         # 4-word chunk into 3 POPC (8 words -> 4 at G = 8192); the first chunk is screened word by word; all-ones queries take
-        # `number` from a per-target depth prefix computed once per 32-query tile; general queries count T & P as well
+        # `number` from a per-target depth prefix computed once per 32-query tile; queries with P == Y need no `number` at all
+        # (it equals yes); general queries count T & P as well
         ch = 8 if words == 256 else 4
         nch, per_chunk = words // ch, (4 if ch == 8 else 3)
         popc_all = per_chunk * (nch - 1) + ch + ch / 8.0 + per_chunk * nch / 32.0
+        popc_pyy = per_chunk * nch
         popc_gen = 2 * per_chunk * (nch - 1) + 2 * ch
-        popc_exec = frac_all * popc_all + (1.0 - frac_all) * popc_gen
+        popc_exec = frac_all * popc_all + frac_pyy * popc_pyy + (1.0 - frac_all - frac_pyy) * popc_gen
         # SURVEY.md section 8(d) counts the straightforward algorithm: 2W POPC per pair when P is all ones, 3W otherwise
         popc_survey = frac_all * 2 * words + (1.0 - frac_all) * 3 * words
         nsm = ctx.counter("num_sms")
@@ -489,7 +494,7 @@ def run_ours(args):
                          "kernel_ms_per_step": pf_ms, "kernel_share_of_step": pf_ms / main["step_ms"],
                          "popc_executed_per_pair": popc_exec, "popc_per_pair_survey_8d": popc_survey,
                          "frac_vs_survey_count": pairs_rate * popc_survey / peaks["popc"] if peaks["popc"] else None,
-                         "pairs_per_s_in_kernel": pairs_rate, "all_ones_presence_fraction": frac_all,
+                         "pairs_per_s_in_kernel": pairs_rate, "all_ones_presence_fraction": frac_all, "p_equals_y_fraction": frac_pyy,
                          "peak_source": "ppp_pipe_peak microbenchmark run in this process after the timed steps (popc.b32 chains, 64 warps/SM)",
                          "peak_analytic": popc_peak_analytic / 1e12,
                          "peak_analytic_source": f"{nsm} SMs x 16 POPC/clk/SM x {clk / 1e6:.0f} MHz (sampled SM clock)",
