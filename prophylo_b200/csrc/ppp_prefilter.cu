@@ -25,7 +25,8 @@
  * at every candidate, so a candidate passes iff yes <= nmax[yes], the slack nmax[y] - y is non-decreasing, and the pair has a
  * passing candidate iff its LAST one passes -- one lookup per pair at the row's total popc(T & Y), no queue, no drain.
  *
- * Everything is doubled (stair values, counts) so that the staircase index is a byte offset and no shift is needed.
+ * The staircase INDEX is kept doubled (a byte offset into the int16 tables: base + 2 * yes, advanced with one shift-add);
+ * counts and staircase values are plain.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -233,16 +234,16 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
                 s_y[i] = 0;
                 if (MODE == 0) s_p[i] = 0;
             }
-            if (tid == 0) s_stair[0] = -2;
-            /* staircases, doubled; entry 0 of each (no candidate has yes == 0) can never pass */
+            if (tid == 0) s_stair[0] = -1;
+            /* staircases; entry 0 of each (no candidate has yes == 0) can never pass */
             for (uint32_t s = tid >> 5; s < nact; s += PF2_THREADS / 32) {
                 const uint32_t qid = s_qid[s];
                 const uint16_t *src = a.nmax + a.nmax_off[qid];
                 const uint32_t len = a.qc[qid].ny + 1;
                 int16_t *dst = s_stair + (s_sbase[s] >> 1);
-                /* P == Y: the doubled SLACK nmax[y] - y instead (number == yes at every candidate: it passes iff this is >= 0) */
+                /* P == Y: the SLACK nmax[y] - y instead (number == yes at every candidate: it passes iff this is >= 0) */
                 for (uint32_t i = lane; i < len; i += 32)
-                    dst[i] = i ? (int16_t)(2 * ((int)__ldg(src + i) - (PYY ? (int)i : 0))) : (int16_t)-2;
+                    dst[i] = i ? (int16_t)((int)__ldg(src + i) - (PYY ? (int)i : 0)) : (int16_t)-1;
             }
             mbar_wait(bar, parity);
             parity ^= 1;
@@ -256,14 +257,14 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
         const uint32_t t = a.t0 + (live ? tl : 0);
         s_pass[tid] = 0; /* by compact slot; written by whichever lane of the warp re-screens this target's entries */
 
-        if (PALL && npad) { /* doubled number (= depth) before every chunk of this thread's target row */
+        if (PALL && npad) { /* number (= depth) before every chunk of this thread's target row */
             uint32_t run = live ? 0u : 40000u; /* threads past the last target: a number no staircase admits, so nothing is queued */
 #pragma unroll 4
             for (int c = 0; c < NCH; ++c) {
                 uint32_t tw[CH];
                 load_chunk<CH>(a.Tt, a.ntt, t, c, live, tw);
                 s_pref[c * PF2_THREADS + tid] = (uint16_t)run;
-                run += 2u * popc_csa<CH>(tw);
+                run += popc_csa<CH>(tw);
             }
         }
 
@@ -328,29 +329,29 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
 #pragma unroll
                         for (int w = 0; w < CH; ++w) {
                             bw[w] &= aw[w];
-                            cyw[w] = 2u * __popc(bw[w]);
-                            cnw[w] = 2u * __popc(aw[w]);
+                            cyw[w] = __popc(bw[w]);
+                            cnw[w] = __popc(aw[w]);
                             if ((uint32_t)w <= wsel) { /* counts from the chunk's start up to and including the entry's word */
                                 cys += cyw[w];
                                 cns += cnw[w];
                             }
                         }
-                        /* state before the chunk: the entry carries the state after its chunk (or word) */
-                        uint32_t yb = (e & 0xffffu) - cys;
+                        /* state before the chunk: the entry carries the state after its chunk (or word); yb = staircase entry index */
+                        uint32_t yb = ((e & 0xffffu) >> 1) - cys;
                         uint32_t nb = PALL ? (uint32_t)s_pref[c * PF2_THREADS + otid] : qe[PF2_THREADS] - cns;
                         const uint32_t wlo = (e & PF2_E_WORD) ? wsel : 0u;
                         bool ok = false;
 #pragma unroll
                         for (int w = 0; w < CH; ++w) {
                             if ((uint32_t)w >= wlo && (uint32_t)w <= wsel && cyw[w] &&
-                                (int)(nb + cyw[w]) <= (int)s_stair[(yb + cyw[w]) >> 1]) {
+                                (int)(nb + cyw[w]) <= (int)s_stair[yb + cyw[w]]) {
                                 PF2_STAT(st_word += 1;)
                                 uint32_t yy = yb, bits = bw[w];
                                 while (bits) {
                                     const uint32_t bit = __ffs(bits) - 1;
                                     bits &= bits - 1;
-                                    yy += 2;
-                                    ok |= (int)(nb + 2u * __popc(aw[w] & ((2u << bit) - 1u))) <= (int)s_stair[yy >> 1];
+                                    ++yy;
+                                    ok |= (int)(nb + __popc(aw[w] & ((2u << bit) - 1u))) <= (int)s_stair[yy];
                                 }
                             }
                             yb += cyw[w];
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
         } else {
         for (uint32_t g0 = 0; g0 < npad; g0 += PF2_QG) {
             uint32_t ys[PF2_QG];  /* doubled staircase index: base + 2 * yes */
-            uint32_t nbq[PF2_QG]; /* doubled number so far (general launch) */
+            uint32_t nbq[PF2_QG]; /* number so far (general launch) */
 #pragma unroll
             for (int j = 0; j < PF2_QG; ++j) {
                 ys[j] = s_sbase[g0 + j];
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
 #pragma unroll
                         for (int w = 0; w < CH; ++w) {
                             nbw[w] = run;
-                            run += 2u * __popc(tw[w]);
+                            run += __popc(tw[w]);
                         }
                     }
 #pragma unroll
@@ -450,12 +451,12 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
 #pragma unroll
                         for (int w = 0; w < CH; ++w) {
                             const uint32_t aw = PALL ? tw[w] : (tw[w] & pw[w]);
-                            const uint32_t cy2 = 2u * __popc(aw & yw[w]);
+                            const uint32_t cy = __popc(aw & yw[w]);
                             const uint32_t nb = PALL ? nbw[w] : nbq[j];
-                            ys[j] += cy2;
-                            if (!PALL) nbq[j] += 2u * __popc(aw);
+                            ys[j] += 2u * cy;
+                            if (!PALL) nbq[j] += __popc(aw);
                             const int lim = (int)*reinterpret_cast<const int16_t *>(s_stair_b + ys[j]);
-                            if ((int)(nb + cy2) <= lim) {
+                            if ((int)(nb + cy) <= lim) {
                                 sts_u32(qa, ys[j] | ctag | ((uint32_t)w << 21) | ((uint32_t)j << 24) | PF2_E_WORD);
                                 if (!PALL) sts_u32(qa + 4u * PF2_THREADS, nbq[j]);
                                 qa += 4u * QSTRIDE;
@@ -485,14 +486,14 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
                                 b[w] &= aw[w];
                             }
                             nb = nbq[j];
-                            nbq[j] = nb + 2u * popc_csa<CH>(aw);
+                            nbq[j] = nb + popc_csa<CH>(aw);
                         }
-                        const uint32_t cy2 = 2u * popc_csa<CH>(b);
-                        ys[j] += cy2;
+                        const uint32_t cy = popc_csa<CH>(b);
+                        ys[j] += 2u * cy; /* one shift-add: the index is a byte offset */
                         const int lim = (int)*reinterpret_cast<const int16_t *>(s_stair_b + ys[j]);
                         /* d < 0: the chunk cannot pass.  One 3-input add and one funnel shift that moves d's sign bit into the
                          * flag word (query j ends up at bit QG-1-j) instead of compare + select + or */
-                        const int d = lim - (int)cy2 - (int)nb;
+                        const int d = lim - (int)cy - (int)nb;
                         flags = __funnelshift_l((uint32_t)d, flags, 1);
                     }
                     /* phase B: predicated pushes */
