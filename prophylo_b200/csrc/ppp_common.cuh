@@ -19,6 +19,11 @@
 #define PPP_QCAP_OF(WPL) ((WPL) == 1 ? 256 : PPP_QCAP_MAX)
 #define PPP_MINBLOCKS_OF(WPL) ((WPL) == 1 ? 2 : 1)
 #define PPP_K_TERMS 8     /* series terms of the float enclosure tier */
+/* Per-CTA dynamic shared-memory limit of sm_100.  Launchers opt every kernel in to THIS constant, not to the launch's own
+ * size: the attribute is per function and device, and two contexts on one device (a device group that lists a GPU twice)
+ * launch the same kernel with different sizes from different host threads -- one thread lowering the attribute under the
+ * other's launch makes that launch fail with "invalid argument". */
+#define PPP_MAX_DYN_SMEM (227 * 1024)
 
 /* per-query flags */
 #define PPP_QF_TRIVIAL 1u /* p == 0, p == 1 or NaN: bdtrc never improves on 1.0 -> (1,0,0,0)             */

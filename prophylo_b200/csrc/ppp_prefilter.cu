@@ -591,7 +591,7 @@ template <int WPL, int MODE>
 static cudaError_t pf2_launch_t(const Pf2Params &p, int nsm, cudaStream_t st)
 {
     const size_t smem = pf2_smem_bytes(WPL, MODE, p.stair_cap);
-    cudaError_t e = cudaFuncSetAttribute(ppp_prefilter2_kernel<WPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppp_prefilter2_kernel<WPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPP_MAX_DYN_SMEM);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_prefilter2_kernel<WPL, MODE>, PF2_THREADS, smem);

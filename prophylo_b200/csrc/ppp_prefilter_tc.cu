@@ -659,7 +659,7 @@ template <int WPL, bool PALL>
 static cudaError_t tc_launch_t(const TcParams &p, int nsm, cudaStream_t st)
 {
     const size_t smem = tc_smem_bytes(PALL, p.stair_cap);
-    cudaError_t e = cudaFuncSetAttribute(ppp_prefilter_tc_kernel<WPL, PALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppp_prefilter_tc_kernel<WPL, PALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPP_MAX_DYN_SMEM);
     if (e != cudaSuccess) return e;
     const uint64_t items = (uint64_t)((p.nqk + TC_NQ(PALL) - 1) / TC_NQ(PALL)) * ((p.nTl + 2 * TC_M - 1) / (2 * TC_M));
     uint64_t grid = std::min<uint64_t>((uint64_t)nsm, items);

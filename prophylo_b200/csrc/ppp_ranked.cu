@@ -174,7 +174,7 @@ static cudaError_t launch_ranked_t(const SweepParams &prm, int nwarps, int nsm, 
 {
     if (nwarps > 8) nwarps = 8;
     const size_t smem = ranked_smem_bytes(WPL, nwarps, prm.qwords);
-    cudaError_t e = cudaFuncSetAttribute(ppp_sweep_ranked_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppp_sweep_ranked_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPP_MAX_DYN_SMEM);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_sweep_ranked_kernel<WPL>, nwarps * 32, smem);

@@ -420,7 +420,6 @@ __global__ void __launch_bounds__(PPP_REFINE_WARPS * 32, PPP_MINBLOCKS_OF(WPL)) 
  * One CTA per (query tile, block of targets): the tile's query planes are staged in shared memory once, every warp takes a
  * target row (registers) and walks the set bits of its mask, so that a flagged pair costs shared-memory reads, a packed warp
  * scan and a few staircase lookups instead of three row loads from L2. */
-#define PPP_MAX_DYN_SMEM (227 * 1024) /* per-CTA limit of sm_100 */
 #define RS_ROWS 256 /* targets per work item */
 template <int WPL>
 __device__ __forceinline__ void load_words_smem(const uint32_t *src, uint32_t (&v)[WPL])
@@ -616,7 +615,7 @@ extern "C" cudaError_t ppp_launch_rescreen_masks(const SweepParams *prm, int wpl
     cudaError_t e = cudaSuccess;
 #define RS_LAUNCH(WPL_, NQ_)                                                                                                                   \
     do {                                                                                                                                       \
-        e = cudaFuncSetAttribute(ppp_rescreen_masks_kernel<WPL_, NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                \
+        e = cudaFuncSetAttribute(ppp_rescreen_masks_kernel<WPL_, NQ_>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPP_MAX_DYN_SMEM);                \
         if (e != cudaSuccess) return e;                                                                                                        \
         ppp_rescreen_masks_kernel<WPL_, NQ_><<<grid, 512, smem, st>>>(*prm, qorder, nqk, pall != 0, masks, out, out_count, out_cap);           \
     } while (0)
@@ -673,7 +672,7 @@ static cudaError_t launch_t(const SweepParams &prm, int nwarps, int nsm, cudaStr
 {
     while (nwarps > 1 && sweep_smem_bytes(WPL, nwarps) > PPP_MAX_DYN_SMEM) --nwarps; /* G = 8192: the tile + table leave room for 15 warps */
     const size_t smem = sweep_smem_bytes(WPL, nwarps);
-    cudaError_t e = cudaFuncSetAttribute(ppp_sweep_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppp_sweep_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPP_MAX_DYN_SMEM);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_sweep_kernel<WPL>, nwarps * 32, smem);
@@ -695,7 +694,7 @@ static cudaError_t launch_filtered_t(const SweepParams &prm, const void *Tt, uin
     cudaError_t e;
     {
         const size_t smem = prefilter_smem_bytes(WPL);
-        e = cudaFuncSetAttribute(ppp_prefilter_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(ppp_prefilter_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPP_MAX_DYN_SMEM);
         if (e != cudaSuccess) return e;
         int per_sm = 1;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_prefilter_kernel<WPL>, 256, smem);
@@ -712,7 +711,7 @@ static cudaError_t launch_filtered_t(const SweepParams &prm, const void *Tt, uin
     {
         while (nwarps > 1 && refine_smem_bytes(WPL, nwarps) > PPP_MAX_DYN_SMEM) --nwarps;
         const size_t smem = refine_smem_bytes(WPL, nwarps);
-        e = cudaFuncSetAttribute(ppp_refine_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(ppp_refine_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPP_MAX_DYN_SMEM);
         if (e != cudaSuccess) return e;
         int per_sm = 1;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_refine_kernel<WPL>, nwarps * 32, smem);
@@ -755,7 +754,7 @@ static cudaError_t launch_refine_t(const SweepParams &prm, const uint32_t *surv,
     if (nwarps == 16) nwarps = PPP_REFINE_WARPS; /* the tuned setting asks for as many warps as the kernel was compiled for */
     while (nwarps > 1 && refine_smem_bytes(WPL, nwarps) > PPP_MAX_DYN_SMEM) --nwarps;
     const size_t smem = refine_smem_bytes(WPL, nwarps);
-    cudaError_t e = cudaFuncSetAttribute(ppp_refine_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(ppp_refine_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPP_MAX_DYN_SMEM);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_refine_kernel<WPL>, nwarps * 32, smem);
