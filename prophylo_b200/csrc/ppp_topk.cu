@@ -1,7 +1,7 @@
 /*
  * prophylo_b200/csrc/ppp_topk.cu -- device side of the result filters:
  *
- *  ppp_build_staircase_kernel   per query, the exact integer pre-filter of a score threshold tau (ln domain):
+ *  ppp_build_staircase_kernel   per query (one CTA of 2, 4 or 8 warps), the exact integer pre-filter of a score threshold tau (ln domain):
  *        nmax[yes] = largest `number` for which P(X >= yes | number, p) can still be <= exp(tau).
  *     The binomial tail increases with number and decreases with yes, so a sweep candidate (yes, number) can
  *     reach the threshold iff number <= nmax[yes]; the sweep kernel rejects a whole lane of words with one
@@ -36,18 +36,61 @@ __device__ static bool tail_may_be_le(int y, int n, const QConst &qc, const doub
     return !(lo > (float)tau + 1e-3f + 1e-6f * fabsf((float)tau)); /* NaN-safe; margin covers the float cast of tau */
 }
 
-/* One staircase: tab[y] (y = 0..ny) = largest number for which P(X >= y | number, p) can still be <= exp(tau); the whole
- * warp works on it (bisection per y, then the monotone fix-up).  Requires tau < -0.70 and an ordinary query. */
-__device__ static void build_staircase(const QConst &c, const double *__restrict__ lf, double tau, uint16_t *__restrict__ tab, int lane)
+/* One staircase: tab[y] (y = 0..ny) = largest number for which P(X >= y | number, p) can still be <= exp(tau).  A TEAM of
+ * warps (one CTA) works on it: thread i searches y = 1 + i, 1 + i + NT, ... (NT = 32 * TEAM), then warp 0 applies the monotone
+ * fix-up.  Requires tau < -0.70 and an ordinary query.
+ *
+ * The search for one y is a bisection on `number` over [y, |P|] with the predicate tail_may_be_le (13 enclosure evaluations at
+ * G = 4096).  From its third value on a thread extrapolates its two previous results linearly (the staircase is smooth: its
+ * second difference over NT entries is a few units), probes there and gallops -- steps of 2, 4, 8 ... -- to a bracket before
+ * bisecting: about 5 evaluations.  Only FALSE probes ever lower the upper end, so the result stays at or above the true boundary
+ * whatever the predicate does beyond it (see tail_may_be_le). */
+template <int TEAM>
+__device__ static void build_staircase(const QConst &c, const double *__restrict__ lf, double tau, uint16_t *__restrict__ tab, int tid)
 {
+    constexpr int NT = 32 * TEAM;
+    const int lane = tid & 31;
     const double tau_m = tau + 1e-5 + 1e-9 * fabs(tau); /* safety margin >> series + table error */
     const int ny = (int)c.ny, np_ = (int)c.npres;
-    if (lane == 0) tab[0] = 0;
-    for (int y = 1 + lane; y <= ny; y += 32) {
+    if (tid == 0) tab[0] = 0;
+    int p1 = 0, p2 = 0; /* this thread's two previous results (0: none, or no valid entry) */
+    for (int y = 1 + tid; y <= ny; y += NT) {
+        int lo = -1, hi = np_; /* lo: a number known to pass (-1: none yet); every number above hi is known to fail or out of range */
+        if (isfinite(tau_m)) {
+            if (p1 > 0 && p2 > 0) {
+                const int g = min(max(p1 + (p1 - p2), y), np_);
+                int d = 2;
+                if (tail_may_be_le(y, g, c, lf, tau_m)) {
+                    lo = g;
+                    while (lo < hi) { /* gallop up */
+                        const int t = min(lo + d, hi);
+                        if (tail_may_be_le(y, t, c, lf, tau_m)) {
+                            lo = t;
+                            d <<= 1;
+                        } else {
+                            hi = t - 1;
+                            break;
+                        }
+                    }
+                } else {
+                    hi = g - 1;
+                    while (hi >= y) { /* gallop down */
+                        const int t = max(hi - d + 1, y);
+                        if (tail_may_be_le(y, t, c, lf, tau_m)) {
+                            lo = t;
+                            break;
+                        }
+                        hi = t - 1;
+                        d <<= 1;
+                    }
+                }
+            } else if (tail_may_be_le(y, y, c, lf, tau_m)) {
+                lo = y;
+            }
+        }
         int res = 0;
-        if (isfinite(tau_m) && tail_may_be_le(y, y, c, lf, tau_m)) {
-            int lo = y, hi = np_; /* invariant: tail_le(lo) true */
-            while (lo < hi) {
+        if (lo >= 0) {
+            while (lo < hi) { /* invariant: lo passes */
                 const int mid = (lo + hi + 1) >> 1;
                 if (tail_may_be_le(y, mid, c, lf, tau_m)) lo = mid;
                 else hi = mid - 1;
@@ -55,15 +98,17 @@ __device__ static void build_staircase(const QConst &c, const double *__restrict
             res = lo;
         }
         tab[y] = (uint16_t)res;
+        p2 = p1;
+        p1 = res;
     }
-    __syncwarp();
+    __syncthreads();
     /* enforce what the true staircase satisfies (independent searches may differ by rounding; only ever loosens):
      * non-decreasing in yes, and nmax[y] >= y  =>  nmax[y+1] >= nmax[y] + 1 (one more trial that is a success cannot
      * raise the tail), i.e. the slack nmax[y] - y is non-decreasing from the first valid entry on -- the chunk-level
      * screen of ppp_prefilter.cu tests only a chunk's last candidate on the strength of this.  Two warp prefix-max
      * scans, 32 entries a round: v1 = running max of the table, then slack = running max of (v1[i] - i) over the
      * valid entries (v1[i] >= i); result = y + slack where a valid entry precedes, v1 otherwise. */
-    {
+    if (tid < 32) {
         uint32_t carry_v = 0;
         int carry_s = -1;
         for (int y0 = 1; y0 <= ny; y0 += 32) {
@@ -88,17 +133,17 @@ __device__ static void build_staircase(const QConst &c, const double *__restrict
             if (in) tab[y] = (uint16_t)min((sl >= 0) ? (uint32_t)(y + sl) : v, 65535u);
         }
     }
-    __syncwarp();
 }
 
-__global__ void ppp_build_staircase_kernel(const QConst *__restrict__ qc, const double *__restrict__ lf, const double *__restrict__ kth,
-                                           int accept_mode, double thresh_ln, const uint32_t *__restrict__ static_off,
-                                           uint16_t *__restrict__ nmax, uint32_t *__restrict__ active_off,
-                                           double *__restrict__ last_tau, uint32_t nQ)
+/* one CTA of TEAM warps per query */
+template <int TEAM>
+__global__ void __launch_bounds__(32 * TEAM) ppp_build_staircase_kernel(const QConst *__restrict__ qc, const double *__restrict__ lf,
+                                                                        const double *__restrict__ kth, int accept_mode, double thresh_ln,
+                                                                        const uint32_t *__restrict__ static_off, uint16_t *__restrict__ nmax,
+                                                                        uint32_t *__restrict__ active_off, double *__restrict__ last_tau, uint32_t nQ)
 {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nQ; q += warps) {
+    const int tid = threadIdx.x;
+    for (uint32_t q = blockIdx.x; q < nQ; q += gridDim.x) {
         const QConst c = qc[q];
         double tau;
         if (accept_mode == 0) {
@@ -108,16 +153,20 @@ __global__ void ppp_build_staircase_kernel(const QConst *__restrict__ qc, const 
             tau = thresh_ln;
         }
         /* no pruning near or above the median, for odd p, or for empty queries */
-        if (!(tau < -0.70) || (c.flags & (PPP_QF_TRIVIAL | PPP_QF_DOMAIN | PPP_QF_EXACT)) || c.ny == 0) {
-            if (lane == 0) active_off[q] = PPP_NO_TABLE;
+        const bool none = !(tau < -0.70) || (c.flags & (PPP_QF_TRIVIAL | PPP_QF_DOMAIN | PPP_QF_EXACT)) || c.ny == 0;
+        /* the k-th score only ever decreases: a staircase built for a slightly larger tau stays valid (just looser) */
+        const bool keep = !none && active_off[q] != PPP_NO_TABLE && tau > last_tau[q] - 0.05;
+        __syncthreads(); /* every thread has read the query's state before thread 0 changes it */
+        if (none) {
+            if (tid == 0) active_off[q] = PPP_NO_TABLE;
             continue;
         }
-        /* the k-th score only ever decreases: a staircase built for a slightly larger tau stays valid (just looser) */
-        if (active_off[q] != PPP_NO_TABLE && tau > last_tau[q] - 0.05) continue;
-        if (lane == 0) last_tau[q] = tau;
-        build_staircase(c, lf, tau, nmax + static_off[q], lane);
-        if (lane == 0) active_off[q] = static_off[q];
-        __syncwarp();
+        if (keep) continue;
+        build_staircase<TEAM>(c, lf, tau, nmax + static_off[q], tid);
+        if (tid == 0) {
+            last_tau[q] = tau;
+            active_off[q] = static_off[q];
+        }
     }
 }
 
@@ -125,7 +174,19 @@ extern "C" cudaError_t ppp_launch_staircase(const QConst *qc, const double *lf, 
                                             const uint32_t *static_off, uint16_t *nmax, uint32_t *active_off, double *last_tau,
                                             uint32_t nQ, int nsm, cudaStream_t st)
 {
-    ppp_build_staircase_kernel<<<nsm * 16, 128, 0, st>>>(qc, lf, kth, accept_mode, thresh_ln, static_off, nmax, active_off, last_tau, nQ);
+    /* The kernel is latency-bound (dependent enclosure evaluations), so what matters is that every warp slot of the chip has
+     * work: the fewer queries, the more warps share one (the query slice of one GPU of an 8-GPU job has 1,250 queries for
+     * 9,472 warp slots).  Two warps per query at least: 32 CTAs per SM of 64 threads fill an SM's 64 warp slots. */
+    const uint32_t slots = (uint32_t)nsm * 64u;
+    if (!nQ) return cudaSuccess;
+    if ((uint64_t)nQ * 8u <= slots) {
+        ppp_build_staircase_kernel<8><<<nQ, 256, 0, st>>>(qc, lf, kth, accept_mode, thresh_ln, static_off, nmax, active_off, last_tau, nQ);
+    } else if ((uint64_t)nQ * 4u <= slots) {
+        ppp_build_staircase_kernel<4><<<nQ, 128, 0, st>>>(qc, lf, kth, accept_mode, thresh_ln, static_off, nmax, active_off, last_tau, nQ);
+    } else {
+        const uint32_t grid = nQ < slots ? nQ : slots; /* grid-stride over the queries beyond the resident CTAs */
+        ppp_build_staircase_kernel<2><<<grid, 64, 0, st>>>(qc, lf, kth, accept_mode, thresh_ln, static_off, nmax, active_off, last_tau, nQ);
+    }
     return cudaGetLastError();
 }
 
