@@ -181,7 +181,7 @@ int ppp_row_words(const ppp_ctx *ctx, size_t *words);
  * seeding pass's bounds), "respec_mult" (a new, tighter speculation level every time the processed targets have grown this
  * many times, in runs of at least 2^"respec_min_pairs_log2" pairs; <= 1: one level), "spec_eps_ppm" (probability, in ppm, with which a speculative threshold may be too tight and
  * the query is re-scanned), "seed_mult" / "chunk0_mult" / "chunk1_mult" (targets of the seeding pass, of the first chunk's
- * head and of the first chunk, in units of k), "prefilter_version" (2 / 1), "prefilter_tc" (bit 0: the chunk screen of the queries
+ * head and of the first chunk, in units of k), "pf_overlap" (0/1: the pre-filter's class launches of a chunk on concurrent streams), "prefilter_tc" (bit 0: the chunk screen of the queries
  * with an all-ones presence plane takes its counts from tcgen05.mma instead of POPC, bit 1: that of the other queries too;
  * prophylo_b200/csrc/ppp_prefilter_tc.cu), "launch_pairs_log2" (pairs per launch of a
  * filtered run: 0 = automatic, the largest of 2^31 / 2^30 / 2^29 whose scratch buffers -- 40 bytes per pair -- stay below half of

@@ -24,11 +24,8 @@
 #include "ppp_common.cuh"
 
 extern "C" cudaError_t ppp_launch_sweep(const SweepParams *prm, int wpl, int nwarps, int nsm, cudaStream_t st);
-extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, const uint32_t *qflags, uint32_t *surv,
-                                           unsigned long long *surv_count, unsigned long long surv_cap, int nwarps, int nsm,
-                                           cudaStream_t st, cudaEvent_t between);
 extern "C" cudaError_t ppp_launch_prefilter2(const SweepParams *prm, int wpl, int pall, const void *Tt, uint32_t ntt, const uint32_t *qorder,
-                                             uint32_t nqk, uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count,
+                                             uint32_t nqk, uint32_t tile_q, uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count,
                                              unsigned long long surv_cap, unsigned long long *stats, int nsm, cudaStream_t st);
 extern "C" uint32_t ppp_prefilter2_max_stair(int wpl, int pall);
 extern "C" cudaError_t ppp_launch_prefilter_tc(const SweepParams *prm, int wpl, int pall, const void *Tt, uint32_t ntt, const uint32_t *qorder,
@@ -116,6 +113,11 @@ struct ppp_ctx {
     size_t pieces_waited = 0;
     const uint32_t *streamed_src = nullptr; /* host planes of a streamed upload whose copies are not queued yet */
     cudaStream_t copy_stream = nullptr;
+    /* the pre-filter's class launches of one target chunk (all-ones presence planes / P == Y / general) are independent: the two
+     * smaller ones go to side streams, so the tail of one launch -- its last items are 150 us each -- overlaps the next one */
+    cudaStream_t pf_stream[2] = {nullptr, nullptr};
+    cudaEvent_t pf_fork = nullptr, pf_join[2] = {nullptr, nullptr};
+    int pf_overlap = 1;
     std::vector<cudaEvent_t> piece_evpool;
     uint32_t *d_surv = nullptr;
     size_t cap_surv = 0;
@@ -136,7 +138,6 @@ struct ppp_ctx {
     /* queries */
     uint32_t *d_Q = nullptr;
     QConst *d_qc = nullptr;
-    uint32_t *d_qflags = nullptr; /* bit 0: presence plane is all ones over the G genomes */
     void *h_stage = nullptr; /* pinned staging buffer of ppp_set_queries */
     size_t cap_stage = 0;
     uint32_t *d_qorder = nullptr; /* query ids by pre-filter class: the n_pall queries with an all-ones presence plane first, then the
@@ -144,7 +145,8 @@ struct ppp_ctx {
     size_t n_pall = 0, n_pyy = 0;
     uint32_t stair_need[3] = {0, 0, 0}; /* largest per-tile staircase footprint (entries) of the general / all-ones / P == Y launch */
     unsigned long long *d_pfstats = nullptr;
-    int prefilter_version = 2; /* 2: ppp_prefilter.cu (queued slow path), 1: the in-line screen of ppp_sweep.cu */
+    uint32_t tile_q[3] = {0, 0, 0}; /* queries per pre-filter tile of each class: the kernel's 16 / 32 / 32 unless a tile's staircases would not fit */
+    uint32_t tile_q_any = 0;        /* the same for a tile of arbitrary queries (re-scan launches) */
     uint32_t stair_need_any = 0; /* staircase footprint of the worst possible general tile (re-scan of arbitrary queries) */
     uint32_t stair_need_tc[2] = {0, 0}; /* largest staircase footprint of a tile of the tensor-core screen: general (64 queries) / all-ones (128) */
     int prefilter_tc = 0;        /* bit 0: the all-ones launch of the chunk screen runs on the tensor cores (ppp_prefilter_tc.cu); bit 1: the general one */
@@ -302,6 +304,19 @@ extern "C" int ppp_init(ppp_ctx **out, const int *devices, int ndev)
             return PPP_ERR_CUDA;
         }
     }
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->pf_stream[i], cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&ctx->pf_join[i], cudaEventDisableTiming)) != cudaSuccess) {
+            fail(nullptr, PPP_ERR_CUDA, "ppp_init: %s", cudaGetErrorString(e));
+            ppp_destroy(ctx);
+            return PPP_ERR_CUDA;
+        }
+    }
+    if ((e = cudaEventCreateWithFlags(&ctx->pf_fork, cudaEventDisableTiming)) != cudaSuccess) {
+        fail(nullptr, PPP_ERR_CUDA, "ppp_init: %s", cudaGetErrorString(e));
+        ppp_destroy(ctx);
+        return PPP_ERR_CUDA;
+    }
     if ((e = cudaMalloc(&ctx->d_counters, CNT_SLOTS * sizeof(unsigned long long))) != cudaSuccess ||
         (e = cudaMalloc(&ctx->d_totals, (CNT_N + 1) * sizeof(unsigned long long))) != cudaSuccess) {
         fail(nullptr, e == cudaErrorMemoryAllocation ? PPP_ERR_NOMEM : PPP_ERR_CUDA, "ppp_init: %s", cudaGetErrorString(e));
@@ -333,7 +348,6 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
     cudaFree(ctx->d_lf);
     cudaFree(ctx->d_Q);
     cudaFree(ctx->d_qc);
-    cudaFree(ctx->d_qflags);
     cudaFree(ctx->d_qorder);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaFree(ctx->d_pfstats);
@@ -363,6 +377,14 @@ extern "C" void ppp_destroy(ppp_ctx *ctx)
         cudaStreamDestroy(ctx->copy_stream);
     }
     for (cudaEvent_t e : ctx->piece_evpool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pf_stream[i]) {
+            cudaStreamSynchronize(ctx->pf_stream[i]);
+            cudaStreamDestroy(ctx->pf_stream[i]);
+        }
+        if (ctx->pf_join[i]) cudaEventDestroy(ctx->pf_join[i]);
+    }
+    if (ctx->pf_fork) cudaEventDestroy(ctx->pf_fork);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -529,11 +551,9 @@ static void free_query_buffers(ppp_ctx *ctx)
 {
     cudaFree(ctx->d_Q);
     cudaFree(ctx->d_qc);
-    cudaFree(ctx->d_qflags);
     cudaFree(ctx->d_qorder);
     ctx->d_Q = nullptr;
     ctx->d_qc = nullptr;
-    ctx->d_qflags = nullptr;
     ctx->d_qorder = nullptr;
     ctx->capQ = 0;
     ctx->nQ = 0;
@@ -644,12 +664,11 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
         const size_t cap = ((nQ + PPP_QTILE - 1) / PPP_QTILE) * PPP_QTILE;
         cudaError_t e;
         if ((e = cudaMalloc(&ctx->d_Q, cap * 2 * W * 4)) != cudaSuccess || (e = cudaMalloc(&ctx->d_qc, cap * sizeof(QConst))) != cudaSuccess ||
-            (e = cudaMalloc(&ctx->d_qflags, cap * sizeof(uint32_t))) != cudaSuccess ||
             (e = cudaMalloc(&ctx->d_qorder, cap * sizeof(uint32_t))) != cudaSuccess) {
             free_query_buffers(ctx); /* no live pointer is left behind a zero capacity */
             return fail(ctx, e == cudaErrorMemoryAllocation ? PPP_ERR_NOMEM : PPP_ERR_CUDA, "ppp_set_queries: %s", cudaGetErrorString(e));
         }
-        ctx->capQ = cap; /* only once all four buffers exist */
+        ctx->capQ = cap; /* only once all three buffers exist */
     }
     ctx->nQ = 0;
     if (!nQ) return PPP_OK;
@@ -707,7 +726,6 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
     CU(cudaMemcpyAsync(ctx->d_qc, qc.data(), nQ * sizeof(QConst), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<uint32_t> qfl(nQ);
     for (size_t q = 0; q < nQ; ++q) qfl[q] = (qc[q].npres == ctx->G) ? 1u : 0u;
-    CU(cudaMemcpyAsync(ctx->d_qflags, qfl.data(), nQ * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     {
         /* processing order of the pre-filter, one launch per class: all-ones presence planes (number == depth), P == Y (number ==
          * yes; Y is a subset of P, so equal counts mean equal planes), everything else */
@@ -724,33 +742,36 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
             if (!qfl[q] && !is_pyy(q)) order.push_back((uint32_t)q);
         /* deal the queries of each class over its tiles by descending |Y| (tile i takes the i-th, (i + ntiles)-th ...
          * largest): every tile then holds about the same staircase footprint, which is what sizes the kernel's shared
-         * memory (and hence its occupancy), and about the same amount of slow-path work */
+         * memory (and hence its occupancy), and about the same amount of slow-path work.  A tile normally has the kernel's
+         * 32 (general launch: 16) queries; when the staircases of such a tile would not fit the kernel's shared memory (very
+         * dense yes planes: 32 queries of |Y| > 1,000 each) the class runs with smaller tiles -- fewer queries share a target
+         * row in registers, nothing else changes. */
         for (int kind = 0; kind < 3; ++kind) {
             size_t b, e;
             class_range(ctx, kind, nQ, &b, &e);
             const size_t n = e - b;
-            const size_t qt = ppp_prefilter2_tile_queries(kind);
-            if (n <= qt) continue;
+            const size_t cap = ppp_prefilter2_max_stair(ctx->wpl, kind);
             std::vector<uint32_t> sorted(order.begin() + b, order.begin() + e);
             std::stable_sort(sorted.begin(), sorted.end(), [&](uint32_t x, uint32_t y) { return qc[x].ny > qc[y].ny; });
-            const size_t ntiles = (n + qt - 1) / qt;
-            size_t o = b;
-            for (size_t tile = 0; tile < ntiles; ++tile)
-                for (size_t j = 0; j * ntiles + tile < n && j < qt; ++j) order[o++] = sorted[j * ntiles + tile];
-        }
-        CU(cudaMemcpyAsync(ctx->d_qorder, order.data(), nQ * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-        for (int kind = 0; kind < 3; ++kind) {
-            size_t b, e;
-            class_range(ctx, kind, nQ, &b, &e);
-            size_t worst = 0;
-            const size_t qt = ppp_prefilter2_tile_queries(kind);
-            for (size_t i = b; i < e; i += qt) {
-                size_t sum = 1;
-                for (size_t j = i; j < std::min(e, i + qt); ++j) sum += (size_t)qc[order[j]].ny + 1;
-                worst = std::max(worst, sum);
+            size_t qt = ppp_prefilter2_tile_queries(kind), worst = 1;
+            for (;; --qt) {
+                const size_t ntiles = n ? (n + qt - 1) / qt : 0;
+                size_t o = b;
+                for (size_t tile = 0; tile < ntiles; ++tile)
+                    for (size_t j = 0; j * ntiles + tile < n && j < qt; ++j) order[o++] = sorted[j * ntiles + tile];
+                /* what the kernel will stage: ITS tiles are the consecutive groups of qt entries of the order */
+                worst = 1;
+                for (size_t i = b; i < e; i += qt) {
+                    size_t sum = 1;
+                    for (size_t j = i; j < std::min(e, i + qt); ++j) sum += (size_t)qc[order[j]].ny + 1;
+                    worst = std::max(worst, sum);
+                }
+                if (worst <= cap || qt == 1) break;
             }
+            ctx->tile_q[kind] = (uint32_t)qt;
             ctx->stair_need[kind] = (uint32_t)std::min<size_t>(worst, 0xffffffffu);
         }
+        CU(cudaMemcpyAsync(ctx->d_qorder, order.data(), nQ * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
         for (int kind = 0; kind < 2; ++kind) {
             size_t b, e;
             class_range(ctx, kind, nQ, &b, &e);
@@ -763,13 +784,15 @@ extern "C" int ppp_set_queries(ppp_ctx *ctx, const uint32_t *P, const uint32_t *
             }
             ctx->stair_need_tc[kind] = (uint32_t)std::min<size_t>(worst, 0xffffffffu);
         }
-        {
+        { /* a tile of ARBITRARY queries (the re-scan of the queries whose speculative threshold failed): the largest tile whose
+           * worst case -- the queries with the longest staircases -- fits */
             std::vector<uint32_t> lens(nQ);
             for (size_t q = 0; q < nQ; ++q) lens[q] = qc[q].ny + 1;
-            const size_t qt = std::min<size_t>(ppp_prefilter2_tile_queries(0), nQ);
+            const size_t qt = std::min<size_t>(ppp_prefilter2_tile_queries(0), nQ), cap = ppp_prefilter2_max_stair(ctx->wpl, 0);
             std::partial_sort(lens.begin(), lens.begin() + qt, lens.end(), std::greater<uint32_t>());
-            size_t sum = 1;
-            for (size_t i = 0; i < qt; ++i) sum += lens[i];
+            size_t sum = 1 + lens[0], t = 1;
+            while (t < qt && sum + lens[t] <= cap) sum += lens[t++];
+            ctx->tile_q_any = (uint32_t)t;
             ctx->stair_need_any = (uint32_t)std::min<size_t>(sum, 0xffffffffu);
         }
     }
@@ -821,35 +844,24 @@ static int mark(ppp_ctx *ctx, size_t *idx)
     return PPP_OK;
 }
 
-/* pre-filter + refine of one target chunk (bit-plane targets).  Version 2 (ppp_prefilter.cu) needs a tile's staircases
- * in shared memory; query sets whose staircases do not fit use the in-line screen of ppp_sweep.cu. */
-static bool use_prefilter2(const ppp_ctx *ctx)
-{
-    if (ctx->prefilter_version != 2) return false;
-    for (int kind = 0; kind < 3; ++kind) {
-        size_t b, e;
-        class_range(ctx, kind, ctx->nQ, &b, &e);
-        if (e > b && ctx->stair_need[kind] > ppp_prefilter2_max_stair(ctx->wpl, kind)) return false;
-    }
-    return true;
-}
-
+/* pre-filter + refine of one target chunk (bit-plane targets): ppp_prefilter.cu screens every pair, the survivors go to the
+ * refine kernel.  A tile's staircases live in shared memory; ppp_set_queries chose tile sizes that fit. */
 static int launch_prefiltered(ppp_ctx *ctx, SweepParams *prm, cudaEvent_t between, const uint32_t *qlist = nullptr, uint32_t nlist = 0)
 {
     unsigned long long *surv_count = ctx->d_counters + CNT_N;
     if (qlist) { /* only the listed queries (any presence plane): one general launch */
-        CU(ppp_launch_prefilter2(prm, ctx->wpl, 0, ctx->d_Tt, (uint32_t)ctx->nT, qlist, nlist, ctx->stair_need_any, ctx->d_surv, surv_count,
-                                 ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));
+        CU(ppp_launch_prefilter2(prm, ctx->wpl, 0, ctx->d_Tt, (uint32_t)ctx->nT, qlist, nlist, ctx->tile_q_any, ctx->stair_need_any, ctx->d_surv,
+                                 surv_count, ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));
         if (between) CU(cudaEventRecord(between, ctx->stream));
         CU(ppp_launch_refine(prm, ctx->wpl, ctx->d_surv, surv_count, ctx->cap_surv, ctx->sweep_warps, ctx->nsm, ctx->stream));
         return PPP_OK;
     }
-    if (!use_prefilter2(ctx)) {
-        CU(ppp_launch_filtered(prm, ctx->wpl, ctx->d_Tt, (uint32_t)ctx->nT, ctx->d_qflags, ctx->d_surv, surv_count, ctx->cap_surv,
-                               ctx->sweep_warps, ctx->nsm, ctx->stream, between));
-        return PPP_OK;
-    }
-    for (int kind : {1, 2, 0}) { /* all-ones presence planes, P == Y, then the general ones */
+    /* all-ones presence planes on the run's stream, the general ones and P == Y on the side streams (the launches append to
+     * the same survivor list with atomics and claim their items from separate counters) */
+    const bool overlap = ctx->pf_overlap && !ctx->prefilter_tc;
+    int nside = 0;
+    if (overlap) CU(cudaEventRecord(ctx->pf_fork, ctx->stream));
+    for (int kind : {1, 0, 2}) {
         size_t cb, ce;
         class_range(ctx, kind, ctx->nQ, &cb, &ce);
         const uint32_t *ql = ctx->d_qorder + cb;
@@ -873,10 +885,20 @@ static int launch_prefiltered(ppp_ctx *ctx, SweepParams *prm, cudaEvent_t betwee
                 CU(ppp_launch_rescreen_masks(prm, ctx->wpl, kind, ql, n, ctx->stair_need_tc[kind], ctx->d_surv1, ctx->d_surv, surv_count, ctx->cap_surv,
                                              ctx->nsm, ctx->stream));
         } else {
-            CU(ppp_launch_prefilter2(prm, ctx->wpl, kind, ctx->d_Tt, (uint32_t)ctx->nT, ql, n, ctx->stair_need[kind], ctx->d_surv, surv_count,
-                                     ctx->cap_surv, ctx->d_pfstats, ctx->nsm, ctx->stream));
+            cudaStream_t st = ctx->stream;
+            if (overlap && kind != 1) {
+                st = ctx->pf_stream[nside];
+                CU(cudaStreamWaitEvent(st, ctx->pf_fork, 0));
+            }
+            CU(ppp_launch_prefilter2(prm, ctx->wpl, kind, ctx->d_Tt, (uint32_t)ctx->nT, ql, n, ctx->tile_q[kind], ctx->stair_need[kind], ctx->d_surv,
+                                     surv_count, ctx->cap_surv, ctx->d_pfstats, ctx->nsm, st));
+            if (st != ctx->stream) {
+                CU(cudaEventRecord(ctx->pf_join[nside], st));
+                ++nside;
+            }
         }
     }
+    for (int i = 0; i < nside; ++i) CU(cudaStreamWaitEvent(ctx->stream, ctx->pf_join[i], 0));
     if (between) CU(cudaEventRecord(between, ctx->stream));
     CU(ppp_launch_refine(prm, ctx->wpl, ctx->d_surv, surv_count, ctx->cap_surv, ctx->sweep_warps, ctx->nsm, ctx->stream));
     return PPP_OK;
@@ -1191,8 +1213,7 @@ extern "C" int ppp_run(ppp_ctx *ctx, const ppp_filter *f)
             const size_t seed_floor = k <= 16 ? 1024 : 256, chunk1_floor = k <= 16 ? 4096 : 1024;
             const size_t chunk1 = std::max<size_t>(chunk1_floor, (size_t)ctx->chunk1_mult * k);      /* first exact chunk */
             const size_t w1 = std::min(std::min(maxw, nT), chunk1);
-            const bool spec_ok = ctx->speculate && !ctx->ranked && use_prefilter2(ctx) && !ctx->force_exact &&
-                                 ctx->stair_need_any <= ppp_prefilter2_max_stair(ctx->wpl, 0);
+            const bool spec_ok = ctx->speculate && !ctx->ranked && !ctx->force_exact;
             /* The first chunk is speculative as well when the bulk will be (its verification covers both): its thresholds are
              * the rs-th smallest upper bounds of the seeding pass instead of the k-th -- at config 3 the guaranteed bound lets
              * 15 % of the first chunk's pairs through to a full evaluation, the speculative one 0.8 %. */
@@ -1677,11 +1698,10 @@ extern "C" int ppp_set_option(ppp_ctx *ctx, const char *name, int64_t value)
     } else if (!strcmp(name, "prefilter_tc")) {
         if (value < 0 || value > 3) return fail(ctx, PPP_ERR_INVALID, "prefilter_tc must be 0 .. 3 (bit 0: all-ones launch, bit 1: general launch)");
         ctx->prefilter_tc = (int)value;
+    } else if (!strcmp(name, "pf_overlap")) {
+        ctx->pf_overlap = value != 0;
     } else if (!strcmp(name, "tc_exact")) {
         ctx->tc_exact = value != 0;
-    } else if (!strcmp(name, "prefilter_version")) {
-        if (value != 1 && value != 2) return fail(ctx, PPP_ERR_INVALID, "prefilter_version must be 1 or 2");
-        ctx->prefilter_version = (int)value;
     } else if (!strcmp(name, "sweep_warps")) {
         if (value < 1 || value > 16) return fail(ctx, PPP_ERR_INVALID, "sweep_warps must be in [1,16]");
         ctx->sweep_warps = (int)value;
@@ -1703,6 +1723,10 @@ extern "C" int ppp_get_counter(const ppp_ctx *ctx, const char *name, int64_t *va
     else if (!strcmp(name, "full_pairs")) i = CNT_FULL;
     else if (!strcmp(name, "num_sms")) { *value = ctx->nsm; return PPP_OK; }
     else if (!strcmp(name, "used_table")) { *value = ctx->last_used_table; return PPP_OK; }
+    else if (!strcmp(name, "pf_tile_q_gen")) { *value = ctx->tile_q[0]; return PPP_OK; }
+    else if (!strcmp(name, "pf_tile_q_all")) { *value = ctx->tile_q[1]; return PPP_OK; }
+    else if (!strcmp(name, "pf_tile_q_pyy")) { *value = ctx->tile_q[2]; return PPP_OK; }
+    else if (!strcmp(name, "pf_tile_q_any")) { *value = ctx->tile_q_any; return PPP_OK; }
     else if (!strcmp(name, "spec_rank")) { *value = ctx->spec_rank; return PPP_OK; }
     else if (!strcmp(name, "spec_failed")) { *value = ctx->spec_failed; return PPP_OK; }
     else if (!strcmp(name, "tc_launches")) { *value = (int64_t)ctx->tc_launches; return PPP_OK; }

@@ -67,6 +67,7 @@ struct Pf2Params {
     unsigned long long *unit_counter; /* next unclaimed item of this launch (zero when the launch starts) */
     uint32_t ntt, t0, nTl, nqk;
     uint32_t stair_cap; /* int16 entries of shared memory reserved for the tile's staircases */
+    uint32_t tile_q;    /* queries per tile, <= PF2_QT(MODE): fewer when the staircases of a full tile would not fit (very dense yes planes) */
 };
 
 __device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c)
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t nTblocks = (a.nTl + PF2_THREADS - 1) / PF2_THREADS;
-    const uint32_t nQtiles = (a.nqk + QT - 1) / QT;
+    const uint32_t nQtiles = (a.nqk + a.tile_q - 1) / a.tile_q;
     const uint32_t nItems = nQtiles * nTblocks; /* a launch covers at most 2^31 pairs = 2^18 items of 16 x 512 */
     /* Items (query tile, block of 512 targets; tile-major) are claimed from a global counter in runs of up to 16 consecutive
      * items, shrinking as the launch drains (guided self-scheduling: remaining / (2 x CTAs)).  Static spans left the CTA slots
@@ -189,8 +190,8 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
         if (qt != cur_qt) {
             /* ---- stage the tile: compact the queries that have a staircase, copy their planes (TMA) and staircases */
             __syncthreads();
-            const uint32_t q0 = qt * QT;
-            const uint32_t nq = min((uint32_t)QT, a.nqk - q0);
+            const uint32_t q0 = qt * a.tile_q;
+            const uint32_t nq = min(a.tile_q, a.nqk - q0);
             if (tid < 32) {
                 uint32_t qid = 0, off = PPP_NO_TABLE, len = 0;
                 if ((uint32_t)tid < nq) {
@@ -597,7 +598,7 @@ static cudaError_t pf2_launch_t(const Pf2Params &p, int nsm, cudaStream_t st)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_prefilter2_kernel<WPL, MODE>, PF2_THREADS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    const uint64_t items = (uint64_t)((p.nqk + PF2_QT(MODE) - 1) / PF2_QT(MODE)) * ((p.nTl + PF2_THREADS - 1) / PF2_THREADS);
+    const uint64_t items = (uint64_t)((p.nqk + p.tile_q - 1) / p.tile_q) * ((p.nTl + PF2_THREADS - 1) / PF2_THREADS);
     uint64_t grid = std::min<uint64_t>((uint64_t)nsm * per_sm, items);
     if (grid < 1) grid = 1;
     ppp_prefilter2_kernel<WPL, MODE><<<(unsigned)grid, PF2_THREADS, smem, st>>>(p);
@@ -605,13 +606,15 @@ static cudaError_t pf2_launch_t(const Pf2Params &p, int nsm, cudaStream_t st)
 }
 
 /* One launch over the queries listed in qorder[0..nqk): pall = 1 -> every listed query has an all-ones presence plane, 2 -> every
- * listed query has P == Y, 0 -> any presence plane.
+ * listed query has P == Y, 0 -> any presence plane.  tile_q consecutive entries of qorder form a tile (<= the kernel's 32 / 16);
+ * stair_cap = the largest staircase footprint of a tile (int16 entries, dummy entry included).
  * *surv_count is NOT reset here (the all-ones and the general launch of a chunk append to the same list). */
 extern "C" cudaError_t ppp_launch_prefilter2(const SweepParams *prm, int wpl, int pall, const void *Tt, uint32_t ntt, const uint32_t *qorder,
-                                             uint32_t nqk, uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count,
+                                             uint32_t nqk, uint32_t tile_q, uint32_t stair_cap, uint32_t *surv, unsigned long long *surv_count,
                                              unsigned long long surv_cap, unsigned long long *stats, int nsm, cudaStream_t st)
 {
     if (!nqk) return cudaSuccess;
+    if (tile_q < 1 || tile_q > (uint32_t)PF2_QT(pall)) return cudaErrorInvalidValue;
     Pf2Params p;
     p.Tt = reinterpret_cast<const uint4 *>(Tt);
     p.Q = prm->Q;
@@ -629,6 +632,7 @@ extern "C" cudaError_t ppp_launch_prefilter2(const SweepParams *prm, int wpl, in
     p.nTl = prm->t1 - prm->t0;
     p.nqk = nqk;
     p.stair_cap = stair_cap;
+    p.tile_q = tile_q;
     switch (wpl * 4 + pall) {
     case 4: return pf2_launch_t<1, 0>(p, nsm, st);
     case 5: return pf2_launch_t<1, 1>(p, nsm, st);

@@ -166,164 +166,6 @@ __global__ void __launch_bounds__(512, PPP_MINBLOCKS_OF(WPL)) ppp_sweep_kernel(c
     flush_counters(prm, wc, lane);
 }
 
-/* ---------------------------------------------------------------- pre-filter kernel (filtered runs): thread per pair
- * Integer-only screen of EVERY pair of the chunk against the query's staircase, one thread per target, a 32-query
- * tile per pass: the thread streams its target row once (transposed planes Tt[w/4][t][4] -> one coalesced 16-byte
- * load per 4 words) and keeps (yes, number) running counts of 32 queries in registers.  For every word it asks
- * "number_before + 1 <= stair[yes_after]": no candidate inside the word can reach the query's threshold otherwise
- * (stair is non-decreasing in yes and a candidate's number exceeds number_before).  Pairs with at least one passing
- * word are appended to the survivor list for the warp-per-pair refine kernel; everything else -- the overwhelming
- * majority -- is finished here with 2 AND + 2 POPC + 1 lookup per word.  */
-/* exact per-candidate test of one word that passed the word-level screen (rare; kept out of line on purpose) */
-__device__ __noinline__ bool word_has_passing_candidate(uint32_t a, uint32_t b, uint32_t nb, uint32_t yy, const uint16_t *__restrict__ stair)
-{
-    bool ok = false;
-    while (b) {
-        const uint32_t bit = __ffs(b) - 1;
-        b &= b - 1;
-        ++yy;
-        ok |= nb + __popc(a & ((2u << bit) - 1u)) <= (uint32_t)__ldg(stair + yy);
-    }
-    return ok;
-}
-
-#ifndef PF_QG
-#define PF_QG 8 /* queries per unrolled group of the pre-filter */
-#endif
-
-template <int WPL>
-__global__ void __launch_bounds__(256) ppp_prefilter_kernel(const SweepParams prm, const uint4 *__restrict__ Tt, uint32_t ntt,
-                                                            const uint32_t *__restrict__ qflags, uint32_t *__restrict__ surv, unsigned long long *__restrict__ surv_count,
-                                                            unsigned long long surv_cap)
-{
-    constexpr int W = 32 * WPL;
-    constexpr int C = W / 4; /* 16-byte chunks per row */
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
-    uint32_t *s_q = reinterpret_cast<uint32_t *>(smem_raw + 128); /* PPP_QTILE * 2 * W words */
-    uint32_t *s_off = s_q + PPP_QTILE * 2 * W;
-    uint32_t *s_pall = s_off + PPP_QTILE; /* 1 = presence plane all ones: T & P == T */
-    const uint32_t nTl = prm.t1 - prm.t0;
-    const uint32_t nQtiles = (prm.nQ + PPP_QTILE - 1) / PPP_QTILE;
-    const uint32_t nTblocks = (nTl + blockDim.x - 1) / blockDim.x;
-    const uint64_t nItems = (uint64_t)nQtiles * nTblocks;
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        fence_barrier_init();
-    }
-    __syncthreads();
-    uint32_t parity = 0, cur_qt = 0xffffffffu;
-    for (uint64_t item = blockIdx.x; item < nItems; item += gridDim.x) {
-        const uint32_t qt = (uint32_t)(item / nTblocks), tb = (uint32_t)(item % nTblocks);
-        const uint32_t q0 = qt * PPP_QTILE;
-        const uint32_t nq = min((uint32_t)PPP_QTILE, prm.nQ - q0);
-        if (qt != cur_qt) {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                fence_proxy_async();
-                const uint32_t b1 = nq * 2 * W * 4;
-                mbar_expect_tx(bar, b1);
-                tma_load_1d(s_q, prm.Q + (size_t)q0 * 2 * W, b1, bar);
-            }
-            if (threadIdx.x < PPP_QTILE) {
-                s_off[threadIdx.x] = (threadIdx.x < nq) ? prm.nmax_off[q0 + threadIdx.x] : PPP_NO_TABLE;
-                s_pall[threadIdx.x] = (threadIdx.x < nq) ? (qflags[q0 + threadIdx.x] & 1u) : 0u;
-            }
-            mbar_wait(bar, parity);
-            parity ^= 1;
-            cur_qt = qt;
-            __syncthreads();
-        }
-        const uint32_t tl = tb * blockDim.x + threadIdx.x;
-        const bool live = tl < nTl;
-        const uint32_t t = prm.t0 + (live ? tl : 0);
-        uint32_t pass = 0;
-        /* PF_QG queries at a time: the unrolled body stays small enough for the instruction cache; the target row is
-         * re-streamed per group from L1/L2 (coalesced 16-byte loads) */
-        for (uint32_t g0 = 0; g0 < nq; g0 += PF_QG) {
-            uint32_t state[PF_QG]; /* yes | number << 16 per query */
-#pragma unroll
-            for (int i = 0; i < PF_QG; ++i) state[i] = 0;
-            for (int c = 0; c < C; ++c) {
-                const uint4 tv = live ? __ldg(Tt + (size_t)c * ntt + t) : make_uint4(0, 0, 0, 0);
-                const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
-                const uint32_t ct = __popc(tw[0]) + __popc(tw[1]) + __popc(tw[2]) + __popc(tw[3]); /* number when P is all ones */
-#pragma unroll
-                for (int qj = 0; qj < PF_QG; ++qj) {
-                    const uint32_t qi = g0 + qj;
-                    if (qi >= nq) break; /* block-uniform */
-                    const uint4 yv = *reinterpret_cast<const uint4 *>(s_q + (size_t)qi * 2 * W + W + c * 4); /* broadcast */
-                    const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
-                    const uint32_t off = s_off[qi];
-                    const uint32_t st0 = state[qj];
-                    uint32_t a[4], b[4], cn;
-                    if (s_pall[qi]) { /* block-uniform: T & P == T, popcount shared by all such queries */
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) a[w] = tw[w];
-                        cn = ct;
-                    } else {
-                        const uint4 pv = *reinterpret_cast<const uint4 *>(s_q + (size_t)qi * 2 * W + c * 4);
-                        a[0] = tw[0] & pv.x; a[1] = tw[1] & pv.y; a[2] = tw[2] & pv.z; a[3] = tw[3] & pv.w;
-                        cn = __popc(a[0]) + __popc(a[1]) + __popc(a[2]) + __popc(a[3]);
-                    }
-#pragma unroll
-                    for (int w = 0; w < 4; ++w) b[w] = a[w] & yw[w];
-                    const uint32_t cy = __popc(b[0]) + __popc(b[1]) + __popc(b[2]) + __popc(b[3]);
-                    const uint32_t st = st0 + cy + (cn << 16);
-                    /* 128-genome screen, one lookup: no candidate of the chunk can pass unless number_before + 1 <=
-                     * stair[yes_after]; the rare chunks that survive it are re-screened word by word, then per candidate */
-                    const uint32_t lim = (off != PPP_NO_TABLE) ? (uint32_t)__ldg(prm.nmax + off + (st & 0xffffu)) : 0xffffu;
-                    if (cy && (st0 >> 16) + 1u <= lim) {
-                        uint32_t sw = st0;
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) {
-                            const uint32_t cyw = __popc(b[w]);
-                            const uint32_t nb = sw >> 16;
-                            sw += cyw + (__popc(a[w]) << 16);
-                            if (cyw) {
-                                const uint32_t l2 = (off != PPP_NO_TABLE) ? (uint32_t)__ldg(prm.nmax + off + (sw & 0xffffu)) : 0xffffu;
-                                if (nb + 1u <= l2 &&
-                                    (off == PPP_NO_TABLE || word_has_passing_candidate(a[w], b[w], nb, (sw & 0xffffu) - cyw, prm.nmax + off))) {
-                                    pass |= 1u << qi;
-                                }
-                            }
-                        }
-                    }
-                    state[qj] = st;
-                }
-            }
-        }
-        if (!live) pass = 0;
-        /* queries without a staircase accept every pair (also the ones with no candidate at all) */
-#pragma unroll
-        for (int qi = 0; qi < PPP_QTILE; ++qi)
-            if (live && (uint32_t)qi < nq && s_off[qi] == PPP_NO_TABLE) pass |= 1u << qi;
-        if ((uint32_t)nq < 32u) pass &= (1u << nq) - 1u;
-        /* append survivors: warp-aggregated reservation */
-        const uint32_t mycnt = __popc(pass);
-        uint32_t incl = mycnt;
-        const int lane = threadIdx.x & 31;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const uint32_t total = __shfl_sync(FULL, incl, 31);
-        if (total) {
-            unsigned long long base = 0;
-            if (lane == 31) base = atomicAdd(surv_count, (unsigned long long)total);
-            base = __shfl_sync(FULL, base, 31);
-            unsigned long long slot = base + (incl - mycnt);
-            while (pass) {
-                const uint32_t qi = __ffs(pass) - 1;
-                pass &= pass - 1;
-                if (slot < surv_cap) surv[slot] = (uint32_t)((uint64_t)(q0 + qi) * nTl + tl);
-                ++slot;
-            }
-        }
-    }
-}
-
 /* ---------------------------------------------------------------- refine kernel: warp per surviving pair */
 #ifndef PPP_REFINE_WARPS
 #define PPP_REFINE_WARPS 16 /* warps per CTA the refine kernel is compiled for (register budget = 65536 / threads) */
@@ -664,7 +506,6 @@ static size_t refine_smem_bytes(int wpl, int nwarps)
     const size_t W = 32 * (size_t)wpl, GD = 32 * W;
     return 128 + ((((GD + 2) * 8) + 127) & ~(size_t)127) + (size_t)nwarps * 3 * PPP_QCAP_OF(wpl) * 4 + 64;
 }
-static size_t prefilter_smem_bytes(int wpl) { return 128 + PPP_QTILE * 2 * 32 * (size_t)wpl * 4 + 2 * PPP_QTILE * 4 + 64; }
 
 
 template <int WPL>
@@ -687,41 +528,6 @@ static cudaError_t launch_t(const SweepParams &prm, int nwarps, int nsm, cudaStr
     return cudaGetLastError();
 }
 
-template <int WPL>
-static cudaError_t launch_filtered_t(const SweepParams &prm, const void *Tt, uint32_t ntt, const uint32_t *qflags, uint32_t *surv, unsigned long long *surv_count,
-                                     unsigned long long surv_cap, int nwarps, int nsm, cudaStream_t st, cudaEvent_t between)
-{
-    cudaError_t e;
-    {
-        const size_t smem = prefilter_smem_bytes(WPL);
-        e = cudaFuncSetAttribute(ppp_prefilter_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPP_MAX_DYN_SMEM);
-        if (e != cudaSuccess) return e;
-        int per_sm = 1;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_prefilter_kernel<WPL>, 256, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        const uint32_t nTl = prm.t1 - prm.t0;
-        const uint64_t items = (uint64_t)((prm.nQ + PPP_QTILE - 1) / PPP_QTILE) * ((nTl + 255) / 256);
-        uint64_t grid = std::min<uint64_t>((uint64_t)nsm * per_sm, items);
-        if (grid < 1) grid = 1;
-        ppp_prefilter_kernel<WPL><<<(unsigned)grid, 256, smem, st>>>(prm, reinterpret_cast<const uint4 *>(Tt), ntt, qflags, surv, surv_count, surv_cap);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (between && (e = cudaEventRecord(between, st)) != cudaSuccess) return e;
-    }
-    {
-        while (nwarps > 1 && refine_smem_bytes(WPL, nwarps) > PPP_MAX_DYN_SMEM) --nwarps;
-        const size_t smem = refine_smem_bytes(WPL, nwarps);
-        e = cudaFuncSetAttribute(ppp_refine_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, PPP_MAX_DYN_SMEM);
-        if (e != cudaSuccess) return e;
-        int per_sm = 1;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ppp_refine_kernel<WPL>, nwarps * 32, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) per_sm = 1;
-        ppp_refine_kernel<WPL><<<(unsigned)(nsm * per_sm), nwarps * 32, smem, st>>>(prm, surv, surv_count, surv_cap);
-        return cudaGetLastError();
-    }
-}
-
 extern "C" cudaError_t ppp_launch_sweep(const SweepParams *prm, int wpl, int nwarps, int nsm, cudaStream_t st)
 {
     switch (wpl) {
@@ -734,19 +540,6 @@ extern "C" cudaError_t ppp_launch_sweep(const SweepParams *prm, int wpl, int nwa
 }
 
 /* pre-filter (thread per pair) + refine (warp per surviving pair); *surv_count must be zero on entry */
-extern "C" cudaError_t ppp_launch_filtered(const SweepParams *prm, int wpl, const void *Tt, uint32_t ntt, const uint32_t *qflags, uint32_t *surv,
-                                           unsigned long long *surv_count, unsigned long long surv_cap, int nwarps, int nsm,
-                                           cudaStream_t st, cudaEvent_t between)
-{
-    switch (wpl) {
-    case 1: return launch_filtered_t<1>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st, between);
-    case 2: return launch_filtered_t<2>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st, between);
-    case 4: return launch_filtered_t<4>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st, between);
-    case 8: return launch_filtered_t<8>(*prm, Tt, ntt, qflags, surv, surv_count, surv_cap, nwarps, nsm, st, between);
-    default: return cudaErrorInvalidValue;
-    }
-}
-
 template <int WPL>
 static cudaError_t launch_refine_t(const SweepParams &prm, const uint32_t *surv, const unsigned long long *surv_count, unsigned long long surv_cap,
                                    int nwarps, int nsm, cudaStream_t st)

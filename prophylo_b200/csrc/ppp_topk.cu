@@ -211,13 +211,17 @@ __device__ __forceinline__ bool key_less(const MKey &a, const MKey &b)
     return a.t < b.t;
 }
 
+/* M = keys sorted at once (a power of two >= 2 k, the kernel's shared memory), PER = winners per thread (256 PER >= k).  Short
+ * lists get a small M and PER = 1: the sort of a few hundred keys is a chain of barrier-separated stages, i.e. latency, so what
+ * counts is how many queries are in flight -- 16 KB and 40 registers let 8 CTAs share an SM where 64 KB and the 8 winners'
+ * records in registers allowed 2. */
+template <int PER>
 __global__ void __launch_bounds__(256) ppp_topk_merge_kernel(const ppp_hit *__restrict__ appended, uint32_t *__restrict__ qcnt,
                                                              uint32_t qcap, ppp_hit *__restrict__ topk, uint32_t *__restrict__ topk_cnt,
-                                                             double *__restrict__ kth, uint32_t k, uint32_t nQ, uint32_t t_offset)
+                                                             double *__restrict__ kth, uint32_t k, uint32_t nQ, uint32_t t_offset, uint32_t M)
 {
     extern __shared__ __align__(16) unsigned char smem_topk[];
     MKey *key = reinterpret_cast<MKey *>(smem_topk);
-    constexpr int PER = (TOPK_M / 2 + 255) / 256; /* winners per thread */
     for (uint32_t q = blockIdx.x; q < nQ; q += gridDim.x) {
         const uint32_t nnew = min(qcnt[q], qcap);
         uint32_t cur = topk_cnt[q];
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(256) ppp_topk_merge_kernel(const ppp_hit *__re
         uint32_t done = 0;
         double kth_new = 0.0;
         while (done < nnew) {
-            const uint32_t batch = min(nnew - done, (uint32_t)TOPK_M - cur);
+            const uint32_t batch = min(nnew - done, M - cur);
             for (uint32_t i = threadIdx.x; i < cur; i += blockDim.x) {
                 MKey m;
                 m.score = list[i].score;
@@ -307,12 +311,22 @@ __global__ void __launch_bounds__(256) ppp_topk_merge_kernel(const ppp_hit *__re
 extern "C" cudaError_t ppp_launch_topk_merge(const void *appended, uint32_t *qcnt, uint32_t qcap, void *topk, uint32_t *topk_cnt,
                                              double *kth, uint32_t k, uint32_t nQ, uint32_t t_offset, int nsm, cudaStream_t st)
 {
-    const int smem = TOPK_M * (int)sizeof(MKey);
-    cudaError_t e = cudaFuncSetAttribute(ppp_topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    const unsigned grid = (unsigned)min((uint32_t)(nsm * 2), nQ);
-    ppp_topk_merge_kernel<<<grid, 256, smem, st>>>(reinterpret_cast<const ppp_hit *>(appended), qcnt, qcap,
-                                                   reinterpret_cast<ppp_hit *>(topk), topk_cnt, kth, k, nQ, t_offset);
+    const ppp_hit *app = reinterpret_cast<const ppp_hit *>(appended);
+    ppp_hit *lists = reinterpret_cast<ppp_hit *>(topk);
+    cudaError_t e;
+    if (k <= 256) {
+        const uint32_t M = 1024;
+        e = cudaFuncSetAttribute(ppp_topk_merge_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOPK_M * (int)sizeof(MKey));
+        if (e != cudaSuccess) return e;
+        const unsigned grid = (unsigned)min((uint32_t)(nsm * 6), nQ); /* 38 registers x 256 threads: 6 CTAs per SM */
+        ppp_topk_merge_kernel<1><<<grid, 256, M * sizeof(MKey), st>>>(app, qcnt, qcap, lists, topk_cnt, kth, k, nQ, t_offset, M);
+    } else {
+        const uint32_t M = TOPK_M;
+        e = cudaFuncSetAttribute(ppp_topk_merge_kernel<TOPK_M / 2 / 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOPK_M * (int)sizeof(MKey));
+        if (e != cudaSuccess) return e;
+        const unsigned grid = (unsigned)min((uint32_t)(nsm * 2), nQ);
+        ppp_topk_merge_kernel<TOPK_M / 2 / 256><<<grid, 256, M * sizeof(MKey), st>>>(app, qcnt, qcap, lists, topk_cnt, kth, k, nQ, t_offset, M);
+    }
     return cudaGetLastError();
 }
 

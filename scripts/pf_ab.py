@@ -1,4 +1,4 @@
-"""Developer probe: config-3 shaped top-k run with the pre-filter version selected by argv[1] (1|2); prints phase times.
+"""Developer probe: config-3 shaped top-k run (argv[1] is ignored: there is one pre-filter); prints phase times.
 With a -DPF2_STATS build (PPP_B200_LIB=ab/...) also the queue statistics of the version-2 pre-filter."""
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,7 +15,6 @@ P, Y, p = synth.make_queries(G, nq, synth.SEED_BASE + seed, kind)
 T = synth.make_targets(G, nt, synth.SEED_BASE + 100 + seed, plant_from=Y, plant_frac=0.01)
 c = capi.Context(0)
 c.set_option("sweep_warps", 16)
-c.set_option("prefilter_version", ver)
 c.set_targets_bits(T, G)
 c.set_queries(P, Y, p)
 lib = capi.load()

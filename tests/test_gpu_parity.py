@@ -1071,3 +1071,49 @@ def test_p_equals_y_class_matches_dense(ctx, G, nq, nt, k):
     assert th.size == exp.size and th.size > 0
     for f in ("q", "t", "score", "yes", "number", "depth"):
         assert np.array_equal(th[f], exp[f]), f
+
+
+def test_dense_yes_planes_run_with_smaller_prefilter_tiles(ctx):
+    """Very dense yes planes (|Y| ~ 4,100 of 8,192 genomes): the staircases of a full 32-query (16-query) tile do not fit the
+    pre-filter's shared memory, so ppp_set_queries gives the class smaller tiles -- one code path for every query set.  All
+    three classes (all-ones presence planes, P == Y, general), top-k (speculative schedule, re-scan tiles) and threshold runs
+    against the dense result."""
+    G, nq, nt, k = 8192, 44, 2600, 8
+    rng = np.random.default_rng(77)
+    Yb = (rng.random((nq, G)) < 0.5).astype(np.uint8)
+    Pb = np.ones((nq, G), dtype=np.uint8)
+    Pb[1::5] = Yb[1::5]                                             # P == Y
+    Pb[2::5] = Yb[2::5] | (rng.random((Yb[2::5].shape[0], G)) < 0.5)  # general
+    P, Y = synth.pack_bits(Pb), synth.pack_bits(Yb)
+    p = Yb.sum(axis=1) / np.where((Pb == Yb).all(axis=1), G, Pb.sum(axis=1))
+    T = synth.make_targets(G, nt, 78, plant_from=Y, plant_frac=0.05)
+    ctx.set_targets_bits(T, G)
+    ctx.set_option("table_mode", 0)
+    try:
+        dense = ctx.score(P, Y, p).reshape(nq, nt)
+    finally:
+        ctx.set_option("table_mode", -1)
+    old = None
+    for lp in (0, 16):  # one launch / several launches per run
+        ctx.set_option("launch_pairs_log2", lp)
+        try:
+            tk = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k)).copy()
+        finally:
+            ctx.set_option("launch_pairs_log2", 0)
+        assert 1 <= ctx.counter("pf_tile_q_all") < 32 and 1 <= ctx.counter("pf_tile_q_pyy") < 32 and 1 <= ctx.counter("pf_tile_q_gen") < 16
+        assert tk.size == nq * k and ctx.counter("full_pairs") < nq * nt
+        for q in range(nq):
+            exp = np.sort(dense[q], order=["score", "t"])[:k]
+            got = tk[q * k:(q + 1) * k]
+            for f in ("q", "t", "score", "yes", "number", "depth"):
+                assert np.array_equal(got[f], exp[f]), (lp, q, f)
+        assert old is None or old.tobytes() == tk.tobytes()
+        old = tk
+    thr = -6.0
+    th = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_THRESH_LOG10, thresh=thr)).copy()
+    with np.errstate(divide="ignore"):
+        keep = np.log10(dense["score"]) < thr
+    exp = np.sort(dense[keep], order=["q", "score", "t"])
+    assert th.size == exp.size and th.size > 0
+    for f in ("q", "t", "score", "yes", "number", "depth"):
+        assert np.array_equal(th[f], exp[f]), f
