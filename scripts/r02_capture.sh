@@ -11,7 +11,7 @@ python bench.py --steps 1 --warmup 2 --profile-step > /dev/null 2> $O/r02_profil
 [ $rc -eq 0 ] || exit 1
 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
     --log-file $O/r02_launches_bench_step.csv python bench.py --steps 1 --warmup 2 --profile-step > $O/r02_ncu_launches.log 2>&1; echo "ncu launch list rc=$?"
-ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:ppp_prefilter2 --launch-skip 12 --launch-count 2 \
+ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:ppp_prefilter2 --launch-skip 15 --launch-count 3 \
     -f -o $O/r02_prefilter2_bench python bench.py --steps 1 --warmup 2 --profile-step > $O/r02_ncu_prefilter2.log 2>&1; echo "ncu prefilter2 rc=$?"
 ncu --profile-from-start off --set full --import-source on --clock-control none -k regex:ppp_refine --launch-skip 8 --launch-count 1 \
     -f -o $O/r02_refine_bench python bench.py --steps 1 --warmup 2 --profile-step > $O/r02_ncu_refine.log 2>&1; echo "ncu refine rc=$?"

@@ -36,11 +36,11 @@ with open("profiles/r02_launches_bench_step_1gpu.txt", "w") as f:
         f.write(f"{k:<58s} {n:4d} {ms:10.3f} ms {100 * ms / tot:6.2f}% {rd / 1e6:10.1f} {wr / 1e6:10.1f}\n")
     f.write(f"{'total':<58s} {sum(a[0] for a in agg.values()):4d} {tot:10.3f} ms\n")
 shutil.copy(G + "launches_bench_step.csv", "profiles/r02_launches_bench_step_1gpu.csv")
-pf = agg["ppp_prefilter2_kernel<4, 1>"], agg["ppp_prefilter2_kernel<4, 0>"]
+pf = [a for k, a in agg.items() if k.startswith("ppp_prefilter2_kernel<")]  # all-ones / general / P == Y instantiations
 traffic = sum(a[2] + a[3] for a in pf)
 cfg = bench["config"]
 json.dump({"workload": [cfg["genomes"], cfg["queries"], cfg["targets"], 100, 1], "dram_bytes_per_step": traffic,
-           "launches_per_step": sum(a[0] for a in pf), "kernel": "ppp_prefilter2_kernel (both instantiations)",
+           "launches_per_step": sum(a[0] for a in pf), "kernel": "ppp_prefilter2_kernel (all three instantiations)",
            "source": f"profiles/r02_launches_bench_step_1gpu.csv: dram__bytes_read.sum + dram__bytes_write.sum over the {sum(a[0] for a in pf)} "
                      f"ppp_prefilter2_kernel launches of one step of `python bench.py --steps 1 --warmup 2 --profile-step` under ncu, commit {commit}"},
           open("profiles/r02_ncu_traffic.json", "w"), indent=1)
@@ -52,7 +52,7 @@ for src, dst in (("bench_1gpu.json", "r02_bench_1gpu.json"), ("bench_reference_a
     shutil.copy(G + src, "profiles/" + dst)
 
 # ---- ncu --set full summaries (bulk launches of the same step)
-for rep, head in (("prefilter2_bench.ncu-rep", "ppp_prefilter2_kernel, two consecutive bulk launches (all-ones / general presence planes)"),
+for rep, head in (("prefilter2_bench.ncu-rep", "ppp_prefilter2_kernel, the three launches of one bulk target range (all-ones presence planes / general / P == Y)"),
                   ("refine_bench.ncu-rep", "ppp_refine_kernel, one bulk launch")):
     txt = subprocess.run([sys.executable, "scripts/ncu_summary.py", G + rep], capture_output=True, text=True).stdout
     open("profiles/r02_ncu_" + rep.replace("_bench.ncu-rep", ".txt"), "w").write(
