@@ -67,6 +67,7 @@ struct Pf2Params {
     unsigned long long *unit_counter; /* next unclaimed item of this launch (zero when the launch starts) */
     uint32_t ntt, t0, nTl, nqk;
     uint32_t stair_cap; /* int16 entries of shared memory reserved for the tile's staircases */
+    uint32_t sb_blocks; /* target blocks per super-block of the item order (see the kernel) */
     uint32_t tile_q;    /* queries per tile, <= PF2_QT(MODE): fewer when the staircases of a full tile would not fit (very dense yes planes) */
 };
 
@@ -158,7 +159,11 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
     const uint32_t nTblocks = (a.nTl + PF2_THREADS - 1) / PF2_THREADS;
     const uint32_t nQtiles = (a.nqk + a.tile_q - 1) / a.tile_q;
     const uint32_t nItems = nQtiles * nTblocks; /* a launch covers at most 2^31 pairs = 2^18 items of 16 x 512 */
-    /* Items (query tile, block of 512 targets; tile-major) are claimed from a global counter in runs of up to 16 consecutive
+    /* Item order: super-blocks of sb_blocks target blocks (32 MB of planes); inside a super-block tile-major, i.e. every query
+     * tile meets the super-block's targets before the next super-block starts.  A launch of 2^31 pairs spans the whole target
+     * set (512 MB at config 3): in plain tile-major order every query tile streamed it from DRAM again (ncu: 81 GB per step);
+     * a super-block stays in L2 while all tiles pass over it.
+     * Items (query tile, block of 512 targets) are claimed from a global counter in runs of up to 16 consecutive
      * items, shrinking as the launch drains (guided self-scheduling: remaining / (2 x CTAs)).  Static spans left the CTA slots
      * 22 % idle on average (ncu: 26 of 32 warps resident per active cycle): item costs differ -- dense targets and dense yes
      * planes queue many more chunks -- and the CTA that finishes first leaves its SM half empty. */
@@ -186,7 +191,10 @@ __global__ void __launch_bounds__(PF2_THREADS) ppp_prefilter2_kernel(const Pf2Pa
     __syncthreads();
     if (s_unit[0] >= nItems) break;
     for (uint32_t item = s_unit[0]; item < s_unit[1]; ++item) {
-        const uint32_t qt = item / nTblocks, tb = item - qt * nTblocks;
+        const uint32_t per_sb = nQtiles * a.sb_blocks;
+        const uint32_t sbi = item / per_sb, r = item - sbi * per_sb;
+        const uint32_t nb = min(a.sb_blocks, nTblocks - sbi * a.sb_blocks); /* blocks of this super-block (the last one may be short) */
+        const uint32_t qt = r / nb, tb = sbi * a.sb_blocks + (r - qt * nb);
         if (qt != cur_qt) {
             /* ---- stage the tile: compact the queries that have a staircase, copy their planes (TMA) and staircases */
             __syncthreads();
@@ -633,6 +641,7 @@ extern "C" cudaError_t ppp_launch_prefilter2(const SweepParams *prm, int wpl, in
     p.nqk = nqk;
     p.stair_cap = stair_cap;
     p.tile_q = tile_q;
+    p.sb_blocks = std::max<uint32_t>(1u, (32u << 20) / (PF2_THREADS * 128u * (uint32_t)wpl));
     switch (wpl * 4 + pall) {
     case 4: return pf2_launch_t<1, 0>(p, nsm, st);
     case 5: return pf2_launch_t<1, 1>(p, nsm, st);
