@@ -114,6 +114,12 @@ int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, uint32_t G)
 int ppp_set_targets_bits_streamed(ppp_ctx *ctx, const uint32_t *T, size_t nT, uint32_t G);
 /* blocks until a streamed upload is complete on the device (no-op otherwise) */
 int ppp_wait_targets(ppp_ctx *ctx);
+/* The same planes, already in DEVICE memory (of the context's GPU or of a peer): copied device to device before returning; all
+ * work that produced dT must be complete (synchronise the producing stream first).  No counterpart in the reference.  This is
+ * the hook for a query-partitioned N-GPU job, where every GPU needs ALL targets: each process uploads 1/N of the planes over
+ * PCIe, the processes exchange their slices over NVLink (NCCL all-gather), and the gathered buffer is handed over here --
+ * 1/N of the host-to-device traffic of N full uploads (bench.py's end-to-end leg at N > 1). */
+int ppp_set_targets_bits_device(ppp_ctx *ctx, const uint32_t *dT, size_t nT, uint32_t G);
 
 /* Targets as ordered hit lists (replaces -prof2 built by BlastResult::get_profile, BlastResult.pm:192-237, or
  * the value-sorted HASH of HMMERResult, ppp.pm:147-149).  For target t, entries row_off[t]..row_off[t+1]) give,

@@ -23,7 +23,7 @@ HIT_DTYPE = np.dtype(
 assert HIT_DTYPE.itemsize == 32
 
 EXPORTS = [
-    "ppp_init", "ppp_destroy", "ppp_last_error", "ppp_abi_version", "ppp_set_targets_bits", "ppp_set_targets_bits_streamed", "ppp_wait_targets", "ppp_set_targets_ranked",
+    "ppp_init", "ppp_destroy", "ppp_last_error", "ppp_abi_version", "ppp_set_targets_bits", "ppp_set_targets_bits_streamed", "ppp_set_targets_bits_device", "ppp_wait_targets", "ppp_set_targets_ranked",
     "ppp_set_queries", "ppp_run", "ppp_result_count", "ppp_fetch", "ppp_score", "ppp_get_stats", "ppp_set_option",
     "ppp_get_counter", "ppp_words_per_row", "ppp_debug_bdtrc", "ppp_topk_device", "ppp_merge_topk_device", "ppp_read_bla", "ppp_read_bla_flags", "ppp_printed_cutoffs",
     "ppp_free_ranked_lists", "ppp_debug_enclosure", "ppp_query_count", "ppp_row_words", "ppp_pipe_peak", "ppp_read_bla_cached", "ppp_read_profiles", "ppp_free_profile_set",
@@ -82,6 +82,8 @@ def load():
     L.ppp_set_targets_bits.argtypes = [vp, vp, sz, u32]
     L.ppp_set_targets_bits_streamed.restype = ctypes.c_int
     L.ppp_set_targets_bits_streamed.argtypes = [vp, vp, sz, u32]
+    L.ppp_set_targets_bits_device.restype = ctypes.c_int
+    L.ppp_set_targets_bits_device.argtypes = [vp, vp, sz, u32]
     L.ppp_wait_targets.restype = ctypes.c_int
     L.ppp_wait_targets.argtypes = [vp]
     L.ppp_set_targets_ranked.restype = ctypes.c_int
@@ -246,6 +248,14 @@ class Context:
             self._check(self.lib.ppp_set_targets_bits(self._h, _ptr(T), T.shape[0], G))
             self._streamed_T = None
         self.G, self.nT = G, T.shape[0]
+
+    def set_targets_bits_device(self, dptr: int, nT: int, G: int):
+        """Packed target planes that already sit in device memory ([nT][words_per_row(G)] uint32 at address dptr, e.g. a torch
+        tensor's data_ptr() after an NCCL all-gather): copied device to device (ppp_set_targets_bits_device).  The producer's
+        stream must have been synchronised."""
+        self._check(self.lib.ppp_set_targets_bits_device(self._h, ctypes.c_void_p(dptr), nT, G))
+        self._streamed_T = None
+        self.G, self.nT = G, nT
 
     def wait_targets(self):
         self._check(self.lib.ppp_wait_targets(self._h))

@@ -535,7 +535,8 @@ extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, 
     if ((rc = grow(ctx, &ctx->d_T, &ctx->cap_T, std::max<size_t>(1, nT * W)))) return rc; /* buffers are reused across calls */
     if (nT) {
         if (wpr != W) CU(cudaMemsetAsync(ctx->d_T, 0, nT * W * 4, ctx->stream));
-        CU(cudaMemcpy2DAsync(ctx->d_T, W * 4, T, wpr * 4, wpr * 4, nT, cudaMemcpyHostToDevice, ctx->stream));
+        /* cudaMemcpyDefault: T may also be device memory (ppp_set_targets_bits_device) */
+        CU(cudaMemcpy2DAsync(ctx->d_T, W * 4, T, wpr * 4, wpr * 4, nT, cudaMemcpyDefault, ctx->stream));
     }
     if ((rc = ensure_lf(ctx))) return rc;
     ctx->ranked = false;
@@ -545,6 +546,19 @@ extern "C" int ppp_set_targets_bits(ppp_ctx *ctx, const uint32_t *T, size_t nT, 
     ctx->G = G;
     ctx->wpl = wpl;
     return PPP_OK;
+}
+
+extern "C" int ppp_set_targets_bits_device(ppp_ctx *ctx, const uint32_t *dT, size_t nT, uint32_t G)
+{
+    if (!ctx) return PPP_ERR_INVALID;
+    if (nT) {
+        cudaPointerAttributes at;
+        if (!dT || cudaPointerGetAttributes(&at, dT) != cudaSuccess || (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged)) {
+            (void)cudaGetLastError();
+            return fail(ctx, PPP_ERR_INVALID, "ppp_set_targets_bits_device: dT is not device memory");
+        }
+    }
+    return ppp_set_targets_bits(ctx, dT, nT, G);
 }
 
 static void free_query_buffers(ppp_ctx *ctx)

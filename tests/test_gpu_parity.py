@@ -1117,3 +1117,29 @@ def test_dense_yes_planes_run_with_smaller_prefilter_tiles(ctx):
     assert th.size == exp.size and th.size > 0
     for f in ("q", "t", "score", "yes", "number", "depth"):
         assert np.array_equal(th[f], exp[f]), f
+
+
+def test_targets_from_device_memory_equal_host_upload(ctx):
+    """ppp_set_targets_bits_device: planes that already sit in device memory (what an NCCL all-gather of per-rank slices leaves
+    behind) give the same records as the host upload -- dense and top-k, G with and without row padding, single context and
+    device group; a host pointer is refused."""
+    import torch
+
+    for G, nq, nt in ((4096, 40, 3000), (1000, 24, 2500)):
+        P, Y, p = synth.make_queries(G, nq, 31 + G, "mixed")
+        T = synth.make_targets(G, nt, 32 + G, plant_from=Y, plant_frac=0.03)
+        Td = torch.from_numpy(T.view(np.int32)).cuda()
+        torch.cuda.synchronize()
+        grp = capi.Context(_devices_for_group(2))
+        try:
+            for c in (ctx, grp):
+                for flt in (None, capi.make_filter(capi.FILTER_TOPK, k=7)):
+                    c.set_targets_bits(T, G)
+                    a = c.score(P, Y, p, flt).copy()
+                    c.set_targets_bits_device(Td.data_ptr(), nt, G)
+                    b = c.score(P, Y, p, flt).copy()
+                    assert a.size > 0 and a.tobytes() == b.tobytes()
+        finally:
+            grp.close()
+    with pytest.raises(capi.PPPError):
+        ctx.set_targets_bits_device(T.ctypes.data, nt, G)
