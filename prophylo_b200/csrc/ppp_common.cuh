@@ -198,7 +198,10 @@ __device__ __forceinline__ void tier_a(int y, int n, const QConst &qc, const dou
     } else {
         const float e = __expf(lead);
         const float glo = e * Rlo * 0.999f, ghi = e * Rhi * 1.001f;
-        hi = (glo < 0.5f) ? fminf(-glo, 0.f) : __logf(fmaxf(1.f - glo, 0.f)) + 1e-4f; /* ln(1-g) <= -g */
+        /* ln(1-g) <= -g is only tight for small g (off by g^2 / 2: 0.045 at g = 0.3, the regime of unrelated pairs); __logf errs
+         * by < 1e-6 absolute on [0.5, 1].  Measured on the dense G = 4096 probe: 3.42 -> 3.33 FP64-tier evaluations per pair --
+         * near the mean the width of the enclosure comes from the series remainder after 8 terms, not from this bound. */
+        hi = (glo < 0.01f) ? fminf(-glo, 0.f) : __logf(fmaxf(1.f - glo, 0.f)) + 1e-4f;
         hi = fminf(hi, 0.f);
         lo = (ghi < 0.9f) ? __logf(1.f - ghi) - 1e-4f : -INFINITY;
         if (ghi < 1e-3f) lo = -ghi * (1.f + ghi) - 1e-30f;
