@@ -25,34 +25,43 @@
 #include <algorithm>
 #include <atomic>
 #include <string>
-#include <string_view>
 #include <thread>
-#include <unordered_map>
 #include <vector>
 
 #include "../../include/ppp_b200.h"
 
 namespace {
 
-bool slurp(const char *path, std::string &buf)
+/* whole file with one open / fstat / read */
+bool slurp(const char *path, std::vector<char> &buf)
 {
-    FILE *f = fopen(path, "rb");
-    if (!f) return false;
-    char tmp[1 << 16];
-    size_t n;
-    buf.clear();
-    while ((n = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.append(tmp, n);
-    const bool ok = !ferror(f);
-    fclose(f);
-    return ok;
+    const int fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return false;
+    struct stat st;
+    size_t cap = (fstat(fd, &st) == 0 && st.st_size > 0) ? (size_t)st.st_size + 1 : (size_t)1 << 16, n = 0;
+    buf.resize(cap);
+    for (;;) {
+        if (n == buf.size()) buf.resize(2 * buf.size());
+        const ssize_t r = read(fd, buf.data() + n, buf.size() - n);
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            close(fd);
+            return false;
+        }
+        if (r == 0) break;
+        n += (size_t)r;
+    }
+    close(fd);
+    buf.resize(n);
+    return true;
 }
 
 /* Perl's numeric value of a string: its leading number, 0 when there is none (`$hash{$taxon} != 0`, Profile.pm:463, 477) */
-double perl_num(std::string_view s)
+double perl_num(const char *s, size_t len)
 {
     char tmp[64];
-    const size_t n = std::min(s.size(), sizeof(tmp) - 1);
-    memcpy(tmp, s.data(), n);
+    const size_t n = std::min(len, sizeof(tmp) - 1);
+    memcpy(tmp, s, n);
     tmp[n] = 0;
     char *end = nullptr;
     const double v = strtod(tmp, &end);
@@ -69,55 +78,92 @@ bool whole_number(const std::string &s, double *v)
     return end == s.c_str() + s.size() && !(*v != *v);
 }
 
+inline uint64_t hash_bytes(const char *p, size_t n)
+{
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)n;
+    while (n >= 8) {
+        uint64_t v;
+        memcpy(&v, p, 8);
+        h = (h ^ v) * 0xff51afd7ed558ccdull;
+        h ^= h >> 32;
+        p += 8;
+        n -= 8;
+    }
+    if (n) {
+        uint64_t v = 0;
+        memcpy(&v, p, n);
+        h = (h ^ v) * 0xff51afd7ed558ccdull;
+        h ^= h >> 32;
+    }
+    return h;
+}
+inline bool same(const char *a, size_t la, const char *b, size_t lb) { return la == lb && (la == 0 || memcmp(a, b, la) == 0); }
+inline size_t pow2_at_least(size_t n)
+{
+    size_t c = 16;
+    while (c < n) c <<= 1;
+    return c;
+}
+
+/* One parsed file: its bytes stay alive and the items point into them (no string per taxon). */
+struct Item {
+    uint32_t off, len; /* taxon = buf[off .. off + len) */
+    bool yes;
+};
 struct ParsedProfile {
-    std::vector<std::pair<std::string, bool>> items; /* (taxon, yes) after the file's own duplicate rule, file order */
+    std::vector<char> buf;
+    std::vector<Item> items; /* (taxon, yes) after the file's own duplicate rule, file order */
     std::string err;
+    const char *taxon(size_t k) const { return buf.data() + items[k].off; }
 };
 
-void parse_profile(const char *path, bool header, ParsedProfile &out)
+void parse_profile(const char *path, bool header, std::vector<uint32_t> &tab, ParsedProfile &out)
 {
-    std::string buf;
-    if (!slurp(path, buf)) {
+    if (!slurp(path, out.buf)) {
         out.err = std::string("Can' open ") + path; /* the reference's own spelling (Profile.pm:436) */
         return;
     }
-    std::unordered_map<std::string_view, size_t> at;
-    size_t pos = 0, lineno = 0;
-    const size_t n = buf.size();
-    while (pos < n) {
-        size_t eol = buf.find('\n', pos);
-        const bool last_unterminated = eol == std::string::npos;
-        if (last_unterminated) eol = n;
-        std::string_view line(buf.data() + pos, eol - pos);
-        pos = eol + 1;
+    const char *const base = out.buf.data(), *p = base, *const end = base + out.buf.size();
+    size_t lines = 1;
+    for (const char *q = p; (q = (const char *)memchr(q, '\n', (size_t)(end - q))) != nullptr; ++q) ++lines;
+    tab.assign(pow2_at_least(2 * lines), 0u); /* taxon -> item index + 1 */
+    const size_t mask = tab.size() - 1;
+    out.items.reserve(lines);
+    size_t lineno = 0;
+    while (p < end) {
+        const char *eol = (const char *)memchr(p, '\n', (size_t)(end - p));
+        if (!eol) eol = end;
+        const char *line = p;
+        p = eol + 1;
         ++lineno;
-        if (header && lineno == 1) continue;           /* physical line 1, whatever it holds (Profile.pm:447-449) */
-        if (!line.empty() && line[0] == '#') continue; /* :450 */
-        /* split(/\t/): trailing empty fields are dropped; exactly two fields must remain (:452-456) */
-        std::vector<std::string_view> f;
-        size_t start = 0;
-        for (;;) {
-            size_t tab = line.find('\t', start);
-            if (tab == std::string_view::npos) {
-                f.push_back(line.substr(start));
-                break;
-            }
-            f.push_back(line.substr(start, tab - start));
-            start = tab + 1;
+        if (header && lineno == 1) continue;     /* physical line 1, whatever it holds (Profile.pm:447-449) */
+        if (line < eol && line[0] == '#') continue; /* :450 */
+        /* split(/\t/): trailing empty fields are dropped; exactly two fields must remain (:452-456), i.e. a tab, a non-empty
+         * second field, and nothing but tabs after it */
+        const char *t0 = (const char *)memchr(line, '\t', (size_t)(eol - line));
+        bool two = false;
+        const char *f1 = nullptr, *t1 = nullptr;
+        if (t0) {
+            f1 = t0 + 1;
+            t1 = (const char *)memchr(f1, '\t', (size_t)(eol - f1));
+            if (!t1) t1 = eol;
+            two = t1 > f1;
+            for (const char *c = t1; two && c < eol; ++c) two = (*c == '\t');
         }
-        while (!f.empty() && f.back().empty()) f.pop_back();
-        if (f.size() != 2) {
+        if (!two) {
             out.err = std::string(path) + " must contain only two fields";
             return;
         }
-        if (f[0].empty() || f[0] == "0") continue; /* `next unless $taxon` (:460) */
-        const bool yes = perl_num(f[1]) != 0.0;
-        auto it = at.find(f[0]);
-        if (it == at.end()) {
-            at.emplace(f[0], out.items.size());
-            out.items.emplace_back(std::string(f[0]), yes);
-        } else if (!out.items[it->second].second) {
-            out.items[it->second].second = yes; /* a non-zero value is never overwritten, a zero one is (:463-468) */
+        const size_t l0 = (size_t)(t0 - line), l1 = (size_t)(t1 - f1);
+        if (l0 == 0 || (l0 == 1 && line[0] == '0')) continue; /* `next unless $taxon` (:460) */
+        const bool yes = (l1 == 1 && f1[0] >= '0' && f1[0] <= '9') ? f1[0] != '0' : perl_num(f1, l1) != 0.0;
+        size_t i = hash_bytes(line, l0) & mask;
+        while (tab[i] && !same(out.taxon(tab[i] - 1), out.items[tab[i] - 1].len, line, l0)) i = (i + 1) & mask;
+        if (!tab[i]) {
+            out.items.push_back({(uint32_t)(line - base), (uint32_t)l0, yes});
+            tab[i] = (uint32_t)out.items.size();
+        } else if (!out.items[tab[i] - 1].yes) {
+            out.items[tab[i] - 1].yes = yes; /* a non-zero value is never overwritten, a zero one is (:463-468) */
         }
     }
 }
@@ -165,37 +211,88 @@ extern "C" int ppp_read_profiles(const char *const *paths, size_t n_paths, int h
     if (!out || (n_paths && !paths)) return set_err(err, errlen, PPP_ERR_INVALID, "ppp_read_profiles: invalid argument");
     memset(out, 0, sizeof(*out));
     std::vector<ParsedProfile> per(n_paths);
-    parallel_for(n_paths, nthreads, [&](size_t i) { parse_profile(paths[i], header != 0, per[i]); });
+    {
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            std::vector<uint32_t> tab; /* per-thread scratch of the duplicate rule */
+            for (size_t i; (i = next.fetch_add(1)) < n_paths;) parse_profile(paths[i], header != 0, tab, per[i]);
+        };
+        size_t nt = nthreads > 0 ? (size_t)nthreads : std::max(1u, std::thread::hardware_concurrency());
+        if (nt > n_paths) nt = n_paths ? n_paths : 1;
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (std::thread &t : pool) t.join();
+    }
     for (size_t i = 0; i < n_paths; ++i)
         if (!per[i].err.empty()) return set_err(err, errlen, PPP_ERR_INVALID, per[i].err);
+    /* The files of a family usually list the SAME taxa in the same order (hmm3profile.pl writes every family over one genome
+     * list): such files share file 0's mapping and never touch the union table. */
+    std::vector<unsigned char> like0(n_paths, 0);
+    parallel_for(n_paths, nthreads, [&](size_t i) {
+        const ParsedProfile &a = per[0], &b = per[i];
+        if (a.items.size() != b.items.size()) return;
+        for (size_t k = 0; k < a.items.size(); ++k)
+            if (!same(a.taxon(k), a.items[k].len, b.taxon(k), b.items[k].len)) return;
+        like0[i] = 1;
+    });
     /* the shared universe: union of the taxa, numeric ids ascending, other names after them by name */
-    std::unordered_map<std::string_view, uint32_t> index;
-    std::vector<const std::string *> taxa;
-    for (const ParsedProfile &p : per)
-        for (const auto &it : p.items)
-            if (index.emplace(std::string_view(it.first), 0u).second) taxa.push_back(&it.first);
+    struct Taxon {
+        const char *s;
+        uint32_t len, g;
+    };
+    std::vector<Taxon> taxa;
+    std::vector<uint32_t> utab(1024, 0u); /* taxon -> index into taxa + 1 */
+    auto intern = [&](const char *t, uint32_t len) -> uint32_t {
+        if (2 * (taxa.size() + 1) > utab.size()) { /* grow and re-insert */
+            utab.assign(2 * utab.size(), 0u);
+            for (size_t j = 0; j < taxa.size(); ++j) {
+                size_t i = hash_bytes(taxa[j].s, taxa[j].len) & (utab.size() - 1);
+                while (utab[i]) i = (i + 1) & (utab.size() - 1);
+                utab[i] = (uint32_t)j + 1;
+            }
+        }
+        size_t i = hash_bytes(t, len) & (utab.size() - 1);
+        while (utab[i] && !same(taxa[utab[i] - 1].s, taxa[utab[i] - 1].len, t, len)) i = (i + 1) & (utab.size() - 1);
+        if (!utab[i]) {
+            taxa.push_back({t, len, 0u});
+            utab[i] = (uint32_t)taxa.size();
+        }
+        return utab[i] - 1;
+    };
+    for (size_t i = 0; i < n_paths; ++i)
+        if (i == 0 || !like0[i])
+            for (size_t k = 0; k < per[i].items.size(); ++k) intern(per[i].taxon(k), per[i].items[k].len);
     struct Key {
         bool numeric;
         double v;
-        const std::string *s;
+        std::string s;
+        uint32_t id;
     };
     std::vector<Key> keys(taxa.size());
     for (size_t i = 0; i < taxa.size(); ++i) {
+        keys[i].s.assign(taxa[i].s, taxa[i].len);
+        keys[i].id = (uint32_t)i;
         double v = 0.0;
-        const bool num = whole_number(*taxa[i], &v);
-        keys[i] = {num, num ? v : 0.0, taxa[i]};
+        keys[i].numeric = whole_number(keys[i].s, &v);
+        keys[i].v = keys[i].numeric ? v : 0.0;
     }
     std::sort(keys.begin(), keys.end(), [](const Key &a, const Key &b) {
         if (a.numeric != b.numeric) return a.numeric;
         if (a.numeric && a.v != b.v) return a.v < b.v;
-        return *a.s < *b.s;
+        return a.s < b.s;
     });
     const size_t G = keys.size();
     if (G > 8192) return set_err(err, errlen, PPP_ERR_INVALID, "ppp_read_profiles: the profiles span " + std::to_string(G) + " taxa; at most 8192 are supported");
-    for (size_t g = 0; g < G; ++g) index[std::string_view(*keys[g].s)] = (uint32_t)g;
+    for (size_t g = 0; g < G; ++g) taxa[keys[g].id].g = (uint32_t)g;
+    std::vector<uint32_t> map0; /* genome index of file 0's k-th item */
+    if (n_paths) {
+        map0.resize(per[0].items.size());
+        for (size_t k = 0; k < map0.size(); ++k) map0[k] = taxa[intern(per[0].taxon(k), per[0].items[k].len)].g;
+    }
     const size_t wpr = G ? ppp_words_per_row((uint32_t)G) : 4;
     size_t ubytes = 0;
-    for (const Key &k : keys) ubytes += k.s->size() + 1;
+    for (const Key &k : keys) ubytes += k.s.size() + 1;
     out->universe_buf = (char *)malloc(ubytes ? ubytes : 1);
     out->universe_off = (size_t *)malloc((G ? G : 1) * sizeof(size_t));
     out->P = (uint32_t *)calloc(n_paths ? n_paths * wpr : 1, sizeof(uint32_t));
@@ -210,16 +307,24 @@ extern "C" int ppp_read_profiles(const char *const *paths, size_t n_paths, int h
     size_t o = 0;
     for (size_t g = 0; g < G; ++g) {
         out->universe_off[g] = o;
-        memcpy(out->universe_buf + o, keys[g].s->c_str(), keys[g].s->size() + 1);
-        o += keys[g].s->size() + 1;
+        memcpy(out->universe_buf + o, keys[g].s.c_str(), keys[g].s.size() + 1);
+        o += keys[g].s.size() + 1;
     }
     parallel_for(n_paths, nthreads, [&](size_t i) {
         uint32_t *P = out->P + i * wpr, *Y = out->Y + i * wpr;
         uint32_t ny = 0;
-        for (const auto &it : per[i].items) {
-            const uint32_t g = index.find(std::string_view(it.first))->second;
+        const ParsedProfile &pp = per[i];
+        for (size_t k = 0; k < pp.items.size(); ++k) {
+            uint32_t g;
+            if (like0[i]) {
+                g = map0[k];
+            } else { /* read-only probe of the union table */
+                size_t j = hash_bytes(pp.taxon(k), pp.items[k].len) & (utab.size() - 1);
+                while (!same(taxa[utab[j] - 1].s, taxa[utab[j] - 1].len, pp.taxon(k), pp.items[k].len)) j = (j + 1) & (utab.size() - 1);
+                g = taxa[utab[j] - 1].g;
+            }
             P[g >> 5] |= 1u << (g & 31);
-            if (it.second) {
+            if (pp.items[k].yes) {
                 Y[g >> 5] |= 1u << (g & 31);
                 ++ny;
             }

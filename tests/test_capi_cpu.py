@@ -118,6 +118,26 @@ def test_native_profile_reader_matches_python_reader(tmp_path):
         assert a[0] == b[0] and a[0][-3:] == ["12abc", "Xca", "gec5"]
         for x, y, name in zip(a[1:], b[1:], ("P", "Y", "p", "T")):
             assert x.dtype == y.dtype and np.array_equal(x, y), (header, name)
+    # families written over ONE genome list (every file the same taxa in the same order: the reader's shared-mapping path), with
+    # one file that adds a taxon, one that drops one and one in another order mixed in
+    same = []
+    for i in range(12):
+        order = list(ids)
+        if i == 4:
+            order.append("777777")
+        if i == 7:
+            order.pop(3)
+        if i == 9:
+            order.reverse()
+        p = tmp_path / f"g{i}.profile"
+        p.write_text("taxon\tvalue\n" + "".join(f"{t}\t{int(rng.random() < 0.3)}\n" for t in order))
+        same.append(str(p))
+    for sel in (same[:4], same):
+        a = drivers.read_profile_family(sel, header=True, native=True)
+        b = drivers.read_profile_family(sel, header=True, native=False)
+        assert a[0] == b[0]
+        for x, y, name in zip(a[1:], b[1:], ("P", "Y", "p", "T")):
+            assert x.dtype == y.dtype and np.array_equal(x, y), name
     bad = tmp_path / "bad.profile"
     bad.write_text("1\t1\n\n2\t0\n")
     with pytest.raises(capi.PPPError, match="must contain only two fields"):
