@@ -179,7 +179,7 @@ int ppp_row_words(const ppp_ctx *ctx, size_t *words);
 
 /* Options (tests / diagnostics): "force_exact" (0/1: every pair through the exact tier),
  * "check_bounds" (0/1: verify the fast tier's enclosures against the accurate tier, count violations),
- * "sweep_warps" (warps per CTA), "table_mode" (-1 auto / 0 off / 1 on: exact (yes, number) table per query for dense
+ * "sweep_warps" (warps per CTA of the tile and refine kernels, default 16), "table_mode" (-1 auto / 0 off / 1 on: exact (yes, number) table per query for dense
  * runs of few queries against many targets), "dup" (0/1: the resident ranked lists were packed for -dup, see
  * ppp_read_bla_flags), "device_rank" (1/0: threshold results ranked on the device / on the host).
  * Top-k schedule (none of them changes a result, only how many pairs need a full evaluation): "speculate" (0/1: screen the

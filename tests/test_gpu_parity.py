@@ -740,23 +740,25 @@ def test_topk_speculative_threshold_is_verified(ctx, front_loaded):
             assert np.array_equal(tk1[f], tk[f]), (opt, val, f)
 
 
-def test_g8192_with_16_sweep_warps(ctx):
-    """G = 8192 with the bench's 16 warps per CTA: the query tile + log-factorial table leave shared memory for 15 warps
-    only -- the launchers must clamp instead of failing (regression), and top-k must still equal the dense result."""
+@pytest.mark.parametrize("warps", [16, 8])
+def test_g8192_sweep_warps(ctx, warps):
+    """G = 8192 with 16 warps per CTA (the library's default): the query tile + log-factorial table leave shared memory for 15
+    warps only -- the launchers must clamp instead of failing (regression), and top-k must still equal the dense result; the
+    same with 8 warps (option sweep_warps)."""
     G, nq, nt, k = 8192, 12, 2600, 7
     P, Y, p = synth.make_queries(G, nq, 91, "family")
     T = synth.make_targets(G, nt, 92, plant_from=Y, plant_frac=0.02)
-    ctx.set_option("sweep_warps", 16)
+    ctx.set_option("sweep_warps", warps)
     ctx.set_option("table_mode", 0)
     try:
         ctx.set_targets_bits(T, G)
         dense = ctx.score(P, Y, p).reshape(nq, nt)
         tk = ctx.score(P, Y, p, capi.make_filter(capi.FILTER_TOPK, k=k))
     finally:
-        ctx.set_option("sweep_warps", 8)
+        ctx.set_option("sweep_warps", 16)
         ctx.set_option("table_mode", -1)
     ref, _ = oracle.score_bits_batch(P, Y, p, T[:64], G, nthreads=os.cpu_count() or 1)
-    assert_hits_match(np.ascontiguousarray(dense[:, :64]).reshape(-1).copy(), ref, "G=8192, 16 warps")
+    assert_hits_match(np.ascontiguousarray(dense[:, :64]).reshape(-1).copy(), ref, f"G=8192, {warps} warps")
     for q in range(nq):
         exp = np.sort(dense[q], order=["score", "t"])[:k]
         got = tk[q * k:(q + 1) * k]
