@@ -538,7 +538,10 @@ def run_ours(args):
                 line["cpu_baseline_port"] = port
             else:
                 line["cpu_baseline"] = port
-            line["other_configs"] = other_configs(ctx, torch)
+            try:
+                line["other_configs"] = other_configs(ctx, torch)
+            except Exception as e:  # the headline line must not depend on the extra configurations
+                line["other_configs"] = {"error": f"{type(e).__name__}: {e}"}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
